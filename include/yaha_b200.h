@@ -1,0 +1,188 @@
+/* yaha_b200.h -- C ABI of libyaha_b200.so: the B200-native replacement for the alignment
+ * hot path of yaha 0.1.83 (seed lookup -> diagonal sort / fragments / regions -> banded
+ * affine-gap DP with X-drop).  Plain C, POD structs, pointers and sizes only.
+ *
+ * Every entry point names the reference interface it replaces ("ref:" = file:line under
+ * /root/reference/src).  All buffers passed in are HOST memory owned by the caller; the
+ * library owns every device allocation.  A ya_ctx is bound to one GPU and must be used from
+ * one host thread at a time (the reference's per-thread QueryState_t plays the same role,
+ * Math.h:587-666).  There is no CPU fallback: if no usable sm_100 device is present ya_open
+ * fails and every other call returns YA_E_CUDA.
+ */
+#ifndef YAHA_B200_H
+#define YAHA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (ref: errors are fatal exit(1), FileHelpers.c:38-42; here they return) ---- */
+#define YA_OK          0
+#define YA_E_ARG       1   /* bad argument / unsupported parameter combination            */
+#define YA_E_CUDA      2   /* CUDA runtime error, text in ya_last_error()                 */
+#define YA_E_CAPACITY  3   /* a caller-provided output buffer is too small; *_needed set  */
+#define YA_E_STATE     4   /* call order violated (e.g. no reads uploaded)                */
+
+/* ---- scoring / seeding parameters: POD copy of the AlignmentArgs_t fields the hot path
+ *      reads (ref: Math.h:281-304, defaults AlignArgs.c:48-87, derived :108-169) ---- */
+typedef struct ya_params {
+    int32_t wordLen;       /* K, from the index header (Query.c:603)                      */
+    int32_t maxHits;       /* min(-H or 650, index header) (Query.c:604-610)              */
+    int32_t bandWidth;     /* -BW                                                         */
+    int32_t maxGap;        /* -G  : cap on insert run length inside the DP (SW.cpp:1050)  */
+    int32_t maxIntron;     /* = maxGap unless set: cap on delete run length (SW.cpp:1032) */
+    int32_t minMatch;      /* -M  : singleton-region filter (QueryMatch.c:284)            */
+    int32_t GOCost, GECost, RCost, MScore;   /* -GOC -GEC -RC -MS                         */
+    int32_t XCutoff;       /* -X                                                          */
+    int32_t minExtLength;  /* derived, AlignArgs.c:141-149 (host-side dispatch only)      */
+} ya_params;
+
+/* ---- Fragment: bit-compatible with the reference's Fragment_t (Math.h:448-455) ---- */
+typedef struct ya_frag {
+    uint32_t startRefOff;
+    uint16_t startQueryOff;
+    uint16_t endQueryOff;
+    uint16_t hitCount;     /* never written by the reference (QueryMatch.c:52-121); 0 here */
+    uint16_t refLen;
+} ya_frag;
+
+/* ---- a batch of reads: forward strand 4-bit codes, one byte per base (the reference's
+ *      QS->forwardCodeBuf, Query.c:161-163).  The reverse-complement strand
+ *      (Query.c:164-167) is derived on the device. ---- */
+typedef struct ya_read_batch {
+    int32_t         n_reads;
+    const uint8_t  *codes;      /* concatenated codes, offsets[n_reads] bytes              */
+    const uint64_t *offsets;    /* n_reads+1 entries, offsets[0] == 0                      */
+} ya_read_batch;
+
+/* ---- stage 1+2 output.  For each (read,strand) the diag-sorted fragment array of
+ *      findFragmentsSort (QueryMatch.c:52) after the region scan of processFragmentsGapped
+ *      (QueryMatch.c:224-303): fragments of singleton regions with refLen < minMatch are
+ *      dropped on the device (they can never reach a clump, QueryMatch.c:281-290); every
+ *      other fragment is returned, in the reference's order, with its region id. ---- */
+typedef struct ya_strand_frags {
+    uint32_t first;        /* index of this strand's first surviving fragment in frags[]  */
+    uint32_t n_frags;      /* surviving fragments                                          */
+    uint32_t n_frags_all;  /* fragCount the reference would have returned                  */
+    uint32_t total_hits;   /* totalCount of Query.c:365-412 (sum of kept k-mer counts)    */
+} ya_strand_frags;
+
+typedef struct ya_frag_batch {
+    /* capacities, set by the caller */
+    size_t           frags_cap;
+    /* outputs */
+    ya_strand_frags *strands;     /* [2*n_reads]: index 2*r + strand (0 fwd, 1 revcomp)   */
+    ya_frag         *frags;       /* [frags_cap]                                           */
+    uint32_t        *region;      /* [frags_cap] region ordinal within its strand; a       */
+                                  /* region with one member is a singleton (-> clump),     */
+                                  /* otherwise it goes to the host graph (GraphPath.cpp)   */
+    size_t           n_frags;     /* total surviving fragments written                     */
+    size_t           frags_needed;/* set when YA_E_CAPACITY is returned                    */
+} ya_frag_batch;
+
+/* ---- stage 3: DP jobs.  Semantics of each kind are those of the reference wrapper named,
+ *      including reference-end clamping (SW.cpp:496-516) and the "<= 0 means no extension,
+ *      no ops" rule (SW.cpp:525,1102). ---- */
+#define YA_DP_FULL     0   /* findAGSAlignment         Math.h:401  SW.cpp:462              */
+#define YA_DP_BANDED   1   /* findAGSAlignmentBanded   Math.h:402  SW.cpp:470              */
+#define YA_DP_EXT_FWD  2   /* findAGSForwardExtension  Math.h:403  SW.cpp:543              */
+#define YA_DP_EXT_BWD  3   /* findAGSBackwardExtension Math.h:407  SW.cpp:537              */
+
+typedef struct ya_dp_job {
+    uint32_t rOff;         /* reference offset argument of the wrapper                     */
+    uint32_t read;         /* read index in the uploaded batch                             */
+    uint16_t rLen;         /* FULL/BANDED only                                             */
+    uint16_t qOff;
+    uint16_t qLen;
+    uint8_t  kind;         /* YA_DP_*                                                      */
+    uint8_t  strand;       /* 0 = forward codes, 1 = reverse-complement codes              */
+} ya_dp_job;
+
+typedef struct ya_dp_result {
+    int32_t  score;        /* return value of the wrapper                                  */
+    uint16_t addedQLen;    /* extensions only (SW.cpp:1109)                                */
+    uint16_t addedRLen;    /* extensions only (SW.cpp:1110)                                */
+    uint32_t ops_off;      /* first op of this job in ops[]                                */
+    uint32_t ops_n;        /* number of run-length ops (0 when score <= 0 for extensions) */
+} ya_dp_result;
+
+/* run-length edit op in genome order (ref: EditOp_t Math.h:371-378 without the links) */
+typedef struct ya_op {
+    uint16_t length;
+    uint8_t  opcode;       /* 'M' 'R' 'I' 'D' (Math.h:354-360)                             */
+    uint8_t  pad;
+} ya_op;
+
+typedef struct ya_counters {
+    uint64_t probes;       /* k-mer probes issued (stage 1)                                */
+    uint64_t hits;         /* seed hits expanded (stage 2a)                                */
+    uint64_t frags_all;    /* fragments formed                                             */
+    uint64_t frags_out;    /* fragments returned to the host                               */
+    uint64_t dp_jobs;
+    uint64_t dp_cells;     /* cells as the reference counts them (SW.cpp:1007-1084 bodies) */
+    double   ms_seed;      /* device time of stage 1+2 kernels (CUDA events)               */
+    double   ms_dp;        /* device time of stage 3 fill kernels                          */
+    double   ms_traceback; /* device time of stage 3 traceback kernels                     */
+    uint64_t launches;     /* kernels launched by this library                             */
+} ya_counters;
+
+typedef struct ya_ctx ya_ctx;
+
+/* Create a context on CUDA device `device` and make the index + genome resident in HBM.
+ *   so  : the index's starting-offset table, 4^K+1 uint32   (ref: AAs->startingOffs, Query.c:625)
+ *   roa : the index's reference-offset array, n_roa uint32  (ref: AAs->ROAPtr, Query.c:626)
+ *   bases: .nib2 base area, 4 bits per base, high nibble first (ref: AAs->basePtr, Query.c:572)
+ *   maxROff: baseSequencesMaxROff (BaseSeq.c:121-125)
+ * Returns NULL on failure; ya_last_error(NULL) describes it. */
+ya_ctx *ya_open(int device, const ya_params *params,
+                const uint32_t *so, size_t n_so, const uint32_t *roa, size_t n_roa,
+                const uint8_t *bases, size_t n_base_bytes, uint32_t maxROff);
+
+/* Same, but clone the device-resident index of `src` (another GPU) by peer copy over
+ * NVLink instead of re-uploading from the host. */
+ya_ctx *ya_open_peer(int device, const ya_ctx *src);
+
+void        ya_close(ya_ctx *);
+const char *ya_last_error(const ya_ctx *);
+
+/* Change scoring parameters without reloading the index (wordLen must not change). */
+int ya_set_params(ya_ctx *, const ya_params *);
+
+/* Run subsequent work on a caller-provided cudaStream_t (e.g. torch's current stream) so
+ * that the caller's CUDA events bracket the kernels.  NULL restores the library's stream. */
+int ya_set_stream(ya_ctx *, void *cuda_stream);
+
+/* Make a batch of reads resident on the device (replaces the per-read buffers filled by
+ * readNextQuery, Query.c:161-168).  Stays valid until the next ya_reads_upload. */
+int ya_reads_upload(ya_ctx *, const ya_read_batch *);
+
+/* Stage 1 + 2 for the uploaded batch.  Replaces, per (read,strand): the seed-lookup loop
+ * Query.c:365-412, findFragmentsSort (Math.h:554, QueryMatch.c:52-121) and the region scan /
+ * singleton filter of processFragmentsGapped (Math.h:555, QueryMatch.c:224-303). */
+int ya_seed_frags(ya_ctx *, ya_frag_batch *out);
+
+/* Stage 3 for n independent jobs against the uploaded batch.  Replaces findAGSAlignment,
+ * findAGSAlignmentBanded, findAGSForwardExtension, findAGSBackwardExtension
+ * (Math.h:401-408) = findAffineGapScore<...> (SW.cpp:798-1208) + decompressRef
+ * (SW.cpp:444-456).  res[i] answers jobs[i].  On YA_E_CAPACITY *ops_needed is set. */
+int ya_sw_batch(ya_ctx *, const ya_dp_job *jobs, int n, ya_dp_result *res,
+                ya_op *ops, size_t ops_cap, size_t *ops_needed);
+
+/* Perfect (exact-match) extension lengths (ref: extendFragment{Forward,Backward}
+ * ToStopPerfectly, AlignExtFrag.cpp:30-48): for job i, count equal codes starting at
+ * (qOff,rOff) walking forward (kind EXT_FWD) or backward (EXT_BWD), at most qLen. */
+int ya_perfect_ext(ya_ctx *, const ya_dp_job *jobs, int n, uint16_t *count);
+
+/* Read-and-reset the counters. */
+int ya_get_counters(ya_ctx *, ya_counters *);
+
+/* Device-side self measurements used by bench.py for roofline denominators. */
+int ya_measure_int32_peak(ya_ctx *, double *giops);   /* sustained INT32 lane-ops/s, all SMs */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YAHA_B200_H */
