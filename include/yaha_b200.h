@@ -180,7 +180,10 @@ int ya_perfect_ext(ya_ctx *, const ya_dp_job *jobs, int n, uint16_t *count);
 int ya_get_counters(ya_ctx *, ya_counters *);
 
 /* Device-side self measurements used by bench.py for roofline denominators. */
-int ya_measure_int32_peak(ya_ctx *, double *giops);   /* sustained INT32 lane-ops/s, all SMs */
+/* Sustained INT32 issue rate of this GPU in 1e9 lane-operations per second, all SMs busy:
+ * *giops_add from a pure dependent-free IADD3 stream, *giops_mix from the add / compare /
+ * select / min-max mix of the DP cell (the roofline denominator of the banded-SW kernel). */
+int ya_measure_int32_peak(ya_ctx *, double *giops_add, double *giops_mix);
 
 #ifdef __cplusplus
 }

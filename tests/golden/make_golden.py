@@ -1,0 +1,56 @@
+"""Regenerates tests/golden/small/ from the UNMODIFIED reference (oracle/_ref/, built by
+oracle/Makefile from /root/reference).  Run in the build container only:
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+Outputs (all gzip'd, deterministic seeds):
+  ref.fa.gz, reads.fa.gz      synthetic 300 kbp / 3-sequence reference and 635 reads incl. the
+                              edge cases of yaha_b200.synth.edge_reads
+  dump_bw5.txt.gz             every call through the hot-path seams with default flags
+  dump_bw10.txt.gz            same with -BW 10 -G 100 (D and G records only)
+  out_bw5.sam.gz, out_bw10.sam.gz   the reference's SAM output (-t 1)
+  files.sha256                digests of the reference-built ref.nib2 and index
+"""
+import gzip, hashlib, os, shutil, subprocess, sys, tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from yaha_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden", "small")
+REF = os.path.join(ROOT, "oracle", "_ref")
+
+
+def gz(src, dst):
+    with open(src, "rb") as f, gzip.GzipFile(dst, "wb", mtime=0) as g:
+        shutil.copyfileobj(f, g)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    tmp = tempfile.mkdtemp()
+    ref = synth.random_reference(300_000, 4242)
+    bounds = [0, 120_000, 200_003, 300_000]
+    synth.write_fasta(tmp + "/ref.fa", [(f"chr{k + 1}", ref[bounds[k]:bounds[k + 1]]) for k in range(3)])
+    reads = list(synth.simulate_reads(ref, 300, 400, 0.05, 99))
+    reads += list(synth.simulate_reads(ref, 150, 500, 0.10, 100))
+    reads += synth.edge_reads(ref, 7, n_each=25, seq_bounds=bounds)
+    synth.write_reads(tmp + "/reads.fa", reads)
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp)
+    idx = "ref.X11_01_65525S"
+    for bw, g, mask in ((5, 50, 15), (10, 100, 5)):
+        env = dict(os.environ, YAHA_DUMP=f"{tmp}/dump_bw{bw}.txt", YAHA_DUMP_MASK=str(mask))
+        subprocess.check_call([REF + "/yaha_dump", "-x", idx, "-q", "reads.fa", "-osh", f"out_bw{bw}.sam", "-t", "1",
+                               "-BW", str(bw), "-G", str(g)], cwd=tmp, env=env)
+        gz(f"{tmp}/dump_bw{bw}.txt", f"{OUT}/dump_bw{bw}.txt.gz")
+        gz(f"{tmp}/out_bw{bw}.sam", f"{OUT}/out_bw{bw}.sam.gz")
+    gz(tmp + "/ref.fa", OUT + "/ref.fa.gz")
+    gz(tmp + "/reads.fa", OUT + "/reads.fa.gz")
+    with open(OUT + "/files.sha256", "w") as f:
+        for name in ("ref.nib2", idx):
+            f.write(hashlib.sha256(open(f"{tmp}/{name}", "rb").read()).hexdigest() + "  " + name + "\n")
+    shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    main()

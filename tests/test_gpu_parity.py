@@ -1,0 +1,203 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against (a) the calls the
+unmodified reference made (golden dumps) and (b) the CPU oracle on seeded synthetic inputs.
+Integer work throughout => bit-exact equality is required."""
+import os
+
+import numpy as np
+import pytest
+
+import support as S
+import yaha_b200
+from yaha_b200 import refio, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aligner(small):
+    al = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11), device=0)
+    al.upload_read_list(small.fwd)
+    yield al
+    al.close()
+
+
+def _res_tuple(res, ops, i):
+    o, n = int(res[i]["ops_off"]), int(res[i]["ops_n"])
+    return (int(res[i]["score"]), int(res[i]["addedQLen"]), int(res[i]["addedRLen"]), S.ops_to_str(ops[o:o + n]))
+
+
+def _golden_jobs(small, bw):
+    jobs, want = [], []
+    for rec in S.parse_dump(small.dump(bw), "D"):
+        _, k, qid, st, roff, rlen, qoff, qlen, score, aq, ar, ops = rec
+        jobs.append((roff, small.read_id[qid], rlen, qoff, qlen, S.KIND_OF_CHAR[k], st))
+        want.append((score, aq, ar, ops))
+    return np.array(jobs, dtype=yaha_b200.JOB_DT), want
+
+
+@pytest.mark.parametrize("mode", ["wave", "thread"])
+@pytest.mark.parametrize("bw,gap", [(5, 50), (10, 100)])
+def test_dp_matches_reference_calls(small, aligner, bw, gap, mode, monkeypatch):
+    """Every DP call of the reference run (all four kinds, both strands, clamped at both reference
+    ends, X-drop terminated and run-to-end) reproduced: score, addedQLen, addedRLen, op runs."""
+    monkeypatch.setenv("YA_DP_MODE", mode)
+    aligner.set_params(yaha_b200.Params.defaults(word_len=11, bw=bw, max_gap=gap))
+    jobs, want = _golden_jobs(small, bw)
+    res, ops = aligner.sw_batch(jobs)
+    bad = [(i, tuple(jobs[i]), _res_tuple(res, ops, i), want[i]) for i in range(len(want))
+           if _res_tuple(res, ops, i) != want[i]]
+    assert not bad, bad[:5]
+    # cell count equals the oracle's (same definition: SW.cpp:1007-1084 bodies executed)
+    p = S.default_params(word_len=11, bw=bw, max_gap=gap)
+    cells = 0
+    for j in jobs[:400]:
+        cells += S.oracle_dp(p, small.nib.bases, small.nib.max_roff,
+                             small.rev[j["read"]] if j["strand"] else small.fwd[j["read"]],
+                             int(j["kind"]), int(j["rOff"]), int(j["rLen"]), int(j["qOff"]), int(j["qLen"]))[4]
+    aligner.counters()
+    aligner.sw_batch(jobs[:400])
+    assert aligner.counters().dp_cells == cells
+
+
+def test_seed_frags_match_reference_and_oracle(small, aligner):
+    """Stage 1+2: per strand, surviving fragments (values and order), fragCount, totalCount and
+    region ids equal the oracle; the oracle equals the reference dump (test_oracle_golden)."""
+    aligner.set_params(yaha_b200.Params.defaults(word_len=11))
+    strands, frags, region = aligner.seed_frags()
+    p = S.default_params(word_len=11)
+    ref_frags = {}
+    for rec in S.parse_dump(small.dump(5), "G"):
+        ref_frags[(rec[1], rec[2])] = rec[3]
+    nonempty = 0
+    for r, name in enumerate(small.names):
+        for st in (0, 1):
+            _, _, total, of, oreg, keep = S.oracle_seed_frags(p, small.idx.so, small.idx.roa, small.codes(name, st))
+            s = strands[2 * r + st]
+            assert int(s["total_hits"]) == total, (name, st)
+            assert int(s["n_frags_all"]) == len(of), (name, st)
+            if (name, st) in ref_frags:
+                assert len(ref_frags[(name, st)]) == len(of)
+            k = keep.astype(bool)
+            a, n = int(s["first"]), int(s["n_frags"])
+            assert n == int(k.sum()), (name, st)
+            mine = frags[a:a + n]
+            for f in ("startRefOff", "startQueryOff", "endQueryOff", "refLen"):
+                assert np.array_equal(mine[f], of[k][f]), (name, st, f)
+            assert np.array_equal(region[a:a + n], oreg[k]), (name, st)
+            nonempty += n > 0
+    assert nonempty > 500
+
+
+def test_seed_frags_capacity_protocol(small, aligner):
+    aligner.set_params(yaha_b200.Params.defaults(word_len=11))
+    s1, f1, r1 = aligner.seed_frags(frags_cap=8)      # forces YA_E_CAPACITY then a retry
+    s2, f2, r2 = aligner.seed_frags()
+    assert np.array_equal(f1, f2) and np.array_equal(r1, r2) and np.array_equal(s1, s2)
+
+
+def test_perfect_extension(small, aligner):
+    rng = np.random.default_rng(5)
+    jobs = []
+    want = []
+    lib = S.oracle()
+    for _ in range(2000):
+        r = int(rng.integers(0, len(small.fwd)))
+        st = int(rng.integers(0, 2))
+        codes = small.rev[r] if st else small.fwd[r]
+        L = len(codes)
+        qoff = int(rng.integers(0, L))
+        name = small.names[r]
+        # aim at the true locus when the name carries it, else anywhere
+        roff = int(rng.integers(40, small.nib.max_roff - 40))
+        fwd_dir = bool(rng.integers(0, 2))
+        ln = int(rng.integers(0, (L - qoff) if fwd_dir else qoff + 1))
+        ln = min(ln, 30)
+        jobs.append((roff, r, 0, qoff, ln, yaha_b200.DP_EXT_FWD if fwd_dir else yaha_b200.DP_EXT_BWD, st))
+        want.append(lib.orc_perfect(S.ptr(small.nib.bases), S.ptr(codes), roff, qoff, ln, 1 if fwd_dir else -1))
+    got = aligner.perfect_ext(np.array(jobs, dtype=yaha_b200.JOB_DT))
+    assert list(got) == want
+
+
+def test_random_jobs_against_oracle(small, aligner):
+    """Seeded random job tuples (not only those the pipeline produces): odd sizes, tiny and wide
+    global jobs, extensions started at arbitrary anchors near both reference ends, non-default
+    scoring -- including caps (maxGap) that bind inside the band."""
+    rng = np.random.default_rng(11)
+    for (bw, gap, goc, gec, rc, ms, x) in [(5, 50, 5, 2, 3, 1, 25), (3, 4, 2, 1, 2, 1, 10), (8, 30, 6, 1, 4, 2, 40),
+                                            (1, 2, 1, 1, 1, 1, 5), (16, 100, 5, 2, 3, 1, 25)]:
+        P = yaha_b200.Params.defaults(word_len=11, bw=bw, max_gap=gap, goc=goc, gec=gec, rc=rc, ms=ms, x=x)
+        aligner.set_params(P)
+        p = S.default_params(word_len=11, bw=bw, max_gap=gap, goc=goc, gec=gec, rc=rc, ms=ms, x=x)
+        jobs = []
+        for _ in range(300):
+            r = int(rng.integers(0, 450))
+            st = int(rng.integers(0, 2))
+            L = len(small.fwd[r])
+            kind = int(rng.integers(0, 4))
+            # true locus from the read name r<i>_<start>_<strand>
+            parts = small.names[r].split("_")
+            start = int(parts[1])
+            gstart = start + (0 if start < 120000 else (0 if start < 200003 else 5)) + (0 if start < 200003 else 0)
+            if kind <= 1:
+                qlen = int(rng.integers(1, 60)); rlen = max(1, qlen + int(rng.integers(-min(gap, qlen - 1) if qlen > 1 else 0, gap + 1)))
+                qoff = int(rng.integers(0, L - qlen))
+                roff = max(0, min(small.nib.max_roff - rlen - 1, gstart + qoff + int(rng.integers(-3, 4))))
+                jobs.append((roff, r, rlen, qoff, qlen, kind, st))
+            else:
+                where = rng.integers(0, 4)
+                if kind == yaha_b200.DP_EXT_FWD:
+                    qoff = int(rng.integers(0, L)); qlen = L - qoff
+                    roff = [gstart + qoff, small.nib.max_roff - int(rng.integers(1, 60)), gstart + qoff + 2, int(rng.integers(0, 50))][where]
+                else:
+                    qoff = int(rng.integers(0, L)); qlen = qoff + 1
+                    roff = [gstart + qoff, int(rng.integers(0, 60)), gstart + qoff - 2, small.nib.max_roff - int(rng.integers(1, 50))][where]
+                roff = max(0, min(small.nib.max_roff - 1, roff))
+                jobs.append((roff, r, 0, qoff, qlen, kind, st))
+        jobs = np.array(jobs, dtype=yaha_b200.JOB_DT)
+        res, ops = aligner.sw_batch(jobs)
+        for i, j in enumerate(jobs):
+            codes = small.rev[j["read"]] if j["strand"] else small.fwd[j["read"]]
+            w = S.oracle_dp(p, small.nib.bases, small.nib.max_roff, codes, int(j["kind"]), int(j["rOff"]),
+                            int(j["rLen"]), int(j["qOff"]), int(j["qLen"]))[:4]
+            assert _res_tuple(res, ops, i) == w, (tuple(j), (bw, gap, goc, gec, rc, ms, x))
+
+
+def test_empty_and_degenerate_inputs(small):
+    al = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11), device=0)
+    # empty batch
+    al.upload_read_list([])
+    strands, frags, region = al.seed_frags()
+    assert len(strands) == 0 and len(frags) == 0
+    # reads shorter than K, all-N reads, one real read
+    reads = [np.zeros(5, np.uint8), np.full(50, 4, np.uint8), small.fwd[0], np.zeros(0, np.uint8)]
+    al.upload_read_list(reads)
+    strands, frags, region = al.seed_frags()
+    assert list(strands["n_frags_all"][:4]) == [0, 0, 0, 0]
+    assert strands["n_frags_all"][4] + strands["n_frags_all"][5] > 0
+    assert list(strands["n_frags_all"][6:]) == [0, 0]
+    res, ops = al.sw_batch(np.zeros(0, dtype=yaha_b200.JOB_DT))
+    assert len(res) == 0
+    # extension with nothing left to extend returns 0 / no ops (SW.cpp:494)
+    j = np.array([(1000, 2, 0, 0, 0, yaha_b200.DP_EXT_FWD, 0)], dtype=yaha_b200.JOB_DT)
+    res, ops = al.sw_batch(j)
+    assert int(res[0]["score"]) == 0 and int(res[0]["ops_n"]) == 0
+    with pytest.raises(yaha_b200.YahaError):
+        al.sw_batch(np.array([(0, 99, 5, 0, 5, 0, 0)], dtype=yaha_b200.JOB_DT))    # bad read index
+    al.close()
+
+
+def test_linearity_of_sharding(small, aligner):
+    """Size-independent property: results for a batch equal the concatenation of results for its
+    shards (reads are independent units)."""
+    aligner.set_params(yaha_b200.Params.defaults(word_len=11))
+    aligner.upload_read_list(small.fwd)
+    s_all, f_all, r_all = aligner.seed_frags()
+    half = len(small.fwd) // 2
+    aligner.upload_read_list(small.fwd[:half])
+    s_a, f_a, r_a = aligner.seed_frags()
+    aligner.upload_read_list(small.fwd[half:])
+    s_b, f_b, r_b = aligner.seed_frags()
+    assert np.array_equal(np.concatenate([f_a, f_b]), f_all)
+    assert np.array_equal(np.concatenate([r_a, r_b]), r_all)
+    assert np.array_equal(np.concatenate([s_a["n_frags"], s_b["n_frags"]]), s_all["n_frags"])
+    aligner.upload_read_list(small.fwd)

@@ -1,0 +1,223 @@
+"""yaha_b200 -- B200-native drop-in for the alignment hot path of yaha 0.1.83.
+
+This package is a thin ctypes binding over the C ABI in ``include/yaha_b200.h``
+(``libyaha_b200.so``, hand-written sm_100a CUDA).  There is NO CPU fallback: importing works
+anywhere, but creating an :class:`Aligner` requires the compiled library and an sm_100 GPU and
+raises otherwise.
+
+Reference seams replaced (file:line under the reference's ``src/``):
+  * seed lookup loop                         Query.c:365-412
+  * findFragmentsSort / processFragmentsGapped region scan   Math.h:554-555, QueryMatch.c:52-303
+  * findAGSAlignment[Banded] / findAGS{Forward,Backward}Extension   Math.h:401-408, SW.cpp:462-1208
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import refio
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyaha_b200.so")
+
+YA_OK, YA_E_ARG, YA_E_CUDA, YA_E_CAPACITY, YA_E_STATE = 0, 1, 2, 3, 4
+DP_FULL, DP_BANDED, DP_EXT_FWD, DP_EXT_BWD = 0, 1, 2, 3
+
+
+class Params(C.Structure):
+    """POD copy of the scoring/seeding fields of AlignmentArgs_t (Math.h:281-304)."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("wordLen", "maxHits", "bandWidth", "maxGap", "maxIntron", "minMatch",
+                 "GOCost", "GECost", "RCost", "MScore", "XCutoff", "minExtLength")]
+
+    @classmethod
+    def defaults(cls, word_len=15, max_hits=650, bw=5, max_gap=50, min_match=25,
+                 goc=5, gec=2, rc=3, ms=1, x=25) -> "Params":
+        """AlignArgs.c:48-87 defaults plus the derived values of AlignArgs.c:108-169."""
+        ln, sc, target = 1, 0, min(rc, goc + gec)
+        while sc <= target:
+            sc += ms
+            ln += 1
+        return cls(word_len, max_hits, bw, max_gap, max_gap, min_match, goc, gec, rc, ms, x, ln)
+
+
+FRAG_DT = np.dtype([("startRefOff", "<u4"), ("startQueryOff", "<u2"), ("endQueryOff", "<u2"),
+                    ("hitCount", "<u2"), ("refLen", "<u2")])
+STRAND_DT = np.dtype([("first", "<u4"), ("n_frags", "<u4"), ("n_frags_all", "<u4"), ("total_hits", "<u4")])
+JOB_DT = np.dtype([("rOff", "<u4"), ("read", "<u4"), ("rLen", "<u2"), ("qOff", "<u2"), ("qLen", "<u2"),
+                   ("kind", "u1"), ("strand", "u1")])
+RES_DT = np.dtype([("score", "<i4"), ("addedQLen", "<u2"), ("addedRLen", "<u2"), ("ops_off", "<u4"), ("ops_n", "<u4")])
+OP_DT = np.dtype([("length", "<u2"), ("opcode", "u1"), ("pad", "u1")])
+
+
+class _ReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("codes", C.c_void_p), ("offsets", C.c_void_p)]
+
+
+class _FragBatch(C.Structure):
+    _fields_ = [("frags_cap", C.c_size_t), ("strands", C.c_void_p), ("frags", C.c_void_p),
+                ("region", C.c_void_p), ("n_frags", C.c_size_t), ("frags_needed", C.c_size_t)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("probes", C.c_uint64), ("hits", C.c_uint64), ("frags_all", C.c_uint64), ("frags_out", C.c_uint64),
+                ("dp_jobs", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_seed", C.c_double), ("ms_dp", C.c_double),
+                ("ms_traceback", C.c_double), ("launches", C.c_uint64)]
+
+
+EXPORTS = ("ya_open", "ya_open_peer", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
+           "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_perfect_ext", "ya_get_counters",
+           "ya_measure_int32_peak")
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libyaha_b200.so (no GPU needed for this) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(yaha_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.ya_open.restype = vp
+    lib.ya_open.argtypes = [C.c_int, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]
+    lib.ya_open_peer.restype = vp
+    lib.ya_open_peer.argtypes = [C.c_int, vp]
+    lib.ya_close.restype = None
+    lib.ya_close.argtypes = [vp]
+    lib.ya_last_error.restype = C.c_char_p
+    lib.ya_last_error.argtypes = [vp]
+    lib.ya_set_params.argtypes = [vp, C.POINTER(Params)]
+    lib.ya_set_stream.argtypes = [vp, vp]
+    lib.ya_reads_upload.argtypes = [vp, C.POINTER(_ReadBatch)]
+    lib.ya_seed_frags.argtypes = [vp, C.POINTER(_FragBatch)]
+    lib.ya_sw_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.ya_perfect_ext.argtypes = [vp, vp, C.c_int, vp]
+    lib.ya_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    lib.ya_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+class YahaError(RuntimeError):
+    pass
+
+
+class Aligner:
+    """One GPU context with a resident index (`ya_ctx`)."""
+
+    def __init__(self, nib2: refio.Nib2, index: refio.Index, params: Params | None = None, device: int = 0,
+                 peer_of: "Aligner | None" = None):
+        self.lib = load_library()
+        self.nib2, self.index = nib2, index
+        if params is None:
+            params = Params.defaults(word_len=index.word_len, max_hits=min(650, index.max_hits))
+        self.params = params
+        if peer_of is not None:
+            self.ctx = self.lib.ya_open_peer(device, peer_of.ctx)
+        else:
+            so = np.ascontiguousarray(index.so)
+            roa = np.ascontiguousarray(index.roa)
+            bases = np.ascontiguousarray(nib2.bases)
+            self.ctx = self.lib.ya_open(device, C.byref(params), so.ctypes.data, len(so), roa.ctypes.data, len(roa),
+                                        bases.ctypes.data, len(bases), nib2.max_roff)
+        if not self.ctx:
+            raise YahaError("ya_open failed: " + self.lib.ya_last_error(None).decode())
+        self.n_reads = 0
+
+    @classmethod
+    def from_files(cls, nib2_path: str, index_path: str, device: int = 0, **param_overrides) -> "Aligner":
+        nib, idx = refio.load_nib2(nib2_path), refio.load_index(index_path)
+        mh = min(param_overrides.pop("max_hits", 650), idx.max_hits)
+        p = Params.defaults(word_len=idx.word_len, max_hits=mh, **param_overrides)
+        return cls(nib, idx, p, device)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.ya_close(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != YA_OK:
+            raise YahaError(f"yaha_b200 error {rc}: {self.lib.ya_last_error(self.ctx).decode()}")
+
+    def set_params(self, p: Params):
+        self._check(self.lib.ya_set_params(self.ctx, C.byref(p)))
+        self.params = p
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self.lib.ya_set_stream(self.ctx, cuda_stream_ptr))
+
+    def upload_reads(self, codes: np.ndarray, offsets: np.ndarray):
+        """codes: concatenated forward 4-bit codes (uint8); offsets: uint64[n+1]."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        b = _ReadBatch(len(offsets) - 1, codes.ctypes.data, offsets.ctypes.data)
+        self._check(self.lib.ya_reads_upload(self.ctx, C.byref(b)))
+        self.n_reads = len(offsets) - 1
+
+    def upload_read_list(self, reads: list[np.ndarray]):
+        offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+        if reads:
+            offs[1:] = np.cumsum([len(r) for r in reads])
+        codes = np.concatenate(reads) if reads else np.zeros(0, np.uint8)
+        self.upload_reads(codes, offs)
+
+    def seed_frags(self, frags_cap: int | None = None):
+        """Stage 1+2 for the uploaded batch -> (strands[2n], frags, region)."""
+        n = self.n_reads
+        strands = np.zeros(2 * n, dtype=STRAND_DT)
+        cap = frags_cap if frags_cap is not None else max(1024, 64 * n)
+        while True:
+            frags = np.zeros(cap, dtype=FRAG_DT)
+            region = np.zeros(cap, dtype=np.uint32)
+            fb = _FragBatch(cap, strands.ctypes.data, frags.ctypes.data, region.ctypes.data, 0, 0)
+            rc = self.lib.ya_seed_frags(self.ctx, C.byref(fb))
+            if rc == YA_E_CAPACITY:
+                cap = int(fb.frags_needed) + 16
+                continue
+            self._check(rc)
+            return strands, frags[:fb.n_frags], region[:fb.n_frags]
+
+    def sw_batch(self, jobs: np.ndarray, ops_cap: int | None = None):
+        """Stage 3 for a structured array of JOB_DT -> (results RES_DT[n], ops OP_DT[total])."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DT)
+        n = len(jobs)
+        res = np.zeros(n, dtype=RES_DT)
+        cap = ops_cap if ops_cap is not None else max(1024, 16 * n)
+        while True:
+            ops = np.zeros(cap, dtype=OP_DT)
+            need = C.c_size_t(0)
+            rc = self.lib.ya_sw_batch(self.ctx, jobs.ctypes.data, n, res.ctypes.data, ops.ctypes.data, cap, C.byref(need))
+            if rc == YA_E_CAPACITY:
+                cap = int(need.value) + 16
+                continue
+            self._check(rc)
+            return res, ops[:need.value]
+
+    def perfect_ext(self, jobs: np.ndarray) -> np.ndarray:
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DT)
+        out = np.zeros(len(jobs), dtype=np.uint16)
+        self._check(self.lib.ya_perfect_ext(self.ctx, jobs.ctypes.data, len(jobs), out.ctypes.data))
+        return out
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self._check(self.lib.ya_get_counters(self.ctx, C.byref(c)))
+        return c
+
+    def int32_peak(self) -> tuple[float, float]:
+        a, m = C.c_double(0), C.c_double(0)
+        self._check(self.lib.ya_measure_int32_peak(self.ctx, C.byref(a), C.byref(m)))
+        return a.value, m.value

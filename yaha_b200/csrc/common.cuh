@@ -1,0 +1,121 @@
+// common.cuh -- internal declarations shared by the translation units of libyaha_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/yaha_b200.h"
+
+#define YA_WORST (-(0x7fffff00))      // "minus infinity" of the reference DP (SW.cpp:356)
+
+// Device-resident growable buffer (never shrinks; reused across batches).
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// Pinned host staging buffer.
+struct PinBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// Job descriptor as the DP kernels see it (built on the host from ya_dp_job).
+struct DevJob {
+    uint64_t tb_off;      // first traceback cell of this job in the scratch (uint16 units)
+    uint32_t rOff;        // first reference base of the window (already clamped)
+    uint32_t qIdx;        // index of the first query code in the strand's code array
+    uint32_t ops_off;     // first slot of this job in the raw op scratch
+    uint16_t rLen;        // window length
+    uint16_t qLen;        // rows
+    uint16_t lb, rb;      // left / right band (band coordinates, SW.cpp:844-871)
+    uint8_t  kind;        // YA_DP_*
+    uint8_t  strand;
+    uint8_t  layout;      // 0: cell (i,j) at i*stride + j ; 1: skewed by lane, (i + j/C)*stride + j
+    uint8_t  colsPerLane; // C of the skewed layout
+    uint32_t stride;      // traceback row stride in cells
+    uint32_t ops_cap;     // slots available in the raw op scratch
+    uint32_t rows_off;    // generic kernel: first int of this job's row state scratch
+};
+
+struct DevJobOut {
+    int32_t  score;       // raw DP score (extension: maxScore; global: last cell)
+    int32_t  maxi, maxj;  // traceback start (band coordinates)
+    uint32_t n_ops;       // filled by the traceback kernel
+    uint32_t cells_lo, cells_hi;   // 64-bit cell count split (avoids alignment padding)
+};
+
+struct ya_ctx {
+    int          device = -1;
+    ya_params    P{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string  err;
+    // index + genome (device resident)
+    uint32_t *d_so = nullptr;   size_t n_so = 0;
+    uint32_t *d_roa = nullptr;  size_t n_roa = 0;
+    uint8_t  *d_bases = nullptr; size_t n_base_bytes = 0;
+    uint32_t  maxROff = 0;
+    bool      owns_index = true;
+    // uploaded read batch
+    int       n_reads = 0;
+    uint64_t  total_bases = 0;
+    DevBuf    d_codes_fwd, d_codes_rev, d_read_off;
+    std::vector<uint64_t> h_read_off;
+    // seed stage scratch
+    DevBuf    d_seg_probe_off, d_cnt, d_soff, d_hit_off, d_keys0, d_keys1, d_scan_tmp, d_hist;
+    DevBuf    d_fragflag, d_fragidx, d_frags_all, d_frag_seg, d_regflag, d_regidx, d_regstart,
+              d_keep, d_keepidx, d_frags_out, d_region_out, d_strand_out, d_misc;
+    PinBuf    h_stage, h_stage2, h_stage3;
+    // dp stage scratch
+    DevBuf    d_jobs, d_jobout, d_tb, d_rows, d_ops_raw, d_ops_cnt, d_ops_off, d_ops_out, d_res;
+    PinBuf    h_jobs, h_res, h_ops;
+    // timing
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    ya_counters ctr{};
+};
+
+#define YA_CUDA(ctx, call)                                                                  \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            return YA_E_CUDA;                                                               \
+        }                                                                                   \
+    } while (0)
+
+static inline int ya_fail(ya_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg;
+    return code;
+}
+
+// scan.cu
+int ya_exclusive_scan_u32(ya_ctx *c, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total);
+// seed.cu / sw.cu / peak.cu hold the C-ABI entry points declared in yaha_b200.h

@@ -1,0 +1,201 @@
+// ctx.cu -- context life-cycle, index residency and read-batch upload for libyaha_b200.so.
+//
+// Replaces the per-run set-up of processQueryFile (Query.c:551-640: mmap of .nib2 and index,
+// pointer carving) with HBM-resident copies, and the per-read buffer fill of readNextQuery
+// (Query.c:161-168: forward + reverse-complement code buffers) with one batched upload plus
+// a device kernel that derives the reverse-complement strand.
+#include "common.cuh"
+
+static thread_local std::string g_open_err;
+
+// complement of a 4-bit code (Math.c:155: fourBitCompCodes)
+__constant__ uint8_t c_comp[16] = {2, 3, 0, 1, 4, 12, 7, 6, 9, 8, 15, 11, 5, 13, 14, 10};
+
+__global__ void revcomp_kernel(const uint8_t *__restrict__ fwd, uint8_t *__restrict__ rev,
+                               const uint64_t *__restrict__ off, int n_reads, uint64_t total)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += step) {
+        // find read r with off[r] <= i < off[r+1]
+        int lo = 0, hi = n_reads;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (off[mid] <= i) lo = mid; else hi = mid;
+        }
+        uint64_t s = off[lo], e = off[lo + 1];
+        rev[s + (e - 1 - i)] = c_comp[fwd[i] & 15];
+    }
+}
+
+static int check_params(const ya_params *p, std::string &why)
+{
+    if (p->wordLen < 1 || p->wordLen > 16) { why = "wordLen must be in 1..16"; return YA_E_ARG; }
+    if (p->bandWidth < 0 || p->bandWidth > 4000) { why = "bandWidth out of range"; return YA_E_ARG; }
+    if (p->maxGap < 0 || p->maxGap > 16383 || p->maxIntron < 0 || p->maxIntron > 16383) {
+        why = "maxGap/maxIntron above 16383 are not supported (14-bit traceback run lengths)";
+        return YA_E_ARG;
+    }
+    if (p->maxHits < 0 || p->maxHits > 65525) { why = "maxHits out of range"; return YA_E_ARG; }
+    return YA_OK;
+}
+
+static ya_ctx *open_common(int device, const ya_params *params)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_open_err = "no CUDA device available: yaha_b200 has no CPU fallback";
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { g_open_err = "bad device ordinal"; return nullptr; }
+    std::string why;
+    if (!params || check_params(params, why) != YA_OK) { g_open_err = "bad ya_params: " + why; return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_open_err = "cudaGetDeviceProperties failed"; return nullptr; }
+    if (prop.major < 10) {
+        g_open_err = std::string("device '") + prop.name + "' is not sm_100 class; this library ships sm_100a code only";
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { g_open_err = "cudaSetDevice failed"; return nullptr; }
+    ya_ctx *c = new ya_ctx();
+    c->device = device;
+    c->P = *params;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_open_err = "cudaStreamCreate failed"; delete c; return nullptr;
+    }
+    c->stream = c->own_stream;
+    for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev[i]);
+    return c;
+}
+
+extern "C" ya_ctx *ya_open(int device, const ya_params *params,
+                           const uint32_t *so, size_t n_so, const uint32_t *roa, size_t n_roa,
+                           const uint8_t *bases, size_t n_base_bytes, uint32_t maxROff)
+{
+    ya_ctx *c = open_common(device, params);
+    if (!c) return nullptr;
+    size_t want_so = ((size_t)1 << (2 * params->wordLen)) + 1;
+    if (!so || n_so != want_so) {
+        g_open_err = "starting-offset table must have 4^wordLen + 1 entries"; ya_close(c); return nullptr;
+    }
+    cudaError_t e;
+    // +8 words of zero padding after the ROA: the over-read of QueryMatch.c:62-67 is bounded
+    // by n_roa in our kernels, the padding only keeps vector loads in bounds.
+    if ((e = cudaMalloc(&c->d_so, n_so * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_roa, (n_roa + 8) * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_bases, n_base_bytes + 64)) != cudaSuccess) {
+        g_open_err = std::string("cudaMalloc(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
+    }
+    if ((e = cudaMemcpy(c->d_so, so, n_so * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (n_roa && (e = cudaMemcpy(c->d_roa, roa, n_roa * 4, cudaMemcpyHostToDevice)) != cudaSuccess) ||
+        (e = cudaMemset(c->d_roa + n_roa, 0, 32)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_bases, bases, n_base_bytes, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemset(c->d_bases + n_base_bytes, 0xEE, 64)) != cudaSuccess) {
+        g_open_err = std::string("cudaMemcpy(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
+    }
+    c->n_so = n_so; c->n_roa = n_roa; c->n_base_bytes = n_base_bytes; c->maxROff = maxROff;
+    return c;
+}
+
+extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
+{
+    if (!src) { g_open_err = "ya_open_peer: null source"; return nullptr; }
+    ya_ctx *c = open_common(device, &src->P);
+    if (!c) return nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_so, src->n_so * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_roa, (src->n_roa + 8) * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_bases, src->n_base_bytes + 64)) != cudaSuccess) {
+        g_open_err = std::string("cudaMalloc(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
+    }
+    // Device-to-device over NVLink when peer access is possible (cudaMemcpyPeer falls back to
+    // a staged copy otherwise).
+    if ((e = cudaMemcpyPeer(c->d_so, device, src->d_so, src->device, src->n_so * 4)) != cudaSuccess ||
+        (e = cudaMemcpyPeer(c->d_roa, device, src->d_roa, src->device, (src->n_roa + 8) * 4)) != cudaSuccess ||
+        (e = cudaMemcpyPeer(c->d_bases, device, src->d_bases, src->device, src->n_base_bytes + 64)) != cudaSuccess) {
+        g_open_err = std::string("cudaMemcpyPeer(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
+    }
+    c->n_so = src->n_so; c->n_roa = src->n_roa; c->n_base_bytes = src->n_base_bytes; c->maxROff = src->maxROff;
+    return c;
+}
+
+extern "C" void ya_close(ya_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->d_so) cudaFree(c->d_so);
+    if (c->d_roa) cudaFree(c->d_roa);
+    if (c->d_bases) cudaFree(c->d_bases);
+    DevBuf *bufs[] = {&c->d_codes_fwd, &c->d_codes_rev, &c->d_read_off, &c->d_seg_probe_off, &c->d_cnt, &c->d_soff,
+                      &c->d_hit_off, &c->d_keys0, &c->d_keys1, &c->d_scan_tmp, &c->d_hist, &c->d_fragflag, &c->d_fragidx,
+                      &c->d_frags_all, &c->d_frag_seg, &c->d_regflag, &c->d_regidx, &c->d_regstart, &c->d_keep,
+                      &c->d_keepidx, &c->d_frags_out, &c->d_region_out, &c->d_strand_out, &c->d_misc, &c->d_jobs,
+                      &c->d_jobout, &c->d_tb, &c->d_rows, &c->d_ops_raw, &c->d_ops_cnt, &c->d_ops_off, &c->d_ops_out, &c->d_res};
+    for (DevBuf *b : bufs) b->release();
+    PinBuf *pins[] = {&c->h_stage, &c->h_stage2, &c->h_stage3, &c->h_jobs, &c->h_res, &c->h_ops};
+    for (PinBuf *b : pins) b->release();
+    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" const char *ya_last_error(const ya_ctx *c)
+{
+    return c ? c->err.c_str() : g_open_err.c_str();
+}
+
+extern "C" int ya_set_params(ya_ctx *c, const ya_params *p)
+{
+    if (!c || !p) return YA_E_ARG;
+    std::string why;
+    if (check_params(p, why) != YA_OK) return ya_fail(c, YA_E_ARG, why);
+    if (p->wordLen != c->P.wordLen) return ya_fail(c, YA_E_ARG, "wordLen is fixed by the resident index");
+    c->P = *p;
+    return YA_OK;
+}
+
+extern "C" int ya_set_stream(ya_ctx *c, void *s)
+{
+    if (!c) return YA_E_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return YA_OK;
+}
+
+extern "C" int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
+{
+    if (!c || !b || b->n_reads < 0 || (b->n_reads && (!b->codes || !b->offsets))) return YA_E_ARG;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    if (b->n_reads > (1 << 21)) return ya_fail(c, YA_E_ARG, "at most 2^21 reads per batch");
+    c->n_reads = b->n_reads;
+    c->h_read_off.assign(b->offsets, b->offsets + b->n_reads + 1);
+    if (c->h_read_off[0] != 0) return ya_fail(c, YA_E_ARG, "offsets[0] must be 0");
+    for (int r = 0; r < b->n_reads; r++) {
+        uint64_t L = c->h_read_off[r + 1] - c->h_read_off[r];
+        if (c->h_read_off[r + 1] < c->h_read_off[r] || L > 32767)
+            return ya_fail(c, YA_E_ARG, "read length must be in 0..32767 (16-bit query offsets, Math.h:104)");
+    }
+    uint64_t total = c->h_read_off[b->n_reads];
+    c->total_bases = total;
+    YA_CUDA(c, c->d_codes_fwd.reserve(total + 64));
+    YA_CUDA(c, c->d_codes_rev.reserve(total + 64));
+    YA_CUDA(c, c->d_read_off.reserve((size_t)(b->n_reads + 1) * 8));
+    YA_CUDA(c, cudaMemcpyAsync(c->d_read_off.p, b->offsets, (size_t)(b->n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (total) {
+        YA_CUDA(c, cudaMemcpyAsync(c->d_codes_fwd.p, b->codes, total, cudaMemcpyHostToDevice, c->stream));
+        int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+        revcomp_kernel<<<blocks, 256, 0, c->stream>>>(c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
+                                                     c->d_read_off.as<uint64_t>(), b->n_reads, total);
+        c->ctr.launches++;
+        YA_CUDA(c, cudaGetLastError());
+    }
+    YA_CUDA(c, cudaStreamSynchronize(c->stream));
+    return YA_OK;
+}
+
+extern "C" int ya_get_counters(ya_ctx *c, ya_counters *out)
+{
+    if (!c || !out) return YA_E_ARG;
+    *out = c->ctr;
+    c->ctr = ya_counters{};
+    return YA_OK;
+}

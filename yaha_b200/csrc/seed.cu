@@ -1,0 +1,494 @@
+// seed.cu -- stages 1 and 2 of the alignment hot path on the device.
+//
+//   K1  seed_count_kernel   k-mer hash + starting-offset gather        (ref: Query.c:233-244, 365-412)
+//   K2a expand_hits_kernel  ROA gather -> 64-bit (segment, diagonal, qo) keys
+//                                                                     (ref: QueryMatch.c:56-69, 95-96)
+//   K2b radix_*             stable LSD radix sort on (segment, diagonal); replaces the binary-heap
+//                           k-way merge (QueryMatch.c:70-116, QueryHeap.inl) -- keys are distinct, so
+//                           the merge order IS ascending key order
+//   K2c frag_*/region_*     head-flag scans: coalesce abutting seeds into fragments
+//                           (QueryMatch.c:99-115), cut regions where neighbouring diagonals differ by
+//                           more than maxGap (QueryMatch.c:146-158), drop singleton regions shorter than
+//                           minMatch (QueryMatch.c:281-290), compact the survivors
+//
+// A "segment" is one (read, strand) pair: index 2*read + strand.  All of this is HBM-bound
+// integer work; no tensor cores.
+#include "common.cuh"
+#include <algorithm>
+
+#define SEG_SHIFT 47           // key = seg << 47 | diag << 15 | qo
+#define QO_BITS   15
+#define QO_MASK   0x7FFFu
+
+// ------------------------------------------------------------------------------------------
+// K1: one warp per segment, lanes stride over query offsets.
+// ------------------------------------------------------------------------------------------
+__global__ void seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev,
+                                  const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ seg_probe_off,
+                                  int seg0, int n_seg, int K, uint32_t maxHits,
+                                  const uint32_t *__restrict__ so, const uint32_t *__restrict__ roa, uint64_t n_roa,
+                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ soff,
+                                  uint32_t *__restrict__ seg_total, uint32_t *__restrict__ seg_eff)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_seg) return;
+    const int seg = seg0 + warp;
+    const int r = seg >> 1;
+    const uint64_t base = read_off[r];
+    const int L = (int)(read_off[r + 1] - base);
+    const uint8_t *codes = ((seg & 1) ? rev : fwd) + base;
+    const uint32_t p0 = seg_probe_off[warp];
+    const int m = L - K + 1;
+    const uint32_t mask = 0xFFFFFFFFu >> (32 - 2 * K);
+    uint32_t tot = 0, eff = 0;
+    for (int qo = lane; qo < m; qo += 32) {
+        uint32_t h = 0, bad = 0;
+        for (int k = 0; k < K; k++) {
+            uint32_t c = codes[qo + k];
+            bad |= c;                                   // any code > 3 sets bit 2 or 3
+            h = (h << 2) | (c & 3);
+        }
+        h &= mask;
+        uint32_t c_eff = 0, s = 0;
+        if (bad < 4) {
+            s = so[h];
+            uint32_t c = so[h + 1] - s;                 // Query.c:391
+            if (c <= maxHits && c > 0) {                // Query.c:392
+                tot += c;
+                c_eff = c;
+                // QueryMatch.c:62-67: if every hit of this k-mer lies below qo the reference keeps
+                // reading past the k-mer's list (no newCount < count guard).  Count the extra reads.
+                if (roa[s + c - 1] < (uint32_t)qo) {
+                    uint64_t at = (uint64_t)s + c;
+                    while (at < n_roa) {
+                        uint32_t x = roa[at++];
+                        c_eff++;
+                        if (x >= (uint32_t)qo) break;
+                    }
+                }
+            }
+        }
+        cnt[p0 + qo] = c_eff;
+        soff[p0 + qo] = s;
+        eff += c_eff;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, d);
+        eff += __shfl_xor_sync(0xffffffffu, eff, d);
+    }
+    if (lane == 0) { seg_total[warp] = tot; seg_eff[warp] = eff; }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2a: one thread per probe writes the keys of its hits (in ROA order = ascending offset).
+// Keys of one segment are generated in ascending qo order, which the stable sort preserves.
+// ------------------------------------------------------------------------------------------
+__global__ void expand_hits_kernel(const uint32_t *__restrict__ seg_probe_off, int n_seg, int seg_local0,
+                                   const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ soff,
+                                   const uint32_t *__restrict__ hit_off, uint32_t probe0, uint32_t n_probes,
+                                   const uint32_t *__restrict__ roa, uint64_t *__restrict__ keys)
+{
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_probes) return;
+    uint32_t c = cnt[probe0 + p];
+    if (c == 0) return;
+    // segment of this probe: binary search in the chunk's probe offsets
+    int lo = 0, hi = n_seg;
+    uint32_t gp = probe0 + p;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (seg_probe_off[seg_local0 + mid] <= gp) lo = mid; else hi = mid;
+    }
+    uint32_t qo = gp - seg_probe_off[seg_local0 + lo];
+    uint64_t hi_bits = (uint64_t)lo << SEG_SHIFT;
+    const uint32_t *list = roa + soff[gp];
+    uint64_t *out = keys + hit_off[p];
+    for (uint32_t t = 0; t < c; t++) {
+        uint32_t diag = list[t] - qo;                   // wraps for roff < qo (QueryHeap.inl:70-73)
+        out[t] = hi_bits | ((uint64_t)diag << QO_BITS) | qo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b: LSD radix sort, 8-bit digits, stable.  Per pass: block histograms -> scan -> scatter.
+// ------------------------------------------------------------------------------------------
+#define RS_WARPS      8
+#define RS_THREADS    (RS_WARPS * 32)
+#define RS_PER_WARP   512
+#define RS_TILE       (RS_WARPS * RS_PER_WARP)
+
+__global__ void radix_hist_kernel(const uint64_t *__restrict__ keys, uint32_t n, int shift,
+                                  uint32_t *__restrict__ hist, uint32_t n_blocks)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * RS_TILE;
+    for (uint32_t i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
+        uint32_t g = base + i;
+        if (g < n) atomicAdd(&h[(uint32_t)(keys[g] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void radix_scatter_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint32_t n,
+                                     int shift, const uint32_t *__restrict__ hist_scanned, uint32_t n_blocks)
+{
+    __shared__ uint32_t wcount[RS_WARPS][256];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t wbase = blockIdx.x * RS_TILE + w * RS_PER_WARP;
+    // pass 1: per-warp digit counts
+    for (int it = 0; it < RS_PER_WARP / 32; it++) {
+        uint32_t g = wbase + it * 32 + lane;
+        if (g < n) atomicAdd(&wcount[w][(uint32_t)(in[g] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    // turn counts into starting positions: global digit base + counts of earlier warps
+    {
+        uint32_t d = threadIdx.x;           // 256 threads, one digit each
+        uint32_t run = hist_scanned[d * n_blocks + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            uint32_t c = wcount[ww][d];
+            wcount[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // pass 2: stable placement, 32 keys at a time in index order
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int it = 0; it < RS_PER_WARP / 32; it++) {
+        uint32_t g = wbase + it * 32 + lane;
+        bool valid = g < n;
+        uint64_t key = valid ? in[g] : 0;
+        uint32_t d = valid ? ((uint32_t)(key >> shift) & 255u) : (0x100u + lane);
+        uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t rank = __popc(peers & lt);
+        int leader = __ffs(peers) - 1;
+        uint32_t pos = 0;
+        if (valid && lane == leader) {
+            pos = wcount[w][d];
+            wcount[w][d] = pos + __popc(peers);
+        }
+        pos = __shfl_sync(0xffffffffu, pos, leader);
+        if (valid) out[pos + rank] = key;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2c: fragments, regions, compaction.
+// ------------------------------------------------------------------------------------------
+struct FragRaw { uint32_t diag; uint16_t sqo; uint16_t seg_lo; uint32_t seg; };   // 12 B
+
+__global__ void frag_flag_kernel(const uint64_t *__restrict__ keys, uint32_t n, int K, uint32_t *__restrict__ flag)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t head = 1;
+    if (i > 0) {
+        uint64_t a = keys[i - 1], b = keys[i];
+        // same segment and diagonal, and this seed starts no later than one past the previous
+        // seed's last base + 1  (QueryMatch.c:99: nextDiag != curDiag || nextQO > curEQO)
+        if ((a >> QO_BITS) == (b >> QO_BITS) && (uint32_t)(b & QO_MASK) <= (uint32_t)(a & QO_MASK) + (uint32_t)K) head = 0;
+    }
+    flag[i] = head;
+}
+
+__global__ void frag_write_kernel(const uint64_t *__restrict__ keys, uint32_t n, int K,
+                                  const uint32_t *__restrict__ flag, const uint32_t *__restrict__ fidx,
+                                  FragRaw *__restrict__ raw, uint16_t *__restrict__ eqo)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i];
+    uint32_t id = fidx[i] + flag[i] - 1;
+    if (flag[i]) {
+        FragRaw f;
+        f.diag = (uint32_t)(k >> QO_BITS);
+        f.sqo = (uint16_t)(k & QO_MASK);
+        f.seg = (uint32_t)(k >> SEG_SHIFT);
+        f.seg_lo = 0;
+        raw[id] = f;
+    }
+    if (i + 1 == n || flag[i + 1]) eqo[id] = (uint16_t)((k & QO_MASK) + K - 1);
+}
+
+__global__ void region_flag_kernel(const FragRaw *__restrict__ raw, uint32_t nf, uint32_t maxGap,
+                                   uint32_t *__restrict__ rflag, uint32_t *__restrict__ seg_first)
+{
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    uint32_t head = 1;
+    bool newseg = true;
+    if (f > 0) {
+        FragRaw a = raw[f - 1], b = raw[f];
+        if (a.seg == b.seg) {
+            newseg = false;
+            uint32_t diff = a.diag > b.diag ? a.diag - b.diag : b.diag - a.diag;    // FragsClumps.inl:133-137
+            if (diff <= maxGap) head = 0;
+        }
+    }
+    rflag[f] = head;
+    if (newseg) seg_first[raw[f].seg] = f;
+}
+
+__global__ void region_start_kernel(const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ ridx,
+                                    uint32_t nf, uint32_t *__restrict__ rstart, uint32_t n_regions)
+{
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f == 0) rstart[n_regions] = nf;
+    if (f >= nf) return;
+    if (rflag[f]) rstart[ridx[f]] = f;
+}
+
+__global__ void keep_flag_kernel(const FragRaw *__restrict__ raw, const uint16_t *__restrict__ eqo,
+                                 const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ ridx,
+                                 const uint32_t *__restrict__ rstart, uint32_t nf, uint32_t minMatch,
+                                 uint32_t *__restrict__ keep)
+{
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    uint32_t rid = ridx[f] + rflag[f] - 1;
+    uint32_t members = rstart[rid + 1] - rstart[rid];
+    uint32_t refLen = (uint32_t)eqo[f] - raw[f].sqo + 1;
+    keep[f] = (members > 1 || refLen >= minMatch) ? 1u : 0u;        // QueryMatch.c:281-290
+}
+
+__global__ void compact_kernel(const FragRaw *__restrict__ raw, const uint16_t *__restrict__ eqo,
+                               const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ ridx,
+                               const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kidx,
+                               const uint32_t *__restrict__ seg_first, uint32_t nf,
+                               ya_frag *__restrict__ out, uint32_t *__restrict__ region_out,
+                               ya_strand_frags *__restrict__ strands)
+{
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    FragRaw r = raw[f];
+    atomicAdd(&strands[r.seg].n_frags_all, 1u);
+    if (!keep[f]) return;
+    uint32_t o = kidx[f];
+    ya_frag g;
+    g.startRefOff = r.diag + r.sqo;
+    g.startQueryOff = r.sqo;
+    g.endQueryOff = eqo[f];
+    g.hitCount = 0;
+    g.refLen = (uint16_t)(g.endQueryOff - g.startQueryOff + 1);      // FragsClumps.inl:44-46
+    out[o] = g;
+    uint32_t f0 = seg_first[r.seg];
+    region_out[o] = (ridx[f] + rflag[f] - 1) - (ridx[f0] + rflag[f0] - 1);
+    atomicAdd(&strands[r.seg].n_frags, 1u);
+    atomicMin(&strands[r.seg].first, o);
+}
+
+__global__ void init_strands_kernel(ya_strand_frags *s, const uint32_t *__restrict__ seg_total, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ya_strand_frags v; v.first = 0xFFFFFFFFu; v.n_frags = 0; v.n_frags_all = 0; v.total_hits = seg_total[i];
+    s[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int radix_sort(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_bit, int hi_bit)
+{
+    uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
+    YA_CUDA(c, c->d_hist.reserve((size_t)256 * n_blocks * 4));
+    uint32_t *hist = c->d_hist.as<uint32_t>();
+    for (int shift = lo_bit; shift < hi_bit; shift += 8) {
+        radix_hist_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(a, n, shift, hist, n_blocks);
+        int rc = ya_exclusive_scan_u32(c, hist, hist, (size_t)256 * n_blocks, nullptr);
+        if (rc != YA_OK) return rc;
+        radix_scatter_kernel<<<n_blocks, RS_THREADS, 0, c->stream>>>(a, b, n, shift, hist, n_blocks);
+        c->ctr.launches += 2;
+        std::swap(a, b);
+    }
+    YA_CUDA(c, cudaGetLastError());
+    return YA_OK;
+}
+
+extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
+{
+    if (!c || !out || !out->strands || (out->frags_cap && (!out->frags || !out->region))) return YA_E_ARG;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    const int n_reads = c->n_reads;
+    const int n_seg = 2 * n_reads;
+    const int K = c->P.wordLen;
+    out->n_frags = 0; out->frags_needed = 0;
+    if (n_reads == 0) return YA_OK;
+    cudaStream_t st = c->stream;
+
+    // probe offsets per segment
+    std::vector<uint32_t> h_po((size_t)n_seg + 1);
+    uint64_t acc = 0;
+    for (int s = 0; s < n_seg; s++) {
+        h_po[s] = (uint32_t)acc;
+        int64_t L = (int64_t)(c->h_read_off[(s >> 1) + 1] - c->h_read_off[s >> 1]);
+        if (L >= K) acc += (uint64_t)(L - K + 1);
+        if (acc >= 0xFFFF0000ull) return ya_fail(c, YA_E_ARG, "batch too large: more than 2^32 k-mer probes");
+    }
+    h_po[n_seg] = (uint32_t)acc;
+    const uint32_t n_probes = (uint32_t)acc;
+    YA_CUDA(c, c->d_seg_probe_off.reserve(((size_t)n_seg + 1) * 4));
+    YA_CUDA(c, c->d_cnt.reserve((size_t)n_probes * 4 + 16));
+    YA_CUDA(c, c->d_soff.reserve((size_t)n_probes * 4 + 16));
+    YA_CUDA(c, c->d_misc.reserve((size_t)n_seg * 8 + 64));
+    YA_CUDA(c, c->d_strand_out.reserve((size_t)n_seg * sizeof(ya_strand_frags)));
+    YA_CUDA(c, c->h_stage.reserve((size_t)n_seg * 8 + 64));
+    uint32_t *d_po = c->d_seg_probe_off.as<uint32_t>();
+    uint32_t *d_cnt = c->d_cnt.as<uint32_t>(), *d_soff = c->d_soff.as<uint32_t>();
+    uint32_t *d_seg_total = c->d_misc.as<uint32_t>(), *d_seg_eff = d_seg_total + n_seg;
+    ya_strand_frags *d_strands = c->d_strand_out.as<ya_strand_frags>();
+
+    YA_CUDA(c, cudaEventRecord(c->ev[0], st));
+    YA_CUDA(c, cudaMemcpyAsync(d_po, h_po.data(), ((size_t)n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
+    {
+        int threads = 128, warps_per_block = threads / 32;
+        int blocks = (n_seg + warps_per_block - 1) / warps_per_block;
+        seed_count_kernel<<<blocks, threads, 0, st>>>(c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
+                                                     c->d_read_off.as<uint64_t>(), d_po, 0, n_seg, K,
+                                                     (uint32_t)c->P.maxHits, c->d_so, c->d_roa, (uint64_t)c->n_roa,
+                                                     d_cnt, d_soff, d_seg_total, d_seg_eff);
+        init_strands_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(d_strands, d_seg_total, n_seg);
+        c->ctr.launches += 2;
+    }
+    uint32_t *h_seg_eff = c->h_stage.as<uint32_t>();
+    YA_CUDA(c, cudaMemcpyAsync(h_seg_eff, d_seg_eff, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaStreamSynchronize(st));
+    c->ctr.probes += n_probes;
+
+    // chunk plan: <= 2^16 reads and <= MAX_KEYS hits per chunk (segment id fits 17 bits)
+    const uint64_t MAX_KEYS = 1ull << 28;
+    size_t out_base = 0;          // survivors written so far (device-side running offset)
+    bool overflow = false;
+    int s0 = 0;
+    while (s0 < n_seg) {
+        int s1 = s0;
+        uint64_t hits = 0;
+        while (s1 < n_seg && (s1 - s0) < (1 << 17)) {
+            uint64_t add = (uint64_t)h_seg_eff[s1] + h_seg_eff[s1 + 1];
+            if (s1 > s0 && hits + add > MAX_KEYS) break;
+            hits += add; s1 += 2;
+        }
+        if (hits >= 0xFFFFFFF0ull) return ya_fail(c, YA_E_ARG, "a single read produces more than 2^32 seed hits");
+        const uint32_t n_keys = (uint32_t)hits;
+        const int cseg = s1 - s0;
+        c->ctr.hits += n_keys;
+        if (n_keys > 0) {
+            const uint32_t probe0 = h_po[s0], cprobes = h_po[s1] - h_po[s0];
+            YA_CUDA(c, c->d_hit_off.reserve((size_t)cprobes * 4 + 16));
+            YA_CUDA(c, c->d_keys0.reserve((size_t)n_keys * 8));
+            YA_CUDA(c, c->d_keys1.reserve((size_t)n_keys * 8));
+            uint32_t *d_hit_off = c->d_hit_off.as<uint32_t>();
+            int rc = ya_exclusive_scan_u32(c, d_cnt + probe0, d_hit_off, cprobes, nullptr);
+            if (rc != YA_OK) return rc;
+            uint64_t *ka = c->d_keys0.as<uint64_t>(), *kb = c->d_keys1.as<uint64_t>();
+            expand_hits_kernel<<<(cprobes + 255) / 256, 256, 0, st>>>(d_po, cseg, s0, d_cnt, d_soff, d_hit_off,
+                                                                       probe0, cprobes, c->d_roa, ka);
+            c->ctr.launches++;
+            int segbits = 1; while ((1 << segbits) < cseg) segbits++;
+            rc = radix_sort(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
+            if (rc != YA_OK) return rc;
+
+            // fragments
+            YA_CUDA(c, c->d_fragflag.reserve((size_t)n_keys * 4));
+            YA_CUDA(c, c->d_fragidx.reserve((size_t)n_keys * 4));
+            uint32_t *fflag = c->d_fragflag.as<uint32_t>(), *fidx = c->d_fragidx.as<uint32_t>();
+            YA_CUDA(c, c->d_regstart.reserve(64));
+            uint32_t nb = (n_keys + 255) / 256;
+            frag_flag_kernel<<<nb, 256, 0, st>>>(ka, n_keys, K, fflag);
+            c->ctr.launches++;
+            uint32_t *d_tot = c->d_misc.as<uint32_t>() + 2 * (size_t)n_seg;    // 4 spare words
+            rc = ya_exclusive_scan_u32(c, fflag, fidx, n_keys, d_tot);
+            if (rc != YA_OK) return rc;
+            uint32_t nf = 0;
+            YA_CUDA(c, cudaMemcpyAsync(&nf, d_tot, 4, cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, cudaStreamSynchronize(st));
+            c->ctr.frags_all += nf;
+            YA_CUDA(c, c->d_frags_all.reserve((size_t)nf * sizeof(FragRaw)));
+            YA_CUDA(c, c->d_frag_seg.reserve((size_t)nf * 2 + 16));
+            FragRaw *raw = c->d_frags_all.as<FragRaw>();
+            uint16_t *eqo = c->d_frag_seg.as<uint16_t>();
+            frag_write_kernel<<<nb, 256, 0, st>>>(ka, n_keys, K, fflag, fidx, raw, eqo);
+            c->ctr.launches++;
+
+            // regions (reuse the key buffers' companions for flags)
+            YA_CUDA(c, c->d_regflag.reserve((size_t)nf * 4));
+            YA_CUDA(c, c->d_regidx.reserve((size_t)nf * 4));
+            YA_CUDA(c, c->d_keep.reserve((size_t)nf * 4));
+            YA_CUDA(c, c->d_keepidx.reserve((size_t)nf * 4));
+            YA_CUDA(c, c->d_fragidx.reserve((size_t)std::max<size_t>(n_keys, cseg) * 4));
+            uint32_t *rflag = c->d_regflag.as<uint32_t>(), *ridx = c->d_regidx.as<uint32_t>();
+            uint32_t *keep = c->d_keep.as<uint32_t>(), *kidx = c->d_keepidx.as<uint32_t>();
+            // seg_first lives in d_hit_off (no longer needed once keys are expanded)
+            YA_CUDA(c, c->d_hit_off.reserve((size_t)std::max<size_t>(cprobes, cseg) * 4 + 16));
+            uint32_t *seg_first = c->d_hit_off.as<uint32_t>();
+            uint32_t fb = (nf + 255) / 256;
+            region_flag_kernel<<<fb, 256, 0, st>>>(raw, nf, (uint32_t)c->P.maxGap, rflag, seg_first);
+            c->ctr.launches++;
+            rc = ya_exclusive_scan_u32(c, rflag, ridx, nf, d_tot + 1);
+            if (rc != YA_OK) return rc;
+            uint32_t nreg = 0;
+            YA_CUDA(c, cudaMemcpyAsync(&nreg, d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, c->d_regstart.reserve(((size_t)nreg + 1) * 4));
+            uint32_t *rstart = c->d_regstart.as<uint32_t>();
+            region_start_kernel<<<fb, 256, 0, st>>>(rflag, ridx, nf, rstart, nreg);
+            keep_flag_kernel<<<fb, 256, 0, st>>>(raw, eqo, rflag, ridx, rstart, nf, (uint32_t)c->P.minMatch, keep);
+            c->ctr.launches += 2;
+            rc = ya_exclusive_scan_u32(c, keep, kidx, nf, d_tot + 2);
+            if (rc != YA_OK) return rc;
+            uint32_t nkeep = 0;
+            YA_CUDA(c, cudaMemcpyAsync(&nkeep, d_tot + 2, 4, cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, c->d_frags_out.reserve((size_t)nkeep * sizeof(ya_frag) + 16));
+            YA_CUDA(c, c->d_region_out.reserve((size_t)nkeep * 4 + 16));
+            compact_kernel<<<fb, 256, 0, st>>>(raw, eqo, rflag, ridx, keep, kidx, seg_first, nf,
+                                               c->d_frags_out.as<ya_frag>(), c->d_region_out.as<uint32_t>(),
+                                               d_strands + s0);
+            c->ctr.launches++;
+            YA_CUDA(c, cudaGetLastError());
+            c->ctr.frags_out += nkeep;
+            if (!overflow && out_base + nkeep <= out->frags_cap) {
+                if (nkeep) {
+                    YA_CUDA(c, cudaMemcpyAsync(out->frags + out_base, c->d_frags_out.p, (size_t)nkeep * sizeof(ya_frag),
+                                               cudaMemcpyDeviceToHost, st));
+                    YA_CUDA(c, cudaMemcpyAsync(out->region + out_base, c->d_region_out.p, (size_t)nkeep * 4,
+                                               cudaMemcpyDeviceToHost, st));
+                }
+            } else overflow = true;
+            // strands of this chunk come back with chunk-relative `first`; fix up on the host
+            YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
+                                       cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, cudaStreamSynchronize(st));
+            for (int s = s0; s < s1; s++) {
+                ya_strand_frags &v = out->strands[s];
+                v.first = v.n_frags ? (uint32_t)(v.first + out_base) : (uint32_t)out_base;
+            }
+            out_base += nkeep;
+        } else {
+            YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
+                                       cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, cudaStreamSynchronize(st));
+            for (int s = s0; s < s1; s++) out->strands[s].first = (uint32_t)out_base;
+        }
+        s0 = s1;
+    }
+    YA_CUDA(c, cudaEventRecord(c->ev[1], st));
+    YA_CUDA(c, cudaEventSynchronize(c->ev[1]));
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->ctr.ms_seed += ms;
+    if (overflow) {
+        out->frags_needed = out_base;
+        return ya_fail(c, YA_E_CAPACITY, "frag output buffer too small");
+    }
+    out->n_frags = out_base;
+    return YA_OK;
+}

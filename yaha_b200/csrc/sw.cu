@@ -1,0 +1,607 @@
+// sw.cu -- stage 3 of the alignment hot path: yaha's affine-gap DP family on the device.
+//
+// Replaces findAffineGapScore<banded,extension,reverse,XCutoff> (SW.cpp:798-1208) behind the four
+// wrappers findAGSAlignment / findAGSAlignmentBanded / findAGSForwardExtension /
+// findAGSBackwardExtension (SW.cpp:462-547), including decompressRef (SW.cpp:444-456).
+//
+// Kernels
+//   dp_wave_kernel<G,C,EXT>  banded DP (X-drop extension or both-ends-anchored), one group of G
+//                            lanes per job, C band columns per lane held in registers, rows flow
+//                            through the lanes as a wavefront (lane l works on row m-l at macro
+//                            step m); neighbour state moves with warp shuffles.  INT32-issue bound.
+//   dp_thread_kernel         generic one-thread-per-job version of the same recurrences, used for
+//                            the tiny full-matrix jobs and as the fall-back for band widths the
+//                            wavefront kernel is not instantiated for.
+//   traceback_kernel         one thread per job walks the back-pointer cells (SW.cpp:1138-1195)
+//   finalize / compact       result assembly and op-list compaction
+//
+// All arithmetic is int32 exactly as in the reference; results are bit-identical by construction
+// and checked against the oracle in tests/.
+#include "common.cuh"
+#include <algorithm>
+
+// back-pointer cell: op in bits 15..14 (0 M, 1 R, 2 D, 3 I), run length in bits 13..0
+#define BP_M 0u
+#define BP_R 1u
+#define BP_D 2u
+#define BP_I 3u
+
+struct DpConst {
+    int GOC, GEC, RC, MS, X, maxIntron, maxGap, BW;
+};
+
+__device__ __forceinline__ int nib(const uint8_t *__restrict__ bases, uint32_t off)
+{
+    uint32_t b = bases[off >> 1];
+    return (off & 1) ? (b & 15u) : (b >> 4);          // Math.c:180-188
+}
+
+// One DP cell (SW.cpp:1017-1063).  (Vl,El,Dl) is the left neighbour's state on entry and this
+// cell's state on exit; (Vu,Fu,Iu) the insert predecessor; Vd the diagonal predecessor.
+template <bool EXT>
+__device__ __forceinline__ void dp_cell(const DpConst &K, bool match, int Vd, int Vu, int Fu, int Iu,
+                                        int &Vl, int &El, int &Dl, int &Fo, int &Io, uint32_t &bp)
+{
+    int v = Vd + (match ? K.MS : -K.RC);
+    uint32_t op = match ? BP_M : BP_R, len = 1;
+    int CE = El - K.GEC, NE = Vl - (K.GOC + K.GEC);
+    bool contE = (CE >= NE) && (Dl + 1 <= K.maxIntron);
+    int E = contE ? CE : NE;
+    int D = contE ? Dl + 1 : 1;
+    bool takeE = EXT ? (E >= v) : (E > v);
+    if (takeE) { v = E; op = BP_D; len = (uint32_t)D; }
+    int CF = Fu - K.GEC, NF = Vu - (K.GOC + K.GEC);
+    bool contF = (CF >= NF) && (Iu + 1 <= K.maxGap);
+    int F = contF ? CF : NF;
+    int I = contF ? Iu + 1 : 1;
+    bool takeF = EXT ? (F >= v) : (F > v);
+    if (takeF) { v = F; op = BP_I; len = (uint32_t)I; }
+    Vl = v; El = E; Dl = D; Fo = F; Io = I;
+    bp = (op << 14) | len;
+}
+
+// ------------------------------------------------------------------------------------------
+// Wavefront kernel.
+// ------------------------------------------------------------------------------------------
+template <int G, int C, bool EXT>
+__global__ void __launch_bounds__(128)
+dp_wave_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ job_ids, int n_jobs,
+               DevJobOut *__restrict__ outs, uint16_t *__restrict__ tb,
+               const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd,
+               const uint8_t *__restrict__ rev, DpConst K)
+{
+    const int gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gidx = gthread / G;
+    const int l = threadIdx.x % G;                       // lane within the group
+    const bool have = gidx < n_jobs;
+    DevJob J;
+    if (have) J = jobs[job_ids[gidx]];
+    const int rows = have ? J.qLen : 0;
+    const int lb = have ? J.lb : 0;
+    const int W = have ? (J.lb + J.rb + 1) : 1;
+    const int rLen = have ? J.rLen : 0;
+    const bool bwd = have && J.kind == YA_DP_EXT_BWD;
+    const uint8_t *codes = (have && J.strand) ? rev : fwd;
+    const uint32_t qIdx = have ? J.qIdx : 0;
+    const uint32_t rOff = have ? J.rOff : 0;
+    uint16_t *mytb = tb + (have ? J.tb_off : 0);
+
+    int Vp[C], Fp[C], Ip[C], rc[C];
+    const int col0 = l * C;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        int col = col0 + k;
+        Fp[k] = YA_WORST; Ip[k] = 0;
+        if (col == lb) { Vp[k] = 0; Fp[k] = 0; }                                   // origin, SW.cpp:914-916
+        else if (col > lb && col < W) Vp[k] = -(K.GOC + (col - lb) * K.GEC);       // leading deletes, :900-910
+        else Vp[k] = YA_WORST;                                                     // unread / sentinel, :894
+    }
+    // reference characters for the row this lane will look at next (row 1 - l at macro step 1)
+    int ridx0 = (1 - l) - lb - 1 + col0;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        int ri = ridx0 + k;
+        rc[k] = (ri >= 0 && ri < rLen) ? nib(bases, bwd ? rOff - (uint32_t)ri : rOff + (uint32_t)ri) : 0xFF;
+    }
+    int qi = 1 - l;                                       // row handled at the coming macro step
+    int qc = (qi >= 1 && qi <= rows) ? codes[bwd ? qIdx - (uint32_t)(qi - 1) : qIdx + (uint32_t)(qi - 1)] : 0xFE;
+
+    // state published to the right neighbour: last column of the row finished in the previous step
+    int pubV = YA_WORST, pubE = YA_WORST, pubD = 0, pubMax = YA_WORST, pubArg = 0;
+    // extension bookkeeping, authoritative on the last lane of the group
+    int maxScore = YA_WORST, maxi = 0, maxj = 0;
+    int stopRow = rows;                                   // last row that counts
+    const unsigned full = 0xffffffffu;
+
+    for (int m = 1;; m++) {
+        const bool group_done = m > stopRow + G - 1;
+        if (__all_sync(full, group_done)) break;
+        const int i = m - l;
+        const bool rowActive = (i >= 1) && (i <= stopRow);
+
+        // 1. left neighbour's state for this row
+        int Vl = __shfl_up_sync(full, pubV, 1, G);
+        int El = __shfl_up_sync(full, pubE, 1, G);
+        int Dl = __shfl_up_sync(full, pubD, 1, G);
+        int rowMax = YA_WORST, rowArg = 0;
+        if (EXT) {
+            rowMax = __shfl_up_sync(full, pubMax, 1, G);
+            rowArg = __shfl_up_sync(full, pubArg, 1, G);
+        }
+        if (l == 0) { Vl = YA_WORST; El = YA_WORST; Dl = 0; rowMax = YA_WORST; rowArg = 0; }
+
+        int startCol = lb + 1 - i;                        // SW.cpp:975-981
+        const int bcol = startCol - 1;                    // boundary cell (leading insert), if >= 0
+        if (startCol < 0) startCol = 0;
+        int endCol = lb + rLen - i; if (endCol > W - 1) endCol = W - 1;    // SW.cpp:983
+        const int bV = -(K.GOC + i * K.GEC);
+
+        // prefetch next row's query / reference characters
+        const int qn = i + 1;
+        int qc_next = (qn >= 1 && qn <= rows) ? codes[bwd ? qIdx - (uint32_t)(qn - 1) : qIdx + (uint32_t)(qn - 1)] : 0xFE;
+        const int rn = ridx0 + C;                         // index of the char entering the window
+        int rc_next = (rn >= 0 && rn < rLen) ? nib(bases, bwd ? rOff - (uint32_t)rn : rOff + (uint32_t)rn) : 0xFF;
+
+        uint16_t *tbrow = mytb + (size_t)m * (G * C) + col0;
+
+        int V0 = 0, F0 = 0, I0 = 0;                       // right neighbour's first column (row i-1)
+#pragma unroll
+        for (int k = 0; k < C; k++) {
+            const int col = col0 + k;
+            if (k == C - 1) {
+                // 3. insert predecessor of the last column lives in the right neighbour, which has
+                //    just finished its first column of row i-1 in this same macro step
+                V0 = __shfl_down_sync(full, Vp[0], 1, G);
+                F0 = __shfl_down_sync(full, Fp[0], 1, G);
+                I0 = __shfl_down_sync(full, Ip[0], 1, G);
+                if (l == G - 1) { V0 = YA_WORST; F0 = YA_WORST; I0 = 0; }          // sentinel column
+            }
+            const int Vu = (k == C - 1) ? V0 : Vp[(k + 1) % C];
+            const int Fu = (k == C - 1) ? F0 : Fp[(k + 1) % C];
+            const int Iu = (k == C - 1) ? I0 : Ip[(k + 1) % C];
+            if (rowActive) {
+                if (col >= startCol && col <= endCol) {
+                    int Fo, Io; uint32_t bp;
+                    dp_cell<EXT>(K, qc == rc[k], Vp[k], Vu, Fu, Iu, Vl, El, Dl, Fo, Io, bp);
+                    Vp[k] = Vl; Fp[k] = Fo; Ip[k] = Io;
+                    tbrow[k] = (uint16_t)bp;
+                    if (EXT && Vl > rowMax) { rowMax = Vl; rowArg = col; }          // SW.cpp:1069
+                } else if (col == bcol) {
+                    Vp[k] = bV; Vl = bV; El = YA_WORST; Dl = 0;                     // SW.cpp:981, 965-966
+                }
+            }
+        }
+        pubV = Vl; pubE = El; pubD = Dl; pubMax = rowMax; pubArg = rowArg;
+
+        // 4. row-major argmax and X-drop, decided by the last lane (SW.cpp:1073-1078, 1091)
+        if (EXT) {
+            int newStop = stopRow;
+            if (l == G - 1 && rowActive) {
+                if (rowMax > maxScore) { maxScore = rowMax; maxi = i; maxj = rowArg; }
+                if (rowMax < maxScore - K.X) newStop = i;
+            }
+            stopRow = __shfl_sync(full, newStop, G - 1, G);
+        }
+        // slide the character windows
+#pragma unroll
+        for (int k = 0; k < C - 1; k++) rc[k] = rc[k + 1];
+        rc[C - 1] = rc_next;
+        ridx0++;
+        qc = qc_next;
+    }
+
+    if (!have) return;
+    if (EXT) {
+        if (l == G - 1) {
+            DevJobOut o;
+            o.score = maxScore; o.maxi = maxi; o.maxj = maxj; o.n_ops = 0;
+            o.cells_lo = (uint32_t)stopRow; o.cells_hi = 0;      // rows executed; cells derived later
+            outs[job_ids[gidx]] = o;
+        }
+    } else {
+        const int rbcol = J.rb;
+        if (rbcol / C == l) {
+            DevJobOut o;
+            int v = 0;
+#pragma unroll
+            for (int k = 0; k < C; k++) if (k == rbcol % C) v = Vp[k];
+            o.score = v; o.maxi = rows; o.maxj = rbcol; o.n_ops = 0;
+            o.cells_lo = (uint32_t)rows; o.cells_hi = 0;
+            outs[job_ids[gidx]] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic one-thread-per-job kernel (all four kinds).  Row state lives in global scratch.
+// FULL jobs are expressed in band coordinates with lb = qLen, rb = rLen, which reproduces the
+// full-matrix recurrences, boundaries and traceback of SW.cpp exactly.
+// ------------------------------------------------------------------------------------------
+__global__ void dp_thread_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ job_ids, int n_jobs,
+                                 DevJobOut *__restrict__ outs, uint16_t *__restrict__ tb, int *__restrict__ rowbuf,
+                                 const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd,
+                                 const uint8_t *__restrict__ rev, DpConst K)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_jobs) return;
+    const DevJob J = jobs[job_ids[t]];
+    const bool ext = J.kind >= YA_DP_EXT_FWD, bwd = J.kind == YA_DP_EXT_BWD;
+    const int rows = J.qLen, lb = J.lb, W = J.lb + J.rb + 1, rLen = J.rLen;
+    const uint8_t *codes = J.strand ? rev : fwd;
+    int *Vp = rowbuf + (size_t)J.rows_off, *Fp = Vp + (W + 1), *Ip = Fp + (W + 1);
+    uint16_t *mytb = tb + J.tb_off;
+    // row 0
+    for (int j = 0; j <= W; j++) { Vp[j] = YA_WORST; Fp[j] = YA_WORST; Ip[j] = 0; }
+    Vp[lb] = 0; Fp[lb] = 0;
+    for (int j = lb + 1, k = 1; j < W; j++, k++) Vp[j] = -(K.GOC + k * K.GEC);
+    int maxScore = YA_WORST, maxi = 0, maxj = 0, lastV = 0, doneRows = rows;
+    for (int i = 1; i <= rows; i++) {
+        int startCol = lb + 1 - i, Vl, El = YA_WORST, Dl = 0;
+        if (startCol <= 0) { startCol = 0; Vl = YA_WORST; }
+        else Vl = -(K.GOC + i * K.GEC);
+        int endCol = lb + rLen - i; if (endCol > W - 1) endCol = W - 1;
+        const int qc = codes[bwd ? J.qIdx - (uint32_t)(i - 1) : J.qIdx + (uint32_t)(i - 1)];
+        int rowMax = YA_WORST;
+        // in-place update: column j reads old [j] (diag) and old [j+1] (insert) before writing [j]
+        int diagV = (startCol > 0) ? Vp[startCol] : Vp[0];
+        // the boundary cell becomes the next row's diagonal predecessor
+        int saveBoundary = Vl;
+        for (int j = startCol; j <= endCol; j++) {
+            const int ri = i - lb - 1 + j;
+            const int rcode = nib(bases, bwd ? J.rOff - (uint32_t)ri : J.rOff + (uint32_t)ri);
+            int Vd = Vp[j], Vu = Vp[j + 1], Fu = Fp[j + 1], Iu = Ip[j + 1], Fo, Io; uint32_t bp;
+            if (ext) dp_cell<true>(K, qc == rcode, Vd, Vu, Fu, Iu, Vl, El, Dl, Fo, Io, bp);
+            else     dp_cell<false>(K, qc == rcode, Vd, Vu, Fu, Iu, Vl, El, Dl, Fo, Io, bp);
+            Vp[j] = Vl; Fp[j] = Fo; Ip[j] = Io;
+            mytb[(size_t)i * J.stride + j] = (uint16_t)bp;
+            if (Vl > rowMax) rowMax = Vl;
+            if (ext && Vl > maxScore) { maxScore = Vl; maxi = i; maxj = j; }
+            lastV = Vl;
+        }
+        (void)diagV;
+        if (startCol > 0) Vp[startCol - 1] = saveBoundary;
+        if (ext && rowMax < maxScore - K.X) { doneRows = i; break; }
+    }
+    DevJobOut o;
+    o.score = ext ? maxScore : lastV;
+    o.maxi = ext ? maxi : rows;
+    o.maxj = ext ? maxj : J.rb;
+    o.n_ops = 0; o.cells_lo = (uint32_t)doneRows; o.cells_hi = 0;
+    outs[job_ids[t]] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// Traceback: one thread per job (SW.cpp:1138-1195).  Emits runs in walking order (end -> start).
+// Row 0 and the leading-insert boundary cells are not stored; they are known in closed form
+// (SW.cpp:900-933).
+// ------------------------------------------------------------------------------------------
+__global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, DevJobOut *__restrict__ outs,
+                                 const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_jobs) return;
+    const DevJob J = jobs[t];
+    DevJobOut o = outs[t];
+    const bool ext = J.kind >= YA_DP_EXT_FWD;
+    const int lb = J.lb, W = J.lb + J.rb + 1;
+    // cells the reference executed: rows 1..doneRows (SW.cpp:1007 loop bounds)
+    {
+        uint64_t cells = 0;
+        int done = (int)o.cells_lo;
+        for (int i = 1; i <= done; i++) {
+            int s = lb + 1 - i; if (s < 0) s = 0;
+            int e = lb + (int)J.rLen - i; if (e > W - 1) e = W - 1;
+            if (e >= s) cells += (uint64_t)(e - s + 1);
+        }
+        o.cells_lo = (uint32_t)cells; o.cells_hi = (uint32_t)(cells >> 32);
+    }
+    uint32_t n = 0;
+    if (!(ext && o.score <= 0)) {
+        const uint16_t *mytb = tb + J.tb_off;
+        ya_op *out = ops_raw + J.ops_off;
+        int y = o.maxi, x = o.maxj;
+        int prev = -1; uint32_t run = 0;
+        for (;;) {
+            uint32_t op, len;
+            if (y == 0) {
+                if (x == lb) break;                      // origin, 'U'
+                op = BP_D; len = (uint32_t)(x - lb);
+            } else if (x == lb - y) {
+                op = BP_I; len = (uint32_t)y;            // leading insert boundary
+            } else {
+                size_t row = J.layout ? (size_t)(y + x / J.colsPerLane) : (size_t)y;
+                uint32_t c = mytb[row * J.stride + x];
+                op = c >> 14; len = c & 0x3FFFu;
+            }
+            if (op == BP_D) x -= (int)len;
+            else if (op == BP_I) { y -= (int)len; x += (int)len; }
+            else { y -= 1; len = 1; }
+            if ((int)op != prev) {
+                if (prev >= 0) {
+                    if (n < J.ops_cap) { out[n].length = (uint16_t)run; out[n].opcode = "MRDI"[prev]; out[n].pad = 0; }
+                    n++;
+                }
+                prev = (int)op; run = len;
+            } else run += len;
+        }
+        if (prev >= 0) {
+            if (n < J.ops_cap) { out[n].length = (uint16_t)run; out[n].opcode = "MRDI"[prev]; out[n].pad = 0; }
+            n++;
+        }
+    }
+    o.n_ops = n;
+    outs[t] = o;
+}
+
+__global__ void finalize_kernel(const DevJob *__restrict__ jobs, const DevJobOut *__restrict__ outs, int n_jobs,
+                                int BW, ya_dp_result *__restrict__ res, uint32_t *__restrict__ ops_cnt)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_jobs) return;
+    const DevJob J = jobs[t];
+    const DevJobOut o = outs[t];
+    ya_dp_result r;
+    r.ops_off = 0;
+    if (J.kind >= YA_DP_EXT_FWD) {
+        if (o.score <= 0) { r.score = 0; r.addedQLen = 0; r.addedRLen = 0; r.ops_n = 0; }       // SW.cpp:525,1102
+        else {
+            r.score = o.score;
+            r.addedQLen = (uint16_t)o.maxi;                                                      // SW.cpp:1109
+            r.addedRLen = (uint16_t)(o.maxi + (o.maxj - 2 * BW));                                // SW.cpp:1110
+            r.ops_n = o.n_ops;
+        }
+    } else { r.score = o.score; r.addedQLen = 0; r.addedRLen = 0; r.ops_n = o.n_ops; }
+    res[t] = r;
+    ops_cnt[t] = r.ops_n;
+}
+
+// Copies each job's runs to their compact position.  Walking order is end -> start; forward and
+// global jobs are reversed into genome order, backward extensions already are (SW.cpp:1184-1185).
+__global__ void compact_ops_kernel(const DevJob *__restrict__ jobs, int n_jobs, const uint32_t *__restrict__ ops_off,
+                                   ya_dp_result *__restrict__ res, const ya_op *__restrict__ ops_raw,
+                                   ya_op *__restrict__ ops_out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_jobs) return;
+    const DevJob J = jobs[t];
+    uint32_t n = res[t].ops_n, o = ops_off[t];
+    res[t].ops_off = o;
+    const ya_op *src = ops_raw + J.ops_off;
+    const bool keepOrder = J.kind == YA_DP_EXT_BWD;
+    for (uint32_t k = 0; k < n; k++) ops_out[o + k] = keepOrder ? src[k] : src[n - 1 - k];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct WaveCfg { int G, C; };
+static const WaveCfg kWaveCfgs[] = {{8, 3}, {8, 4}, {8, 6}, {8, 8}, {16, 6}, {16, 8}, {32, 8}};
+static const int kNumWaveCfgs = sizeof(kWaveCfgs) / sizeof(kWaveCfgs[0]);
+
+template <int G, int C>
+static void launch_wave(ya_ctx *c, bool ext, const uint32_t *d_ids, int n, const DpConst &K)
+{
+    const int threads = 128;
+    const int groups_per_block = threads / G;
+    int blocks = (n + groups_per_block - 1) / groups_per_block;
+    if (ext)
+        dp_wave_kernel<G, C, true><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
+            c->d_tb.as<uint16_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+    else
+        dp_wave_kernel<G, C, false><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
+            c->d_tb.as<uint16_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+    c->ctr.launches++;
+}
+
+static void launch_wave_cfg(ya_ctx *c, int cfg, bool ext, const uint32_t *d_ids, int n, const DpConst &K)
+{
+    switch (cfg) {
+    case 0: launch_wave<8, 3>(c, ext, d_ids, n, K); break;
+    case 1: launch_wave<8, 4>(c, ext, d_ids, n, K); break;
+    case 2: launch_wave<8, 6>(c, ext, d_ids, n, K); break;
+    case 3: launch_wave<8, 8>(c, ext, d_ids, n, K); break;
+    case 4: launch_wave<16, 6>(c, ext, d_ids, n, K); break;
+    case 5: launch_wave<16, 8>(c, ext, d_ids, n, K); break;
+    default: launch_wave<32, 8>(c, ext, d_ids, n, K); break;
+    }
+}
+
+// YA_DP_MODE environment switch (tests): "thread" forces the generic kernel for every job.
+static bool force_thread_kernel()
+{
+    const char *e = getenv("YA_DP_MODE");
+    return e && strcmp(e, "thread") == 0;
+}
+
+extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res,
+                           ya_op *ops, size_t ops_cap, size_t *ops_needed)
+{
+    if (!c || n < 0 || (n && (!jobs || !res))) return YA_E_ARG;
+    if (ops_needed) *ops_needed = 0;
+    if (n == 0) return YA_OK;
+    if (c->n_reads == 0) return ya_fail(c, YA_E_STATE, "ya_sw_batch: no read batch uploaded");
+    YA_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const ya_params &P = c->P;
+    const int bw2 = 2 * P.bandWidth;
+    const bool forceThread = force_thread_kernel();
+
+    YA_CUDA(c, c->h_jobs.reserve((size_t)n * sizeof(DevJob)));
+    DevJob *hj = c->h_jobs.as<DevJob>();
+    // job id lists per kernel class: [0..kNumWaveCfgs) ext, [kNumWaveCfgs..2k) banded, last = thread
+    std::vector<std::vector<uint32_t>> lists(2 * kNumWaveCfgs + 1);
+    uint64_t tb_cells = 0, rows_ints = 0, ops_slots = 0;
+    int n_live = 0;
+    std::vector<uint32_t> live_of(n);     // device job index -> caller job index
+    for (int i = 0; i < n; i++) {
+        const ya_dp_job &j = jobs[i];
+        res[i].score = 0; res[i].addedQLen = 0; res[i].addedRLen = 0; res[i].ops_off = 0; res[i].ops_n = 0;
+        if (j.read >= (uint32_t)c->n_reads || j.kind > YA_DP_EXT_BWD || j.strand > 1)
+            return ya_fail(c, YA_E_ARG, "ya_sw_batch: bad job");
+        const uint64_t rbase = c->h_read_off[j.read];
+        const int L = (int)(c->h_read_off[j.read + 1] - rbase);
+        int qLen = j.qLen, rLen = j.rLen;
+        uint32_t rOff = j.rOff;
+        DevJob d{};
+        d.kind = j.kind; d.strand = j.strand;
+        if (j.kind >= YA_DP_EXT_FWD) {
+            // clamping of findAGSExtension (SW.cpp:492-516)
+            const bool reverse = j.kind == YA_DP_EXT_BWD;
+            if (qLen <= 0) continue;
+            uint32_t rl = (uint32_t)(qLen + bw2);
+            if (reverse && rl > rOff) { rl = rOff + 1; qLen = (int)(rl - (uint32_t)bw2); if (qLen <= 0) continue; }
+            if (!reverse && rOff + rl > c->maxROff) { rl = c->maxROff - rOff; qLen = (int)(rl - (uint32_t)bw2); if (qLen <= 0) continue; }
+            rLen = (int)rl;
+            if (reverse ? ((int)j.qOff - (qLen - 1) < 0 || (int)j.qOff >= L) : ((int)j.qOff + qLen > L))
+                return ya_fail(c, YA_E_ARG, "ya_sw_batch: extension runs outside the read");
+            d.lb = (uint16_t)bw2; d.rb = (uint16_t)bw2;
+        } else {
+            if (qLen <= 0 || rLen <= 0) return ya_fail(c, YA_E_ARG, "ya_sw_batch: global job with empty side");
+            if ((int)j.qOff + qLen > L) return ya_fail(c, YA_E_ARG, "ya_sw_batch: global job runs outside the read");
+            if ((uint64_t)rOff + (uint64_t)rLen > (uint64_t)c->n_base_bytes * 2)
+                return ya_fail(c, YA_E_ARG, "ya_sw_batch: global job runs outside the reference");
+            if (j.kind == YA_DP_BANDED) {
+                d.lb = (uint16_t)(P.bandWidth + (qLen > rLen ? qLen - rLen : 0));     // SW.cpp:856-866
+                d.rb = (uint16_t)(P.bandWidth + (rLen > qLen ? rLen - qLen : 0));
+            } else { d.lb = (uint16_t)qLen; d.rb = (uint16_t)rLen; }                  // full matrix as a band
+        }
+        d.rOff = rOff; d.rLen = (uint16_t)rLen; d.qLen = (uint16_t)qLen;
+        d.qIdx = (uint32_t)(rbase + j.qOff);
+        const int W = d.lb + d.rb + 1;
+        int cls = -1;
+        if (!forceThread && j.kind != YA_DP_FULL) {
+            for (int k = 0; k < kNumWaveCfgs; k++)
+                if (kWaveCfgs[k].G * kWaveCfgs[k].C >= W) { cls = k; break; }
+        }
+        if (cls >= 0) {
+            const int G = kWaveCfgs[cls].G, C = kWaveCfgs[cls].C;
+            d.layout = 1; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * C);
+            d.tb_off = tb_cells;
+            tb_cells += (uint64_t)(qLen + G + 1) * d.stride;
+            lists[(j.kind >= YA_DP_EXT_FWD ? 0 : kNumWaveCfgs) + cls].push_back((uint32_t)n_live);
+        } else {
+            d.layout = 0; d.colsPerLane = 1; d.stride = (uint32_t)W;
+            d.tb_off = tb_cells;
+            tb_cells += (uint64_t)(qLen + 1) * d.stride;
+            d.rows_off = (uint32_t)rows_ints;
+            rows_ints += 3ull * (W + 1);
+            lists[2 * kNumWaveCfgs].push_back((uint32_t)n_live);
+        }
+        d.ops_off = (uint32_t)ops_slots;
+        d.ops_cap = (uint32_t)(qLen + rLen + 2);
+        ops_slots += d.ops_cap;
+        if (ops_slots >= 0xFFFF0000ull || rows_ints >= 0xFFFF0000ull)
+            return ya_fail(c, YA_E_ARG, "ya_sw_batch: batch too large, split it");
+        hj[n_live] = d;
+        live_of[n_live] = (uint32_t)i;
+        n_live++;
+    }
+    c->ctr.dp_jobs += (uint64_t)n;
+    if (n_live == 0) return YA_OK;
+
+    YA_CUDA(c, c->d_jobs.reserve((size_t)n_live * sizeof(DevJob)));
+    YA_CUDA(c, c->d_jobout.reserve((size_t)n_live * sizeof(DevJobOut)));
+    YA_CUDA(c, c->d_tb.reserve(tb_cells * 2 + 64));
+    YA_CUDA(c, c->d_rows.reserve(rows_ints * 4 + 64));
+    YA_CUDA(c, c->d_ops_raw.reserve(ops_slots * sizeof(ya_op) + 64));
+    YA_CUDA(c, c->d_ops_cnt.reserve((size_t)n_live * 4 + 64));
+    YA_CUDA(c, c->d_ops_off.reserve((size_t)n_live * 4 + 64));
+    YA_CUDA(c, c->d_res.reserve((size_t)n_live * sizeof(ya_dp_result)));
+    YA_CUDA(c, c->d_misc.reserve((size_t)n_live * 4 + 64));
+    YA_CUDA(c, c->h_res.reserve((size_t)n_live * (sizeof(ya_dp_result) + sizeof(DevJobOut)) + 64));
+    YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, hj, (size_t)n_live * sizeof(DevJob), cudaMemcpyHostToDevice, st));
+    // id lists
+    std::vector<uint32_t> flat; flat.reserve(n_live);
+    std::vector<size_t> start(lists.size());
+    for (size_t k = 0; k < lists.size(); k++) { start[k] = flat.size(); flat.insert(flat.end(), lists[k].begin(), lists[k].end()); }
+    uint32_t *d_ids = c->d_misc.as<uint32_t>();
+    YA_CUDA(c, cudaMemcpyAsync(d_ids, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
+
+    DpConst K{P.GOCost, P.GECost, P.RCost, P.MScore, P.XCutoff, P.maxIntron, P.maxGap, P.bandWidth};
+    YA_CUDA(c, cudaEventRecord(c->ev[0], st));
+    for (int k = 0; k < kNumWaveCfgs; k++) {
+        if (!lists[k].empty()) launch_wave_cfg(c, k, true, d_ids + start[k], (int)lists[k].size(), K);
+        if (!lists[kNumWaveCfgs + k].empty())
+            launch_wave_cfg(c, k, false, d_ids + start[kNumWaveCfgs + k], (int)lists[kNumWaveCfgs + k].size(), K);
+    }
+    if (!lists[2 * kNumWaveCfgs].empty()) {
+        int nt = (int)lists[2 * kNumWaveCfgs].size();
+        dp_thread_kernel<<<(nt + 63) / 64, 64, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids + start[2 * kNumWaveCfgs], nt,
+            c->d_jobout.as<DevJobOut>(), c->d_tb.as<uint16_t>(), c->d_rows.as<int>(), c->d_bases,
+            c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+        c->ctr.launches++;
+    }
+    YA_CUDA(c, cudaEventRecord(c->ev[1], st));
+    const int tbk = (n_live + 127) / 128;
+    traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_jobout.as<DevJobOut>(),
+                                          c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>());
+    finalize_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), c->d_jobout.as<DevJobOut>(), n_live, P.bandWidth,
+                                         c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
+    c->ctr.launches += 2;
+    uint32_t *d_tot = c->d_ops_cnt.as<uint32_t>() + n_live;      // spare word after the counts
+    int rc = ya_exclusive_scan_u32(c, c->d_ops_cnt.as<uint32_t>(), c->d_ops_off.as<uint32_t>(), (size_t)n_live, d_tot);
+    if (rc != YA_OK) return rc;
+    uint32_t total_ops = 0;
+    YA_CUDA(c, cudaMemcpyAsync(&total_ops, d_tot, 4, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaStreamSynchronize(st));
+    YA_CUDA(c, c->d_ops_out.reserve((size_t)total_ops * sizeof(ya_op) + 64));
+    compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
+                                            c->d_res.as<ya_dp_result>(), c->d_ops_raw.as<ya_op>(), c->d_ops_out.as<ya_op>());
+    c->ctr.launches++;
+    YA_CUDA(c, cudaEventRecord(c->ev[2], st));
+    ya_dp_result *hres = c->h_res.as<ya_dp_result>();
+    DevJobOut *hout = (DevJobOut *)(hres + n_live);
+    YA_CUDA(c, cudaMemcpyAsync(hres, c->d_res.p, (size_t)n_live * sizeof(ya_dp_result), cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(hout, c->d_jobout.p, (size_t)n_live * sizeof(DevJobOut), cudaMemcpyDeviceToHost, st));
+    const bool fits = total_ops <= ops_cap && (total_ops == 0 || ops != nullptr);
+    if (fits && total_ops)
+        YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaStreamSynchronize(st));
+    YA_CUDA(c, cudaGetLastError());
+    float ms0 = 0, ms1 = 0;
+    cudaEventElapsedTime(&ms0, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]);
+    c->ctr.ms_dp += ms0; c->ctr.ms_traceback += ms1;
+    for (int k = 0; k < n_live; k++) {
+        res[live_of[k]] = hres[k];
+        c->ctr.dp_cells += ((uint64_t)hout[k].cells_hi << 32) | hout[k].cells_lo;
+        if (hres[k].ops_n > hj[k].ops_cap) return ya_fail(c, YA_E_STATE, "internal: op scratch overflow");
+    }
+    if (ops_needed) *ops_needed = total_ops;
+    if (!fits) return ya_fail(c, YA_E_CAPACITY, "op output buffer too small");
+    return YA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Perfect extension (AlignExtFrag.cpp:30-48)
+// ------------------------------------------------------------------------------------------
+__global__ void perfect_kernel(const ya_dp_job *__restrict__ jobs, const uint64_t *__restrict__ read_off, int n,
+                               const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd,
+                               const uint8_t *__restrict__ rev, uint16_t *__restrict__ count)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const ya_dp_job j = jobs[t];
+    const uint8_t *codes = (j.strand ? rev : fwd) + read_off[j.read];
+    const int dir = (j.kind == YA_DP_EXT_BWD) ? -1 : 1;
+    int k = 0;
+    while (k < (int)j.qLen && codes[(int)j.qOff + dir * k] == nib(bases, j.rOff + (uint32_t)(dir * k))) k++;
+    count[t] = (uint16_t)k;
+}
+
+extern "C" int ya_perfect_ext(ya_ctx *c, const ya_dp_job *jobs, int n, uint16_t *count)
+{
+    if (!c || n < 0 || (n && (!jobs || !count))) return YA_E_ARG;
+    if (n == 0) return YA_OK;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    YA_CUDA(c, c->d_jobs.reserve((size_t)n * sizeof(ya_dp_job)));
+    YA_CUDA(c, c->d_res.reserve((size_t)n * 2 + 64));
+    YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, jobs, (size_t)n * sizeof(ya_dp_job), cudaMemcpyHostToDevice, c->stream));
+    perfect_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_jobs.as<ya_dp_job>(), c->d_read_off.as<uint64_t>(), n,
+        c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), c->d_res.as<uint16_t>());
+    c->ctr.launches++;
+    YA_CUDA(c, cudaMemcpyAsync(count, c->d_res.p, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream));
+    YA_CUDA(c, cudaStreamSynchronize(c->stream));
+    YA_CUDA(c, cudaGetLastError());
+    return YA_OK;
+}

@@ -139,3 +139,113 @@ def read_queries(path: str, word_len: int = 15, max_len: int = 32000):
             if word_len <= len(s) <= max_len:
                 out.append((name.replace(b" ", b"_").decode(), s))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Writers (small inputs; the tests use them so that no reference binary is needed at run time)
+# ---------------------------------------------------------------------------------------------
+def read_fasta(path: str):
+    """[(name, bases_bytes)]; names are cut at the first space (Compress.c:277-284)."""
+    out = []
+    for rec in open(path, "rb").read().split(b">")[1:]:
+        nl = rec.find(b"\n")
+        name = rec[:nl].split(b" ")[0]
+        out.append((name.decode(), rec[nl + 1:].replace(b"\n", b"").replace(b"\r", b"")))
+    return out
+
+
+def build_nib2(seqs) -> bytes:
+    """.nib2 v2 image for [(name, bases)] (layout: Compress.c:28-63,140-191,199-218)."""
+    names = b"".join(n.encode() for n, _ in seqs)
+    names_pad = names + b"\0" * (-len(names) % 4)
+    nseq = len(seqs)
+    bases_off = 20 + 16 * nseq + len(names_pad)
+    recs, blobs = [], []
+    byte_off, name_off = 0, 0
+    for n, s in seqs:
+        codes = encode(s)
+        L = len(codes)
+        pad = (-L) % 8                      # pad with X (14) to a 4-byte boundary (Compress.c:206-215)
+        c = np.concatenate([codes, np.full(pad, 14, np.uint8)])
+        packed = (c[0::2] << 4) | c[1::2]
+        recs.append(np.array([byte_off, L, name_off, len(n.encode())], dtype="<u4").tobytes())
+        blobs.append(packed.astype(np.uint8).tobytes())
+        byte_off += len(packed)
+        name_off += len(n.encode())
+    head = np.array([NIB2_MARKER, 2, bases_off, nseq], dtype="<u4").tobytes()
+    return head + b"".join(recs) + np.array([0], dtype="<u4").tobytes() + names_pad + b"".join(blobs)
+
+
+def _marsaglia(state):
+    """Math.c:274-284 xorshift step; state is a list of 5 python ints (uint32)."""
+    M = 0xFFFFFFFF
+    t = state[0] ^ (state[0] >> 7)
+    state[0], state[1], state[2], state[3] = state[1], state[2], state[3], state[4]
+    state[4] = ((state[4] ^ ((state[4] << 6) & M)) ^ (t ^ ((t << 13) & M))) & M
+    return ((state[1] + state[1] + 1) * state[4]) & M
+
+
+def _rand_sample(state, inp: np.ndarray, out_len: int) -> np.ndarray:
+    """Order-preserving Floyd sample (Math.c:304-343)."""
+    n = len(inp)
+    marked = np.zeros(n, dtype=bool)
+    keep_marked, select = True, out_len
+    if out_len > n // 2:
+        keep_marked, select = False, n - out_len
+    for i in range(n - select, n):
+        pos = int((_marsaglia(state) / 4294967296.0) * (i + 1))
+        if marked[pos]:
+            marked[i] = True
+        else:
+            marked[pos] = True
+    return inp[marked == keep_marked]
+
+
+def build_index(nib: Nib2, word_len: int, max_hits: int = 65525, skip: int = 1) -> bytes:
+    """Index image (Index.c:95-331) for a loaded .nib2.  skip (-S) must be 1."""
+    if skip != 1:
+        raise NotImplementedError("only -S 1 indexes are built here")
+    K = word_len
+    pos_all, hash_all = [], []
+    for st, ln in zip(nib.starts, nib.lengths):
+        st, ln = int(st), int(ln)
+        if ln < K:
+            continue
+        codes = nib.unpack(st, ln).astype(np.uint32)
+        bad = (codes > 3).astype(np.int64)
+        cb = np.concatenate([[0], np.cumsum(bad)])
+        ok = (cb[K:] - cb[:-K]) == 0                    # window free of non-ACGT (Index.c:105-128)
+        h = np.zeros(ln - K + 1, dtype=np.uint32)
+        for k in range(K):
+            h = (h << 2) | (codes[k:ln - K + 1 + k] & 3)
+        p = np.nonzero(ok)[0]
+        pos_all.append((p + st).astype(np.uint32))
+        hash_all.append(h[p])
+    pos = np.concatenate(pos_all) if pos_all else np.zeros(0, np.uint32)
+    hsh = np.concatenate(hash_all) if hash_all else np.zeros(0, np.uint32)
+    order = np.argsort(hsh, kind="stable")              # ascending offset inside each k-mer list
+    roa = pos[order]
+    counts = np.bincount(hsh, minlength=4 ** K).astype(np.int64)
+    so = np.zeros(4 ** K + 1, dtype=np.int64)
+    np.cumsum(counts, out=so[1:])
+    over = np.nonzero(counts > max_hits)[0]
+    if len(over):                                       # pass 3: down-sample (Index.c:271-315)
+        state = [123456789, 362436069, 521288629, 88675123, 886756453]
+        pieces, new_counts = [], counts.copy()
+        prev = 0
+        for hcode in over:
+            a, b = int(so[hcode]), int(so[hcode + 1])
+            pieces.append(roa[prev:a])
+            pieces.append(_rand_sample(state, roa[a:b], max_hits))
+            new_counts[hcode] = max_hits
+            prev = b
+        pieces.append(roa[prev:])
+        roa = np.concatenate(pieces)
+        np.cumsum(new_counts, out=so[1:])
+    head = np.array([INDEX_VERSION, K, max_hits, len(roa)], dtype="<u4")
+    return head.tobytes() + so.astype("<u4").tobytes() + roa.astype("<u4").tobytes()
+
+
+def index_file_name(stem: str, word_len: int, skip: int, max_hits: int) -> str:
+    """Main.c:559-563: <stem>.X<LL>_<SS>_<HHHHH>S"""
+    return f"{stem}.X{word_len:02d}_{skip:02d}_{max_hits:05d}S"
