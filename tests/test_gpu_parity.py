@@ -201,3 +201,24 @@ def test_linearity_of_sharding(small, aligner):
     assert np.array_equal(np.concatenate([r_a, r_b]), r_all)
     assert np.array_equal(np.concatenate([s_a["n_frags"], s_b["n_frags"]]), s_all["n_frags"])
     aligner.upload_read_list(small.fwd)
+
+
+def test_device_index_build_is_bit_identical(small):
+    """ya_open_build (Index.c:49-331 replacement) must reproduce the reference's SO and ROA
+    arrays exactly (the golden index digest is checked in test_formats)."""
+    al = yaha_b200.Aligner(small.nib, None, yaha_b200.Params.defaults(word_len=11), device=0)
+    idx = al.download_index()
+    assert np.array_equal(idx.so, np.asarray(small.idx.so))
+    assert np.array_equal(idx.roa, np.asarray(small.idx.roa))
+    # and it aligns identically
+    al.upload_read_list(small.fwd[:50])
+    s1, f1, r1 = al.seed_frags()
+    al.close()
+    al2 = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11), device=0)
+    al2.upload_read_list(small.fwd[:50])
+    s2, f2, r2 = al2.seed_frags()
+    al2.close()
+    assert np.array_equal(f1, f2) and np.array_equal(s1, s2)
+    # a k-mer above the limit must be reported, not approximated
+    with pytest.raises(yaha_b200.YahaError):
+        yaha_b200.Aligner(small.nib, None, yaha_b200.Params.defaults(word_len=11), device=0, build_max_hits=1)

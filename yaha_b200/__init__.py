@@ -67,7 +67,7 @@ class Counters(C.Structure):
                 ("ms_traceback", C.c_double), ("launches", C.c_uint64)]
 
 
-EXPORTS = ("ya_open", "ya_open_peer", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
+EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
            "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_perfect_ext", "ya_get_counters",
            "ya_measure_int32_peak")
 
@@ -86,6 +86,10 @@ def load_library() -> C.CDLL:
     vp = C.c_void_p
     lib.ya_open.restype = vp
     lib.ya_open.argtypes = [C.c_int, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]
+    lib.ya_open_build.restype = vp
+    lib.ya_open_build.argtypes = [C.c_int, C.POINTER(Params), vp, C.c_size_t, vp, vp, C.c_int, C.c_uint32]
+    lib.ya_index_sizes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.ya_index_download.argtypes = [vp, vp, vp]
     lib.ya_open_peer.restype = vp
     lib.ya_open_peer.argtypes = [C.c_int, vp]
     lib.ya_close.restype = None
@@ -111,8 +115,8 @@ class YahaError(RuntimeError):
 class Aligner:
     """One GPU context with a resident index (`ya_ctx`)."""
 
-    def __init__(self, nib2: refio.Nib2, index: refio.Index, params: Params | None = None, device: int = 0,
-                 peer_of: "Aligner | None" = None):
+    def __init__(self, nib2: refio.Nib2, index: "refio.Index | None", params: Params | None = None, device: int = 0,
+                 peer_of: "Aligner | None" = None, build_max_hits: int = 65525):
         self.lib = load_library()
         self.nib2, self.index = nib2, index
         if params is None:
@@ -120,6 +124,13 @@ class Aligner:
         self.params = params
         if peer_of is not None:
             self.ctx = self.lib.ya_open_peer(device, peer_of.ctx)
+        elif index is None:
+            # build the index on the device from the .nib2 bases (Index.c:49-331 replacement)
+            bases = np.ascontiguousarray(nib2.bases)
+            st = np.ascontiguousarray(nib2.starts, dtype=np.uint32)
+            ln = np.ascontiguousarray(nib2.lengths, dtype=np.uint32)
+            self.ctx = self.lib.ya_open_build(device, C.byref(params), bases.ctypes.data, len(bases),
+                                              st.ctypes.data, ln.ctypes.data, len(st), build_max_hits)
         else:
             so = np.ascontiguousarray(index.so)
             roa = np.ascontiguousarray(index.roa)
@@ -136,6 +147,15 @@ class Aligner:
         mh = min(param_overrides.pop("max_hits", 650), idx.max_hits)
         p = Params.defaults(word_len=idx.word_len, max_hits=mh, **param_overrides)
         return cls(nib, idx, p, device)
+
+    def download_index(self, max_hits: int = 65525) -> refio.Index:
+        """Copy the device-resident index back (e.g. one built by ya_open_build)."""
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        self._check(self.lib.ya_index_sizes(self.ctx, C.byref(a), C.byref(b)))
+        so = np.zeros(a.value, dtype=np.uint32)
+        roa = np.zeros(max(b.value, 1), dtype=np.uint32)
+        self._check(self.lib.ya_index_download(self.ctx, so.ctypes.data, roa.ctypes.data))
+        return refio.Index(self.params.wordLen, max_hits, int(b.value), so, roa[:b.value])
 
     def close(self):
         if getattr(self, "ctx", None):

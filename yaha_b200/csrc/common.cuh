@@ -118,4 +118,10 @@ static inline int ya_fail(ya_ctx *c, int code, const std::string &msg)
 
 // scan.cu
 int ya_exclusive_scan_u32(ya_ctx *c, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total);
-// seed.cu / sw.cu / peak.cu hold the C-ABI entry points declared in yaha_b200.h
+// seed.cu: stable LSD radix sort of 64-bit keys on bits [lo_bit, hi_bit); result ends up in `a`
+int ya_radix_sort_u64(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_bit, int hi_bit);
+// seed.cu / sw.cu / peak.cu / index.cu hold the C-ABI entry points declared in yaha_b200.h
+
+// ctx.cu
+ya_ctx *ya_open_common_for_index(int device, const ya_params *params);
+void ya_set_open_error(const std::string &m);

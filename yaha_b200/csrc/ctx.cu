@@ -68,6 +68,9 @@ static ya_ctx *open_common(int device, const ya_params *params)
     return c;
 }
 
+ya_ctx *ya_open_common_for_index(int device, const ya_params *params) { return open_common(device, params); }
+void ya_set_open_error(const std::string &m) { g_open_err = m; }
+
 extern "C" ya_ctx *ya_open(int device, const ya_params *params,
                            const uint32_t *so, size_t n_so, const uint32_t *roa, size_t n_roa,
                            const uint8_t *bases, size_t n_base_bytes, uint32_t maxROff)

@@ -297,7 +297,7 @@ __global__ void init_strands_kernel(ya_strand_frags *s, const uint32_t *__restri
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int radix_sort(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_bit, int hi_bit)
+int ya_radix_sort_u64(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_bit, int hi_bit)
 {
     uint32_t n_blocks = (n + RS_TILE - 1) / RS_TILE;
     YA_CUDA(c, c->d_hist.reserve((size_t)256 * n_blocks * 4));
@@ -394,7 +394,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
                                                                        probe0, cprobes, c->d_roa, ka);
             c->ctr.launches++;
             int segbits = 1; while ((1 << segbits) < cseg) segbits++;
-            rc = radix_sort(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
+            rc = ya_radix_sort_u64(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
             if (rc != YA_OK) return rc;
 
             // fragments

@@ -243,7 +243,6 @@ __global__ void dp_thread_kernel(const DevJob *__restrict__ jobs, const uint32_t
         const int qc = codes[bwd ? J.qIdx - (uint32_t)(i - 1) : J.qIdx + (uint32_t)(i - 1)];
         int rowMax = YA_WORST;
         // in-place update: column j reads old [j] (diag) and old [j+1] (insert) before writing [j]
-        int diagV = (startCol > 0) ? Vp[startCol] : Vp[0];
         // the boundary cell becomes the next row's diagonal predecessor
         int saveBoundary = Vl;
         for (int j = startCol; j <= endCol; j++) {
@@ -258,7 +257,6 @@ __global__ void dp_thread_kernel(const DevJob *__restrict__ jobs, const uint32_t
             if (ext && Vl > maxScore) { maxScore = Vl; maxi = i; maxj = j; }
             lastV = Vl;
         }
-        (void)diagV;
         if (startCol > 0) Vp[startCol - 1] = saveBoundary;
         if (ext && rowMax < maxScore - K.X) { doneRows = i; break; }
     }

@@ -249,3 +249,11 @@ def build_index(nib: Nib2, word_len: int, max_hits: int = 65525, skip: int = 1) 
 def index_file_name(stem: str, word_len: int, skip: int, max_hits: int) -> str:
     """Main.c:559-563: <stem>.X<LL>_<SS>_<HHHHH>S"""
     return f"{stem}.X{word_len:02d}_{skip:02d}_{max_hits:05d}S"
+
+
+def write_index(path: str, idx: Index) -> None:
+    """Write an Index in the reference's file layout (Index.c:171-176,331)."""
+    with open(path, "wb") as f:
+        np.array([INDEX_VERSION, idx.word_len, idx.max_hits, len(idx.roa)], dtype="<u4").tofile(f)
+        np.ascontiguousarray(idx.so, dtype="<u4").tofile(f)
+        np.ascontiguousarray(idx.roa, dtype="<u4").tofile(f)
