@@ -1,0 +1,214 @@
+// graph.cpp -- fragments -> clumps on the host (kept on the CPU by north_star: "the branchy
+// GraphPath ... stay in the host C code").  Input is the device's stage-2 output: the
+// diag-sorted surviving fragments of one strand with their region ordinals.
+//
+// Follows: processFragmentsGapped region loop          QueryMatch.c:224-303
+//          processFragmentRangeUsingGraph               GraphPath.cpp:272-292
+//          buildBestClumpFromFragmentRange              GraphPath.cpp:161-270
+//          eliminateFragments / checkStartEndCoverage   QueryMatch.c:170-215
+//          addFragment / insertFragment / cleanUpClump  AlignHelpers.c:48-193
+#include <algorithm>
+#include <string.h>
+#include "host.hpp"
+
+namespace yh {
+
+static const int kWorst = -(0x7fffff00);
+
+void disposeClump(Clump *c) { delete c; }
+
+static void addFragment(Clump &c, const Frag &f)                      // AlignHelpers.c:48-56
+{
+    c.matchedBases = (uint16_t)(c.matchedBases + f.refLen);
+    SFrag s; s.frag = f; s.frag.hitCount = 0;
+    c.sf.push_front(std::move(s));
+}
+
+static void insertFragment(Clump &c, Frag &f1)                        // AlignHelpers.c:60-90
+{
+    if (c.sf.empty()) { addFragment(c, f1); return; }
+    SFrag &nextS = c.sf.front();
+    Frag &f2 = nextS.frag;
+    int maxOverlap = (int)std::max(calcOverlap(f1.endQueryOff, f2.startQueryOff), calcOverlapU(fragERO(f1), f2.startRefOff));
+    if (maxOverlap > 0) {
+        int l1 = fragQLen(f1), l2 = fragQLen(f2);
+        bool chop1 = (l1 != l2) ? (l1 < l2) : (c.sf.size() == 1);
+        if (chop1) { f1.endQueryOff = (uint16_t)(f1.endQueryOff - maxOverlap); f1.refLen = (uint16_t)(f1.refLen - maxOverlap); }
+        else { f2.startQueryOff = (uint16_t)(f2.startQueryOff + maxOverlap); f2.startRefOff += (uint32_t)maxOverlap;
+               f2.refLen = (uint16_t)(f2.refLen - maxOverlap); }
+    }
+    addFragment(c, f1);
+}
+
+static void cleanUpClump(const Args &A, Clump &c)                     // AlignHelpers.c:92-193
+{
+    typedef std::list<SFrag>::iterator It;
+    const It END = c.sf.end();
+    It s1 = c.sf.begin();
+    It s2 = (s1 == END) ? END : std::next(s1);
+    It s3 = (s2 == END) ? END : std::next(s2);
+    while (s2 != END && s3 != END) {
+        if (fragQLen(s2->frag) < A.wordLen) {
+            It anchor = s3;
+            while (fragQLen(anchor->frag) < A.wordLen && std::next(anchor) != END) ++anchor;
+            uint32_t d1 = fragDiag(s1->frag), da = fragDiag(anchor->frag);
+            if (absDiff(d1, da) <= (uint32_t)A.maxGap) {
+                It del = s2;
+                while (del != anchor) {
+                    It nxt = std::next(del);
+                    uint32_t dd = fragDiag(del->frag);
+                    bool outside = (dd < d1 && dd < da) || (dd > d1 && dd > da);
+                    if (!outside || std::min(absDiff(d1, dd), absDiff(dd, da)) <= (uint32_t)A.bandWidth) c.sf.erase(del);
+                    del = nxt;
+                }
+            }
+            s1 = anchor; s2 = std::next(anchor);
+        } else { s1 = s2; s2 = s3; }
+        if (s2 != END) s3 = std::next(s2);
+    }
+    // first and last fragments: only dropped when they abut their neighbour (AlignHelpers.c:154-192)
+    if (c.sf.empty()) return;
+    It first = c.sf.begin();
+    if (fragQLen(first->frag) < A.wordLen && std::next(first) != END) {
+        const Frag &f1 = first->frag, &f2 = std::next(first)->frag;
+        int qGap = (int)calcGap(f1.endQueryOff, f2.startQueryOff), rGap = (int)calcGapU(fragERO(f1), f2.startRefOff);
+        if ((qGap == 0 && rGap <= 2 * A.bandWidth) || (rGap == 0 && qGap <= 2 * A.bandWidth)) c.sf.erase(first);
+    }
+    It last = std::prev(c.sf.end());
+    if (fragQLen(last->frag) < A.wordLen) {
+        if (last == c.sf.begin()) return;
+        const Frag &f1 = std::prev(last)->frag, &f2 = last->frag;
+        int qGap = (int)calcGap(f1.endQueryOff, f2.startQueryOff), rGap = (int)calcGapU(fragERO(f1), f2.startRefOff);
+        if ((qGap == 0 && rGap <= 2 * A.bandWidth) || (rGap == 0 && qGap <= 2 * A.bandWidth)) c.sf.erase(last);
+    }
+}
+
+struct FNode {                       // fGraphNode, GraphPath.cpp:65-79 (16-bit score fields kept)
+    int      prev;                   // index of best predecessor, -1 none
+    Frag    *frag;
+    int16_t  bestScore, pathLength;
+    uint16_t pathSQO;
+    uint32_t diag;
+    int16_t  nodeLength;
+    uint16_t SQO, EQO;
+};
+
+static void buildBestClump(const Args &A, std::vector<Frag> &frags, int lo, int hi, std::vector<char> &used,
+                           std::vector<FNode> &nodes, Clump &clump)   // GraphPath.cpp:161-270
+{
+    nodes.clear();
+    for (int i = lo; i <= hi; i++) {
+        if (used[i - lo]) continue;
+        Frag &f = frags[i];
+        FNode n; n.prev = -1; n.pathLength = 1; n.frag = &f; n.diag = fragDiag(f);
+        n.nodeLength = (int16_t)f.refLen; n.bestScore = (int16_t)(n.nodeLength * A.MScore);
+        n.SQO = f.startQueryOff; n.EQO = f.endQueryOff; n.pathSQO = n.SQO;
+        nodes.push_back(n);
+    }
+    const int nc = (int)nodes.size();
+    if (nc == 0) return;
+    std::sort(nodes.begin(), nodes.end(), [](const FNode &a, const FNode &b) {
+        if (a.SQO != b.SQO) return a.SQO < b.SQO;
+        return a.diag < b.diag;                                      // GraphPath.cpp:148-159
+    });
+    int bestScore = kWorst, best = -1;
+    const uint32_t maxGap = (uint32_t)A.maxGap;
+    for (int i = 0; i < nc; i++) {
+        FNode &L = nodes[i];
+        const int lSQO = L.SQO, lEQO = L.EQO;
+        const uint32_t lSRO = L.diag + (uint32_t)lSQO, lERO = L.diag + (uint32_t)L.EQO;
+        for (int j = nc - 1; j > i; j--) {
+            FNode &R = nodes[j];
+            const int rSQO = R.SQO;
+            if (rSQO == lSQO) break;
+            const uint32_t diagGap = absDiff(L.diag, R.diag);
+            if (diagGap > maxGap) continue;
+            const uint32_t rSRO = R.diag + (uint32_t)rSQO;
+            if (lSRO >= rSRO) continue;
+            int desert = (int)std::min(calcGap(lEQO, rSQO), calcGapU(lERO, rSRO));
+            if (desert > A.maxDesert) continue;
+            int maxOverlap = (int)std::max(calcOverlap(lEQO, rSQO), calcOverlapU(lERO, rSRO));
+            int newbases = R.nodeLength - maxOverlap;
+            if (newbases < 1) continue;
+            int gapCost = diagGap > 0 ? -(A.GOCost + (int)diagGap * A.GECost) : 0;     // calcGapCost
+            int newScore = L.bestScore + newbases * A.MScore + gapCost;
+            if (R.bestScore > newScore) continue;
+            if (R.bestScore == newScore) {
+                if (R.prev < 0) continue;
+                const FNode &P = nodes[R.prev];
+                int diagCompare = (int)(absDiff(L.diag, R.diag) - absDiff(P.diag, R.diag));
+                if (diagCompare > 0) continue;
+                if (diagCompare == 0) {
+                    int gapCompare = (int)(calcGap(L.EQO, R.SQO) - calcGap(P.EQO, R.SQO));
+                    if (gapCompare > 0) continue;
+                    if (gapCompare == 0 && L.pathSQO <= P.pathSQO) continue;
+                }
+            }
+            R.bestScore = (int16_t)newScore; R.prev = i; R.pathLength = (int16_t)(L.pathLength + 1); R.pathSQO = L.pathSQO;
+        }
+        if (L.bestScore < bestScore) continue;
+        bool take = L.bestScore > bestScore;
+        if (!take) {                                                  // GraphPath.cpp:88-94
+            const FNode &B = nodes[best];
+            take = (L.EQO != B.EQO) ? (L.EQO < B.EQO) : (L.pathSQO > B.pathSQO);
+        }
+        if (take) { best = i; bestScore = L.bestScore; }
+    }
+    for (int k = best; k >= 0; k = nodes[k].prev) insertFragment(clump, *nodes[k].frag);     // GraphPath.cpp:134-146
+    if ((int)clump.matchedBases < A.minMatch) { clump.sf.clear(); clump.ops.clear(); clump.matchedBases = 0; clump.status = 0; }
+    else cleanUpClump(A, clump);
+}
+
+static bool regionFree(const std::vector<char> &cov, int a, int b)
+{
+    for (int i = a; i <= b; i++) if (cov[i]) return false;
+    return true;
+}
+
+void formClumps(const Env &E, ReadCtx &rc, bool rev)
+{
+    const Args &A = *E.A;
+    std::vector<Frag> &frags = rc.frags[rev];
+    const std::vector<uint32_t> &reg = rc.region[rev];
+    const int n = (int)frags.size();
+    std::vector<char> coverage, used;
+    std::vector<FNode> nodes;
+    int i = 0;
+    while (i < n) {
+        int j = i;
+        while (j + 1 < n && reg[j + 1] == reg[i]) j++;
+        if (j == i) {                                                 // QueryMatch.c:281-290
+            if ((int)frags[i].refLen >= A.minMatch) {
+                Clump *c = new Clump();
+                addFragment(*c, frags[i]);
+                c->set(kReversed, rev);                               // addClump, QueryState.c:156-161
+                rc.clumps.push_back(c);
+            }
+        } else {                                                      // GraphPath.cpp:272-292
+            coverage.assign((size_t)rc.read->len() + 1, 0);
+            used.assign((size_t)(j - i + 1), 0);
+            for (;;) {
+                Clump *c = new Clump();
+                buildBestClump(A, frags, i, j, used, nodes, *c);
+                if (c->sf.empty()) { delete c; break; }
+                int sqo = c->SQO(), qlen = (uint16_t)(1 + c->EQO() - c->SQO());
+                for (int k = 0; k < qlen && sqo + k < (int)coverage.size(); k++) coverage[sqo + k] = 1;
+                // eliminateFragments, QueryMatch.c:201-215 (+ :177-197)
+                const int minLeft = A.minNonOverlap - 1;
+                for (int k = i; k <= j; k++) {
+                    if (used[k - i]) continue;
+                    const int SQO = frags[k].startQueryOff, EQO = frags[k].endQueryOff;
+                    bool keep = false;
+                    if (EQO - SQO >= minLeft)
+                        keep = regionFree(coverage, SQO, SQO + minLeft) || regionFree(coverage, EQO - minLeft, EQO);
+                    if (!keep) used[k - i] = 1;
+                }
+                c->set(kReversed, rev);
+                rc.clumps.push_back(c);
+            }
+        }
+        i = j + 1;
+    }
+}
+
+}  // namespace yh

@@ -1,0 +1,170 @@
+// host.hpp -- host side of yaha_b200: a from-scratch C++ restatement of the parts of yaha 0.1.83
+// that north_star keeps on the CPU (fragment graph, clump assembly, score/split, OQC/FBS, SAM
+// output, CLI), re-driven in BATCHES so that the three device stages run through the C ABI
+// (include/yaha_b200.h) on thousands of reads at a time.
+//
+// Structure (ours, not the reference's): every read of a batch is a lightweight fiber that runs
+// the reference's per-read control flow; whenever it needs DP results it posts jobs and yields;
+// when every fiber of the batch is parked the scheduler executes one ya_sw_batch for all posted
+// jobs and resumes them.  Semantics follow the reference file:line cited at each function.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <list>
+#include "../../include/yaha_b200.h"
+
+namespace yh {
+
+// ----------------------------------------------------------------------------- arguments
+struct Args {                       // AlignmentArgs_t, Math.h:257-334; defaults AlignArgs.c:48-87
+    std::string gfile, xfile, qfile = "stdin", ofile;
+    bool  haveG = false, haveX = false, haveO = false;
+    int   numThreads = 1;
+    bool  fastq = false;
+    int   wordLen = 15, skipDist = 1, maxHits = -1;
+    int   bandWidth = 5, maxIntron = -1, minMatch = 25, maxGap = 50, maxDesert = 50, minNonOverlap = -1;
+    float minIdentity = 0.9f;
+    int   minRawScore = -1;
+    bool  affineGapScoring = true;
+    int   minExtLength = 0;
+    int   GOCost = 5, GECost = 2, RCost = 3, MScore = 1, XCutoff = 25;
+    bool  OQC = true;
+    int   OQCMinNonOverlap = -1, BPCost = 5, maxBPLog = 5;
+    bool  FBS = false;
+    float FBS_PSLength = 0.90f, FBS_PSScore = 0.90f;
+    int   maxQueryLength = 32000;
+    bool  verbose = false, outputBlast8 = false, outputSAM = true, hardClip = true;
+    // yaha_b200 extensions (not echoed in @PG)
+    int   gpus = 1;                 // -gpus N : shard the read file over N devices
+    int   batchReads = 8192;        // -batch N: reads in flight per device
+    bool  query = false, index = true;
+    void  postProcess(bool queryMode);           // AlignArgs.c:108-169
+    ya_params deviceParams() const;
+};
+int parseArgs(int argc, char **argv, Args &a);   // Main.c:187-565 (flags, checks, file names)
+
+// ----------------------------------------------------------------------------- reference genome
+struct BaseSeq { std::string name; uint32_t start, length; };       // BaseSequence_t, Math.h:218-225
+struct Genome {
+    const uint8_t *bases = nullptr;  size_t nBaseBytes = 0;         // packed 4-bit codes
+    std::vector<BaseSeq> seqs;
+    uint32_t maxROff = 0;                                           // BaseSeq.c:121-125
+    const void *map = nullptr; size_t mapLen = 0;
+    int code(uint32_t off) const { uint8_t b = bases[off >> 1]; return (off & 1) ? (b & 15) : (b >> 4); }   // Math.c:180-188
+    int findSeq(uint32_t off) const;                                // BaseSeq.c:81-90 (-1 if none)
+    bool load(const std::string &nib2Path, std::string &err);       // Compress.c:76-134 + BaseSeq.c:115-119
+};
+struct IndexFile {
+    const uint32_t *so = nullptr, *roa = nullptr; size_t nSo = 0, nRoa = 0;
+    int wordLen = 0, maxHits = 0;
+    const void *map = nullptr; size_t mapLen = 0;
+    bool load(const std::string &path, std::string &err);           // Query.c:594-626
+};
+extern const char kCharOfCode[16];   // Math.c:154
+extern const char kCompCharOfCode[16];
+extern const uint8_t kCompCode[16];  // Math.c:155
+int codeOfChar(int c);               // Math.c:141-152
+
+// ----------------------------------------------------------------------------- reads
+struct Read {
+    std::string id;                  // <= 200 chars, spaces -> '_' (Query.c:111-135)
+    std::string fwd, rev;            // characters, forward and reverse-complement (Query.c:161-168)
+    std::string qual;                // FASTQ only
+    std::vector<uint8_t> fcode, rcode;
+    int len() const { return (int)fwd.size(); }
+};
+struct QueryReader {                 // readNextQuery, Query.c:102-228
+    FILE *f = nullptr; bool fastq = false; int maxLen = 32000, wordLen = 15;
+    bool open(const std::string &path, std::string &err);     // Query.c:63-74
+    bool next(Read &r);                                        // false at EOF
+    void close();
+};
+
+// ----------------------------------------------------------------------------- edit ops
+struct Op { uint16_t len; char code; };
+struct OpList {                      // EditOpList_t semantics, SW.cpp:114-283, SW.inl:66-78
+    std::vector<Op> v;
+    bool empty() const { return v.empty(); }
+    void clear() { v.clear(); }
+    void pushFront(char c, int len) { v.insert(v.begin(), Op{(uint16_t)len, c}); }    // no coalescing
+    void pushBack(char c, int len) { v.push_back(Op{(uint16_t)len, c}); }
+    void mergeToFront(OpList &src);  // this = src + this, coalescing the junction (SW.cpp:151-205)
+    void mergeToBack(OpList &src);   // this = this + src, coalescing the junction (SW.cpp:207-261)
+};
+
+// ----------------------------------------------------------------------------- clumps
+typedef ya_frag Frag;                // Fragment_t, Math.h:448-455
+inline int      fragQLen(const Frag &f) { return 1 + (int)f.endQueryOff - (int)f.startQueryOff; }
+inline uint32_t fragERO(const Frag &f) { return f.startRefOff + f.refLen - 1; }
+inline void     fragSetERO(Frag &f, uint32_t ro) { f.refLen = (uint16_t)(1 + ro - f.startRefOff); }
+inline uint32_t fragDiag(const Frag &f) { return f.startRefOff - f.startQueryOff; }
+inline uint32_t absDiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }     // FragsClumps.inl:133-137
+inline unsigned calcGap(int lo, int hi) { return hi > lo ? (unsigned)(hi - lo) - 1 : 0; }           // :157
+inline unsigned calcOverlap(int lo, int hi) { return lo >= hi ? (unsigned)(lo - hi) + 1 : 0; }      // :158
+inline unsigned calcGapU(uint32_t lo, uint32_t hi) { return hi > lo ? (hi - lo) - 1 : 0; }
+inline unsigned calcOverlapU(uint32_t lo, uint32_t hi) { return lo >= hi ? (lo - hi) + 1 : 0; }
+
+struct SFrag { Frag frag; int score = 0; OpList ops; };              // SFragment_t, Math.h:469-477
+enum { kReversed = 1, kFormed = 2, kAligned = 4, kScored = 8, kSplit = 16, kPrimary = 32 };   // FragsClumps.inl:221-226
+struct Clump {                       // Clump_t, Math.h:511-527
+    OpList ops;
+    std::list<SFrag> sf;
+    uint16_t totScore = 0, totLength = 0, matchedBases = 0, mismatchedBases = 0, gapBases = 0;
+    uint16_t numSecondaries = 0, matchedPrimary = 0;
+    uint8_t  status = 0, mapQuality = 255;
+    bool is(int flag) const { return (status & flag) != 0; }
+    void set(int flag, bool on) { if (on) status |= flag; else status &= ~flag; }
+    bool reversed() const { return is(kReversed); }
+    uint16_t SQO() const { return sf.front().frag.startQueryOff; }
+    uint16_t EQO() const { return sf.back().frag.endQueryOff; }
+    uint32_t SRO() const { return sf.front().frag.startRefOff; }
+    uint32_t ERO() const { return fragERO(sf.back().frag); }
+};
+
+struct RandState { uint32_t s[5]; uint32_t bits(); };               // Math.c:274-284
+
+// ----------------------------------------------------------------------------- per-read state
+struct DpFuture { int slot = -1; };  // index into the round's job list
+struct DpAnswer { int score = 0; int addedQ = 0, addedR = 0; OpList ops; };
+
+struct Batch;
+struct ReadCtx {                     // the per-read half of QueryState_t (Math.h:587-666)
+    Batch *batch = nullptr;
+    int    idx = 0;                  // index in the batch == read id on the device
+    Read  *read = nullptr;
+    std::vector<Clump *> clumps;     // LIFO list: back() is the reference's list head
+    int    primaryCount = 0;
+    RandState rng;
+    std::vector<Frag> frags[2];      // mutable copy of the device's surviving fragments, per strand
+    std::vector<uint32_t> region[2];
+    std::string out;                 // formatted SAM / Blast8 records of this read
+    const uint8_t *codes(bool rev) const { return rev ? read->rcode.data() : read->fcode.data(); }
+    const std::string &chars(bool rev) const { return rev ? read->rev : read->fwd; }
+};
+
+// Implemented by the scheduler (pipeline.cpp); callable from inside a read fiber.
+DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen);
+void     dpWait(ReadCtx &rc);                      // park until the round's jobs are done
+DpAnswer &dpGet(ReadCtx &rc, DpFuture f);
+
+// ----------------------------------------------------------------------------- algorithms
+struct Env { const Args *A; const Genome *G; };
+// graph.cpp: fragments -> clumps (QueryMatch.c:224-303, GraphPath.cpp:57-292, AlignHelpers.c:48-193)
+void formClumps(const Env &E, ReadCtx &rc, bool rev);
+// align.cpp: AlignHelpers.c:205-579, AlignExtFrag.cpp:30-234, careful trimming SW.cpp:553-788
+void postProcessClumps(const Env &E, ReadCtx &rc);
+// oqc.cpp: GraphPath.cpp:294-1174
+void postFilterBySimilarity(const Env &E, ReadCtx &rc);
+void postFilterRemoveDups(const Env &E, ReadCtx &rc);
+// sam.cpp: AlignOutput.c:30-321
+void writeHeader(const Env &E, FILE *out);
+void formatClumps(const Env &E, ReadCtx &rc);
+
+// pipeline.cpp
+int runQueries(const Args &A);      // processQueryFile, Query.c:551-709, batched
+int runIndex(const Args &A);        // indexFile / compressFile front end, Main.c:567-634
+void disposeClump(Clump *c);
+
+}  // namespace yh
