@@ -9,6 +9,7 @@ Outputs (all gzip'd, deterministic seeds):
   dump_bw5.txt.gz             every call through the hot-path seams with default flags
   dump_bw10.txt.gz            same with -BW 10 -G 100 (D and G records only)
   out_bw5.sam.gz, out_bw10.sam.gz   the reference's SAM output (-t 1)
+  out_{fbs,nooqc,fastq_oss,blast8}.sam.gz   more reference outputs (-FBS Y, -OQC N, FASTQ input with -oss, -o8)
   files.sha256                digests of the reference-built ref.nib2 and index
 """
 import gzip, hashlib, os, shutil, subprocess, sys, tempfile
@@ -44,6 +45,26 @@ def main():
                                "-BW", str(bw), "-G", str(g)], cwd=tmp, env=env)
         gz(f"{tmp}/dump_bw{bw}.txt", f"{OUT}/dump_bw{bw}.txt.gz")
         gz(f"{tmp}/out_bw{bw}.sam", f"{OUT}/out_bw{bw}.sam.gz")
+    # extra flag sets and FASTQ input (multi-line records, lower case, a long id with spaces)
+    sub = reads[:60] + reads[450:520]
+    with open(tmp + "/reads.fq", "w") as f:
+        for k, (name, seq) in enumerate(sub):
+            s = seq.tobytes().decode()
+            if k % 3 == 1:
+                s = s.lower()
+            q = "".join(chr(33 + (i * 7 + k) % 40) for i in range(len(s)))
+            if k % 4 == 2:            # multi-line sequence and quality
+                h = len(s) // 2
+                f.write(f"@{name} extra words here\n{s[:h]}\n{s[h:]}\n+{name}\n{q[:h]}\n{q[h:]}\n")
+            else:
+                f.write(f"@{name}\n{s}\n+\n{q}\n")
+    for tag, flags, rd in (("fbs", ["-FBS", "Y"], "reads.fa"), ("nooqc", ["-OQC", "N"], "reads.fa"),
+                           ("fastq_oss", ["-oss"], "reads.fq"), ("blast8", ["-o8"], "reads.fa")):
+        outflag = flags[0] if flags[0] in ("-oss", "-o8") else "-osh"
+        extra = [] if flags[0] in ("-oss", "-o8") else flags
+        subprocess.check_call([REF + "/yaha", "-x", idx, "-q", rd, outflag, f"out_{tag}.sam", "-t", "1"] + extra, cwd=tmp)
+        gz(f"{tmp}/out_{tag}.sam", f"{OUT}/out_{tag}.sam.gz")
+    gz(tmp + "/reads.fq", OUT + "/reads.fq.gz")
     gz(tmp + "/ref.fa", OUT + "/ref.fa.gz")
     gz(tmp + "/reads.fa", OUT + "/reads.fa.gz")
     with open(OUT + "/files.sha256", "w") as f:

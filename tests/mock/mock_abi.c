@@ -1,0 +1,121 @@
+/* tests/mock/mock_abi.c -- TEST INFRASTRUCTURE ONLY.
+ * Implements the C ABI of include/yaha_b200.h on top of the CPU oracle (oracle/oracle_*.c) so
+ * that the host program's logic (graph, split/score, OQC, SAM, fiber scheduler) can be tested
+ * and run under sanitizers on machines without a GPU.  It is linked only into
+ * tests/_build/yaha_host_mock; the product never sees it. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../oracle/oracle.h"
+
+struct ya_ctx {
+    ya_params P;
+    const uint32_t *so, *roa; size_t n_so, n_roa;
+    const uint8_t *bases; size_t n_base_bytes; uint32_t maxROff;
+    int n_reads; uint8_t *fwd, *rev; uint64_t *off;
+    ya_counters ctr;
+    char err[256];
+};
+static const uint8_t comp[16] = {2, 3, 0, 1, 4, 12, 7, 6, 9, 8, 15, 11, 5, 13, 14, 10};
+
+ya_ctx *ya_open(int device, const ya_params *p, const uint32_t *so, size_t n_so, const uint32_t *roa, size_t n_roa,
+                const uint8_t *bases, size_t n_base_bytes, uint32_t maxROff)
+{
+    ya_ctx *c = calloc(1, sizeof *c);
+    c->P = *p; c->so = so; c->roa = roa; c->n_so = n_so; c->n_roa = n_roa; c->bases = bases; c->n_base_bytes = n_base_bytes;
+    c->maxROff = maxROff;
+    (void)device;
+    return c;
+}
+ya_ctx *ya_open_peer(int device, const ya_ctx *src) { ya_ctx *c = malloc(sizeof *c); *c = *src; c->fwd = c->rev = NULL; c->off = NULL; c->n_reads = 0; (void)device; return c; }
+ya_ctx *ya_open_build(int d, const ya_params *p, const uint8_t *b, size_t n, const uint32_t *s, const uint32_t *l, int ns, uint32_t mh)
+{ (void)d; (void)p; (void)b; (void)n; (void)s; (void)l; (void)ns; (void)mh; return NULL; }
+int ya_index_sizes(const ya_ctx *c, size_t *a, size_t *b) { *a = c->n_so; *b = c->n_roa; return 0; }
+int ya_index_download(ya_ctx *c, uint32_t *so, uint32_t *roa) { (void)c; (void)so; (void)roa; return YA_E_STATE; }
+void ya_close(ya_ctx *c) { if (!c) return; free(c->fwd); free(c->rev); free(c->off); free(c); }
+const char *ya_last_error(const ya_ctx *c) { return c ? c->err : "mock"; }
+int ya_set_params(ya_ctx *c, const ya_params *p) { c->P = *p; return 0; }
+int ya_set_stream(ya_ctx *c, void *s) { (void)c; (void)s; return 0; }
+int ya_get_counters(ya_ctx *c, ya_counters *o) { *o = c->ctr; memset(&c->ctr, 0, sizeof c->ctr); return 0; }
+int ya_measure_int32_peak(ya_ctx *c, double *a, double *b) { (void)c; *a = *b = 0; return 0; }
+
+int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
+{
+    free(c->fwd); free(c->rev); free(c->off);
+    c->n_reads = b->n_reads;
+    uint64_t total = b->n_reads ? b->offsets[b->n_reads] : 0;
+    c->fwd = malloc(total + 1); c->rev = malloc(total + 1); c->off = malloc((b->n_reads + 1) * sizeof(uint64_t));
+    memcpy(c->off, b->offsets, (b->n_reads + 1) * sizeof(uint64_t));
+    if (total) memcpy(c->fwd, b->codes, total);
+    for (int r = 0; r < b->n_reads; r++) {
+        uint64_t s = c->off[r], e = c->off[r + 1];
+        for (uint64_t i = s; i < e; i++) c->rev[s + (e - 1 - i)] = comp[c->fwd[i] & 15];
+    }
+    return 0;
+}
+
+int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
+{
+    size_t n_out = 0;
+    int overflow = 0;
+    for (int seg = 0; seg < 2 * c->n_reads; seg++) {
+        int r = seg >> 1;
+        int L = (int)(c->off[r + 1] - c->off[r]);
+        const uint8_t *codes = ((seg & 1) ? c->rev : c->fwd) + c->off[r];
+        ya_strand_frags *s = &out->strands[seg];
+        s->first = (uint32_t)n_out; s->n_frags = 0; s->n_frags_all = 0; s->total_hits = 0;
+        int m = L - c->P.wordLen + 1;
+        if (m <= 0) continue;
+        uint32_t *soff = malloc(m * 4), *cnt = malloc(m * 4);
+        uint32_t total = orc_seed_lookup(&c->P, c->so, codes, L, soff, cnt);
+        s->total_hits = total;
+        if (total) {
+            int cap = (int)total + 4 * L + 64;
+            ya_frag *fr = malloc((size_t)cap * sizeof(ya_frag));
+            int nf;
+            while ((nf = orc_find_frags(&c->P, c->roa, c->n_roa, soff, cnt, m, fr, cap)) < 0) { cap *= 2; fr = realloc(fr, (size_t)cap * sizeof(ya_frag)); }
+            uint32_t *reg = malloc((nf + 1) * 4); uint8_t *keep = malloc(nf + 1);
+            orc_regions(&c->P, fr, nf, reg, keep);
+            s->n_frags_all = (uint32_t)nf;
+            for (int k = 0; k < nf; k++) {
+                if (!keep[k]) continue;
+                if (n_out < out->frags_cap) { out->frags[n_out] = fr[k]; out->region[n_out] = reg[k]; } else overflow = 1;
+                n_out++; s->n_frags++;
+            }
+            free(fr); free(reg); free(keep);
+        }
+        free(soff); free(cnt);
+    }
+    if (overflow) { out->frags_needed = n_out; return YA_E_CAPACITY; }
+    out->n_frags = n_out;
+    return 0;
+}
+
+int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res, ya_op *ops, size_t ops_cap, size_t *ops_needed)
+{
+    size_t used = 0;
+    int overflow = 0;
+    ya_op *tmp = malloc(70000 * sizeof(ya_op));
+    for (int i = 0; i < n; i++) {
+        const ya_dp_job *j = &jobs[i];
+        const uint8_t *codes = (j->strand ? c->rev : c->fwd) + c->off[j->read];
+        int aq = 0, ar = 0, no = 0; int64_t cells = 0;
+        int score = orc_dp(&c->P, c->bases, c->maxROff, codes, j->kind, j->rOff, j->rLen, j->qOff, j->qLen, &aq, &ar, tmp, 70000, &no, &cells);
+        res[i].score = score; res[i].addedQLen = (uint16_t)aq; res[i].addedRLen = (uint16_t)ar; res[i].ops_off = (uint32_t)used; res[i].ops_n = (uint32_t)no;
+        if (used + no <= ops_cap) memcpy(ops + used, tmp, no * sizeof(ya_op)); else overflow = 1;
+        used += no;
+        c->ctr.dp_cells += cells; c->ctr.dp_jobs++;
+    }
+    free(tmp);
+    if (ops_needed) *ops_needed = used;
+    return overflow ? YA_E_CAPACITY : 0;
+}
+
+int ya_perfect_ext(ya_ctx *c, const ya_dp_job *jobs, int n, uint16_t *count)
+{
+    for (int i = 0; i < n; i++) {
+        const uint8_t *codes = (jobs[i].strand ? c->rev : c->fwd) + c->off[jobs[i].read];
+        count[i] = (uint16_t)orc_perfect(c->bases, codes, jobs[i].rOff, jobs[i].qOff, jobs[i].qLen, jobs[i].kind == YA_DP_EXT_BWD ? -1 : 1);
+    }
+    return 0;
+}

@@ -1,0 +1,49 @@
+"""Host logic on the CPU: the product's host sources (yaha_b200/host/*.cpp: fragment graph, clump
+assembly, split/score, OQC/FBS, SAM writer, fiber scheduler) linked against an oracle-backed mock
+of the C ABI (tests/mock/mock_abi.c) must reproduce the reference's SAM byte for byte.  The same
+cases run against the real CUDA library in test_host_sam.py (-m gpu)."""
+import os
+import subprocess
+
+import pytest
+
+import hostcases as H
+import support as S
+
+MOCK = os.path.join(S.ROOT, "tests", "_build", "yaha_host_mock")
+
+
+@pytest.fixture(scope="module")
+def mock_host():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(S.ROOT, "tests", "mock"), "SAN="])
+    return MOCK
+
+
+@pytest.mark.parametrize("golden,reads,outflag,extra", H.CASES)
+def test_host_logic_reproduces_reference_sam(small, mock_host, tmp_path, golden, reads, outflag, extra):
+    out = str(tmp_path / "o.sam")
+    p = subprocess.run(H.command(mock_host, small, reads, outflag, out, extra), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    got, want = H.sam_lines(open(out).read()), H.expected(small, golden)
+    diff = [(i, x, y) for i, (x, y) in enumerate(zip(got, want)) if x != y]
+    assert not diff, diff[:2]
+    assert len(got) == len(want)
+
+
+def test_output_order_independent_of_threads_and_batch(small, mock_host, tmp_path):
+    want = H.expected(small, "out_bw5.sam.gz")
+    for k, extra in enumerate((["-t", "3"], ["-batch", "37"], ["-t", "2", "-batch", "100"])):
+        out = str(tmp_path / f"o{k}.sam")
+        cmd = [mock_host, "-x", small.idx_path, "-q", os.path.join(small.dir, "reads.fa"), "-osh", out] + extra
+        subprocess.run(cmd, check=True, capture_output=True, timeout=600)
+        assert H.sam_lines(open(out).read()) == want
+
+
+def test_cli_errors_match_reference_behaviour(small, mock_host):
+    # missing -x for query mode, bad flag, bad bool: message + non-zero exit like Main.c
+    p = subprocess.run([mock_host, "-q", "x.fa"], capture_output=True, text=True)
+    assert p.returncode != 0 and "Index file specification (-x) is required" in p.stderr
+    p = subprocess.run([mock_host, "-bogus"], capture_output=True, text=True)
+    assert p.returncode != 0 and "is not a valid option" in p.stderr
+    p = subprocess.run([mock_host, "-x", small.idx_path, "-q", "r.fa", "-OQC", "maybe"], capture_output=True, text=True)
+    assert p.returncode != 0 and "is not a valid value for parameter -OQC" in p.stderr

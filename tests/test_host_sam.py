@@ -1,0 +1,58 @@
+"""End-to-end drop-in check on the GPU: the batched host program (yaha_b200/host) with the CUDA
+hot path behind the C ABI must write the same SAM as the unmodified reference `yaha -t 1` --
+every line except @PG, in the same order -- for every golden flag set."""
+import os
+import subprocess
+
+import pytest
+
+import hostcases as H
+import support as S
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(S.ROOT, "yaha_b200", "yaha_b200_host")
+
+
+@pytest.mark.parametrize("golden,reads,outflag,extra", H.CASES)
+def test_sam_identical_to_reference(small, tmp_path, golden, reads, outflag, extra):
+    out = str(tmp_path / "o.sam")
+    p = subprocess.run(H.command(HOST, small, reads, outflag, out, extra), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    got, want = H.sam_lines(open(out).read()), H.expected(small, golden)
+    diff = [(i, x, y) for i, (x, y) in enumerate(zip(got, want)) if x != y]
+    assert not diff, diff[:2]
+    assert len(got) == len(want)
+
+
+def test_sam_independent_of_threads_and_batch(small, tmp_path):
+    want = H.expected(small, "out_bw5.sam.gz")
+    for k, extra in enumerate((["-t", "4"], ["-batch", "37"], ["-t", "3", "-batch", "100"])):
+        out = str(tmp_path / f"o{k}.sam")
+        cmd = [HOST, "-x", small.idx_path, "-q", os.path.join(small.dir, "reads.fa"), "-osh", out] + extra
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert H.sam_lines(open(out).read()) == want
+
+
+def test_sam_identical_on_10k_long_reads(tmp_path):
+    """BASELINE configs[0] shape at reduced reference size, against the reference binary when it is
+    on this box (oracle/_ref travels with the snapshot): 1 Mbp, 2 000 x 1000 bp reads at 2 %."""
+    if not os.path.exists(S.REF_BIN):
+        pytest.skip("oracle/_ref/yaha not present")
+    import numpy as np
+    import yaha_b200
+    from yaha_b200 import refio, synth
+    d = str(tmp_path)
+    ref = synth.random_reference(1_000_000, 31)
+    synth.write_fasta(d + "/ref.fa", [("chrA", ref[:600_000]), ("chrB", ref[600_000:])])
+    synth.write_reads(d + "/reads.fa", synth.simulate_reads(ref, 2000, 1000, 0.02, 5))
+    open(d + "/ref.nib2", "wb").write(refio.build_nib2(refio.read_fasta(d + "/ref.fa")))
+    nib = refio.load_nib2(d + "/ref.nib2")
+    al = yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=13), device=0)
+    idx_path = d + "/" + refio.index_file_name("ref", 13, 1, 65525)
+    refio.write_index(idx_path, al.download_index())
+    al.close()
+    subprocess.run([S.REF_BIN, "-x", idx_path, "-q", d + "/reads.fa", "-osh", d + "/r.sam", "-t", "1"], check=True, capture_output=True)
+    p = subprocess.run([HOST, "-x", idx_path, "-q", d + "/reads.fa", "-osh", d + "/m.sam", "-t", "4"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert H.sam_lines(open(d + "/m.sam").read()) == H.sam_lines(open(d + "/r.sam").read())

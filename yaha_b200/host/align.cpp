@@ -1,0 +1,434 @@
+// align.cpp -- clump alignment, scoring and splitting on the host, with every DP call turned
+// into a posted device job (dpSubmit / dpWait / dpGet).
+//
+// Follows: alignClump, collapseSFragments           AlignHelpers.c:205-300
+//          scoreClump                               AlignHelpers.c:302-366
+//          splitClump / splitClumpHelper            AlignHelpers.c:374-579
+//          extendFragment*ToStopPerfectly           AlignExtFrag.cpp:30-48
+//          extendClumpForwardReverseTemplated       AlignExtFrag.cpp:64-156
+//          makeAndAlignSFragmentToFillGap           AlignExtFrag.cpp:164-234
+//          findAGS{Forward,Backward}ExtensionCarefully (post-DP trimming)   SW.cpp:553-788
+//          mergeEOLToFront/Back                     SW.cpp:151-261
+//
+// Because a DP result is a pure function of its job tuple, all gap fills of all
+// clumps of a read are posted together, then all first extensions, and only the (rare) careful
+// re-extensions of split pieces are demand driven.
+#include <algorithm>
+#include "host.hpp"
+
+namespace yh {
+
+void OpList::mergeToFront(OpList &src)
+{
+    if (src.v.empty()) return;
+    if (!v.empty() && src.v.back().code == v.front().code) {
+        src.v.back().len = (uint16_t)(src.v.back().len + v.front().len);
+        v.erase(v.begin());
+    }
+    src.v.insert(src.v.end(), v.begin(), v.end());
+    v.swap(src.v);
+    src.v.clear();
+}
+
+void OpList::mergeToBack(OpList &src)
+{
+    if (src.v.empty()) return;
+    size_t from = 0;
+    if (!v.empty() && v.back().code == src.v.front().code) {
+        v.back().len = (uint16_t)(v.back().len + src.v.front().len);
+        from = 1;
+    }
+    v.insert(v.end(), src.v.begin() + from, src.v.end());
+    src.v.clear();
+}
+
+static inline int opScore(const Args &A, const Op &o)
+{
+    switch (o.code) {
+    case 'M': return A.MScore * o.len;
+    case 'R': return -(A.RCost * o.len);
+    case 'I': case 'D': return -(A.GOCost + A.GECost * o.len);
+    default: return 0;
+    }
+}
+
+static int perfectForward(const Env &E, const uint8_t *q, Frag &f, int len)      // AlignExtFrag.cpp:30-38
+{
+    uint16_t qOff = (uint16_t)(f.endQueryOff + 1);
+    uint32_t rOff = fragERO(f) + 1;
+    int n = 0;
+    while (n < len && q[qOff + n] == E.G->code(rOff + (uint32_t)n)) n++;
+    if (n > 0) { f.endQueryOff = (uint16_t)(f.endQueryOff + n); f.refLen = (uint16_t)(f.refLen + n); }
+    return n;
+}
+
+static int perfectBackward(const Env &E, const uint8_t *q, Frag &f, int len)     // AlignExtFrag.cpp:40-48
+{
+    uint16_t qOff = (uint16_t)(f.startQueryOff - 1);
+    uint32_t rOff = f.startRefOff - 1;
+    int n = 0;
+    while (n < len && q[qOff - n] == E.G->code(rOff - (uint32_t)n)) n++;
+    if (n > 0) { f.startQueryOff = (uint16_t)(f.startQueryOff - n); f.startRefOff -= (uint32_t)n; f.refLen = (uint16_t)(f.refLen + n); }
+    return n;
+}
+
+// ---- phase 1 of alignClump: perfect extensions between neighbours, "nM" lists, post gap jobs
+struct GapJob { std::list<SFrag>::iterator after; SFrag piece; DpFuture fut; bool needDp; };
+
+static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, std::vector<GapJob> &gaps)
+{
+    const Args &A = *E.A;
+    const bool rev = c.reversed();
+    const uint8_t *q = rc.codes(rev);
+    auto s1 = c.sf.begin();
+    for (auto s2 = std::next(s1); s2 != c.sf.end(); ++s2) {          // AlignHelpers.c:226-237
+        int gap = (int)std::min(calcGap(s1->frag.endQueryOff, s2->frag.startQueryOff), calcGapU(fragERO(s1->frag), s2->frag.startRefOff));
+        gap -= perfectBackward(E, q, s2->frag, gap);
+        gap -= perfectForward(E, q, s1->frag, gap);
+        s1 = s2;
+    }
+    for (auto &s : c.sf) {                                             // AlignHelpers.c:241-246
+        int ql = fragQLen(s.frag);
+        s.ops.pushFront('M', ql);
+        s.score = A.MScore * ql;
+    }
+    for (auto a = c.sf.begin(); std::next(a) != c.sf.end(); ++a) {    // AlignHelpers.c:251-261 + AlignExtFrag.cpp:164-234
+        const Frag &f1 = a->frag, &f2 = std::next(a)->frag;
+        uint16_t qGap = (uint16_t)calcGap(f1.endQueryOff, f2.startQueryOff);
+        uint16_t rGap = (uint16_t)calcGapU(fragERO(f1), f2.startRefOff);
+        if (qGap == 0 && rGap == 0) continue;
+        GapJob g; g.after = a; g.needDp = false;
+        Frag &nf = g.piece.frag;
+        nf.hitCount = 0;
+        nf.startQueryOff = (uint16_t)(f1.endQueryOff + 1);
+        nf.endQueryOff = (uint16_t)(f2.startQueryOff - 1);
+        nf.startRefOff = fragERO(f1) + 1;
+        fragSetERO(nf, f2.startRefOff - 1);
+        if (qGap == 0) { g.piece.ops.pushFront('D', rGap); g.piece.score = -(A.GOCost + rGap * A.GECost); }
+        else if (rGap == 0) { g.piece.ops.pushFront('I', qGap); g.piece.score = -(A.GOCost + qGap * A.GECost); }
+        else if (rGap == 1 && qGap == 1) { g.piece.ops.pushFront('R', 1); g.piece.score = -A.RCost; }
+        else {
+            int lenDiff = std::abs((int)qGap - (int)rGap);
+            bool banded = lenDiff + A.bandWidth * 2 + 1 < (int)rGap;
+            g.needDp = true;
+            g.fut = dpSubmit(rc, banded ? YA_DP_BANDED : YA_DP_FULL, rev, nf.startRefOff, rGap, nf.startQueryOff, qGap);
+        }
+        gaps.push_back(std::move(g));
+    }
+}
+
+// ---- phase 2: splice the gap pieces, collapse, perfect-extend the ends, post both extensions
+struct ExtState { int backLen = 0, forwLen = 0; DpFuture fb, ff; bool doB = false, doF = false; };
+
+static void collapse(Clump &c)                                          // AlignHelpers.c:274-300
+{
+    int total = 0;
+    for (auto &s : c.sf) { total += s.score; c.ops.mergeToBack(s.ops); }
+    SFrag &s0 = c.sf.front();
+    const Frag fn = c.sf.back().frag;
+    s0.frag.endQueryOff = fn.endQueryOff;
+    fragSetERO(s0.frag, fragERO(fn));
+    s0.score = total;
+    c.sf.erase(std::next(c.sf.begin()), c.sf.end());
+}
+
+// perfect part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:76-107)
+static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool goForw, int &score, ExtState &x)
+{
+    const Args &A = *E.A;
+    const uint8_t *q = rc.codes(c.reversed());
+    Frag &f = c.sf.front().frag;
+    x.backLen = x.forwLen = 0;
+    if (goBack) {
+        x.backLen = (int)std::min<uint32_t>(f.startQueryOff, f.startRefOff);
+        if (x.backLen > 0) {
+            int m = perfectBackward(E, q, f, x.backLen);
+            if (m > 0) { c.ops.v.front().len = (uint16_t)(c.ops.v.front().len + m); score += m * A.MScore; x.backLen -= m; }
+        }
+    }
+    if (goForw) {
+        uint16_t qlen = (uint16_t)((rc.read->len() - 1) - f.endQueryOff);
+        uint32_t rlen = E.G->maxROff - fragERO(f);
+        x.forwLen = (int)std::min<uint32_t>(qlen, rlen);
+        if (x.forwLen > 0) {
+            int m = perfectForward(E, q, f, x.forwLen);
+            if (m > 0) { c.ops.v.back().len = (uint16_t)(c.ops.v.back().len + m); score += m * A.MScore; x.forwLen -= m; }
+        }
+    }
+    x.doB = goBack && x.backLen >= A.minExtLength;
+    x.doF = goForw && x.forwLen >= A.minExtLength;
+    // Both DP jobs can be posted now: the backward extension never moves the fragment's end
+    // (FragsClumps.inl:81-85), so the forward job's anchor is already final.
+    if (x.doB) x.fb = dpSubmit(rc, YA_DP_EXT_BWD, c.reversed(), f.startRefOff - 1, 0, f.startQueryOff - 1, x.backLen);
+    if (x.doF) x.ff = dpSubmit(rc, YA_DP_EXT_FWD, c.reversed(), fragERO(f) + 1, 0, f.endQueryOff + 1, x.forwLen);
+}
+
+// SW.cpp:671-788: trim a backward extension so the running score never reaches zero
+static int carefulBackward(const Args &A, DpAnswer &r, OpList &list, int score, int &addQ, int &addR)
+{
+    addQ = addR = 0;
+    if (r.score <= 0) return 0;
+    OpList &t = r.ops;
+    int QLen = 0, RLen = 0, AGS = 0, maxAGS = 0, startItem = -1;
+    for (int k = 0; k < (int)t.v.size(); k++) {
+        const Op &o = t.v[k];
+        if (o.code == 'M') { QLen += o.len; RLen += o.len; }
+        else if (o.code == 'R') { QLen += o.len; RLen += o.len; }
+        else if (o.code == 'I') QLen += o.len;
+        else if (o.code == 'D') RLen += o.len;
+        AGS += opScore(A, o);
+        if (AGS <= 0) { AGS = 0; maxAGS = 0; QLen = 0; RLen = 0; startItem = k; }
+        if (AGS > maxAGS) maxAGS = AGS;
+    }
+    if (AGS <= 0 || maxAGS >= AGS + score) { t.clear(); return 0; }
+    if (startItem >= 0) t.v.erase(t.v.begin(), t.v.begin() + startItem + 1);
+    list.mergeToFront(t);
+    addQ = QLen; addR = RLen;
+    return AGS;
+}
+
+// SW.cpp:553-669: trim a forward extension at its best point if the running score hits zero
+static int carefulForward(const Args &A, DpAnswer &r, OpList &list, int score, int &addQ, int &addR)
+{
+    addQ = addR = 0;
+    if (r.score <= 0) return 0;
+    OpList &t = r.ops;
+    int initAGS = r.score;
+    addQ = r.addedQ; addR = r.addedR;
+    int QLen = 0, RLen = 0, AGS = score, maxAGS = score, maxItem = -1, maxQ = 0, maxR = 0;
+    for (int k = 0; k < (int)t.v.size(); k++) {
+        const Op &o = t.v[k];
+        if (o.code == 'M' || o.code == 'R') { QLen += o.len; RLen += o.len; }
+        else if (o.code == 'I') QLen += o.len;
+        else if (o.code == 'D') RLen += o.len;
+        AGS += opScore(A, o);
+        if (AGS > maxAGS) { maxAGS = AGS; maxQ = QLen; maxR = RLen; maxItem = k; }
+        else if (AGS <= 0) {
+            if (maxAGS <= score) { t.clear(); addQ = addR = 0; return 0; }
+            t.v.erase(t.v.begin() + maxItem + 1, t.v.end());
+            addQ = maxQ; addR = maxR;
+            initAGS = maxAGS - score;
+            break;
+        }
+    }
+    list.mergeToBack(t);
+    return initAGS;
+}
+
+// DP part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:109-143)
+static void extendApply(const Env &E, ReadCtx &rc, Clump &c, ExtState &x, bool careful, int score)
+{
+    const Args &A = *E.A;
+    Frag &f = c.sf.front().frag;
+    if (x.doB) {
+        DpAnswer &r = dpGet(rc, x.fb);
+        int ns, aq, ar;
+        if (careful) ns = carefulBackward(A, r, c.ops, score, aq, ar);
+        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToFront(r.ops); }
+        if (ns > 0) {
+            score += ns;
+            f.startQueryOff = (uint16_t)(f.startQueryOff - aq);
+            f.startRefOff -= (uint32_t)ar; f.refLen = (uint16_t)(f.refLen + ar);
+        }
+    }
+    if (x.doF) {
+        DpAnswer &r = dpGet(rc, x.ff);
+        int ns, aq, ar;
+        if (careful) ns = carefulForward(A, r, c.ops, score, aq, ar);
+        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToBack(r.ops); }
+        if (ns > 0) {
+            score += ns;
+            f.endQueryOff = (uint16_t)(f.endQueryOff + aq);
+            f.refLen = (uint16_t)(f.refLen + ar);
+        }
+    }
+    c.sf.front().score = score;
+}
+
+static int scoreClump(const Env &E, ReadCtx &rc, Clump *c);
+
+// AlignHelpers.c:374-557
+static int splitHelper(const Env &E, ReadCtx &rc, Clump *c, int wSQO, int wEQO)
+{
+    const Args &A = *E.A;
+    SFrag &cs = c->sf.front();
+    Frag &cf = cs.frag;
+    OpList &list = cs.ops;
+    list.mergeToFront(c->ops);
+    uint16_t sQO = 0, eQO = 0; uint32_t sRO = 0, eRO = 0;
+    int matches = 0, mism = 0, ins = 0, del = 0, AGS = 0, maxAGS = -10000, maxItem = -1, minItem = -1;
+    const int n = (int)list.v.size();
+    for (int k = 0; k < n; k++) {
+        const Op &o = list.v[k];
+        if (o.code == 'M') matches += o.len; else if (o.code == 'R') mism += o.len;
+        else if (o.code == 'I') ins += o.len; else if (o.code == 'D') del += o.len;
+        AGS += opScore(A, o);
+        if (AGS < 0) AGS = 0;
+        if (AGS > maxAGS) {
+            maxAGS = AGS; maxItem = k;
+            eQO = (uint16_t)(cf.startQueryOff + matches + mism + ins - 1);
+            eRO = cf.startRefOff + (uint32_t)(matches + mism + del) - 1;
+        }
+    }
+    AGS = maxAGS; matches = mism = ins = del = 0;
+    int maxMatch = 0;
+    for (int k = maxItem; k >= 0; k--) {
+        const Op &o = list.v[k];
+        if (o.code == 'M') { matches += o.len; if ((int)o.len > maxMatch) maxMatch = o.len; }
+        else if (o.code == 'R') mism += o.len; else if (o.code == 'I') ins += o.len; else if (o.code == 'D') del += o.len;
+        AGS -= opScore(A, o);
+        if (AGS <= 0) {
+            minItem = k;
+            sQO = (uint16_t)(eQO - (matches + mism + ins - 1));
+            sRO = eRO - (uint32_t)(matches + mism + del - 1);
+            break;
+        }
+    }
+    if (maxMatch < A.wordLen) return 0;
+
+    int retval = 0;
+    auto hasSeed = [&](const OpList &l) {                             // EditOpList2Maxmatch, SW.cpp:1215-1222
+        for (const Op &o : l.v) if (o.code == 'M' && (int)o.len >= A.wordLen) return true;
+        return false;
+    };
+    auto finishChild = [&](Clump *nc) {
+        if (nc->is(kScored)) {
+            nc->set(kSplit, true); nc->set(kAligned, true);
+            nc->set(kReversed, c->reversed());
+            rc.clumps.push_back(nc);                                  // addClump
+        } else delete nc;
+    };
+    const Frag cur = cf;                                              // offsets before this piece is cut
+    if (minItem > 0) {                                                // head piece, AlignHelpers.c:463-495
+        Clump *nc = new Clump();
+        nc->set(kReversed, c->reversed());
+        nc->sf.emplace_back();
+        SFrag &ns = nc->sf.front();
+        ns.ops.v.assign(list.v.begin(), list.v.begin() + minItem);
+        list.v.erase(list.v.begin(), list.v.begin() + minItem);
+        maxItem -= minItem;
+        if (hasSeed(ns.ops)) {
+            ns.frag.hitCount = 0;
+            ns.frag.startQueryOff = cur.startQueryOff; ns.frag.endQueryOff = (uint16_t)(sQO - 1);
+            ns.frag.startRefOff = cur.startRefOff; fragSetERO(ns.frag, sRO - 1);
+            retval += splitHelper(E, rc, nc, wSQO, wEQO);
+        }
+        finishChild(nc);
+    }
+    SFrag &cs2 = c->sf.front();                                       // (references stay valid; re-read for clarity)
+    OpList &list2 = cs2.ops;
+    if (maxItem != (int)list2.v.size() - 1) {                         // tail piece, AlignHelpers.c:500-531
+        Clump *nc = new Clump();
+        nc->set(kReversed, c->reversed());
+        nc->sf.emplace_back();
+        SFrag &ns = nc->sf.front();
+        ns.ops.v.assign(list2.v.begin() + maxItem + 1, list2.v.end());
+        list2.v.erase(list2.v.begin() + maxItem + 1, list2.v.end());
+        if (hasSeed(ns.ops)) {
+            ns.frag.hitCount = 0;
+            ns.frag.startQueryOff = (uint16_t)(eQO + 1); ns.frag.endQueryOff = cur.endQueryOff;
+            ns.frag.startRefOff = eRO + 1; fragSetERO(ns.frag, fragERO(cur));
+            retval += splitHelper(E, rc, nc, wSQO, wEQO);
+        }
+        finishChild(nc);
+    }
+    Frag &f = c->sf.front().frag;
+    f.startQueryOff = sQO; f.endQueryOff = eQO; f.startRefOff = sRO; fragSetERO(f, eRO);
+    c->sf.front().score = maxAGS;
+    c->ops.mergeToFront(c->sf.front().ops);
+    // careful re-extension (AlignHelpers.c:549-551, dispatch AlignExtFrag.cpp:151-156: when neither
+    // direction is requested the reference still extends forward)
+    bool goBack = (sQO != wSQO), goForw = (eQO != wEQO);
+    bool doBack = goBack, doForw = (goBack && goForw) || !goBack;
+    ExtState x;
+    int score = c->sf.front().score;
+    extendPerfect(E, rc, *c, doBack, doForw, score, x);
+    if (x.doB || x.doF) dpWait(rc);
+    extendApply(E, rc, *c, x, true, score);
+    c->set(kSplit, true);
+    retval += scoreClump(E, rc, c);
+    return retval;
+}
+
+static int scoreClump(const Env &E, ReadCtx &rc, Clump *c)             // AlignHelpers.c:302-366
+{
+    const Args &A = *E.A;
+    if (c->is(kScored)) return 1;
+    int AGS = 0, maxAGS = 0, matches = 0, mism = 0, ins = 0, del = 0;
+    const int alignedScore = c->sf.front().score;
+    const int n = (int)c->ops.v.size();
+    bool split = false;
+    for (int k = 0; k < n; k++) {
+        const Op &o = c->ops.v[k];
+        if (o.code == 'M') matches += o.len; else if (o.code == 'R') mism += o.len;
+        else if (o.code == 'I') ins += o.len; else if (o.code == 'D') del += o.len;
+        AGS += opScore(A, o);
+        if (AGS <= 0 || (AGS >= alignedScore && k != n - 1)) { split = true; break; }
+        if (AGS > maxAGS) maxAGS = AGS;
+    }
+    if (!split && matches >= A.minRawScore && maxAGS > AGS) split = true;
+    if (split) {                                                       // splitClump, AlignHelpers.c:561-579
+        const Frag &f = c->sf.front().frag;
+        return splitHelper(E, rc, c, f.startQueryOff, f.endQueryOff);
+    }
+    if (matches < A.minRawScore) return 0;
+    c->matchedBases = (uint16_t)matches; c->mismatchedBases = (uint16_t)mism; c->gapBases = (uint16_t)(ins + del);
+    c->totLength = (uint16_t)(matches + mism + ins + del); c->totScore = (uint16_t)AGS;
+    double percent = (double)c->matchedBases / c->totLength;
+    if (percent < A.minIdentity) return 0;
+    c->set(kScored, true);
+    return 1;
+}
+
+void postProcessClumps(const Env &E, ReadCtx &rc)                       // QueryMatch.c:306-331
+{
+    std::vector<Clump *> old;
+    old.swap(rc.clumps);
+    std::reverse(old.begin(), old.end());                               // reference walks from the list head
+    // phase 1: everything up to the gap-fill jobs, for all clumps of the read
+    std::vector<std::vector<GapJob>> gaps(old.size());
+    bool any = false;
+    for (size_t k = 0; k < old.size(); k++) {
+        if (old[k]->is(kAligned)) continue;
+        alignPrepare(E, rc, *old[k], gaps[k]);
+        for (auto &g : gaps[k]) any |= g.needDp;
+    }
+    if (any) dpWait(rc);
+    // phase 2: splice, collapse, perfect-extend and post the first extensions
+    std::vector<ExtState> xs(old.size());
+    std::vector<int> scores(old.size(), 0);
+    any = false;
+    for (size_t k = 0; k < old.size(); k++) {
+        Clump &c = *old[k];
+        if (c.is(kAligned)) continue;
+        for (auto &g : gaps[k]) {
+            if (g.needDp) {
+                DpAnswer &r = dpGet(rc, g.fut);
+                g.piece.score = r.score;
+                g.piece.ops.v.swap(r.ops.v);
+            }
+            c.sf.insert(std::next(g.after), std::move(g.piece));
+        }
+        collapse(c);
+        scores[k] = c.sf.front().score;
+        extendPerfect(E, rc, c, true, true, scores[k], xs[k]);
+        any |= xs[k].doB || xs[k].doF;
+    }
+    if (any) dpWait(rc);
+    // phase 3: apply every extension first (answers of a round are only valid until this fiber
+    // parks again), then score -- and split, which may park -- in list order
+    for (size_t k = 0; k < old.size(); k++) {
+        Clump *c = old[k];
+        if (c->is(kAligned)) continue;
+        extendApply(E, rc, *c, xs[k], false, scores[k]);
+        c->set(kAligned, true);
+    }
+    for (size_t k = 0; k < old.size(); k++) {
+        Clump *c = old[k];
+        scoreClump(E, rc, c);
+        if (c->is(kScored)) rc.clumps.push_back(c);
+        else delete c;
+    }
+}
+
+}  // namespace yh

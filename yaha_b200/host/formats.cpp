@@ -1,0 +1,187 @@
+// formats.cpp -- readers for yaha's on-disk formats and the FASTA/FASTQ query reader.
+// Follows: loadBaseSequences Compress.c:76-134, normalizeBaseSequences / maxROff BaseSeq.c:115-125,
+//          findBaseSequenceNum BaseSeq.c:81-90, index header Query.c:594-626,
+//          code tables Math.c:141-157, readNextQuery Query.c:102-228, openQueryFile Query.c:63-74.
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "host.hpp"
+
+namespace yh {
+
+const char kCharOfCode[16] = {'T', 'C', 'A', 'G', 'N', 'B', 'D', 'H', 'K', 'M', 'R', 'S', 'V', 'W', 'X', 'Y'};
+const char kCompCharOfCode[16] = {'A', 'G', 'T', 'C', 'N', 'V', 'H', 'D', 'M', 'K', 'Y', 'S', 'B', 'W', 'X', 'R'};
+const uint8_t kCompCode[16] = {2, 3, 0, 1, 4, 12, 7, 6, 9, 8, 15, 11, 5, 13, 14, 10};
+
+int codeOfChar(int c)
+{
+    static int8_t table[128];
+    static bool ready = false;
+    if (!ready) {
+        memset(table, 14, sizeof table);
+        for (int i = 0; i < 16; i++) { table[(int)kCharOfCode[i]] = (int8_t)i; table[(int)kCharOfCode[i] + 32] = (int8_t)i; }
+        table['U'] = table['u'] = 0;
+        ready = true;
+    }
+    return (c >= 0 && c < 128) ? table[c] : 14;
+}
+
+static const void *mapFile(const std::string &path, size_t &len, std::string &err)
+{
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = (errno == ENOENT) ? "File '" + path + "' does not exist." : "cannot open '" + path + "'"; return nullptr; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { err = "cannot stat '" + path + "'"; close(fd); return nullptr; }
+    len = (size_t)st.st_size;
+    void *p = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { err = "cannot mmap '" + path + "'"; return nullptr; }
+    return p;
+}
+
+bool Genome::load(const std::string &path, std::string &err)
+{
+    map = mapFile(path, mapLen, err);
+    if (!map) return false;
+    const uint32_t *h = (const uint32_t *)map;
+    const int ver = (int)h[1];
+    if (h[0] != 0x01020304u || (ver != 1 && ver != 2)) { err = "Input nib2 file bad header format."; return false; }
+    const int blk = ver == 2 ? 16 : 12;
+    const int n = (int)h[3];
+    bases = (const uint8_t *)map + h[2];
+    nBaseBytes = mapLen - h[2];
+    const char *names = (const char *)map + 16 + blk * n + 4;
+    const uint32_t *rec = h + 4;
+    seqs.clear();
+    for (int i = 0; i < n; i++) {
+        BaseSeq b;
+        b.start = rec[0] * 2;                        // byte offset -> base offset (BaseSeq.c:115-119)
+        b.length = rec[1];
+        if (ver == 1) { uint32_t info = rec[2]; b.name.assign(names + (uint16_t)(info >> 16), info & 0xFFFF); rec += 3; }
+        else { b.name.assign(names + rec[2], rec[3]); rec += 4; }
+        seqs.push_back(b);
+    }
+    if (seqs.empty()) { err = "nib2 file without sequences"; return false; }
+    maxROff = seqs.back().start + seqs.back().length;
+    return true;
+}
+
+int Genome::findSeq(uint32_t off) const
+{
+    for (size_t i = 0; i < seqs.size(); i++)
+        if (off >= seqs[i].start && off < seqs[i].start + seqs[i].length) return (int)i;
+    return -1;
+}
+
+bool IndexFile::load(const std::string &path, std::string &err)
+{
+    map = mapFile(path, mapLen, err);
+    if (!map) return false;
+    const uint32_t *u = (const uint32_t *)map;
+    if (mapLen < 16 || (int)u[0] != -1) { err = "Index file version is out of date.\nPlease remake index file and try again."; return false; }
+    wordLen = (int)u[1]; maxHits = (int)u[2];
+    if (wordLen < 1 || wordLen > 16) { err = "Index file has an unsupported word length."; return false; }
+    nSo = ((size_t)1 << (2 * wordLen)) + 1;
+    so = u + 4;
+    roa = so + nSo;
+    if (mapLen < 16 + nSo * 4) { err = "Index file is truncated."; return false; }
+    nRoa = (mapLen - 16 - nSo * 4) / 4;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+bool QueryReader::open(const std::string &path, std::string &err)
+{
+    if (path == "stdin" || path == "-") { fprintf(stderr, "Reading queries from stdin.\n"); f = stdin; }
+    else f = fopen(path.c_str(), "r");
+    if (!f) { err = "Failure to open input file: " + path + ".  Error number:" + std::to_string(errno); return false; }
+    static char iobuf[1 << 20];
+    setvbuf(f, iobuf, _IOFBF, sizeof iobuf);
+    fastq = (getc_unlocked(f) == '@');               // also positions the stream after the first marker
+    return true;
+}
+
+void QueryReader::close() { if (f && f != stdin) fclose(f); f = nullptr; }
+
+static void readToChar(FILE *f, int target, bool afterNewline)          // Query.c:52-61
+{
+    int prev = 0;
+    for (;;) {
+        int c = getc_unlocked(f);
+        if ((c == target && (!afterNewline || prev == '\n')) || c == EOF) return;
+        prev = c;
+    }
+}
+
+bool QueryReader::next(Read &r)
+{
+    for (;;) {
+        r.id.clear(); r.fwd.clear(); r.qual.clear();
+        int idChars = 0;
+        for (;;) {
+            int c = getc_unlocked(f);
+            if (c == '\n' || c == EOF) break;
+            if (idChars < 200) r.id.push_back(c == ' ' ? '_' : (char)c);
+            idChars++;
+        }
+        if (idChars > 200)
+            fprintf(stderr, "Warning, Query Id length of %d exceeds maximum length %d.  Id will be truncated.\n", idChars, 200);
+        const int brk = fastq ? '+' : '>';
+        bool fail = false;
+        for (;;) {
+            int c = getc_unlocked(f);
+            if (c == brk || c == EOF) break;
+            if (c == '\n') continue;
+            if ((int)r.fwd.size() >= maxLen) {
+                fprintf(stderr, "Warning.  Query sequence exceeds maximum length of %d.  Query will be skipped.\n", maxLen);
+                readToChar(f, brk, false);
+                fail = true;
+                break;
+            }
+            r.fwd.push_back((char)c);
+        }
+        if (fastq) {
+            readToChar(f, '\n', false);
+            int prev = 0;
+            for (;;) {
+                int c = getc_unlocked(f);
+                if ((c == '@' && prev == '\n') || c == EOF) break;
+                prev = c;
+                if (c == '\n') continue;
+                if ((int)r.qual.size() >= maxLen) {
+                    fprintf(stderr, "Warning.  Quality score sequence exceeds maximum length of %d.  Query will be skipped.\n", maxLen);
+                    readToChar(f, '@', true);
+                    fail = true;
+                    break;
+                }
+                r.qual.push_back((char)c);
+            }
+            if (r.fwd.size() != r.qual.size()) {
+                fprintf(stderr, "Warning.  Query sequence (%d) and quality score sequence (%d) have different lengths in fastq file."
+                        "  Query will be skipped.\n", (int)r.fwd.size(), (int)r.qual.size());
+                fail = true;
+            }
+        }
+        const int n = (int)r.fwd.size();
+        if (n > 0 && n < wordLen) {
+            fprintf(stderr, "Query length must be at least wordlen bases long. Query will be skipped.\n");
+            fail = true;
+        }
+        if (fail) continue;
+        if (n == 0) return false;                    // end of input (or an empty record, as in the reference)
+        r.fcode.resize((size_t)n); r.rcode.resize((size_t)n); r.rev.resize((size_t)n);
+        for (int i = 0; i < n; i++) {
+            int code = codeOfChar((unsigned char)r.fwd[(size_t)i] < 128 ? r.fwd[(size_t)i] : 0);
+            r.fcode[(size_t)i] = (uint8_t)code;
+            int rc = kCompCode[code];
+            r.rcode[(size_t)(n - 1 - i)] = (uint8_t)rc;
+            r.rev[(size_t)(n - 1 - i)] = kCharOfCode[rc];
+        }
+        return true;
+    }
+}
+
+}  // namespace yh

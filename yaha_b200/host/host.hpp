@@ -129,9 +129,8 @@ struct RandState { uint32_t s[5]; uint32_t bits(); };               // Math.c:27
 struct DpFuture { int slot = -1; };  // index into the round's job list
 struct DpAnswer { int score = 0; int addedQ = 0, addedR = 0; OpList ops; };
 
-struct Batch;
 struct ReadCtx {                     // the per-read half of QueryState_t (Math.h:587-666)
-    Batch *batch = nullptr;
+    void  *owner = nullptr;         // the fiber running this read (scheduler private)
     int    idx = 0;                  // index in the batch == read id on the device
     Read  *read = nullptr;
     std::vector<Clump *> clumps;     // LIFO list: back() is the reference's list head

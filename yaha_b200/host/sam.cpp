@@ -1,0 +1,133 @@
+// sam.cpp -- SAM / Blast8 record formatting (host-kept).
+// Follows: outputFileHeader AlignOutput.c:30-111, printClump AlignOutput.c:115-321,
+//          printClumps QueryMatch.c:333-344.  Records of one read are formatted into the read's
+// own buffer so that the writer can emit reads in input order regardless of completion order.
+#include <string.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <algorithm>
+#include "host.hpp"
+
+namespace yh {
+
+static void appendf(std::string &s, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+static void appendf(std::string &s, const char *fmt, ...)
+{
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (n > 0) s.append(buf, (size_t)std::min<int>(n, (int)sizeof buf - 1));
+}
+
+void writeHeader(const Env &E, FILE *out)
+{
+    const Args &A = *E.A;
+    if (!A.outputSAM) return;
+    fprintf(out, "@HD\tVN:1.0\n");
+    for (const BaseSeq &b : E.G->seqs) fprintf(out, "@SQ\tSN:%s\tLN:%u\n", b.name.c_str(), b.length);
+    fprintf(out, "@PG\tID:YAHA\tVN:0.1.83\tCL:yaha");
+    fprintf(out, " -q %s -x %s -os%c %s -t %d", A.qfile.c_str(), A.xfile.c_str(), A.hardClip ? 'h' : 's', A.ofile.c_str(), A.numThreads);
+    fprintf(out, " -BW %d -G %d -H %d -M %d -MD %d -P %4.2f -X %d", A.bandWidth, A.maxGap, A.maxHits, A.minMatch, A.maxDesert,
+            A.minIdentity, A.XCutoff);
+    if (A.affineGapScoring) fprintf(out, " -AGS Y -GEC %d -GOC %d -MS %d -RC %d", A.GECost, A.GOCost, A.MScore, A.RCost);
+    else fprintf(out, " -AGS N");
+    if (A.OQC) {
+        fprintf(out, " -OQC Y -BP %d -MGDP %d -MNO %d", A.BPCost, A.maxBPLog, A.OQCMinNonOverlap);
+        if (A.FBS) fprintf(out, " -FBS Y -PRL %4.2f -PSS %4.2f", A.FBS_PSLength, A.FBS_PSScore);
+        else fprintf(out, " -FBS N");
+    } else fprintf(out, " -OQC N");
+    fputc('\n', out);
+}
+
+static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
+{
+    const Args &A = *E.A;
+    const Genome &G = *E.G;
+    std::string &o = rc.out;
+    const Frag &f0 = c.sf.front().frag, &fn = c.sf.back().frag;
+    uint32_t sStart = f0.startRefOff, sEnd = fragERO(fn);
+    int si = G.findSeq(sStart);
+    if (si < 0 || sEnd >= G.seqs[si].start + G.seqs[si].length) return;        // AlignOutput.c:129-136
+    const BaseSeq &BS = G.seqs[si];
+    sStart -= BS.start; sEnd -= BS.start;
+    const std::string &q = rc.chars(c.reversed());
+    const int L = rc.read->len();
+    if (A.outputSAM) {
+        o += rc.read->id;
+        appendf(o, "\t%d\t", c.reversed() ? 0x10 : 0x00);
+        o += BS.name;
+        appendf(o, "\t%u\t%u\t", sStart + 1, (unsigned)c.mapQuality);
+        OpList &list = c.ops;
+        int clip = L - 1 - f0.endQueryOff;
+        if (clip > 0) list.pushBack(A.hardClip ? 'H' : 'S', clip);
+        clip = f0.startQueryOff;
+        if (clip > 0) list.pushFront(A.hardClip ? 'H' : 'S', clip);
+        int matches = 0;
+        for (const Op &op : list.v) {
+            if (op.code == 'M' || op.code == 'R') { matches += op.len; continue; }
+            if (matches > 0) { appendf(o, "%dM", matches); matches = 0; }
+            appendf(o, "%d%c", (int)op.len, op.code);
+        }
+        if (matches > 0) appendf(o, "%dM", matches);
+        o += "\t*\t0\t0\t";
+        int qs = 0, qe = L - 1;
+        if (A.hardClip) { qs = f0.startQueryOff; qe = fn.endQueryOff; }
+        if (qe >= qs) o.append(q, (size_t)qs, (size_t)(qe - qs + 1));
+        o += '\t';
+        if (A.fastq) {
+            const std::string &ql = rc.read->qual;
+            if (c.reversed()) for (int i = qe; i >= qs; i--) o += ql[(size_t)i];
+            else if (qe >= qs) o.append(ql, (size_t)qs, (size_t)(qe - qs + 1));
+        } else o += '*';
+        o += '\t';
+        appendf(o, "AS:i:%d\t", (int)c.totScore);
+        appendf(o, "NM:i:%d\t", (int)c.gapBases + (int)c.mismatchedBases);
+        o += "MD:Z:";
+        matches = 0;
+        char prev = 'U';
+        uint32_t ro = f0.startRefOff;
+        for (const Op &op : list.v) {
+            if (op.code == prev) {                                              // AlignOutput.c:232-240
+                fprintf(stderr, "Two identical codes in a row in EditOpList\n%s\n", rc.read->id.c_str());
+                abort();
+            }
+            if (op.code == 'M') { matches += op.len; ro += op.len; }
+            else if (op.code == 'R') {
+                if (matches > 0) { appendf(o, "%d", matches); matches = 0; }
+                if (prev == 'D') o += '0';
+                for (int i = 0; i < op.len; i++) o += kCharOfCode[G.code(ro + (uint32_t)i)];
+                ro += op.len;
+            } else if (op.code == 'D') {
+                if (matches > 0) { appendf(o, "%d", matches); matches = 0; }
+                o += '^';
+                for (int i = 0; i < op.len; i++) o += kCharOfCode[G.code(ro + (uint32_t)i)];
+                ro += op.len;
+            }
+            prev = op.code;
+        }
+        if (matches > 0) appendf(o, "%d", matches);
+        appendf(o, "\tYF:H:%02X", (unsigned)c.status);
+        if (A.OQC) {
+            appendf(o, "\tYI:i:%d", (int)c.matchedPrimary);
+            appendf(o, "\tYP:i:%d", rc.primaryCount);
+            if (c.is(kPrimary)) appendf(o, "\tYS:i:%d", (int)c.numSecondaries);
+        }
+        o += '\n';
+    }
+    if (A.outputBlast8) {                                                       // AlignOutput.c:307-318
+        o += rc.read->id; o += '\t'; o += BS.name;
+        appendf(o, "\t%4.2f\t%d\t%d\t%d", 0.8 * 100, (int)c.totLength, (int)c.mismatchedBases, (int)c.gapBases);
+        if (c.reversed()) appendf(o, "\t%d\t%d\t%d\t%d\t%c", L - fn.endQueryOff, L - f0.startQueryOff, sEnd + 1, sStart + 1, '-');
+        else appendf(o, "\t%d\t%d\t%d\t%d\t%c", f0.startQueryOff + 1, fn.endQueryOff + 1, sStart + 1, sEnd + 1, '+');
+        appendf(o, "\t%d\t%d\t%4.2f\n", (int)c.totScore, L, ((double)c.matchedBases / L) * 100);
+    }
+}
+
+void formatClumps(const Env &E, ReadCtx &rc)
+{
+    for (int k = (int)rc.clumps.size() - 1; k >= 0; k--) formatClump(E, rc, *rc.clumps[k]);   // from the list head
+}
+
+}  // namespace yh
