@@ -39,6 +39,8 @@ struct Args {                       // AlignmentArgs_t, Math.h:257-334; defaults
     // yaha_b200 extensions (not echoed in @PG)
     int   gpus = 1;                 // -gpus N : shard the read file over N devices
     int   batchReads = 8192;        // -batch N: reads in flight per device
+    int   firstDev = 0;             // -dev D  : first CUDA device ordinal
+    int   passes = 1;               // -passes N: repeat the whole job N times (bench.py), one stats line per pass
     bool  query = false, index = true;
     void  postProcess(bool queryMode);           // AlignArgs.c:108-169
     ya_params deviceParams() const;

@@ -154,7 +154,7 @@ struct Device {
     std::vector<ya_dp_job> jobs;
     std::vector<ya_dp_result> res;
     std::vector<ya_op> ops;
-    double tSeed = 0, tDp = 0, tHost = 0;
+    double tSeed = 0, tDp = 0, tHost = 0, tUpload = 0;
     uint64_t nJobs = 0, nRounds = 0;
 };
 
@@ -184,6 +184,8 @@ static void processBatch(const Env &E, Device &D, Batch &B, int nThreads)
     for (int i = 0; i < n; i++) memcpy(D.codes.data() + D.offs[(size_t)i], B.reads[(size_t)i].fcode.data(), B.reads[(size_t)i].fcode.size());
     ya_read_batch rb; rb.n_reads = n; rb.codes = D.codes.data(); rb.offsets = D.offs.data();
     if (ya_reads_upload(D.ctx, &rb) != YA_OK) die(D.ctx, "ya_reads_upload");
+    D.tUpload += nowSec() - t0;
+    t0 = nowSec();
     // stages 1+2
     D.strands.resize((size_t)2 * n);
     if (D.frags.size() < (size_t)64 * n) { D.frags.resize((size_t)64 * n); D.region.resize((size_t)64 * n); }
@@ -325,58 +327,78 @@ int runQueries(const Args &A0)
     double tOpen = nowSec();
     for (int d = 0; d < nDev; d++) {
         devs[(size_t)d].ordinal = d;
-        devs[(size_t)d].ctx = (d == 0) ? ya_open(0, &P, X.so, X.nSo, X.roa, X.nRoa, G.bases, G.nBaseBytes, G.maxROff)
-                                       : ya_open_peer(d, devs[0].ctx);   // index replica over NVLink
+        devs[(size_t)d].ctx = (d == 0) ? ya_open(A.firstDev, &P, X.so, X.nSo, X.roa, X.nRoa, G.bases, G.nBaseBytes, G.maxROff)
+                                       : ya_open_peer(A.firstDev + d, devs[0].ctx);   // index replica over NVLink
         if (!devs[(size_t)d].ctx) { fprintf(stderr, "yaha_b200: cannot open device %d: %s\n", d, ya_last_error(nullptr)); return 1; }
     }
     tOpen = nowSec() - tOpen;
 
     // Reads are dealt to devices in contiguous blocks of batchReads; blocks are written in order.
     const int threadsPerDev = std::max(1, nThreads / nDev);
-    uint64_t nReads = 0;
-    double tAlign = nowSec();
-    bool eof = false;
-    while (!eof) {
-        std::vector<Batch> batches((size_t)nDev);
-        int used = 0;
-        for (int d = 0; d < nDev && !eof; d++) {
-            Batch &B = batches[(size_t)d];
-            B.reads.reserve((size_t)A.batchReads);
-            while ((int)B.reads.size() < A.batchReads) {
-                B.reads.emplace_back();
-                if (!qr.next(B.reads.back())) { B.reads.pop_back(); eof = true; break; }
+    for (int pass = 0; pass < std::max(1, A.passes); pass++) {
+        if (pass > 0) {                                                 // -passes N (bench): redo the whole job
+            qr.close();
+            if (!qr.open(A.qfile == "stdout" ? "stdin" : A.qfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+            qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
+            if (out != stdout) { out = freopen(A.ofile.c_str(), "w", out); setvbuf(out, obuf, _IOFBF, sizeof obuf); }
+            writeHeader(E, out);
+        }
+        for (Device &d : devs) { d.tSeed = d.tDp = d.tHost = d.tUpload = 0; d.nJobs = d.nRounds = 0; ya_counters c; ya_get_counters(d.ctx, &c); }
+        uint64_t nReads = 0;
+        double tRead = 0, tWrite = 0;
+        double tAlign = nowSec();
+        bool eof = false;
+        while (!eof) {
+            std::vector<Batch> batches((size_t)nDev);
+            int used = 0;
+            double r0 = nowSec();
+            for (int d = 0; d < nDev && !eof; d++) {
+                Batch &B = batches[(size_t)d];
+                B.reads.reserve((size_t)A.batchReads);
+                while ((int)B.reads.size() < A.batchReads) {
+                    B.reads.emplace_back();
+                    if (!qr.next(B.reads.back())) { B.reads.pop_back(); eof = true; break; }
+                }
+                if (!B.reads.empty()) used = d + 1;
             }
-            if (!B.reads.empty()) used = d + 1;
+            tRead += nowSec() - r0;
+            if (used == 0) break;
+            if (used == 1) processBatch(E, devs[0], batches[0], nThreads);
+            else {
+                std::vector<std::thread> th;
+                for (int d = 0; d < used; d++) th.emplace_back([&, d]() { processBatch(E, devs[(size_t)d], batches[(size_t)d], threadsPerDev); });
+                for (auto &x : th) x.join();
+            }
+            double w0 = nowSec();
+            for (int d = 0; d < used; d++) {
+                for (auto &f : batches[(size_t)d].fibers) fwrite(f->rc.out.data(), 1, f->rc.out.size(), out);
+                nReads += batches[(size_t)d].reads.size();
+            }
+            tWrite += nowSec() - w0;
         }
-        if (used == 0) break;
-        if (used == 1) processBatch(E, devs[0], batches[0], nThreads);
-        else {
-            std::vector<std::thread> th;
-            for (int d = 0; d < used; d++) th.emplace_back([&, d]() { processBatch(E, devs[(size_t)d], batches[(size_t)d], threadsPerDev); });
-            for (auto &x : th) x.join();
-        }
-        for (int d = 0; d < used; d++) {
-            for (auto &f : batches[(size_t)d].fibers) fwrite(f->rc.out.data(), 1, f->rc.out.size(), out);
-            nReads += batches[(size_t)d].reads.size();
+        fflush(out);
+        tAlign = nowSec() - tAlign;
+        if (A.verbose || A.passes > 1 || getenv("YAHA_B200_STATS")) {
+            ya_counters c{};
+            double seed = 0, dp = 0, host = 0, upl = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
+            double msdp = 0, msseed = 0, mstb = 0;
+            for (Device &d : devs) {
+                ya_get_counters(d.ctx, &c);
+                seed += d.tSeed; dp += d.tDp; host += d.tHost; upl += d.tUpload; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
+                msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback; launches += c.launches; probes += c.probes; hits += c.hits;
+                fragsAll += c.frags_all;
+            }
+            fprintf(stderr, "{\"pass\": %d, \"reads\": %llu, \"align_s\": %.5f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"read_parse_s\": %.5f, "
+                    "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
+                    "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
+                    "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d}\n",
+                    pass, (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), tRead, upl, tWrite, seed, dp, host,
+                    (unsigned long long)jobs, (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb,
+                    (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads);
         }
     }
-    tAlign = nowSec() - tAlign;
     if (out != stdout) fclose(out); else fflush(out);
     qr.close();
-    if (A.verbose || getenv("YAHA_B200_STATS")) {
-        ya_counters c{};
-        double seed = 0, dp = 0, host = 0; uint64_t jobs = 0, rounds = 0, cells = 0; double msdp = 0, msseed = 0, mstb = 0;
-        for (Device &d : devs) {
-            ya_get_counters(d.ctx, &c);
-            seed += d.tSeed; dp += d.tDp; host += d.tHost; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
-            msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback;
-        }
-        fprintf(stderr, "{\"reads\": %llu, \"align_s\": %.4f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"seed_wall_s\": %.4f, \"dp_wall_s\": %.4f, "
-                "\"host_wall_s\": %.4f, \"dp_jobs\": %llu, \"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, "
-                "\"dev_ms_traceback\": %.3f, \"gpus\": %d, \"threads\": %d}\n",
-                (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), seed, dp, host, (unsigned long long)jobs,
-                (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb, nDev, nThreads);
-    }
     for (Device &d : devs) ya_close(d.ctx);
     return 0;
 }
