@@ -128,13 +128,13 @@ def tiny_aligner(device: int):
     return yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=8), device=device)
 
 
-def run_host(idx_path, reads_path, out_path, flags, threads, device, passes):
+def run_host(idx_path, reads_path, out_path, flags, threads, device, passes, batch, pipes, replay=False):
     """Run the product's host program (the call a user makes) and return its per-pass stats."""
     host = os.path.join(ROOT, "yaha_b200", "yaha_b200_host")
     if not os.path.exists(host):
         raise SystemExit("yaha_b200/yaha_b200_host is missing: run __graft_entry__.build() first (no CPU fallback)")
     cmd = [host, "-x", idx_path, "-q", reads_path, "-osh", out_path, "-t", str(threads), "-dev", str(device),
-           "-passes", str(passes), "-batch", "20000"] + flags
+           "-passes", str(passes), "-batch", str(batch), "-pipes", str(pipes)] + (["-replay"] if replay else []) + flags
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise SystemExit("yaha_b200_host failed:\n" + p.stderr[-3000:])
@@ -190,13 +190,18 @@ def run_ours(args):
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    stats = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, args.warmup + args.steps)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    # run A: the job exactly as a user runs it (FASTA parsed, SAM written) -> e2e
+    stats = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, args.warmup + args.steps, args.batch, args.pipes)
     timed = stats[args.warmup:]
     assert len(timed) == args.steps, (len(stats), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed)
-    el_res = sum(s["align_s"] - s["read_parse_s"] - s["upload_s"] - s["write_s"] for s in timed)
+    # run B: parsed reads replayed from host memory, SAM formatted but not written -> value
+    stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + args.warmup + args.steps,
+                       args.batch, args.pipes, replay=True)
+    timed_b = stats_b[1 + args.warmup:]
+    el_res = sum(s["align_s"] for s in timed_b)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
     if world > 1:
         tt = torch.tensor([el_e2e, el_res], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -232,7 +237,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD_DESC[wl], "reads_per_gpu": n_reads, "read_len": rl, "error": err,
                    "flags": REF_FLAGS[wl], "host_threads_per_gpu": threads,
                    "l2": "inputs larger than L2 (4.3 GB index gathers; reads re-uploaded every step)",
-                   "value_excludes": "FASTA parsing, H2D of reads and SAM fwrite (inputs resident); e2e includes them",
+                   "batch_reads": args.batch, "pipelines_per_gpu": args.pipes,
+                   "value_excludes": "FASTA parsing and SAM fwrite (reads replayed from host memory; the 10 MB/step H2D of "
+                                     "read codes is still inside); e2e includes everything",
                    "setup_s": round(t_setup, 2)},
         "gcups": gcups, "dp_cells_per_step": cells // max(args.steps, 1), "dp_jobs_per_step": tot("dp_jobs") // args.steps,
         "dp_rounds_per_step": tot("dp_rounds") // args.steps,
@@ -365,6 +372,8 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=5000, help="reads per device batch")
+    ap.add_argument("--pipes", type=int, default=2, help="concurrent batch pipelines per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -156,6 +156,11 @@ ya_ctx *ya_open_build(int device, const ya_params *params, const uint8_t *bases,
 int     ya_index_sizes(const ya_ctx *, size_t *n_so, size_t *n_roa);
 int     ya_index_download(ya_ctx *, uint32_t *so, uint32_t *roa);
 
+/* A second context on the SAME device that borrows src's resident index (no copy) but has its own
+ * stream, read batch and scratch, so that two host pipelines can overlap their device and host
+ * phases (one QueryState_t per thread in the reference, Query.c:660-667).  src must outlive it. */
+ya_ctx *ya_open_shared(const ya_ctx *src);
+
 void        ya_close(ya_ctx *);
 const char *ya_last_error(const ya_ctx *);
 

@@ -67,7 +67,7 @@ class Counters(C.Structure):
                 ("ms_traceback", C.c_double), ("launches", C.c_uint64)]
 
 
-EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
+EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
            "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_perfect_ext", "ya_get_counters",
            "ya_measure_int32_peak")
 
@@ -92,6 +92,8 @@ def load_library() -> C.CDLL:
     lib.ya_index_download.argtypes = [vp, vp, vp]
     lib.ya_open_peer.restype = vp
     lib.ya_open_peer.argtypes = [C.c_int, vp]
+    lib.ya_open_shared.restype = vp
+    lib.ya_open_shared.argtypes = [vp]
     lib.ya_close.restype = None
     lib.ya_close.argtypes = [vp]
     lib.ya_last_error.restype = C.c_char_p

@@ -122,13 +122,26 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
     return c;
 }
 
+extern "C" ya_ctx *ya_open_shared(const ya_ctx *src)
+{
+    if (!src) { g_open_err = "ya_open_shared: null source"; return nullptr; }
+    ya_ctx *c = open_common(src->device, &src->P);
+    if (!c) return nullptr;
+    c->d_so = src->d_so; c->d_roa = src->d_roa; c->d_bases = src->d_bases;
+    c->n_so = src->n_so; c->n_roa = src->n_roa; c->n_base_bytes = src->n_base_bytes; c->maxROff = src->maxROff;
+    c->owns_index = false;
+    return c;
+}
+
 extern "C" void ya_close(ya_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->d_so) cudaFree(c->d_so);
-    if (c->d_roa) cudaFree(c->d_roa);
-    if (c->d_bases) cudaFree(c->d_bases);
+    if (c->owns_index) {
+        if (c->d_so) cudaFree(c->d_so);
+        if (c->d_roa) cudaFree(c->d_roa);
+        if (c->d_bases) cudaFree(c->d_bases);
+    }
     DevBuf *bufs[] = {&c->d_codes_fwd, &c->d_codes_rev, &c->d_read_off, &c->d_seg_probe_off, &c->d_cnt, &c->d_soff,
                       &c->d_hit_off, &c->d_keys0, &c->d_keys1, &c->d_scan_tmp, &c->d_hist, &c->d_fragflag, &c->d_fragidx,
                       &c->d_frags_all, &c->d_frag_seg, &c->d_regflag, &c->d_regidx, &c->d_regstart, &c->d_keep,

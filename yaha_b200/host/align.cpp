@@ -30,6 +30,29 @@ void OpList::mergeToFront(OpList &src)
     src.v.clear();
 }
 
+void OpList::mergeToFront(const ya_op *o, int n)
+{
+    if (n <= 0) return;
+    int drop = 0;
+    uint16_t lastLen = o[n - 1].length;
+    if (!v.empty() && (char)o[n - 1].opcode == v.front().code) { lastLen = (uint16_t)(lastLen + v.front().len); drop = 1; }
+    std::vector<Op> nv;
+    nv.reserve((size_t)n + v.size());
+    for (int k = 0; k < n; k++) nv.push_back(Op{o[k].length, (char)o[k].opcode});
+    nv.back().len = lastLen;
+    nv.insert(nv.end(), v.begin() + drop, v.end());
+    v.swap(nv);
+}
+
+void OpList::mergeToBack(const ya_op *o, int n)
+{
+    if (n <= 0) return;
+    int from = 0;
+    if (!v.empty() && v.back().code == (char)o[0].opcode) { v.back().len = (uint16_t)(v.back().len + o[0].length); from = 1; }
+    v.reserve(v.size() + (size_t)(n - from));
+    for (int k = from; k < n; k++) v.push_back(Op{o[k].length, (char)o[k].opcode});
+}
+
 void OpList::mergeToBack(OpList &src)
 {
     if (src.v.empty()) return;
@@ -164,14 +187,13 @@ static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool
 }
 
 // SW.cpp:671-788: trim a backward extension so the running score never reaches zero
-static int carefulBackward(const Args &A, DpAnswer &r, OpList &list, int score, int &addQ, int &addR)
+static int carefulBackward(const Args &A, const DpAnswer &r, OpList &list, int score, int &addQ, int &addR)
 {
     addQ = addR = 0;
     if (r.score <= 0) return 0;
-    OpList &t = r.ops;
     int QLen = 0, RLen = 0, AGS = 0, maxAGS = 0, startItem = -1;
-    for (int k = 0; k < (int)t.v.size(); k++) {
-        const Op &o = t.v[k];
+    for (int k = 0; k < r.n; k++) {
+        const Op o{r.ops[k].length, (char)r.ops[k].opcode};
         if (o.code == 'M') { QLen += o.len; RLen += o.len; }
         else if (o.code == 'R') { QLen += o.len; RLen += o.len; }
         else if (o.code == 'I') QLen += o.len;
@@ -180,38 +202,36 @@ static int carefulBackward(const Args &A, DpAnswer &r, OpList &list, int score, 
         if (AGS <= 0) { AGS = 0; maxAGS = 0; QLen = 0; RLen = 0; startItem = k; }
         if (AGS > maxAGS) maxAGS = AGS;
     }
-    if (AGS <= 0 || maxAGS >= AGS + score) { t.clear(); return 0; }
-    if (startItem >= 0) t.v.erase(t.v.begin(), t.v.begin() + startItem + 1);
-    list.mergeToFront(t);
+    if (AGS <= 0 || maxAGS >= AGS + score) return 0;
+    list.mergeToFront(r.ops + (startItem + 1), r.n - (startItem + 1));
     addQ = QLen; addR = RLen;
     return AGS;
 }
 
 // SW.cpp:553-669: trim a forward extension at its best point if the running score hits zero
-static int carefulForward(const Args &A, DpAnswer &r, OpList &list, int score, int &addQ, int &addR)
+static int carefulForward(const Args &A, const DpAnswer &r, OpList &list, int score, int &addQ, int &addR)
 {
     addQ = addR = 0;
     if (r.score <= 0) return 0;
-    OpList &t = r.ops;
-    int initAGS = r.score;
+    int initAGS = r.score, keep = r.n;
     addQ = r.addedQ; addR = r.addedR;
     int QLen = 0, RLen = 0, AGS = score, maxAGS = score, maxItem = -1, maxQ = 0, maxR = 0;
-    for (int k = 0; k < (int)t.v.size(); k++) {
-        const Op &o = t.v[k];
+    for (int k = 0; k < r.n; k++) {
+        const Op o{r.ops[k].length, (char)r.ops[k].opcode};
         if (o.code == 'M' || o.code == 'R') { QLen += o.len; RLen += o.len; }
         else if (o.code == 'I') QLen += o.len;
         else if (o.code == 'D') RLen += o.len;
         AGS += opScore(A, o);
         if (AGS > maxAGS) { maxAGS = AGS; maxQ = QLen; maxR = RLen; maxItem = k; }
         else if (AGS <= 0) {
-            if (maxAGS <= score) { t.clear(); addQ = addR = 0; return 0; }
-            t.v.erase(t.v.begin() + maxItem + 1, t.v.end());
+            if (maxAGS <= score) { addQ = addR = 0; return 0; }
+            keep = maxItem + 1;
             addQ = maxQ; addR = maxR;
             initAGS = maxAGS - score;
             break;
         }
     }
-    list.mergeToBack(t);
+    list.mergeToBack(r.ops, keep);
     return initAGS;
 }
 
@@ -221,10 +241,10 @@ static void extendApply(const Env &E, ReadCtx &rc, Clump &c, ExtState &x, bool c
     const Args &A = *E.A;
     Frag &f = c.sf.front().frag;
     if (x.doB) {
-        DpAnswer &r = dpGet(rc, x.fb);
+        const DpAnswer r = dpGet(rc, x.fb);
         int ns, aq, ar;
         if (careful) ns = carefulBackward(A, r, c.ops, score, aq, ar);
-        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToFront(r.ops); }
+        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToFront(r.ops, r.n); }
         if (ns > 0) {
             score += ns;
             f.startQueryOff = (uint16_t)(f.startQueryOff - aq);
@@ -232,10 +252,10 @@ static void extendApply(const Env &E, ReadCtx &rc, Clump &c, ExtState &x, bool c
         }
     }
     if (x.doF) {
-        DpAnswer &r = dpGet(rc, x.ff);
+        const DpAnswer r = dpGet(rc, x.ff);
         int ns, aq, ar;
         if (careful) ns = carefulForward(A, r, c.ops, score, aq, ar);
-        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToBack(r.ops); }
+        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToBack(r.ops, r.n); }
         if (ns > 0) {
             score += ns;
             f.endQueryOff = (uint16_t)(f.endQueryOff + aq);
@@ -403,9 +423,10 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         if (c.is(kAligned)) continue;
         for (auto &g : gaps[k]) {
             if (g.needDp) {
-                DpAnswer &r = dpGet(rc, g.fut);
+                const DpAnswer r = dpGet(rc, g.fut);
                 g.piece.score = r.score;
-                g.piece.ops.v.swap(r.ops.v);
+                g.piece.ops.v.resize((size_t)r.n);
+                for (int q = 0; q < r.n; q++) g.piece.ops.v[(size_t)q] = Op{r.ops[q].length, (char)r.ops[q].opcode};
             }
             c.sf.insert(std::next(g.after), std::move(g.piece));
         }

@@ -42,7 +42,7 @@ static void usage()
         "  align : yaha_b200 -x index -q reads.(fa|fq) [-osh|-oss|-o8 out] [-t threads]\n"
         "          [-BW n] [-G n] [-H n] [-M n] [-MD n] [-P f] [-X n] [-AGS Y|N] [-GEC n] [-GOC n] [-MS n] [-RC n]\n"
         "          [-OQC Y|N] [-BP n] [-MGDP n] [-MNO n] [-FBS Y|N] [-PRL f] [-PSS f]\n"
-        "  yaha_b200 only: [-gpus N] [-dev first-device] [-batch reads-in-flight] [-passes N]\n");
+        "  yaha_b200 only: [-gpus N] [-dev first-device] [-batch reads-in-flight] [-passes N] [-pipes P] [-replay]\n");
 }
 
 static bool parseBool(const char *s, const char *key)
@@ -114,6 +114,8 @@ int parseArgs(int argc, char **argv, Args &a)
         else if (!strcmp(k, "-batch")) a.batchReads = std::max(1, parseInt(val(), "-batch"));
         else if (!strcmp(k, "-dev")) a.firstDev = parseInt(val(), "-dev");
         else if (!strcmp(k, "-passes")) a.passes = std::max(1, parseInt(val(), "-passes"));
+        else if (!strcmp(k, "-pipes")) a.pipes = std::max(1, parseInt(val(), "-pipes"));
+        else if (!strcmp(k, "-replay")) a.replay = true;
         else { fprintf(stderr, "%s is not a valid option.\n\n", k); usage(); exit(1); }
     }
     if (index) {

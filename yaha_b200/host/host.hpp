@@ -41,6 +41,8 @@ struct Args {                       // AlignmentArgs_t, Math.h:257-334; defaults
     int   batchReads = 8192;        // -batch N: reads in flight per device
     int   firstDev = 0;             // -dev D  : first CUDA device ordinal
     int   passes = 1;               // -passes N: repeat the whole job N times (bench.py), one stats line per pass
+    int   pipes = 2;                // -pipes P : concurrent batch pipelines per device (overlap host and device phases)
+    bool  replay = false;           // -replay  : passes after the first reuse the parsed reads and skip the SAM fwrite
     bool  query = false, index = true;
     void  postProcess(bool queryMode);           // AlignArgs.c:108-169
     ya_params deviceParams() const;
@@ -94,6 +96,8 @@ struct OpList {                      // EditOpList_t semantics, SW.cpp:114-283, 
     void pushBack(char c, int len) { v.push_back(Op{(uint16_t)len, c}); }
     void mergeToFront(OpList &src);  // this = src + this, coalescing the junction (SW.cpp:151-205)
     void mergeToBack(OpList &src);   // this = this + src, coalescing the junction (SW.cpp:207-261)
+    void mergeToFront(const ya_op *o, int n);   // same, from a device result range
+    void mergeToBack(const ya_op *o, int n);
 };
 
 // ----------------------------------------------------------------------------- clumps
@@ -129,7 +133,7 @@ struct RandState { uint32_t s[5]; uint32_t bits(); };               // Math.c:27
 
 // ----------------------------------------------------------------------------- per-read state
 struct DpFuture { int slot = -1; };  // index into the round's job list
-struct DpAnswer { int score = 0; int addedQ = 0, addedR = 0; OpList ops; };
+struct DpAnswer { int score = 0; int addedQ = 0, addedR = 0; const ya_op *ops = nullptr; int n = 0; };   // view into the round's result arrays
 
 struct ReadCtx {                     // the per-read half of QueryState_t (Math.h:587-666)
     void  *owner = nullptr;         // the fiber running this read (scheduler private)
@@ -148,7 +152,7 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
 // Implemented by the scheduler (pipeline.cpp); callable from inside a read fiber.
 DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen);
 void     dpWait(ReadCtx &rc);                      // park until the round's jobs are done
-DpAnswer &dpGet(ReadCtx &rc, DpFuture f);
+DpAnswer dpGet(ReadCtx &rc, DpFuture f);        // valid until this fiber parks again
 
 // ----------------------------------------------------------------------------- algorithms
 struct Env { const Args *A; const Genome *G; };

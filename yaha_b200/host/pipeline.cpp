@@ -1,16 +1,21 @@
 // pipeline.cpp -- the batched alignment driver: what processQueryFile / processQueries
 // (Query.c:255-709) become when the three hot stages run on the device.
 //
-//   reader  : fills a batch of reads (sequential, input order)
-//   device  : ya_reads_upload + ya_seed_frags for the whole batch          (stages 1+2)
-//   fibers  : one per read, running the reference's per-read control flow; each parks in dpWait()
-//   rounds  : when all fibers of the batch are parked, ONE ya_sw_batch executes every posted job
-//             (stage 3), answers are distributed and the fibers resume
-//   writer  : emits the per-read record buffers in input order (== `yaha -t 1` order)
+//   reader thread : parses the query file into batches of reads (input order, bounded queue)
+//   pipelines     : P per device, each with its own ya_ctx (sharing the device's resident index),
+//                   its own host worker threads and its own fibers.  For one batch:
+//                     ya_reads_upload + ya_seed_frags                          (stages 1+2)
+//                     one fiber per read runs the reference's per-read control flow and parks in
+//                     dpWait(); when all fibers are parked ONE ya_sw_batch executes every posted
+//                     job (stage 3); repeat until every fiber has finished
+//                   Two pipelines per device overlap one batch's host phase with the other's device
+//                   phase.
+//   writer        : emits finished batches in input order (== `yaha -t 1` order)
 //
-// -t N gives N host worker threads per device, each owning a slice of the batch's fibers.
-// -gpus G shards the read stream over G devices in contiguous blocks (replicated index, no
-// collective on the data path); blocks are written in input order.
+// -t N  : host worker threads in total (split over the pipelines)
+// -gpus G: G devices, index replicated by peer copy; batches are dealt to whichever pipeline is free,
+//          no collective on the data path.
+#include <errno.h>
 #include <pthread.h>
 #include <string.h>
 #include <sys/mman.h>
@@ -21,6 +26,8 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -43,13 +50,14 @@ struct Worker {
     ucontext_t mainCtx;
     std::vector<Fiber *> fibers;
     std::vector<ya_dp_job> jobs;          // posted in the current round
-    std::vector<DpAnswer> answers;        // results of the previous round's jobs
-    Fiber *cur = nullptr;
+    const ya_dp_result *res = nullptr;    // previous round's results (this worker's jobs start at ansBase)
+    const ya_op *ops = nullptr;
+    size_t ansBase = 0, ansCount = 0;
     const Env *E = nullptr;
-    size_t jobBase = 0;                   // offset of this worker's jobs in the merged round list
 };
 
 struct Batch {
+    uint64_t seq = 0;
     std::vector<Read> reads;
     std::vector<std::unique_ptr<Fiber>> fibers;
 };
@@ -71,17 +79,19 @@ void dpWait(ReadCtx &rc)
     swapcontext(&f->ctx, &f->w->mainCtx);
 }
 
-DpAnswer &dpGet(ReadCtx &rc, DpFuture fu)
+DpAnswer dpGet(ReadCtx &rc, DpFuture fu)
 {
     Worker *w = ((Fiber *)rc.owner)->w;
-    return w->answers[(size_t)fu.slot];
+    const ya_dp_result &r = w->res[w->ansBase + (size_t)fu.slot];
+    DpAnswer a;
+    a.score = r.score; a.addedQ = r.addedQLen; a.addedR = r.addedRLen; a.ops = w->ops + r.ops_off; a.n = (int)r.ops_n;
+    return a;
 }
 
 static void readMain(const Env &E, ReadCtx &rc)                       // body of the Query.c:306-497 loop
 {
     const Args &A = *E.A;
-    // generateRandomSeed, QueryState.c:172-187
-    {
+    {                                                                  // generateRandomSeed, QueryState.c:172-187
         const std::vector<uint8_t> &c = rc.read->fcode;
         size_t q = 0;
         for (int i = 0; i < 5; i++) {
@@ -112,7 +122,6 @@ static int workerRound(Worker &w)
     int live = 0;
     for (Fiber *f : w.fibers) {
         if (f->done) continue;
-        w.cur = f;
         if (!f->started) {
             f->started = true;
             getcontext(&f->ctx);
@@ -142,10 +151,9 @@ struct StackPool {
 };
 static StackPool gStacks;
 
-struct Device {
+struct Pipe {                              // one batch pipeline: a ya_ctx plus reusable host buffers
     ya_ctx *ctx = nullptr;
-    int ordinal = 0;
-    // stage outputs
+    int device = 0;
     std::vector<ya_strand_frags> strands;
     std::vector<ya_frag> frags;
     std::vector<uint32_t> region;
@@ -169,13 +177,12 @@ static double nowSec()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Align one batch on one device with `nThreads` host workers.  Results land in each read's rc.out.
-static void processBatch(const Env &E, Device &D, Batch &B, int nThreads)
+// Align one batch on one pipeline with `nThreads` host workers.  Results land in each read's rc.out.
+static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
 {
     const int n = (int)B.reads.size();
     if (n == 0) return;
     double t0 = nowSec();
-    // upload forward codes
     D.offs.resize((size_t)n + 1);
     size_t total = 0;
     for (int i = 0; i < n; i++) { D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fcode.size(); }
@@ -197,10 +204,9 @@ static void processBatch(const Env &E, Device &D, Batch &B, int nThreads)
         if (rcode != YA_OK) die(D.ctx, "ya_seed_frags");
         break;
     }
-    double t1 = nowSec();
-    D.tSeed += t1 - t0;
+    D.tSeed += nowSec() - t0;
 
-    // fibers
+    // fibers, dealt to the workers in contiguous slices
     B.fibers.clear();
     B.fibers.reserve((size_t)n);
     std::vector<Worker> workers((size_t)nThreads);
@@ -227,7 +233,11 @@ static void processBatch(const Env &E, Device &D, Batch &B, int nThreads)
     auto deviceRound = [&]() {
         double h1 = nowSec();
         D.jobs.clear();
-        for (Worker &w : workers) { w.jobBase = D.jobs.size(); D.jobs.insert(D.jobs.end(), w.jobs.begin(), w.jobs.end()); }
+        for (Worker &w : workers) {
+            w.ansBase = D.jobs.size(); w.ansCount = w.jobs.size();
+            D.jobs.insert(D.jobs.end(), w.jobs.begin(), w.jobs.end());
+            w.jobs.clear();
+        }
         if (D.jobs.empty()) {
             if (live.load() != 0) { fprintf(stderr, "yaha_b200: internal error: parked fibers without jobs\n"); exit(1); }
             finished = true;
@@ -244,19 +254,7 @@ static void processBatch(const Env &E, Device &D, Batch &B, int nThreads)
             break;
         }
         D.nJobs += (uint64_t)nj; D.nRounds++;
-        for (Worker &w : workers) {
-            const size_t m = w.jobs.size();
-            w.answers.clear();
-            w.answers.resize(m);
-            for (size_t k = 0; k < m; k++) {
-                const ya_dp_result &r = D.res[w.jobBase + k];
-                DpAnswer &a = w.answers[k];
-                a.score = r.score; a.addedQ = r.addedQLen; a.addedR = r.addedRLen;
-                a.ops.v.resize(r.ops_n);
-                for (uint32_t q = 0; q < r.ops_n; q++) { const ya_op &o = D.ops[r.ops_off + q]; a.ops.v[q] = Op{o.length, (char)o.opcode}; }
-            }
-            w.jobs.clear();
-        }
+        for (Worker &w : workers) { w.res = D.res.data(); w.ops = D.ops.data(); }
         live.store(0);
         D.tDp += nowSec() - h1;
     };
@@ -288,20 +286,24 @@ static void processBatch(const Env &E, Device &D, Batch &B, int nThreads)
     for (auto &f : B.fibers) { gStacks.put(f->stack); f->stack = nullptr; }
 }
 
+// bounded, ordered hand-off between reader, pipelines and writer
+struct Flow {
+    std::mutex mu;
+    std::condition_variable cvIn, cvOut, cvSpace;
+    std::deque<std::unique_ptr<Batch>> in;
+    std::map<uint64_t, std::unique_ptr<Batch>> done;
+    bool readerDone = false;
+    uint64_t produced = 0;
+    size_t maxQueued = 4;
+};
+
 int runQueries(const Args &A0)
 {
     Args A = A0;
     std::string err;
-    QueryReader qr;
-    if (!qr.open(A.qfile == "stdout" ? "stdin" : A.qfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-    A.fastq = qr.fastq;
     Genome G;
     if (!G.load(A.gfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     if (A.verbose) fprintf(stderr, "Read in %d reference sequences from %s.\n", (int)G.seqs.size(), A.gfile.c_str());
-    FILE *out = (A.ofile == "stdout") ? stdout : fopen(A.ofile.c_str(), "w");
-    if (!out) { fprintf(stderr, "Failure to open output file: %s.  Error number:%d\n", A.ofile.c_str(), errno); return 1; }
-    static char obuf[1 << 22];
-    setvbuf(out, obuf, _IOFBF, sizeof obuf);
     IndexFile X;
     if (!X.load(A.xfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     A.wordLen = X.wordLen;                                              // Query.c:603-610
@@ -310,9 +312,21 @@ int runQueries(const Args &A0)
                 "Mimimum of two (%d) will be used.\n", X.maxHits, A.maxHits, X.maxHits);
         A.maxHits = X.maxHits;
     }
+    {
+        QueryReader probe;                                              // sniff FASTA vs FASTQ before the header is written
+        if (A.qfile == "stdout" || A.qfile == "stdin" || A.qfile == "-") {
+            fprintf(stderr, "yaha_b200: reading queries from stdin is not supported; give -q a file\n");
+            return 1;
+        }
+        if (!probe.open(A.qfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        A.fastq = probe.fastq;
+        probe.close();
+    }
+    FILE *out = (A.ofile == "stdout") ? stdout : fopen(A.ofile.c_str(), "w");
+    if (!out) { fprintf(stderr, "Failure to open output file: %s.  Error number:%d\n", A.ofile.c_str(), errno); return 1; }
+    static char obuf[1 << 22];
+    setvbuf(out, obuf, _IOFBF, sizeof obuf);
     Env E{&A, &G};
-    writeHeader(E, out);
-    qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
 
     int nproc = get_nprocs();
     int nThreads = std::max(1, A.numThreads);
@@ -323,66 +337,126 @@ int runQueries(const Args &A0)
     }
     ya_params P = A.deviceParams();
     const int nDev = std::max(1, A.gpus);
-    std::vector<Device> devs((size_t)nDev);
+    int pipesPerDev = std::max(1, A.pipes);
+    if (nThreads < nDev * pipesPerDev) pipesPerDev = std::max(1, nThreads / nDev);
+    const int nPipes = nDev * pipesPerDev;
+    const int threadsPerPipe = std::max(1, nThreads / nPipes);
+    std::vector<Pipe> pipes((size_t)nPipes);
     double tOpen = nowSec();
     for (int d = 0; d < nDev; d++) {
-        devs[(size_t)d].ordinal = d;
-        devs[(size_t)d].ctx = (d == 0) ? ya_open(A.firstDev, &P, X.so, X.nSo, X.roa, X.nRoa, G.bases, G.nBaseBytes, G.maxROff)
-                                       : ya_open_peer(A.firstDev + d, devs[0].ctx);   // index replica over NVLink
-        if (!devs[(size_t)d].ctx) { fprintf(stderr, "yaha_b200: cannot open device %d: %s\n", d, ya_last_error(nullptr)); return 1; }
+        Pipe &first = pipes[(size_t)d * pipesPerDev];
+        first.device = A.firstDev + d;
+        first.ctx = (d == 0) ? ya_open(A.firstDev, &P, X.so, X.nSo, X.roa, X.nRoa, G.bases, G.nBaseBytes, G.maxROff)
+                             : ya_open_peer(A.firstDev + d, pipes[0].ctx);                 // index replica over NVLink
+        if (!first.ctx) { fprintf(stderr, "yaha_b200: cannot open device %d: %s\n", A.firstDev + d, ya_last_error(nullptr)); return 1; }
+        for (int k = 1; k < pipesPerDev; k++) {
+            Pipe &p = pipes[(size_t)d * pipesPerDev + k];
+            p.device = first.device;
+            p.ctx = ya_open_shared(first.ctx);
+            if (!p.ctx) { fprintf(stderr, "yaha_b200: cannot open shared context: %s\n", ya_last_error(nullptr)); return 1; }
+        }
     }
     tOpen = nowSec() - tOpen;
 
-    // Reads are dealt to devices in contiguous blocks of batchReads; blocks are written in order.
-    const int threadsPerDev = std::max(1, nThreads / nDev);
+    std::vector<std::unique_ptr<Batch>> cache;                          // -replay: parsed batches of pass 0
     for (int pass = 0; pass < std::max(1, A.passes); pass++) {
-        if (pass > 0) {                                                 // -passes N (bench): redo the whole job
-            qr.close();
-            if (!qr.open(A.qfile == "stdout" ? "stdin" : A.qfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
-            qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
-            if (out != stdout) { out = freopen(A.ofile.c_str(), "w", out); setvbuf(out, obuf, _IOFBF, sizeof obuf); }
-            writeHeader(E, out);
-        }
-        for (Device &d : devs) { d.tSeed = d.tDp = d.tHost = d.tUpload = 0; d.nJobs = d.nRounds = 0; ya_counters c; ya_get_counters(d.ctx, &c); }
-        uint64_t nReads = 0;
+        const bool replaying = A.replay && pass > 0;
+        if (pass > 0 && out != stdout) { out = freopen(A.ofile.c_str(), "w", out); setvbuf(out, obuf, _IOFBF, sizeof obuf); }
+        writeHeader(E, out);
+        for (Pipe &p : pipes) { p.tSeed = p.tDp = p.tHost = p.tUpload = 0; p.nJobs = p.nRounds = 0; ya_counters c; ya_get_counters(p.ctx, &c); }
+        Flow F;
+        F.maxQueued = (size_t)nPipes + 2;
         double tRead = 0, tWrite = 0;
-        double tAlign = nowSec();
-        bool eof = false;
-        while (!eof) {
-            std::vector<Batch> batches((size_t)nDev);
-            int used = 0;
-            double r0 = nowSec();
-            for (int d = 0; d < nDev && !eof; d++) {
-                Batch &B = batches[(size_t)d];
-                B.reads.reserve((size_t)A.batchReads);
-                while ((int)B.reads.size() < A.batchReads) {
-                    B.reads.emplace_back();
-                    if (!qr.next(B.reads.back())) { B.reads.pop_back(); eof = true; break; }
+        uint64_t nReads = 0;
+        std::vector<std::unique_ptr<Batch>> replayIn;
+        replayIn.swap(cache);
+        const double tStart = nowSec();
+
+        std::thread reader([&]() {
+            uint64_t seq = 0;
+            if (replaying) {
+                for (auto &b : replayIn) {
+                    std::unique_lock<std::mutex> lk(F.mu);
+                    F.cvSpace.wait(lk, [&] { return F.in.size() < F.maxQueued; });
+                    b->seq = seq++;
+                    F.in.push_back(std::move(b));
+                    F.cvIn.notify_one();
                 }
-                if (!B.reads.empty()) used = d + 1;
+            } else {
+                QueryReader qr;
+                std::string e2;
+                if (!qr.open(A.qfile, e2)) { fprintf(stderr, "%s\n", e2.c_str()); exit(1); }
+                qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
+                bool eof = false;
+                while (!eof) {
+                    double r0 = nowSec();
+                    std::unique_ptr<Batch> b(new Batch());
+                    b->reads.reserve((size_t)A.batchReads);
+                    while ((int)b->reads.size() < A.batchReads) {
+                        b->reads.emplace_back();
+                        if (!qr.next(b->reads.back())) { b->reads.pop_back(); eof = true; break; }
+                    }
+                    tRead += nowSec() - r0;
+                    if (b->reads.empty()) break;
+                    b->seq = seq++;
+                    std::unique_lock<std::mutex> lk(F.mu);
+                    F.cvSpace.wait(lk, [&] { return F.in.size() < F.maxQueued; });
+                    F.in.push_back(std::move(b));
+                    F.cvIn.notify_one();
+                }
+                qr.close();
             }
-            tRead += nowSec() - r0;
-            if (used == 0) break;
-            if (used == 1) processBatch(E, devs[0], batches[0], nThreads);
-            else {
-                std::vector<std::thread> th;
-                for (int d = 0; d < used; d++) th.emplace_back([&, d]() { processBatch(E, devs[(size_t)d], batches[(size_t)d], threadsPerDev); });
-                for (auto &x : th) x.join();
+            std::lock_guard<std::mutex> lk(F.mu);
+            F.readerDone = true; F.produced = seq;
+            F.cvIn.notify_all(); F.cvOut.notify_all();
+        });
+
+        std::vector<std::thread> pth;
+        for (int p = 0; p < nPipes; p++)
+            pth.emplace_back([&, p]() {
+                for (;;) {
+                    std::unique_ptr<Batch> b;
+                    {
+                        std::unique_lock<std::mutex> lk(F.mu);
+                        F.cvIn.wait(lk, [&] { return !F.in.empty() || F.readerDone; });
+                        if (F.in.empty()) return;
+                        b = std::move(F.in.front());
+                        F.in.pop_front();
+                        F.cvSpace.notify_one();
+                    }
+                    processBatch(E, pipes[(size_t)p], *b, threadsPerPipe);
+                    std::lock_guard<std::mutex> lk(F.mu);
+                    uint64_t s = b->seq;
+                    F.done[s] = std::move(b);
+                    F.cvOut.notify_all();
+                }
+            });
+
+        // writer: input order
+        for (uint64_t next = 0;; next++) {
+            std::unique_ptr<Batch> b;
+            {
+                std::unique_lock<std::mutex> lk(F.mu);
+                F.cvOut.wait(lk, [&] { return F.done.count(next) || (F.readerDone && next >= F.produced); });
+                if (!F.done.count(next)) break;
+                b = std::move(F.done[next]);
+                F.done.erase(next);
             }
             double w0 = nowSec();
-            for (int d = 0; d < used; d++) {
-                for (auto &f : batches[(size_t)d].fibers) fwrite(f->rc.out.data(), 1, f->rc.out.size(), out);
-                nReads += batches[(size_t)d].reads.size();
-            }
+            if (!replaying) for (auto &f : b->fibers) fwrite(f->rc.out.data(), 1, f->rc.out.size(), out);
+            nReads += b->reads.size();
             tWrite += nowSec() - w0;
+            if (A.replay) { b->fibers.clear(); cache.push_back(std::move(b)); }
         }
+        reader.join();
+        for (auto &t : pth) t.join();
         fflush(out);
-        tAlign = nowSec() - tAlign;
+        const double tAlign = nowSec() - tStart;
         if (A.verbose || A.passes > 1 || getenv("YAHA_B200_STATS")) {
             ya_counters c{};
             double seed = 0, dp = 0, host = 0, upl = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
             double msdp = 0, msseed = 0, mstb = 0;
-            for (Device &d : devs) {
+            for (Pipe &d : pipes) {
                 ya_get_counters(d.ctx, &c);
                 seed += d.tSeed; dp += d.tDp; host += d.tHost; upl += d.tUpload; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
                 msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback; launches += c.launches; probes += c.probes; hits += c.hits;
@@ -391,15 +465,16 @@ int runQueries(const Args &A0)
             fprintf(stderr, "{\"pass\": %d, \"reads\": %llu, \"align_s\": %.5f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"read_parse_s\": %.5f, "
                     "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
                     "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
-                    "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d}\n",
+                    "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d, \"pipes\": %d, "
+                    "\"replay\": %d}\n",
                     pass, (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), tRead, upl, tWrite, seed, dp, host,
                     (unsigned long long)jobs, (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb,
-                    (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads);
+                    (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads,
+                    nPipes, replaying ? 1 : 0);
         }
     }
     if (out != stdout) fclose(out); else fflush(out);
-    qr.close();
-    for (Device &d : devs) ya_close(d.ctx);
+    for (int p = nPipes - 1; p >= 0; p--) ya_close(pipes[(size_t)p].ctx);      // shared contexts before their owners
     return 0;
 }
 
