@@ -64,6 +64,21 @@ def main():
         extra = [] if flags[0] in ("-oss", "-o8") else flags
         subprocess.check_call([REF + "/yaha", "-x", idx, "-q", rd, outflag, f"out_{tag}.sam", "-t", "1"] + extra, cwd=tmp)
         gz(f"{tmp}/out_{tag}.sam", f"{OUT}/out_{tag}.sam.gz")
+    # reader corner cases (Query.c:102-228): long id with spaces, blank line, CRLF, '>' in the middle of a
+    # sequence line, a read over 32 000 bases (skipped), lower case, exactly 32 000 bases, no final newline
+    rs = [(n, q.tobytes().decode()) for n, q in reads[:5]]
+    with open(tmp + "/weird.fa", "w") as f:
+        f.write(f">{rs[0][0]} with spaces " + "x" * 250 + "\n" + rs[0][1][:100] + "\n\n" + rs[0][1][100:] + "\n")
+        f.write(f">{rs[1][0]}\r\n" + rs[1][1][:150] + "\r\n" + rs[1][1][150:] + "\r\n")
+        f.write(f">{rs[2][0]}\n" + rs[2][1][:200] + ">inline_break\n" + rs[2][1][200:] + "\n")
+        big = ref[1000:34000].tobytes().decode()
+        f.write(">toolong\n" + "\n".join(big[i:i + 70] for i in range(0, len(big), 70)) + "\n")
+        f.write(f">{rs[3][0]}\n" + rs[3][1].lower() + "\n")
+        f.write(">exact32000\n" + ref[50000:82000].tobytes().decode() + "\n")
+        f.write(f">{rs[4][0]}\n" + rs[4][1])
+    subprocess.check_call([REF + "/yaha", "-x", idx, "-q", "weird.fa", "-osh", "out_weird.sam", "-t", "1"], cwd=tmp)
+    gz(tmp + "/out_weird.sam", OUT + "/out_weird.sam.gz")
+    gz(tmp + "/weird.fa", OUT + "/weird.fa.gz")
     gz(tmp + "/reads.fq", OUT + "/reads.fq.gz")
     gz(tmp + "/ref.fa", OUT + "/ref.fa.gz")
     gz(tmp + "/reads.fa", OUT + "/reads.fa.gz")

@@ -11,6 +11,7 @@ CASES = [
     ("out_nooqc.sam.gz", "reads.fa", "-osh", ["-OQC", "N"]),
     ("out_fastq_oss.sam.gz", "reads.fq", "-oss", []),
     ("out_blast8.sam.gz", "reads.fa", "-o8", []),
+    ("out_weird.sam.gz", "weird.fa", "-osh", []),
 ]
 
 

@@ -93,24 +93,53 @@ bool IndexFile::load(const std::string &path, std::string &err)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Query reader.  Same record semantics as readNextQuery (Query.c:102-228) -- id cut at newline, spaces
+// -> '_', only '\n' skipped inside sequences, the break character ('>' / '+') ends a sequence wherever
+// it occurs, over-long and too-short reads skipped with the reference's warnings -- but reading
+// through a private 4 MiB buffer with whole-line copies instead of one getc per character.
+struct QueryReader::Buf {
+    std::vector<char> b;
+    size_t p = 0, e = 0;
+    bool eof = false;
+    Buf() : b((size_t)4 << 20) {}
+    bool fill(FILE *f)
+    {
+        if (eof) return false;
+        p = 0;
+        e = fread(b.data(), 1, b.size(), f);
+        if (e == 0) { eof = true; return false; }
+        return true;
+    }
+    inline int get(FILE *f)
+    {
+        if (p == e && !fill(f)) return EOF;
+        return (unsigned char)b[p++];
+    }
+};
+
 bool QueryReader::open(const std::string &path, std::string &err)
 {
-    if (path == "stdin" || path == "-") { fprintf(stderr, "Reading queries from stdin.\n"); f = stdin; }
-    else f = fopen(path.c_str(), "r");
+    f = fopen(path.c_str(), "r");
     if (!f) { err = "Failure to open input file: " + path + ".  Error number:" + std::to_string(errno); return false; }
-    static char iobuf[1 << 20];
-    setvbuf(f, iobuf, _IOFBF, sizeof iobuf);
-    fastq = (getc_unlocked(f) == '@');               // also positions the stream after the first marker
+    setvbuf(f, nullptr, _IONBF, 0);
+    buf = new Buf();
+    fastq = (buf->get(f) == '@');                    // also positions the stream after the first marker
     return true;
 }
 
-void QueryReader::close() { if (f && f != stdin) fclose(f); f = nullptr; }
+void QueryReader::close()
+{
+    if (f) fclose(f);
+    f = nullptr;
+    delete buf;
+    buf = nullptr;
+}
 
-static void readToChar(FILE *f, int target, bool afterNewline)          // Query.c:52-61
+static void readToChar(QueryReader::Buf &B, FILE *f, int target, bool afterNewline)          // Query.c:52-61
 {
     int prev = 0;
     for (;;) {
-        int c = getc_unlocked(f);
+        int c = B.get(f);
         if ((c == target && (!afterNewline || prev == '\n')) || c == EOF) return;
         prev = c;
     }
@@ -118,42 +147,61 @@ static void readToChar(FILE *f, int target, bool afterNewline)          // Query
 
 bool QueryReader::next(Read &r)
 {
+    Buf &B = *buf;
+    static uint8_t codeTab[256];
+    static bool tabReady = false;
+    if (!tabReady) { for (int c = 0; c < 256; c++) codeTab[c] = (uint8_t)codeOfChar(c < 128 ? c : 0); tabReady = true; }
     for (;;) {
         r.id.clear(); r.fwd.clear(); r.qual.clear();
         int idChars = 0;
-        for (;;) {
-            int c = getc_unlocked(f);
-            if (c == '\n' || c == EOF) break;
-            if (idChars < 200) r.id.push_back(c == ' ' ? '_' : (char)c);
-            idChars++;
+        for (;;) {                                   // id line
+            if (B.p == B.e && !B.fill(f)) break;
+            const char *s = B.b.data() + B.p;
+            const char *nl = (const char *)memchr(s, '\n', B.e - B.p);
+            size_t len = nl ? (size_t)(nl - s) : B.e - B.p;
+            for (size_t k = 0; k < len; k++, idChars++)
+                if (idChars < 200) r.id.push_back(s[k] == ' ' ? '_' : s[k]);
+            B.p += len;
+            if (nl) { B.p++; break; }
         }
         if (idChars > 200)
             fprintf(stderr, "Warning, Query Id length of %d exceeds maximum length %d.  Id will be truncated.\n", idChars, 200);
         const int brk = fastq ? '+' : '>';
         bool fail = false;
-        for (;;) {
-            int c = getc_unlocked(f);
-            if (c == brk || c == EOF) break;
-            if (c == '\n') continue;
-            if ((int)r.fwd.size() >= maxLen) {
+        for (;;) {                                   // sequence lines
+            if (B.p == B.e && !B.fill(f)) break;
+            const char *s = B.b.data() + B.p;
+            size_t avail = B.e - B.p;
+            const char *nl = (const char *)memchr(s, '\n', avail);
+            size_t len = nl ? (size_t)(nl - s) : avail;
+            const char *bk = (const char *)memchr(s, brk, len);
+            if (bk) len = (size_t)(bk - s);
+            if ((int)(r.fwd.size() + len) > maxLen) {
+                size_t room = (size_t)maxLen - r.fwd.size();
+                r.fwd.append(s, room);
+                B.p += room;
                 fprintf(stderr, "Warning.  Query sequence exceeds maximum length of %d.  Query will be skipped.\n", maxLen);
-                readToChar(f, brk, false);
+                B.p += 1;                            // the character that did not fit is consumed (Query.c:144-155)
+                readToChar(B, f, brk, false);
                 fail = true;
                 break;
             }
-            r.fwd.push_back((char)c);
+            r.fwd.append(s, len);
+            B.p += len;
+            if (bk) { B.p++; break; }
+            if (nl) B.p++;
         }
         if (fastq) {
-            readToChar(f, '\n', false);
+            readToChar(B, f, '\n', false);
             int prev = 0;
             for (;;) {
-                int c = getc_unlocked(f);
+                int c = B.get(f);
                 if ((c == '@' && prev == '\n') || c == EOF) break;
                 prev = c;
                 if (c == '\n') continue;
                 if ((int)r.qual.size() >= maxLen) {
                     fprintf(stderr, "Warning.  Quality score sequence exceeds maximum length of %d.  Query will be skipped.\n", maxLen);
-                    readToChar(f, '@', true);
+                    readToChar(B, f, '@', true);
                     fail = true;
                     break;
                 }
@@ -173,12 +221,15 @@ bool QueryReader::next(Read &r)
         if (fail) continue;
         if (n == 0) return false;                    // end of input (or an empty record, as in the reference)
         r.fcode.resize((size_t)n); r.rcode.resize((size_t)n); r.rev.resize((size_t)n);
+        const unsigned char *src = (const unsigned char *)r.fwd.data();
+        uint8_t *fc = r.fcode.data(), *rcd = r.rcode.data() + n - 1;
+        char *rv = &r.rev[0] + n - 1;
         for (int i = 0; i < n; i++) {
-            int code = codeOfChar((unsigned char)r.fwd[(size_t)i] < 128 ? r.fwd[(size_t)i] : 0);
-            r.fcode[(size_t)i] = (uint8_t)code;
-            int rc = kCompCode[code];
-            r.rcode[(size_t)(n - 1 - i)] = (uint8_t)rc;
-            r.rev[(size_t)(n - 1 - i)] = kCharOfCode[rc];
+            const uint8_t code = codeTab[src[i]];
+            fc[i] = code;
+            const uint8_t cc = kCompCode[code];
+            *rcd-- = cc;
+            *rv-- = kCharOfCode[cc];
         }
         return true;
     }

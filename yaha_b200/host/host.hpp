@@ -80,7 +80,8 @@ struct Read {
     int len() const { return (int)fwd.size(); }
 };
 struct QueryReader {                 // readNextQuery, Query.c:102-228
-    FILE *f = nullptr; bool fastq = false; int maxLen = 32000, wordLen = 15;
+    struct Buf;
+    FILE *f = nullptr; Buf *buf = nullptr; bool fastq = false; int maxLen = 32000, wordLen = 15;
     bool open(const std::string &path, std::string &err);     // Query.c:63-74
     bool next(Read &r);                                        // false at EOF
     void close();
