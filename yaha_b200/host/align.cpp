@@ -400,8 +400,11 @@ static int scoreClump(const Env &E, ReadCtx &rc, Clump *c)             // AlignH
     return 1;
 }
 
+uint64_t gAlignProf[4];
+static inline uint64_t rdtsc_() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
 void postProcessClumps(const Env &E, ReadCtx &rc)                       // QueryMatch.c:306-331
 {
+    uint64_t q0 = rdtsc_();
     std::vector<Clump *> old;
     old.swap(rc.clumps);
     std::reverse(old.begin(), old.end());                               // reference walks from the list head
@@ -413,7 +416,9 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         alignPrepare(E, rc, *old[k], gaps[k]);
         for (auto &g : gaps[k]) any |= g.needDp;
     }
+    gAlignProf[0] += rdtsc_() - q0;
     if (any) dpWait(rc);
+    q0 = rdtsc_();
     // phase 2: splice, collapse, perfect-extend and post the first extensions
     std::vector<ExtState> xs(old.size());
     std::vector<int> scores(old.size(), 0);
@@ -435,7 +440,9 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         extendPerfect(E, rc, c, true, true, scores[k], xs[k]);
         any |= xs[k].doB || xs[k].doF;
     }
+    gAlignProf[1] += rdtsc_() - q0;
     if (any) dpWait(rc);
+    q0 = rdtsc_();
     // phase 3: apply every extension first (answers of a round are only valid until this fiber
     // parks again), then score -- and split, which may park -- in list order
     for (size_t k = 0; k < old.size(); k++) {
@@ -444,12 +451,15 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         extendApply(E, rc, *c, xs[k], false, scores[k]);
         c->set(kAligned, true);
     }
+    gAlignProf[2] += rdtsc_() - q0;
+    q0 = rdtsc_();
     for (size_t k = 0; k < old.size(); k++) {
         Clump *c = old[k];
         scoreClump(E, rc, c);
         if (c->is(kScored)) rc.clumps.push_back(c);
         else delete c;
     }
+    gAlignProf[3] += rdtsc_() - q0;
 }
 
 }  // namespace yh

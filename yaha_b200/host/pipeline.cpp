@@ -20,7 +20,6 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/sysinfo.h>
-#include <ucontext.h>
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
@@ -37,9 +36,22 @@ namespace yh {
 
 static const size_t kStackBytes = 512 * 1024;
 
+// Minimal x86-64 System V context switch: callee-saved registers + stack pointer.  glibc's swapcontext
+// makes a signal-mask system call on every switch, which costs more than the rest of a round trip.
+extern "C" void yh_switch(void **saveSp, void *loadSp);
+__asm__(
+    ".text\n.globl yh_switch\n.type yh_switch,@function\n"
+    "yh_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size yh_switch,.-yh_switch\n");
+
 struct Worker;
 struct Fiber {
-    ucontext_t ctx;
+    void *sp = nullptr;                   // saved stack pointer while not running
     void *stack = nullptr;
     bool done = false, started = false;
     ReadCtx rc;
@@ -47,7 +59,7 @@ struct Fiber {
 };
 
 struct Worker {
-    ucontext_t mainCtx;
+    void *mainSp = nullptr;
     std::vector<Fiber *> fibers;
     std::vector<ya_dp_job> jobs;          // posted in the current round
     const ya_dp_result *res = nullptr;    // previous round's results (this worker's jobs start at ansBase)
@@ -76,7 +88,7 @@ DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int 
 void dpWait(ReadCtx &rc)
 {
     Fiber *f = (Fiber *)rc.owner;
-    swapcontext(&f->ctx, &f->w->mainCtx);
+    yh_switch(&f->sp, f->w->mainSp);
 }
 
 DpAnswer dpGet(ReadCtx &rc, DpFuture fu)
@@ -88,8 +100,11 @@ DpAnswer dpGet(ReadCtx &rc, DpFuture fu)
     return a;
 }
 
+static std::atomic<uint64_t> gProf[8];
+static inline uint64_t rdtsc() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
 static void readMain(const Env &E, ReadCtx &rc)                       // body of the Query.c:306-497 loop
 {
+    uint64_t t0 = rdtsc();
     const Args &A = *E.A;
     {                                                                  // generateRandomSeed, QueryState.c:172-187
         const std::vector<uint8_t> &c = rc.read->fcode;
@@ -101,19 +116,26 @@ static void readMain(const Env &E, ReadCtx &rc)                       // body of
         }
     }
     for (int rev = 0; rev <= 1; rev++) formClumps(E, rc, rev != 0);
+    uint64_t t1 = rdtsc();
     postProcessClumps(E, rc);
+    uint64_t t2 = rdtsc();
     if (A.OQC) postFilterBySimilarity(E, rc); else postFilterRemoveDups(E, rc);
+    uint64_t t3 = rdtsc();
     formatClumps(E, rc);
+    uint64_t t4 = rdtsc();
     for (Clump *c : rc.clumps) delete c;
     rc.clumps.clear();
+    gProf[0] += t1 - t0; gProf[1] += t2 - t1; gProf[2] += t3 - t2; gProf[3] += t4 - t3; gProf[4] += rdtsc() - t4;
 }
 
-static void fiberEntry(unsigned lo, unsigned hi)
+static thread_local Fiber *tBoot;
+static void fiberEntry()
 {
-    Fiber *f = (Fiber *)(((uintptr_t)hi << 32) | (uintptr_t)lo);
+    Fiber *f = tBoot;
     readMain(*f->w->E, f->rc);
     f->done = true;
-    swapcontext(&f->ctx, &f->w->mainCtx);
+    yh_switch(&f->sp, f->w->mainSp);
+    __builtin_trap();                     // a finished fiber is never resumed
 }
 
 // run every unfinished fiber of this worker until it parks or finishes; returns #unfinished
@@ -124,14 +146,17 @@ static int workerRound(Worker &w)
         if (f->done) continue;
         if (!f->started) {
             f->started = true;
-            getcontext(&f->ctx);
-            f->ctx.uc_stack.ss_sp = f->stack;
-            f->ctx.uc_stack.ss_size = kStackBytes;
-            f->ctx.uc_link = &w.mainCtx;
-            uintptr_t p = (uintptr_t)f;
-            makecontext(&f->ctx, (void (*)())fiberEntry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+            // initial frame: six zeroed callee-saved registers, then the entry point as return address;
+            // the slot above keeps (%rsp + 8) 16-byte aligned at function entry as the ABI requires
+            uintptr_t top = ((uintptr_t)f->stack + kStackBytes) & ~(uintptr_t)15;
+            void **sp = (void **)top;
+            *--sp = nullptr;
+            *--sp = (void *)fiberEntry;
+            for (int k = 0; k < 6; k++) *--sp = nullptr;
+            f->sp = sp;
+            tBoot = f;
         }
-        swapcontext(&w.mainCtx, &f->ctx);
+        yh_switch(&w.mainSp, f->sp);
         if (!f->done) live++;
     }
     return live;
@@ -473,6 +498,12 @@ int runQueries(const Args &A0)
                     nPipes, replaying ? 1 : 0);
         }
     }
+    extern uint64_t gAlignProf[4];
+    if (getenv("YAHA_B200_PROF")) fprintf(stderr, "prof align Mcycles: prepare %.1f collapse+ext %.1f apply %.1f score(incl parked) %.1f\n",
+                                          gAlignProf[0] / 1e6, gAlignProf[1] / 1e6, gAlignProf[2] / 1e6, gAlignProf[3] / 1e6);
+    if (getenv("YAHA_B200_PROF"))
+        fprintf(stderr, "prof Mcycles: formClumps %.1f postProcess(incl. parked time) %.1f oqc %.1f format %.1f free %.1f\n", gProf[0] / 1e6,
+                gProf[1] / 1e6, gProf[2] / 1e6, gProf[3] / 1e6, gProf[4] / 1e6);
     if (out != stdout) fclose(out); else fflush(out);
     for (int p = nPipes - 1; p >= 0; p--) ya_close(pipes[(size_t)p].ctx);      // shared contexts before their owners
     return 0;

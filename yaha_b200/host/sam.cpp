@@ -21,6 +21,18 @@ static void appendf(std::string &s, const char *fmt, ...)
     if (n > 0) s.append(buf, (size_t)std::min<int>(n, (int)sizeof buf - 1));
 }
 
+static inline void appendUInt(std::string &s, unsigned v)
+{
+    char buf[12];
+    int n = 0;
+    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) s.push_back(buf[--n]);
+}
+static inline void appendInt(std::string &s, int v)
+{
+    if (v < 0) { s.push_back('-'); appendUInt(s, (unsigned)(-(long)v)); } else appendUInt(s, (unsigned)v);
+}
+
 void writeHeader(const Env &E, FILE *out)
 {
     const Args &A = *E.A;
@@ -67,10 +79,10 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
         int matches = 0;
         for (const Op &op : list.v) {
             if (op.code == 'M' || op.code == 'R') { matches += op.len; continue; }
-            if (matches > 0) { appendf(o, "%dM", matches); matches = 0; }
-            appendf(o, "%d%c", (int)op.len, op.code);
+            if (matches > 0) { appendInt(o, matches); o += 'M'; matches = 0; }
+            appendInt(o, (int)op.len); o += op.code;
         }
-        if (matches > 0) appendf(o, "%dM", matches);
+        if (matches > 0) { appendInt(o, matches); o += 'M'; }
         o += "\t*\t0\t0\t";
         int qs = 0, qe = L - 1;
         if (A.hardClip) { qs = f0.startQueryOff; qe = fn.endQueryOff; }
@@ -95,19 +107,19 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
             }
             if (op.code == 'M') { matches += op.len; ro += op.len; }
             else if (op.code == 'R') {
-                if (matches > 0) { appendf(o, "%d", matches); matches = 0; }
+                if (matches > 0) { appendInt(o, matches); matches = 0; }
                 if (prev == 'D') o += '0';
                 for (int i = 0; i < op.len; i++) o += kCharOfCode[G.code(ro + (uint32_t)i)];
                 ro += op.len;
             } else if (op.code == 'D') {
-                if (matches > 0) { appendf(o, "%d", matches); matches = 0; }
+                if (matches > 0) { appendInt(o, matches); matches = 0; }
                 o += '^';
                 for (int i = 0; i < op.len; i++) o += kCharOfCode[G.code(ro + (uint32_t)i)];
                 ro += op.len;
             }
             prev = op.code;
         }
-        if (matches > 0) appendf(o, "%d", matches);
+        if (matches > 0) appendInt(o, matches);
         appendf(o, "\tYF:H:%02X", (unsigned)c.status);
         if (A.OQC) {
             appendf(o, "\tYI:i:%d", (int)c.matchedPrimary);
