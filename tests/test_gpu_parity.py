@@ -35,7 +35,7 @@ def _golden_jobs(small, bw):
     return np.array(jobs, dtype=yaha_b200.JOB_DT), want
 
 
-@pytest.mark.parametrize("mode", ["wave", "thread"])
+@pytest.mark.parametrize("mode", ["packed", "wave", "thread"])
 @pytest.mark.parametrize("bw,gap", [(5, 50), (10, 100)])
 def test_dp_matches_reference_calls(small, aligner, bw, gap, mode, monkeypatch):
     """Every DP call of the reference run (all four kinds, both strands, clamped at both reference

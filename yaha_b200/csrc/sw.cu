@@ -19,6 +19,7 @@
 // and checked against the oracle in tests/.
 #include "common.cuh"
 #include <algorithm>
+#include <climits>
 
 // back-pointer cell: op in bits 15..14 (0 M, 1 R, 2 D, 3 I), run length in bits 13..0
 #define BP_M 0u
@@ -213,6 +214,220 @@ dp_wave_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ job
 }
 
 // ------------------------------------------------------------------------------------------
+// Packed X-drop extension kernel (the hot kernel): same wavefront as dp_wave_kernel, but every
+// score lives in a register scaled by 256 with the low byte carrying what the reference keeps in
+// side arrays:
+//     E-chain word = E*256 + 0x40 + (D-1)      F-chain word = F*256 + 0x80 + (I-1)
+// A continued gap is "word + 1 - GEC*256", a new gap "V*256 + tag - (GOC+GEC)*256", so ONE
+// VIADDMNMX yields the better of the two with the reference's tie rule (continue on equality,
+// SW.cpp:1032,1050) and the run length D / I for free.  The cell value is ONE VIMNMX3 over
+// {diag, E word, F word}: equal scores resolve by tag, i.e. insert over delete over match/replace,
+// exactly the extension tie rule (SW.cpp:1036,1054), and the low byte of the winner IS the
+// back-pointer (op tag + run length - 1).  Row maximum and its first column ride in one key
+// V*256 + (255 - col).  Valid while run lengths fit 6 bits and the gap-length caps cannot bind
+// (W <= 64, W <= maxGap, W <= maxIntron); other parameter sets use dp_wave_kernel.
+// Back-pointer bytes are accumulated 4 macro steps per 32-bit word and stored 16 B at a time.
+// ------------------------------------------------------------------------------------------
+#define PK_WORST (-(1 << 29))
+#define PK_TAGE  0x40
+#define PK_TAGF  0x80
+
+template <int G, int C, int W>
+__global__ void __launch_bounds__(128)
+dp_ext_packed_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ job_ids, int n_jobs,
+                     DevJobOut *__restrict__ outs, uint32_t *__restrict__ tbw,
+                     const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd,
+                     const uint8_t *__restrict__ rev, DpConst K)
+{
+    constexpr int GPW = 32 / G;                  // groups (jobs) per warp
+    constexpr int LB = (W - 1) / 2;              // left band = 2*BW
+    constexpr int CP = (C + 3) & ~3;             // words reserved per lane and 4-step block (16 B aligned)
+    constexpr int KB = W - (G - 1) * C;          // first blocked column index in the last lane
+    static_assert(G * C >= W && (G - 1) * C < W, "last lane must hold the band's right edge");
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = lane / G, l = lane % G;
+    const bool laneUsed = g < GPW;
+    const int gidx = warpGlobal * GPW + g;
+    const bool have = laneUsed && gidx < n_jobs;
+    const int leftLane = (l > 0) ? lane - 1 : lane;
+    const int rightLane = (l < G - 1 && lane < 31) ? lane + 1 : lane;
+    const int lastLane = g * G + (G - 1);
+    uint32_t jid = 0;
+    DevJob J;
+    if (have) { jid = job_ids[gidx]; J = jobs[jid]; }
+    const int rows = have ? J.qLen : 0;
+    const int rLen = have ? J.rLen : 0;
+    const bool bwd = have && J.kind == YA_DP_EXT_BWD;
+    const uint8_t *codes = (have && J.strand) ? rev : fwd;
+    const uint32_t qIdx = have ? J.qIdx : 0;
+    const uint32_t rOff = have ? J.rOff : 0;
+    uint32_t *mytb = tbw + (have ? J.tb_off : 0);
+
+    const int MS8 = K.MS << 8, RC8 = K.RC << 8;
+    const int CONT = 1 - (K.GEC << 8);
+    const int NEWE = PK_TAGE - ((K.GOC + K.GEC) << 8), NEWF = PK_TAGF - ((K.GOC + K.GEC) << 8);
+    const int E_NONE = PK_WORST + PK_TAGE - 1;    // "no gap yet" (D = 0): continuing it gives D = 1
+    const int F_NONE = PK_WORST + PK_TAGF - 1;
+
+    int V[C], F[C], rc[C];
+    uint32_t acc[C];
+    const int col0 = l * C;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        const int col = col0 + k;
+        F[k] = F_NONE; acc[k] = 0;
+        if (col == LB) V[k] = 0;                                                  // origin (SW.cpp:914-916)
+        else if (col > LB && col < W) V[k] = -((K.GOC + (col - LB) * K.GEC) << 8);  // leading deletes (:900-910)
+        else V[k] = PK_WORST;                                                     // unread / sentinel (:894)
+    }
+    int ridx0 = (1 - l) - LB - 1 + col0;
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+        const int ri = ridx0 + k;
+        rc[k] = (ri >= 0 && ri < rLen) ? nib(bases, bwd ? rOff - (uint32_t)ri : rOff + (uint32_t)ri) : 0xFF;
+    }
+    int qi = 1 - l;
+    int qc = (qi >= 1 && qi <= rows) ? codes[bwd ? qIdx - (uint32_t)(qi - 1) : qIdx + (uint32_t)(qi - 1)] : 0xFE;
+
+    int pubV = PK_WORST, pubE = E_NONE, pubRm = INT_MIN;
+    int maxScore = YA_WORST, maxi = 0, maxj = 0;
+    int stopRow = rows;
+    const int kbase = 255 - col0;
+
+    int m = 1;
+    for (;; m++) {
+        const bool group_done = m > stopRow + G - 1;
+        if (__all_sync(full, group_done)) break;
+        const int i = m - l;
+        const bool rowActive = (i >= 1) && (i <= stopRow);
+
+        int Vl = __shfl_sync(full, pubV, leftLane);
+        int El = __shfl_sync(full, pubE, leftLane);
+        int rm = __shfl_sync(full, pubRm, leftLane);
+        if (l == 0) { Vl = PK_WORST; El = E_NONE; rm = INT_MIN; }
+
+        const int qn = i + 1;
+        const int qc_next = (qn >= 1 && qn <= rows) ? codes[bwd ? qIdx - (uint32_t)(qn - 1) : qIdx + (uint32_t)(qn - 1)] : 0xFE;
+        const int rn = ridx0 + C;
+        const int rc_next = (rn >= 0 && rn < rLen) ? nib(bases, bwd ? rOff - (uint32_t)rn : rOff + (uint32_t)rn) : 0xFF;
+
+        const bool general = m < LB + G;          // some lane of the group may still be inside the leading triangle
+        int V0r = PK_WORST, F0r = F_NONE;
+        if (general) {
+            // ---- leading triangle: per-cell activity tests (rows 1..LB have a moving left edge)
+            const int startCol = (LB + 1 - i) > 0 ? (LB + 1 - i) : 0;
+            const int bcol = LB - i;
+            const int bV = -((K.GOC + i * K.GEC) << 8);
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                const int col = col0 + k;
+                if (k == 1) {
+                    V0r = __shfl_sync(full, V[0], rightLane);
+                    F0r = __shfl_sync(full, F[0], rightLane);
+                    if (l == G - 1) { V0r = PK_WORST; F0r = F_NONE; }
+                }
+                const bool blocked = (k >= KB) && (l == G - 1);
+                bool doCell = rowActive && !blocked;
+                if (doCell && col < startCol) {
+                    doCell = false;
+                    if (col == bcol) { V[k] = bV; Vl = bV; El = E_NONE; }         // leading-insert boundary (SW.cpp:981)
+                }
+                if (doCell) {
+                    const int Vu = (k == C - 1) ? V0r : V[(k + 1) % C];
+                    const int Fu = (k == C - 1) ? F0r : F[(k + 1) % C];
+                    const int diag = V[k] + ((qc == rc[k]) ? MS8 : -RC8);
+                    const int Et = __viaddmax_s32(El, CONT, Vl + NEWE);
+                    const int Ft = __viaddmax_s32(Fu, CONT, Vu + NEWF);
+                    const int r = __vimax3_s32(diag, Et, Ft);
+                    const int Vn = r & ~255;
+                    acc[k] = acc[k] * 256u + (uint32_t)(r - Vn);
+                    rm = max(rm, Vn + kbase - k);
+                    V[k] = Vn; F[k] = Ft; Vl = Vn; El = Et;
+                } else {
+                    acc[k] = acc[k] * 256u;
+                }
+            }
+        } else {
+            // ---- steady state: straight-line code, no per-cell tests.  Lanes whose row is outside
+            // 1..stopRow compute on dead registers (nothing reads them any more); only the
+            // sentinel column right of the band (cell KB of the last lane) must be kept intact,
+            // and blocked cells must not enter the row maximum.
+            const bool lastL = (l == G - 1);
+#pragma unroll
+            for (int k = 0; k < C; k++) {
+                if (k == 1) {
+                    V0r = __shfl_sync(full, V[0], rightLane);
+                    F0r = __shfl_sync(full, F[0], rightLane);
+                    if (lastL) { V0r = PK_WORST; F0r = F_NONE; }
+                }
+                const int Vu = (k == C - 1) ? V0r : V[(k + 1) % C];
+                const int Fu = (k == C - 1) ? F0r : F[(k + 1) % C];
+                const int diag = V[k] + ((qc == rc[k]) ? MS8 : -RC8);
+                const int Et = __viaddmax_s32(El, CONT, Vl + NEWE);
+                const int Ft = __viaddmax_s32(Fu, CONT, Vu + NEWF);
+                const int r = __vimax3_s32(diag, Et, Ft);
+                const int Vn = r & ~255;
+                acc[k] = acc[k] * 256u + (uint32_t)(r - Vn);
+                if (k >= KB) {
+                    rm = lastL ? rm : max(rm, Vn + kbase - k);
+                    if (k == KB) { V[k] = lastL ? PK_WORST : Vn; F[k] = lastL ? F_NONE : Ft; }
+                    else { V[k] = Vn; F[k] = Ft; }
+                } else {
+                    rm = max(rm, Vn + kbase - k);
+                    V[k] = Vn; F[k] = Ft;
+                }
+                Vl = Vn; El = Et;
+            }
+        }
+        pubV = Vl; pubE = El; pubRm = rm;
+
+        if ((m & 3) == 0) {                       // one 16 B-aligned burst per lane every 4 macro steps
+            uint32_t *dst = mytb + (size_t)((m >> 2) - 1) * (G * CP) + l * CP;
+            if (have && m <= rows + G + 3) {
+#pragma unroll
+                for (int k = 0; k < CP; k += 4) {
+                    uint4 w;
+                    w.x = acc[k < C ? k : 0]; w.y = (k + 1 < C) ? acc[k + 1] : 0u;
+                    w.z = (k + 2 < C) ? acc[k + 2] : 0u; w.w = (k + 3 < C) ? acc[k + 3] : 0u;
+                    *reinterpret_cast<uint4 *>(dst + k) = w;
+                }
+            }
+        }
+
+        int newStop = stopRow;
+        if (lane == lastLane && rowActive) {      // row-major argmax + X-drop (SW.cpp:1073-1078, 1091)
+            const int rV = rm >> 8;
+            if (rV > maxScore) { maxScore = rV; maxi = i; maxj = 255 - (rm & 255); }
+            if (rV < maxScore - K.X) newStop = i;
+        }
+        stopRow = __shfl_sync(full, newStop, laneUsed ? lastLane : lane);
+#pragma unroll
+        for (int k = 0; k < C - 1; k++) rc[k] = rc[k + 1];
+        rc[C - 1] = rc_next;
+        ridx0++;
+        qc = qc_next;
+    }
+    // flush the partial 4-step block (m is one past the last executed macro step)
+    {
+        const int done = m - 1;
+        if ((done & 3) != 0 && have && done <= rows + G + 3) {
+            const int sh = 8 * (4 - (done & 3));
+            uint32_t *dst = mytb + (size_t)(done >> 2) * (G * CP) + l * CP;
+#pragma unroll
+            for (int k = 0; k < C; k++) dst[k] = acc[k] << sh;
+        }
+    }
+    if (have && lane == lastLane) {
+        DevJobOut o;
+        o.score = maxScore; o.maxi = maxi; o.maxj = maxj; o.n_ops = 0;
+        o.cells_lo = (uint32_t)stopRow; o.cells_hi = 0;
+        outs[jid] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic one-thread-per-job kernel (all four kinds).  Row state lives in global scratch.
 // FULL jobs are expressed in band coordinates with lb = qLen, rb = rLen, which reproduces the
 // full-matrix recurrences, boundaries and traceback of SW.cpp exactly.
@@ -274,7 +489,9 @@ __global__ void dp_thread_kernel(const DevJob *__restrict__ jobs, const uint32_t
 // (SW.cpp:900-933).
 // ------------------------------------------------------------------------------------------
 __global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, DevJobOut *__restrict__ outs,
-                                 const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw)
+                                 const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw,
+                                 const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd,
+                                 const uint8_t *__restrict__ rev)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
@@ -295,17 +512,37 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, De
     }
     uint32_t n = 0;
     if (!(ext && o.score <= 0)) {
-        const uint16_t *mytb = tb + J.tb_off;
+        const uint16_t *mytb = tb + (J.layout == 2 ? 0 : J.tb_off);
         ya_op *out = ops_raw + J.ops_off;
         int y = o.maxi, x = o.maxj;
         int prev = -1; uint32_t run = 0;
+        int guard = (int)J.qLen + (int)J.rLen + 8;     // a valid walk consumes a row or a column per step
         for (;;) {
+            if (--guard < 0 || x < 0 || x > W || y < 0) { n = 0xFFFFFFF0u; prev = -1; break; }   // corrupt back-pointers
             uint32_t op, len;
             if (y == 0) {
                 if (x == lb) break;                      // origin, 'U'
                 op = BP_D; len = (uint32_t)(x - lb);
             } else if (x == lb - y) {
                 op = BP_I; len = (uint32_t)y;            // leading insert boundary
+            } else if (J.layout == 2) {
+                // packed bytes, 4 macro steps per word (dp_ext_packed_kernel); M vs R is not stored
+                const int C = J.colsPerLane, CP = (C + 3) & ~3;
+                const int s = y + x / C;
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(tb) + J.tb_off;
+                const uint32_t word = w[(size_t)((s - 1) >> 2) * J.stride + (x / C) * CP + (x % C)];
+                const uint32_t b = (word >> (8 * (3 - ((s - 1) & 3)))) & 0xFFu;
+                len = (b & 63u) + 1u;
+                if ((b >> 6) == 1u) op = BP_D;
+                else if ((b >> 6) == 2u) op = BP_I;
+                else {
+                    const bool bwd = J.kind == YA_DP_EXT_BWD;
+                    const uint8_t *codes = J.strand ? rev : fwd;
+                    const int qc = codes[bwd ? J.qIdx - (uint32_t)(y - 1) : J.qIdx + (uint32_t)(y - 1)];
+                    const int ri = y - lb - 1 + x;
+                    const int rcode = nib(bases, bwd ? J.rOff - (uint32_t)ri : J.rOff + (uint32_t)ri);
+                    op = (qc == rcode) ? BP_M : BP_R;
+                }
             } else {
                 size_t row = J.layout ? (size_t)(y + x / J.colsPerLane) : (size_t)y;
                 uint32_t c = mytb[row * J.stride + x];
@@ -337,7 +574,8 @@ __global__ void finalize_kernel(const DevJob *__restrict__ jobs, const DevJobOut
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
     const DevJob J = jobs[t];
-    const DevJobOut o = outs[t];
+    DevJobOut o = outs[t];
+    if (o.n_ops >= 0xFFFFFFF0u) o.n_ops = 0;          // traceback error marker, reported by the host
     ya_dp_result r;
     r.ops_off = 0;
     if (J.kind >= YA_DP_EXT_FWD) {
@@ -404,11 +642,32 @@ static void launch_wave_cfg(ya_ctx *c, int cfg, bool ext, const uint32_t *d_ids,
     }
 }
 
-// YA_DP_MODE environment switch (tests): "thread" forces the generic kernel for every job.
+// YA_DP_MODE environment switch (tests): "thread" forces the generic kernel for every job,
+// "wave" keeps extensions on dp_wave_kernel instead of the packed kernel.
 static bool force_thread_kernel()
 {
     const char *e = getenv("YA_DP_MODE");
     return e && strcmp(e, "thread") == 0;
+}
+static bool forbid_packed_kernel()
+{
+    const char *e = getenv("YA_DP_MODE");
+    return e && (strcmp(e, "thread") == 0 || strcmp(e, "wave") == 0);
+}
+
+struct PackedCfg { int G, C, W; };
+static const PackedCfg kPackedCfgs[] = {{2, 11, 21}, {4, 11, 41}};
+static const int kNumPackedCfgs = sizeof(kPackedCfgs) / sizeof(kPackedCfgs[0]);
+
+template <int G, int C, int W>
+static void launch_packed(ya_ctx *c, const uint32_t *d_ids, int n, const DpConst &K)
+{
+    const int threads = 128;
+    const int groups_per_block = (threads / 32) * (32 / G);
+    int blocks = (n + groups_per_block - 1) / groups_per_block;
+    dp_ext_packed_kernel<G, C, W><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
+        c->d_tb.as<uint32_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+    c->ctr.launches++;
 }
 
 extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res,
@@ -423,11 +682,13 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     const ya_params &P = c->P;
     const int bw2 = 2 * P.bandWidth;
     const bool forceThread = force_thread_kernel();
+    const bool allowPacked = !forbid_packed_kernel();
 
     YA_CUDA(c, c->h_jobs.reserve((size_t)n * sizeof(DevJob)));
     DevJob *hj = c->h_jobs.as<DevJob>();
     // job id lists per kernel class: [0..kNumWaveCfgs) ext, [kNumWaveCfgs..2k) banded, last = thread
-    std::vector<std::vector<uint32_t>> lists(2 * kNumWaveCfgs + 1);
+    std::vector<std::vector<uint32_t>> lists(2 * kNumWaveCfgs + 1 + kNumPackedCfgs);
+    const int packedBase = 2 * kNumWaveCfgs + 1;
     uint64_t tb_cells = 0, rows_ints = 0, ops_slots = 0;
     int n_live = 0;
     std::vector<uint32_t> live_of(n);     // device job index -> caller job index
@@ -466,12 +727,22 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         d.rOff = rOff; d.rLen = (uint16_t)rLen; d.qLen = (uint16_t)qLen;
         d.qIdx = (uint32_t)(rbase + j.qOff);
         const int W = d.lb + d.rb + 1;
-        int cls = -1;
-        if (!forceThread && j.kind != YA_DP_FULL) {
+        int cls = -1, pcls = -1;
+        if (allowPacked && j.kind >= YA_DP_EXT_FWD && W <= P.maxGap && W <= P.maxIntron)
+            for (int k = 0; k < kNumPackedCfgs; k++) if (kPackedCfgs[k].W == W) pcls = k;
+        if (pcls >= 0) {
+            const int G = kPackedCfgs[pcls].G, C = kPackedCfgs[pcls].C, CP = (C + 3) & ~3;
+            d.layout = 2; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * CP);
+            tb_cells = (tb_cells + 7) & ~7ull;                         // 16-byte alignment for the 128-bit stores
+            d.tb_off = tb_cells / 2;                                  // in 32-bit words
+            tb_cells += 2ull * (uint64_t)((qLen + G + 3) / 4 + 1) * d.stride;
+            lists[packedBase + pcls].push_back((uint32_t)n_live);
+        } else if (!forceThread && j.kind != YA_DP_FULL) {
             for (int k = 0; k < kNumWaveCfgs; k++)
                 if (kWaveCfgs[k].G * kWaveCfgs[k].C >= W) { cls = k; break; }
         }
-        if (cls >= 0) {
+        if (pcls >= 0) {
+        } else if (cls >= 0) {
             const int G = kWaveCfgs[cls].G, C = kWaveCfgs[cls].C;
             d.layout = 1; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * C);
             d.tb_off = tb_cells;
@@ -508,6 +779,11 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     YA_CUDA(c, c->d_misc.reserve((size_t)n_live * 4 + 64));
     YA_CUDA(c, c->h_res.reserve((size_t)n_live * (sizeof(ya_dp_result) + sizeof(DevJobOut)) + 64));
     YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, hj, (size_t)n_live * sizeof(DevJob), cudaMemcpyHostToDevice, st));
+    // longest jobs first inside each packed class: groups sharing a warp get similar row counts
+    for (int k = 0; k < kNumPackedCfgs; k++) {
+        std::vector<uint32_t> &v = lists[packedBase + k];
+        std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return hj[a].qLen != hj[b].qLen ? hj[a].qLen > hj[b].qLen : a < b; });
+    }
     // id lists
     std::vector<uint32_t> flat; flat.reserve(n_live);
     std::vector<size_t> start(lists.size());
@@ -522,6 +798,8 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         if (!lists[kNumWaveCfgs + k].empty())
             launch_wave_cfg(c, k, false, d_ids + start[kNumWaveCfgs + k], (int)lists[kNumWaveCfgs + k].size(), K);
     }
+    if (!lists[packedBase + 0].empty()) launch_packed<2, 11, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
+    if (!lists[packedBase + 1].empty()) launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
     if (!lists[2 * kNumWaveCfgs].empty()) {
         int nt = (int)lists[2 * kNumWaveCfgs].size();
         dp_thread_kernel<<<(nt + 63) / 64, 64, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids + start[2 * kNumWaveCfgs], nt,
@@ -532,7 +810,8 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     const int tbk = (n_live + 127) / 128;
     traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_jobout.as<DevJobOut>(),
-                                          c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>());
+                                          c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
+                                          c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
     finalize_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), c->d_jobout.as<DevJobOut>(), n_live, P.bandWidth,
                                          c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
     c->ctr.launches += 2;
@@ -561,6 +840,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]);
     c->ctr.ms_dp += ms0; c->ctr.ms_traceback += ms1;
     for (int k = 0; k < n_live; k++) {
+        if (hout[k].n_ops >= 0xFFFFFFF0u) return ya_fail(c, YA_E_STATE, "internal: traceback walked off the band (corrupt back-pointers)");
         res[live_of[k]] = hres[k];
         c->ctr.dp_cells += ((uint64_t)hout[k].cells_hi << 32) | hout[k].cells_lo;
         if (hres[k].ops_n > hj[k].ops_cap) return ya_fail(c, YA_E_STATE, "internal: op scratch overflow");
