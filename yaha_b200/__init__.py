@@ -64,7 +64,8 @@ class _FragBatch(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("probes", C.c_uint64), ("hits", C.c_uint64), ("frags_all", C.c_uint64), ("frags_out", C.c_uint64),
                 ("dp_jobs", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_seed", C.c_double), ("ms_dp", C.c_double),
-                ("ms_traceback", C.c_double), ("launches", C.c_uint64)]
+                ("ms_traceback", C.c_double), ("launches", C.c_uint64), ("ext_cells", C.c_uint64), ("ms_ext", C.c_double),
+                ("ext_launches", C.c_uint64)]
 
 
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",

@@ -97,7 +97,7 @@ struct ya_ctx {
     DevBuf    d_jobs, d_jobout, d_tb, d_rows, d_ops_raw, d_ops_cnt, d_ops_off, d_ops_out, d_res;
     PinBuf    h_jobs, h_res, h_ops;
     // timing
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ya_counters ctr{};
 };
 

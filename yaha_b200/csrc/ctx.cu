@@ -64,7 +64,7 @@ static ya_ctx *open_common(int device, const ya_params *params)
         g_open_err = "cudaStreamCreate failed"; delete c; return nullptr;
     }
     c->stream = c->own_stream;
-    for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     return c;
 }
 
@@ -150,7 +150,7 @@ extern "C" void ya_close(ya_ctx *c)
     for (DevBuf *b : bufs) b->release();
     PinBuf *pins[] = {&c->h_stage, &c->h_stage2, &c->h_stage3, &c->h_jobs, &c->h_res, &c->h_ops};
     for (PinBuf *b : pins) b->release();
-    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

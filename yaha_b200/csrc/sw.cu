@@ -516,6 +516,7 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, De
         ya_op *out = ops_raw + J.ops_off;
         int y = o.maxi, x = o.maxj;
         int prev = -1; uint32_t run = 0;
+        size_t cachedIdx = (size_t)-1; uint32_t cachedWord = 0;
         int guard = (int)J.qLen + (int)J.rLen + 8;     // a valid walk consumes a row or a column per step
         for (;;) {
             if (--guard < 0 || x < 0 || x > W || y < 0) { n = 0xFFFFFFF0u; prev = -1; break; }   // corrupt back-pointers
@@ -530,7 +531,11 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, De
                 const int C = J.colsPerLane, CP = (C + 3) & ~3;
                 const int s = y + x / C;
                 const uint32_t *w = reinterpret_cast<const uint32_t *>(tb) + J.tb_off;
-                const uint32_t word = w[(size_t)((s - 1) >> 2) * J.stride + (x / C) * CP + (x % C)];
+                // a word holds 4 consecutive macro steps of one column: a run of match/replace steps
+                // (same column, rows y, y-1, ...) is served by one load per 4 rows
+                const size_t widx = (size_t)((s - 1) >> 2) * J.stride + (x / C) * CP + (x % C);
+                if (widx != cachedIdx) { cachedIdx = widx; cachedWord = w[widx]; }
+                const uint32_t word = cachedWord;
                 const uint32_t b = (word >> (8 * (3 - ((s - 1) & 3)))) & 0xFFu;
                 len = (b & 63u) + 1u;
                 if ((b >> 6) == 1u) op = BP_D;
@@ -798,8 +803,11 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         if (!lists[kNumWaveCfgs + k].empty())
             launch_wave_cfg(c, k, false, d_ids + start[kNumWaveCfgs + k], (int)lists[kNumWaveCfgs + k].size(), K);
     }
+    const bool anyPacked = !lists[packedBase + 0].empty() || !lists[packedBase + 1].empty();
+    if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[3], st));
     if (!lists[packedBase + 0].empty()) launch_packed<2, 11, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
     if (!lists[packedBase + 1].empty()) launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
+    if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[4], st));
     if (!lists[2 * kNumWaveCfgs].empty()) {
         int nt = (int)lists[2 * kNumWaveCfgs].size();
         dp_thread_kernel<<<(nt + 63) / 64, 64, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids + start[2 * kNumWaveCfgs], nt,
@@ -839,10 +847,18 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     cudaEventElapsedTime(&ms0, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]);
     c->ctr.ms_dp += ms0; c->ctr.ms_traceback += ms1;
+    if (anyPacked) {
+        float ms2 = 0;
+        cudaEventElapsedTime(&ms2, c->ev[3], c->ev[4]);
+        c->ctr.ms_ext += ms2;
+        c->ctr.ext_launches += (lists[packedBase + 0].empty() ? 0 : 1) + (lists[packedBase + 1].empty() ? 0 : 1);
+    }
     for (int k = 0; k < n_live; k++) {
         if (hout[k].n_ops >= 0xFFFFFFF0u) return ya_fail(c, YA_E_STATE, "internal: traceback walked off the band (corrupt back-pointers)");
         res[live_of[k]] = hres[k];
-        c->ctr.dp_cells += ((uint64_t)hout[k].cells_hi << 32) | hout[k].cells_lo;
+        const uint64_t jc = ((uint64_t)hout[k].cells_hi << 32) | hout[k].cells_lo;
+        c->ctr.dp_cells += jc;
+        if (hj[k].layout == 2) c->ctr.ext_cells += jc;
         if (hres[k].ops_n > hj[k].ops_cap) return ya_fail(c, YA_E_STATE, "internal: op scratch overflow");
     }
     if (ops_needed) *ops_needed = total_ops;
