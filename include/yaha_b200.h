@@ -127,7 +127,7 @@ typedef struct ya_counters {
     double   ms_dp;        /* device time of stage 3 fill kernels                          */
     double   ms_traceback; /* device time of stage 3 traceback kernels                     */
     uint64_t launches;     /* kernels launched by this library                             */
-    uint64_t ext_cells;    /* cells of the X-drop extension jobs run by dp_ext_packed_kernel  */
+    uint64_t ext_cells;    /* cells of the bulk (>= 4096 jobs) dp_ext_packed_kernel launches */
     double   ms_ext;       /* device time of dp_ext_packed_kernel launches (CUDA events)      */
     uint64_t ext_launches; /* number of dp_ext_packed_kernel launches in ms_ext               */
 } ya_counters;

@@ -847,7 +847,11 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     cudaEventElapsedTime(&ms0, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]);
     c->ctr.ms_dp += ms0; c->ctr.ms_traceback += ms1;
-    if (anyPacked) {
+    // Roofline accounting covers the bulk launches only (>= 4096 jobs): the demand-driven careful
+    // re-extension rounds launch a handful of jobs and are bound by one job's serial latency.
+    const size_t nPackedJobs = lists[packedBase + 0].size() + lists[packedBase + 1].size();
+    const bool bulkPacked = nPackedJobs >= 4096;
+    if (bulkPacked) {
         float ms2 = 0;
         cudaEventElapsedTime(&ms2, c->ev[3], c->ev[4]);
         c->ctr.ms_ext += ms2;
@@ -858,7 +862,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         res[live_of[k]] = hres[k];
         const uint64_t jc = ((uint64_t)hout[k].cells_hi << 32) | hout[k].cells_lo;
         c->ctr.dp_cells += jc;
-        if (hj[k].layout == 2) c->ctr.ext_cells += jc;
+        if (hj[k].layout == 2 && bulkPacked) c->ctr.ext_cells += jc;
         if (hres[k].ops_n > hj[k].ops_cap) return ya_fail(c, YA_E_STATE, "internal: op scratch overflow");
     }
     if (ops_needed) *ops_needed = total_ops;
