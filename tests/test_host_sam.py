@@ -56,3 +56,16 @@ def test_sam_identical_on_10k_long_reads(tmp_path):
     p = subprocess.run([HOST, "-x", idx_path, "-q", d + "/reads.fa", "-osh", d + "/m.sam", "-t", "4"], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr[-2000:]
     assert H.sam_lines(open(d + "/m.sam").read()) == H.sam_lines(open(d + "/r.sam").read())
+
+
+def test_reference_host_through_the_abi(small, tmp_path):
+    """Mode A: the UNMODIFIED reference host, its hot-path seams redirected with
+    -Wl,--wrap to libyaha_b200.so (oracle/modeA_shim.c), must write the stock binary's SAM."""
+    modea = os.path.join(S.ORACLE_DIR, "_ref", "yaha_modeA")
+    if not os.path.exists(modea):
+        pytest.skip("oracle/_ref/yaha_modeA not present")
+    out = str(tmp_path / "a.sam")
+    p = subprocess.run([modea, "-x", small.idx_path, "-q", os.path.join(small.dir, "reads.fa"), "-osh", out, "-t", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert H.sam_lines(open(out).read()) == H.expected(small, "out_bw5.sam.gz")
