@@ -32,7 +32,8 @@ def test_host_logic_reproduces_reference_sam(small, mock_host, tmp_path, golden,
 
 def test_output_order_independent_of_threads_and_batch(small, mock_host, tmp_path):
     want = H.expected(small, "out_bw5.sam.gz")
-    for k, extra in enumerate((["-t", "3"], ["-batch", "37"], ["-t", "2", "-batch", "100"])):
+    for k, extra in enumerate((["-t", "3"], ["-batch", "37"], ["-t", "2", "-batch", "100"], ["-t", "4", "-gpus", "2", "-batch", "50", "-pipes", "2"],
+                               ["-t", "3", "-pipes", "3", "-batch", "64"])):
         out = str(tmp_path / f"o{k}.sam")
         cmd = [mock_host, "-x", small.idx_path, "-q", os.path.join(small.dir, "reads.fa"), "-osh", out] + extra
         subprocess.run(cmd, check=True, capture_output=True, timeout=600)
