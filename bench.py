@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=5000, help="reads per device batch")
+    ap.add_argument("--batch", type=int, default=10000, help="reads per device batch")
     ap.add_argument("--pipes", type=int, default=2, help="concurrent batch pipelines per GPU")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -171,8 +171,8 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
     std::vector<Frag> &frags = rc.frags[rev];
     const std::vector<uint32_t> &reg = rc.region[rev];
     const int n = (int)frags.size();
-    std::vector<char> coverage, used;
-    std::vector<FNode> nodes;
+    static thread_local std::vector<char> coverage, used;      // per-thread scratch, reused across reads
+    static thread_local std::vector<FNode> nodes;
     int i = 0;
     while (i < n) {
         int j = i;

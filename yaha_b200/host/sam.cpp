@@ -67,10 +67,11 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
     const std::string &q = rc.chars(c.reversed());
     const int L = rc.read->len();
     if (A.outputSAM) {
+        o.reserve(o.size() + 2 * (size_t)L + 512);
         o += rc.read->id;
-        appendf(o, "\t%d\t", c.reversed() ? 0x10 : 0x00);
+        o += c.reversed() ? "\t16\t" : "\t0\t";
         o += BS.name;
-        appendf(o, "\t%u\t%u\t", sStart + 1, (unsigned)c.mapQuality);
+        o += '\t'; appendUInt(o, sStart + 1); o += '\t'; appendUInt(o, (unsigned)c.mapQuality); o += '\t';
         OpList &list = c.ops;
         int clip = L - 1 - f0.endQueryOff;
         if (clip > 0) list.pushBack(A.hardClip ? 'H' : 'S', clip);
@@ -94,9 +95,9 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
             else if (qe >= qs) o.append(ql, (size_t)qs, (size_t)(qe - qs + 1));
         } else o += '*';
         o += '\t';
-        appendf(o, "AS:i:%d\t", (int)c.totScore);
-        appendf(o, "NM:i:%d\t", (int)c.gapBases + (int)c.mismatchedBases);
-        o += "MD:Z:";
+        o += "AS:i:"; appendInt(o, (int)c.totScore);
+        o += "\tNM:i:"; appendInt(o, (int)c.gapBases + (int)c.mismatchedBases);
+        o += "\tMD:Z:";
         matches = 0;
         char prev = 'U';
         uint32_t ro = f0.startRefOff;
@@ -122,9 +123,9 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
         if (matches > 0) appendInt(o, matches);
         appendf(o, "\tYF:H:%02X", (unsigned)c.status);
         if (A.OQC) {
-            appendf(o, "\tYI:i:%d", (int)c.matchedPrimary);
-            appendf(o, "\tYP:i:%d", rc.primaryCount);
-            if (c.is(kPrimary)) appendf(o, "\tYS:i:%d", (int)c.numSecondaries);
+            o += "\tYI:i:"; appendInt(o, (int)c.matchedPrimary);
+            o += "\tYP:i:"; appendInt(o, rc.primaryCount);
+            if (c.is(kPrimary)) { o += "\tYS:i:"; appendInt(o, (int)c.numSecondaries); }
         }
         o += '\n';
     }
