@@ -675,9 +675,16 @@ static void launch_packed(ya_ctx *c, const uint32_t *d_ids, int n, const DpConst
     c->ctr.launches++;
 }
 
+#include <chrono>
+static double g_prof_sw[6];
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct SwProfPrinter { ~SwProfPrinter() { if (getenv("YA_PROF")) fprintf(stderr, "ya_sw_batch wall s: prep %.4f alloc+h2d %.4f launch..scan-sync %.4f compact+d2h-sync %.4f post %.4f\n",
+    g_prof_sw[0], g_prof_sw[1], g_prof_sw[2], g_prof_sw[3], g_prof_sw[4]); } } g_sw_prof_printer;
+
 extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res,
                            ya_op *ops, size_t ops_cap, size_t *ops_needed)
 {
+    double tp0 = now_s();
     if (!c || n < 0 || (n && (!jobs || !res))) return YA_E_ARG;
     if (ops_needed) *ops_needed = 0;
     if (n == 0) return YA_OK;
@@ -692,11 +699,16 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     YA_CUDA(c, c->h_jobs.reserve((size_t)n * sizeof(DevJob)));
     DevJob *hj = c->h_jobs.as<DevJob>();
     // job id lists per kernel class: [0..kNumWaveCfgs) ext, [kNumWaveCfgs..2k) banded, last = thread
-    std::vector<std::vector<uint32_t>> lists(2 * kNumWaveCfgs + 1 + kNumPackedCfgs);
+    // (persistent per-context vectors: no allocation on the steady-state path)
+    const int nClasses = 2 * kNumWaveCfgs + 1 + kNumPackedCfgs;
+    std::vector<std::vector<uint32_t>> &lists = c->sw_lists;
+    if ((int)lists.size() != nClasses) lists.assign((size_t)nClasses, std::vector<uint32_t>());
+    for (auto &v : lists) v.clear();
     const int packedBase = 2 * kNumWaveCfgs + 1;
     uint64_t tb_cells = 0, rows_ints = 0, ops_slots = 0;
     int n_live = 0;
-    std::vector<uint32_t> live_of(n);     // device job index -> caller job index
+    std::vector<uint32_t> &live_of = c->sw_live_of;   // device job index -> caller job index
+    if ((int)live_of.size() < n) live_of.resize((size_t)n);
     for (int i = 0; i < n; i++) {
         const ya_dp_job &j = jobs[i];
         res[i].score = 0; res[i].addedQLen = 0; res[i].addedRLen = 0; res[i].ops_off = 0; res[i].ops_n = 0;
@@ -772,6 +784,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     }
     c->ctr.dp_jobs += (uint64_t)n;
     if (n_live == 0) return YA_OK;
+    double tp1 = now_s(); g_prof_sw[0] += tp1 - tp0;
 
     YA_CUDA(c, c->d_jobs.reserve((size_t)n_live * sizeof(DevJob)));
     YA_CUDA(c, c->d_jobout.reserve((size_t)n_live * sizeof(DevJobOut)));
@@ -790,13 +803,14 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return hj[a].qLen != hj[b].qLen ? hj[a].qLen > hj[b].qLen : a < b; });
     }
     // id lists
-    std::vector<uint32_t> flat; flat.reserve(n_live);
+    std::vector<uint32_t> &flat = c->sw_flat; flat.clear(); flat.reserve(n_live);
     std::vector<size_t> start(lists.size());
     for (size_t k = 0; k < lists.size(); k++) { start[k] = flat.size(); flat.insert(flat.end(), lists[k].begin(), lists[k].end()); }
     uint32_t *d_ids = c->d_misc.as<uint32_t>();
     YA_CUDA(c, cudaMemcpyAsync(d_ids, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, st));
 
     DpConst K{P.GOCost, P.GECost, P.RCost, P.MScore, P.XCutoff, P.maxIntron, P.maxGap, P.bandWidth};
+    double tp2 = now_s(); g_prof_sw[1] += tp2 - tp1;
     YA_CUDA(c, cudaEventRecord(c->ev[0], st));
     for (int k = 0; k < kNumWaveCfgs; k++) {
         if (!lists[k].empty()) launch_wave_cfg(c, k, true, d_ids + start[k], (int)lists[k].size(), K);
@@ -829,6 +843,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     uint32_t total_ops = 0;
     YA_CUDA(c, cudaMemcpyAsync(&total_ops, d_tot, 4, cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaStreamSynchronize(st));
+    double tp3 = now_s(); g_prof_sw[2] += tp3 - tp2;
     YA_CUDA(c, c->d_ops_out.reserve((size_t)total_ops * sizeof(ya_op) + 64));
     compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
                                             c->d_res.as<ya_dp_result>(), c->d_ops_raw.as<ya_op>(), c->d_ops_out.as<ya_op>());
@@ -843,6 +858,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaStreamSynchronize(st));
     YA_CUDA(c, cudaGetLastError());
+    double tp4 = now_s(); g_prof_sw[3] += tp4 - tp3;
     float ms0 = 0, ms1 = 0;
     cudaEventElapsedTime(&ms0, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]);
@@ -866,6 +882,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         if (hres[k].ops_n > hj[k].ops_cap) return ya_fail(c, YA_E_STATE, "internal: op scratch overflow");
     }
     if (ops_needed) *ops_needed = total_ops;
+    g_prof_sw[4] += now_s() - tp4;
     if (!fits) return ya_fail(c, YA_E_CAPACITY, "op output buffer too small");
     return YA_OK;
 }

@@ -220,18 +220,26 @@ bool QueryReader::next(Read &r)
         }
         if (fail) continue;
         if (n == 0) return false;                    // end of input (or an empty record, as in the reference)
-        r.fcode.resize((size_t)n); r.rcode.resize((size_t)n); r.rev.resize((size_t)n);
+        // forward codes now (the device upload needs them); the reverse-complement strand is derived
+        // later, in parallel, by the worker that owns the read (Read::finish)
+        r.fcode.resize((size_t)n);
         const unsigned char *src = (const unsigned char *)r.fwd.data();
-        uint8_t *fc = r.fcode.data(), *rcd = r.rcode.data() + n - 1;
-        char *rv = &r.rev[0] + n - 1;
-        for (int i = 0; i < n; i++) {
-            const uint8_t code = codeTab[src[i]];
-            fc[i] = code;
-            const uint8_t cc = kCompCode[code];
-            *rcd-- = cc;
-            *rv-- = kCharOfCode[cc];
-        }
+        uint8_t *fc = r.fcode.data();
+        for (int i = 0; i < n; i++) fc[i] = codeTab[src[i]];
+        r.rcode.clear(); r.rev.clear();
         return true;
+    }
+}
+
+void Read::finish()                                 // Query.c:164-167
+{
+    const int n = (int)fcode.size();
+    if ((int)rcode.size() == n) return;
+    rcode.resize((size_t)n); rev.resize((size_t)n);
+    for (int i = 0; i < n; i++) {
+        const uint8_t cc = kCompCode[fcode[(size_t)i]];
+        rcode[(size_t)(n - 1 - i)] = cc;
+        rev[(size_t)(n - 1 - i)] = kCharOfCode[cc];
     }
 }
 

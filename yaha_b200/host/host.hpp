@@ -78,6 +78,7 @@ struct Read {
     std::string qual;                // FASTQ only
     std::vector<uint8_t> fcode, rcode;
     int len() const { return (int)fwd.size(); }
+    void finish();                   // derive rcode / rev from fcode (idempotent)
 };
 struct QueryReader {                 // readNextQuery, Query.c:102-228
     struct Buf;
