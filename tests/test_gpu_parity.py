@@ -59,10 +59,14 @@ def test_dp_matches_reference_calls(small, aligner, bw, gap, mode, monkeypatch):
     assert aligner.counters().dp_cells == cells
 
 
-def test_seed_frags_match_reference_and_oracle(small, aligner):
+@pytest.mark.parametrize("sorter", ["segmented", "radix"])
+def test_seed_frags_match_reference_and_oracle(small, aligner, sorter, monkeypatch):
     """Stage 1+2: per strand, surviving fragments (values and order), fragCount, totalCount and
     region ids equal the oracle; the oracle equals the reference dump (test_oracle_golden)."""
+    if sorter == "radix":
+        monkeypatch.setenv("YA_SEED_RADIX", "1")      # force the global LSD radix sort instead of the shared-memory sort
     aligner.set_params(yaha_b200.Params.defaults(word_len=11))
+    aligner.upload_read_list(small.fwd)
     strands, frags, region = aligner.seed_frags()
     p = S.default_params(word_len=11)
     ref_frags = {}

@@ -98,6 +98,7 @@ struct ya_ctx {
     PinBuf    h_jobs, h_res, h_ops;
     std::vector<std::vector<uint32_t>> sw_lists;      // ya_sw_batch host scratch (reused)
     std::vector<uint32_t> sw_live_of, sw_flat;
+    std::vector<uint32_t> seed_small, seed_big;       // ya_seed_frags host scratch (segment id lists)
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ya_counters ctr{};

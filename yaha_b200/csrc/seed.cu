@@ -21,14 +21,19 @@
 #define QO_MASK   0x7FFFu
 
 // ------------------------------------------------------------------------------------------
-// K1: one warp per segment, lanes stride over query offsets.
+// K1: one warp per segment.  Each lane takes 4 consecutive query offsets per iteration: 18 code
+// bytes give 4 rolling hashes (Query.c:233-244,409-411), and all 8 starting-offset gathers of the
+// lane are in flight before the first is consumed (the table is 4 GiB: every probe is a DRAM
+// sector miss, so memory-level parallelism is what sets the rate).
 // ------------------------------------------------------------------------------------------
-__global__ void seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev,
-                                  const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ seg_probe_off,
-                                  int seg0, int n_seg, int K, uint32_t maxHits,
-                                  const uint32_t *__restrict__ so, const uint32_t *__restrict__ roa, uint64_t n_roa,
-                                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ soff,
-                                  uint32_t *__restrict__ seg_total, uint32_t *__restrict__ seg_eff)
+#define K1_Q 4
+__global__ void __launch_bounds__(128)
+seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev,
+                  const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ seg_probe_off,
+                  int seg0, int n_seg, int K, uint32_t maxHits,
+                  const uint32_t *__restrict__ so, const uint32_t *__restrict__ roa, uint64_t n_roa,
+                  uint32_t *__restrict__ cnt, uint32_t *__restrict__ soff,
+                  uint32_t *__restrict__ seg_total, uint32_t *__restrict__ seg_eff)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -39,39 +44,65 @@ __global__ void seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t
     const int L = (int)(read_off[r + 1] - base);
     const uint8_t *codes = ((seg & 1) ? rev : fwd) + base;
     const uint32_t p0 = seg_probe_off[warp];
-    const int m = L - K + 1;
+    const int m = L - K + 1;                                     // number of probes (Query.c:341)
     const uint32_t mask = 0xFFFFFFFFu >> (32 - 2 * K);
     uint32_t tot = 0, eff = 0;
-    for (int qo = lane; qo < m; qo += 32) {
-        uint32_t h = 0, bad = 0;
-        for (int k = 0; k < K; k++) {
-            uint32_t c = codes[qo + k];
-            bad |= c;                                   // any code > 3 sets bit 2 or 3
-            h = (h << 2) | (c & 3);
+    for (int q0 = lane * K1_Q; q0 < m; q0 += 32 * K1_Q) {
+        // rolling hashes of the K-mers starting at q0 .. q0+3
+        uint32_t h = 0;
+        uint32_t badmask = 0;                                    // bit j set: code at q0+j is not ACGT
+        uint32_t hs[K1_Q];
+        bool ok[K1_Q];
+        for (int j = 0; j < K - 1; j++) {
+            const int pos = q0 + j;
+            const uint32_t cde = (pos < L) ? codes[pos] : 4u;
+            if (cde > 3) badmask |= 1u << j;
+            h = (h << 2) | (cde & 3u);
         }
-        h &= mask;
-        uint32_t c_eff = 0, s = 0;
-        if (bad < 4) {
-            s = so[h];
-            uint32_t c = so[h + 1] - s;                 // Query.c:391
-            if (c <= maxHits && c > 0) {                // Query.c:392
-                tot += c;
-                c_eff = c;
-                // QueryMatch.c:62-67: if every hit of this k-mer lies below qo the reference keeps
-                // reading past the k-mer's list (no newCount < count guard).  Count the extra reads.
-                if (roa[s + c - 1] < (uint32_t)qo) {
-                    uint64_t at = (uint64_t)s + c;
-                    while (at < n_roa) {
-                        uint32_t x = roa[at++];
-                        c_eff++;
-                        if (x >= (uint32_t)qo) break;
-                    }
+#pragma unroll
+        for (int t = 0; t < K1_Q; t++) {
+            const int pos = q0 + K - 1 + t;
+            const uint32_t cde = (pos < L) ? codes[pos] : 4u;
+            if (cde > 3) badmask |= 1u << (K - 1 + t);
+            h = ((h << 2) | (cde & 3u)) & mask;
+            hs[t] = h;
+        }
+        const uint32_t win = (K >= 32) ? 0xFFFFFFFFu : ((1u << K) - 1u);
+#pragma unroll
+        for (int t = 0; t < K1_Q; t++) ok[t] = (q0 + t < m) && ((badmask >> t) & win) == 0;
+        uint32_t s_lo[K1_Q], s_hi[K1_Q];
+#pragma unroll
+        for (int t = 0; t < K1_Q; t++) {                         // all gathers issued before any use
+            s_lo[t] = ok[t] ? __ldg(so + hs[t]) : 0u;
+            s_hi[t] = ok[t] ? __ldg(so + hs[t] + 1) : 0u;
+        }
+        uint32_t c_eff[K1_Q], lastHit[K1_Q];
+#pragma unroll
+        for (int t = 0; t < K1_Q; t++) {
+            const uint32_t c = s_hi[t] - s_lo[t];                // Query.c:391
+            c_eff[t] = (ok[t] && c <= maxHits) ? c : 0u;         // Query.c:392
+            lastHit[t] = c_eff[t] ? __ldg(roa + s_lo[t] + c_eff[t] - 1) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int t = 0; t < K1_Q; t++) {
+            const int qo = q0 + t;
+            if (qo >= m) break;
+            tot += c_eff[t];
+            uint32_t ce = c_eff[t];
+            // QueryMatch.c:62-67: if every hit of this k-mer lies below qo the reference keeps
+            // reading past the k-mer's list (no newCount < count guard).  Count the extra reads.
+            if (ce && lastHit[t] < (uint32_t)qo) {
+                uint64_t at = (uint64_t)s_lo[t] + ce;
+                while (at < n_roa) {
+                    uint32_t x = roa[at++];
+                    ce++;
+                    if (x >= (uint32_t)qo) break;
                 }
             }
+            cnt[p0 + qo] = ce;
+            soff[p0 + qo] = s_lo[t];
+            eff += ce;
         }
-        cnt[p0 + qo] = c_eff;
-        soff[p0 + qo] = s;
-        eff += c_eff;
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -82,33 +113,78 @@ __global__ void seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------
-// K2a: one thread per probe writes the keys of its hits (in ROA order = ascending offset).
-// Keys of one segment are generated in ascending qo order, which the stable sort preserves.
+// K2a: one warp per segment writes the keys of its probes' hits (ROA order = ascending offset).
+// Keys of one segment are generated in ascending qo order.
 // ------------------------------------------------------------------------------------------
-__global__ void expand_hits_kernel(const uint32_t *__restrict__ seg_probe_off, int n_seg, int seg_local0,
-                                   const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ soff,
-                                   const uint32_t *__restrict__ hit_off, uint32_t probe0, uint32_t n_probes,
-                                   const uint32_t *__restrict__ roa, uint64_t *__restrict__ keys)
+__global__ void __launch_bounds__(128)
+expand_hits_kernel(const uint32_t *__restrict__ seg_probe_off, int n_seg, int seg_local0,
+                   const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ soff,
+                   const uint32_t *__restrict__ hit_off, uint32_t probe0,
+                   const uint32_t *__restrict__ roa, uint64_t *__restrict__ keys)
 {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_probes) return;
-    uint32_t c = cnt[probe0 + p];
-    if (c == 0) return;
-    // segment of this probe: binary search in the chunk's probe offsets
-    int lo = 0, hi = n_seg;
-    uint32_t gp = probe0 + p;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (seg_probe_off[seg_local0 + mid] <= gp) lo = mid; else hi = mid;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_seg) return;
+    const uint32_t pa = seg_probe_off[seg_local0 + warp], pb = seg_probe_off[seg_local0 + warp + 1];
+    const uint64_t hi_bits = (uint64_t)warp << SEG_SHIFT;
+    for (uint32_t gp = pa + lane; gp < pb; gp += 32) {
+        const uint32_t c = cnt[gp];
+        if (c == 0) continue;
+        const uint32_t qo = gp - pa;
+        const uint32_t *list = roa + soff[gp];
+        uint64_t *out = keys + hit_off[gp - probe0];
+        for (uint32_t t = 0; t < c; t++) {
+            const uint32_t diag = list[t] - qo;                  // wraps for roff < qo (QueryHeap.inl:70-73)
+            out[t] = hi_bits | ((uint64_t)diag << QO_BITS) | qo;
+        }
     }
-    uint32_t qo = gp - seg_probe_off[seg_local0 + lo];
-    uint64_t hi_bits = (uint64_t)lo << SEG_SHIFT;
-    const uint32_t *list = roa + soff[gp];
-    uint64_t *out = keys + hit_off[p];
-    for (uint32_t t = 0; t < c; t++) {
-        uint32_t diag = list[t] - qo;                   // wraps for roff < qo (QueryHeap.inl:70-73)
-        out[t] = hi_bits | ((uint64_t)diag << QO_BITS) | qo;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2b (common case): segmented sort in shared memory -- one warp (<= 512 keys) or one block
+// (<= 8192 keys) per segment, bitonic network on the full 64-bit key (keys are distinct, so no
+// stability is needed).  One HBM read and one write per key instead of one per radix pass.
+// ------------------------------------------------------------------------------------------
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+seg_sort_kernel(uint64_t *__restrict__ keys, const uint32_t *__restrict__ seg_key_off, const uint32_t *__restrict__ seg_ids,
+                int n_list)
+{
+    extern __shared__ uint64_t sh[];
+    const int item = blockIdx.x;
+    if (item >= n_list) return;
+    const uint32_t seg = seg_ids[item];
+    const uint32_t a = seg_key_off[seg], b = seg_key_off[seg + 1];
+    const int n = (int)(b - a);
+    if (n <= 1) return;
+    int P = 1; while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += THREADS) sh[i] = (i < n) ? keys[a + i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < P; i += THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t x = sh[i], y = sh[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { sh[i] = y; sh[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
     }
+    for (int i = threadIdx.x; i < n; i += THREADS) keys[a + i] = sh[i];
+}
+
+__global__ void seg_key_off_kernel(const uint32_t *__restrict__ seg_probe_off, int seg_local0, int n_seg, uint32_t probe0,
+                                   const uint32_t *__restrict__ hit_off, uint32_t n_probes, uint32_t n_keys,
+                                   uint32_t *__restrict__ seg_key_off)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_seg) return;
+    if (s == n_seg) { seg_key_off[s] = n_keys; return; }
+    const uint32_t p = seg_probe_off[seg_local0 + s] - probe0;
+    seg_key_off[s] = (p < n_probes) ? hit_off[p] : n_keys;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -390,12 +466,42 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             int rc = ya_exclusive_scan_u32(c, d_cnt + probe0, d_hit_off, cprobes, nullptr);
             if (rc != YA_OK) return rc;
             uint64_t *ka = c->d_keys0.as<uint64_t>(), *kb = c->d_keys1.as<uint64_t>();
-            expand_hits_kernel<<<(cprobes + 255) / 256, 256, 0, st>>>(d_po, cseg, s0, d_cnt, d_soff, d_hit_off,
-                                                                       probe0, cprobes, c->d_roa, ka);
+            expand_hits_kernel<<<(cseg + 3) / 4, 128, 0, st>>>(d_po, cseg, s0, d_cnt, d_soff, d_hit_off, probe0, c->d_roa, ka);
             c->ctr.launches++;
-            int segbits = 1; while ((1 << segbits) < cseg) segbits++;
-            rc = ya_radix_sort_u64(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
-            if (rc != YA_OK) return rc;
+            // sort: segmented shared-memory sort when every segment fits a block, else the global radix sort
+            uint32_t maxSeg = 0;
+            for (int sgi = s0; sgi < s1; sgi++) maxSeg = std::max(maxSeg, h_seg_eff[sgi]);
+            if (maxSeg <= 8192 && !getenv("YA_SEED_RADIX")) {
+                std::vector<uint32_t> &small = c->seed_small, &big = c->seed_big;
+                small.clear(); big.clear();
+                for (int sgi = s0; sgi < s1; sgi++) {
+                    const uint32_t e = h_seg_eff[sgi];
+                    if (e >= 2 && e <= 512) small.push_back((uint32_t)(sgi - s0));
+                    else if (e > 512) big.push_back((uint32_t)(sgi - s0));
+                }
+                YA_CUDA(c, c->d_regstart.reserve(((size_t)cseg + 1) * 4 + (small.size() + big.size()) * 4 + 64));
+                uint32_t *d_sko = c->d_regstart.as<uint32_t>();
+                uint32_t *d_small = d_sko + cseg + 1, *d_big = d_small + small.size();
+                seg_key_off_kernel<<<(cseg + 256) / 256, 256, 0, st>>>(d_po, s0, cseg, probe0, d_hit_off, cprobes, n_keys, d_sko);
+                c->ctr.launches++;
+                if (!small.empty()) {
+                    YA_CUDA(c, cudaMemcpyAsync(d_small, small.data(), small.size() * 4, cudaMemcpyHostToDevice, st));
+                    seg_sort_kernel<512, 32><<<(unsigned)small.size(), 32, 512 * 8, st>>>(ka, d_sko, d_small, (int)small.size());
+                    c->ctr.launches++;
+                }
+                if (!big.empty()) {
+                    static bool attr = false;
+                    if (!attr) { cudaFuncSetAttribute(seg_sort_kernel<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8); attr = true; }
+                    YA_CUDA(c, cudaMemcpyAsync(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice, st));
+                    seg_sort_kernel<8192, 256><<<(unsigned)big.size(), 256, 8192 * 8, st>>>(ka, d_sko, d_big, (int)big.size());
+                    c->ctr.launches++;
+                }
+                YA_CUDA(c, cudaStreamSynchronize(st));              // the id vectors are reused by the next chunk
+            } else {
+                int segbits = 1; while ((1 << segbits) < cseg) segbits++;
+                rc = ya_radix_sort_u64(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
+                if (rc != YA_OK) return rc;
+            }
 
             // fragments
             YA_CUDA(c, c->d_fragflag.reserve((size_t)n_keys * 4));
