@@ -130,6 +130,7 @@ typedef struct ya_counters {
     uint64_t ext_cells;    /* cells of the bulk (>= 4096 jobs) dp_ext_packed_kernel launches */
     double   ms_ext;       /* device time of dp_ext_packed_kernel launches (CUDA events)      */
     uint64_t ext_launches; /* number of dp_ext_packed_kernel launches in ms_ext               */
+    double   ms_lookup;    /* device time of seed_count_kernel (the SO gathers) alone         */
 } ya_counters;
 
 typedef struct ya_ctx ya_ctx;
@@ -203,6 +204,10 @@ int ya_get_counters(ya_ctx *, ya_counters *);
  * *giops_add from a pure dependent-free IADD3 stream, *giops_mix from the add / compare /
  * select / min-max mix of the DP cell (the roofline denominator of the banded-SW kernel). */
 int ya_measure_int32_peak(ya_ctx *, double *giops_add, double *giops_mix);
+
+/* Independent random 4-byte gathers per second over the resident starting-offset table (all SMs, 8 in
+ * flight per thread): the HBM sector-miss rate that bounds the seed lookup (Query.c:391). */
+int ya_measure_gather_peak(ya_ctx *, double *gather_per_s);
 
 #ifdef __cplusplus
 }

@@ -39,6 +39,7 @@ int ya_set_params(ya_ctx *c, const ya_params *p) { c->P = *p; return 0; }
 int ya_set_stream(ya_ctx *c, void *s) { (void)c; (void)s; return 0; }
 int ya_get_counters(ya_ctx *c, ya_counters *o) { *o = c->ctr; memset(&c->ctr, 0, sizeof c->ctr); return 0; }
 int ya_measure_int32_peak(ya_ctx *c, double *a, double *b) { (void)c; *a = *b = 0; return 0; }
+int ya_measure_gather_peak(ya_ctx *c, double *a) { (void)c; *a = 0; return 0; }
 
 int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
 {

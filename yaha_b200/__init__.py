@@ -65,12 +65,12 @@ class Counters(C.Structure):
     _fields_ = [("probes", C.c_uint64), ("hits", C.c_uint64), ("frags_all", C.c_uint64), ("frags_out", C.c_uint64),
                 ("dp_jobs", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_seed", C.c_double), ("ms_dp", C.c_double),
                 ("ms_traceback", C.c_double), ("launches", C.c_uint64), ("ext_cells", C.c_uint64), ("ms_ext", C.c_double),
-                ("ext_launches", C.c_uint64)]
+                ("ext_launches", C.c_uint64), ("ms_lookup", C.c_double)]
 
 
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
            "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_perfect_ext", "ya_get_counters",
-           "ya_measure_int32_peak")
+           "ya_measure_int32_peak", "ya_measure_gather_peak")
 
 _lib = None
 
@@ -107,6 +107,7 @@ def load_library() -> C.CDLL:
     lib.ya_perfect_ext.argtypes = [vp, vp, C.c_int, vp]
     lib.ya_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.ya_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ya_measure_gather_peak.argtypes = [vp, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -239,6 +240,11 @@ class Aligner:
         c = Counters()
         self._check(self.lib.ya_get_counters(self.ctx, C.byref(c)))
         return c
+
+    def gather_peak(self) -> float:
+        g = C.c_double(0)
+        self._check(self.lib.ya_measure_gather_peak(self.ctx, C.byref(g)))
+        return g.value
 
     def int32_peak(self) -> tuple[float, float]:
         a, m = C.c_double(0), C.c_double(0)

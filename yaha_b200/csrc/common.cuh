@@ -83,6 +83,7 @@ struct ya_ctx {
     uint8_t  *d_bases = nullptr; size_t n_base_bytes = 0;
     uint32_t  maxROff = 0;
     bool      owns_index = true;
+    uint32_t *d_lowmask = nullptr;   // 2^20-bit filter: k-mers (hash & 0xFFFFF) occurring in the first 32 K reference bases
     // uploaded read batch
     int       n_reads = 0;
     uint64_t  total_bases = 0;
@@ -126,5 +127,6 @@ int ya_radix_sort_u64(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_
 // seed.cu / sw.cu / peak.cu / index.cu hold the C-ABI entry points declared in yaha_b200.h
 
 // ctx.cu
+int ya_build_lowmask(ya_ctx *c, const uint8_t *host_bases, size_t n_base_bytes);
 ya_ctx *ya_open_common_for_index(int device, const ya_params *params);
 void ya_set_open_error(const std::string &m);

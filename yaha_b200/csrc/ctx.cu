@@ -5,6 +5,7 @@
 // (Query.c:161-168: forward + reverse-complement code buffers) with one batched upload plus
 // a device kernel that derives the reverse-complement strand.
 #include "common.cuh"
+#include <algorithm>
 
 static thread_local std::string g_open_err;
 
@@ -57,6 +58,14 @@ static ya_ctx *open_common(int device, const ya_params *params)
         return nullptr;
     }
     if (cudaSetDevice(device) != cudaSuccess) { g_open_err = "cudaSetDevice failed"; return nullptr; }
+    {
+        // Every hot access of this library is a random gather (starting-offset table, ROA lists,
+        // back-pointer walk): ask L2 to fetch 32 B sectors instead of whole 128 B lines so that a
+        // probe costs one DRAM sector, not four (measured: 4.85 sectors/probe at the default).
+        const char *e = getenv("YA_L2_FETCH");
+        size_t gran = e ? (size_t)atoi(e) : 32;
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
     ya_ctx *c = new ya_ctx();
     c->device = device;
     c->P = *params;
@@ -66,6 +75,29 @@ static ya_ctx *open_common(int device, const ya_params *params)
     c->stream = c->own_stream;
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     return c;
+}
+
+// The over-read quirk of QueryMatch.c:62-67 can only trigger for a k-mer whose LAST occurrence lies
+// below the query offset, i.e. inside the first 32 767 reference bases.  A 2^20-bit filter of the
+// k-mers that occur there lets the seed kernel skip the extra ROA gather for everything else.
+#define YA_LOWMASK_WORDS (1u << 15)
+int ya_build_lowmask(ya_ctx *c, const uint8_t *bases, size_t n_base_bytes)
+{
+    std::vector<uint32_t> m(YA_LOWMASK_WORDS, 0u);
+    const int K = c->P.wordLen;
+    const uint32_t mask = 0xFFFFFFFFu >> (32 - 2 * K);
+    const uint64_t limit = std::min<uint64_t>((uint64_t)n_base_bytes * 2, (uint64_t)32768 + K);
+    uint32_t h = 0; int good = 0;
+    for (uint64_t pos = 0; pos < limit; pos++) {
+        const uint8_t b = bases[pos >> 1];
+        const uint32_t code = (pos & 1) ? (b & 15u) : (b >> 4);
+        if (code > 3) { good = 0; h = 0; continue; }
+        h = ((h << 2) | code) & mask;
+        if (++good >= K) m[(h & 0xFFFFFu) >> 5] |= 1u << (h & 31u);
+    }
+    if (!c->d_lowmask && cudaMalloc(&c->d_lowmask, YA_LOWMASK_WORDS * 4) != cudaSuccess) return YA_E_CUDA;
+    if (cudaMemcpy(c->d_lowmask, m.data(), YA_LOWMASK_WORDS * 4, cudaMemcpyHostToDevice) != cudaSuccess) return YA_E_CUDA;
+    return YA_OK;
 }
 
 ya_ctx *ya_open_common_for_index(int device, const ya_params *params) { return open_common(device, params); }
@@ -97,6 +129,7 @@ extern "C" ya_ctx *ya_open(int device, const ya_params *params,
         g_open_err = std::string("cudaMemcpy(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
     }
     c->n_so = n_so; c->n_roa = n_roa; c->n_base_bytes = n_base_bytes; c->maxROff = maxROff;
+    if (ya_build_lowmask(c, bases, n_base_bytes) != YA_OK) { g_open_err = "cudaMalloc(lowmask) failed"; ya_close(c); return nullptr; }
     return c;
 }
 
@@ -119,6 +152,10 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
         g_open_err = std::string("cudaMemcpyPeer(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
     }
     c->n_so = src->n_so; c->n_roa = src->n_roa; c->n_base_bytes = src->n_base_bytes; c->maxROff = src->maxROff;
+    if (cudaMalloc(&c->d_lowmask, YA_LOWMASK_WORDS * 4) != cudaSuccess ||
+        cudaMemcpyPeer(c->d_lowmask, device, src->d_lowmask, src->device, YA_LOWMASK_WORDS * 4) != cudaSuccess) {
+        g_open_err = "lowmask peer copy failed"; ya_close(c); return nullptr;
+    }
     return c;
 }
 
@@ -127,7 +164,7 @@ extern "C" ya_ctx *ya_open_shared(const ya_ctx *src)
     if (!src) { g_open_err = "ya_open_shared: null source"; return nullptr; }
     ya_ctx *c = open_common(src->device, &src->P);
     if (!c) return nullptr;
-    c->d_so = src->d_so; c->d_roa = src->d_roa; c->d_bases = src->d_bases;
+    c->d_so = src->d_so; c->d_roa = src->d_roa; c->d_bases = src->d_bases; c->d_lowmask = src->d_lowmask;
     c->n_so = src->n_so; c->n_roa = src->n_roa; c->n_base_bytes = src->n_base_bytes; c->maxROff = src->maxROff;
     c->owns_index = false;
     return c;
@@ -141,6 +178,7 @@ extern "C" void ya_close(ya_ctx *c)
         if (c->d_so) cudaFree(c->d_so);
         if (c->d_roa) cudaFree(c->d_roa);
         if (c->d_bases) cudaFree(c->d_bases);
+        if (c->d_lowmask) cudaFree(c->d_lowmask);
     }
     DevBuf *bufs[] = {&c->d_codes_fwd, &c->d_codes_rev, &c->d_read_off, &c->d_seg_probe_off, &c->d_cnt, &c->d_soff,
                       &c->d_hit_off, &c->d_keys0, &c->d_keys1, &c->d_scan_tmp, &c->d_hist, &c->d_fragflag, &c->d_fragidx,

@@ -108,6 +108,7 @@ extern "C" ya_ctx *ya_open_build(int device, const ya_params *params, const uint
     if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
         return fail("index build: kernel failure");
     c->n_roa = total;
+    if (ya_build_lowmask(c, bases, n_base_bytes) != YA_OK) return fail("cudaMalloc(lowmask) failed");
     c->d_keys0.release(); c->d_keys1.release();
     return c;
 }

@@ -65,3 +65,47 @@ extern "C" int ya_measure_int32_peak(ya_ctx *c, double *giops_add, double *giops
     YA_CUDA(c, cudaGetLastError());
     return YA_OK;
 }
+
+// Random 4-byte gathers over the resident starting-offset table (4 GiB at K=15): the rate at which
+// this GPU's HBM serves independent sector misses, which -- not streaming bandwidth -- bounds the
+// seed lookup.  8 independent gathers in flight per thread, all SMs.
+__global__ void gather_peak_kernel(const uint32_t *__restrict__ table, uint64_t n_words, uint32_t *out, uint32_t seed, int iters)
+{
+    uint32_t x = seed ^ (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; i++) {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x = x * 1664525u + 1013904223u;
+            uint64_t idx = ((uint64_t)x * n_words) >> 32;
+            asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v[k]) : "l"(table + idx));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc += v[k];
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+extern "C" int ya_measure_gather_peak(ya_ctx *c, double *gather_per_s)
+{
+    if (!c || !gather_per_s) return YA_E_ARG;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    YA_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    YA_CUDA(c, c->d_misc.reserve(256));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 64;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        YA_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        gather_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->d_so, (uint64_t)c->n_so, c->d_misc.as<uint32_t>(), 77u + rep, iters);
+        YA_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        YA_CUDA(c, cudaEventSynchronize(c->ev[1]));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        if (rep > 0 && ms < best) best = ms;
+        c->ctr.launches++;
+    }
+    *gather_per_s = (double)threads * blocks * iters * 8 / (best * 1e-3);
+    YA_CUDA(c, cudaGetLastError());
+    return YA_OK;
+}

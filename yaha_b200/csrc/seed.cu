@@ -27,11 +27,20 @@
 // sector miss, so memory-level parallelism is what sets the rate).
 // ------------------------------------------------------------------------------------------
 #define K1_Q 4
+// Random 4-byte gather with the smallest L2 prefetch size PTX offers (64 B): the default on this part
+// fills a whole 128 B line per miss, which quadruples the DRAM traffic of a one-word probe.
+__device__ __forceinline__ uint32_t gather_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::64B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
 __global__ void __launch_bounds__(128)
 seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev,
                   const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ seg_probe_off,
                   int seg0, int n_seg, int K, uint32_t maxHits,
                   const uint32_t *__restrict__ so, const uint32_t *__restrict__ roa, uint64_t n_roa,
+                  const uint32_t *__restrict__ lowmask,
                   uint32_t *__restrict__ cnt, uint32_t *__restrict__ soff,
                   uint32_t *__restrict__ seg_total, uint32_t *__restrict__ seg_eff)
 {
@@ -73,15 +82,17 @@ seed_count_kernel(const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ r
         uint32_t s_lo[K1_Q], s_hi[K1_Q];
 #pragma unroll
         for (int t = 0; t < K1_Q; t++) {                         // all gathers issued before any use
-            s_lo[t] = ok[t] ? __ldg(so + hs[t]) : 0u;
-            s_hi[t] = ok[t] ? __ldg(so + hs[t] + 1) : 0u;
+            s_lo[t] = ok[t] ? gather_u32(so + hs[t]) : 0u;
+            s_hi[t] = ok[t] ? gather_u32(so + hs[t] + 1) : 0u;
         }
         uint32_t c_eff[K1_Q], lastHit[K1_Q];
 #pragma unroll
         for (int t = 0; t < K1_Q; t++) {
             const uint32_t c = s_hi[t] - s_lo[t];                // Query.c:391
             c_eff[t] = (ok[t] && c <= maxHits) ? c : 0u;         // Query.c:392
-            lastHit[t] = c_eff[t] ? __ldg(roa + s_lo[t] + c_eff[t] - 1) : 0xFFFFFFFFu;
+            // only k-mers that occur in the first 32 K reference bases can have all hits below qo
+            const bool maybeLow = c_eff[t] && ((__ldg(lowmask + ((hs[t] & 0xFFFFFu) >> 5)) >> (hs[t] & 31u)) & 1u);
+            lastHit[t] = maybeLow ? gather_u32(roa + s_lo[t] + c_eff[t] - 1) : 0xFFFFFFFFu;
         }
 #pragma unroll
         for (int t = 0; t < K1_Q; t++) {
@@ -428,10 +439,12 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     {
         int threads = 128, warps_per_block = threads / 32;
         int blocks = (n_seg + warps_per_block - 1) / warps_per_block;
+        YA_CUDA(c, cudaEventRecord(c->ev[3], st));
         seed_count_kernel<<<blocks, threads, 0, st>>>(c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
                                                      c->d_read_off.as<uint64_t>(), d_po, 0, n_seg, K,
-                                                     (uint32_t)c->P.maxHits, c->d_so, c->d_roa, (uint64_t)c->n_roa,
+                                                     (uint32_t)c->P.maxHits, c->d_so, c->d_roa, (uint64_t)c->n_roa, c->d_lowmask,
                                                      d_cnt, d_soff, d_seg_total, d_seg_eff);
+        YA_CUDA(c, cudaEventRecord(c->ev[4], st));
         init_strands_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>(d_strands, d_seg_total, n_seg);
         c->ctr.launches += 2;
     }
@@ -439,6 +452,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     YA_CUDA(c, cudaMemcpyAsync(h_seg_eff, d_seg_eff, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaStreamSynchronize(st));
     c->ctr.probes += n_probes;
+    { float msl = 0; cudaEventElapsedTime(&msl, c->ev[3], c->ev[4]); c->ctr.ms_lookup += msl; }
 
     // chunk plan: <= 2^16 reads and <= MAX_KEYS hits per chunk (segment id fits 17 bits)
     const uint64_t MAX_KEYS = 1ull << 28;

@@ -516,7 +516,7 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, De
         ya_op *out = ops_raw + J.ops_off;
         int y = o.maxi, x = o.maxj;
         int prev = -1; uint32_t run = 0;
-        size_t cachedIdx = (size_t)-1; uint32_t cachedWord = 0;
+        size_t cachedIdx = (size_t)-1, nextIdx = (size_t)-1; uint32_t cachedWord = 0, nextWord = 0;
         int guard = (int)J.qLen + (int)J.rLen + 8;     // a valid walk consumes a row or a column per step
         for (;;) {
             if (--guard < 0 || x < 0 || x > W || y < 0) { n = 0xFFFFFFF0u; prev = -1; break; }   // corrupt back-pointers
@@ -534,7 +534,13 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, De
                 // a word holds 4 consecutive macro steps of one column: a run of match/replace steps
                 // (same column, rows y, y-1, ...) is served by one load per 4 rows
                 const size_t widx = (size_t)((s - 1) >> 2) * J.stride + (x / C) * CP + (x % C);
-                if (widx != cachedIdx) { cachedIdx = widx; cachedWord = w[widx]; }
+                if (widx != cachedIdx) {
+                    // the walk is latency bound: the word one block up in the same column (where a
+                    // match/replace run continues) is requested together with the one needed now
+                    cachedWord = (widx == nextIdx) ? nextWord : w[widx];
+                    cachedIdx = widx;
+                    if (widx >= J.stride) { nextIdx = widx - J.stride; nextWord = w[nextIdx]; } else nextIdx = (size_t)-1;
+                }
                 const uint32_t word = cachedWord;
                 const uint32_t b = (word >> (8 * (3 - ((s - 1) & 3)))) & 0xFFu;
                 len = (b & 63u) + 1u;

@@ -481,22 +481,22 @@ int runQueries(const Args &A0)
         if (A.verbose || A.passes > 1 || getenv("YAHA_B200_STATS")) {
             ya_counters c{};
             double seed = 0, dp = 0, host = 0, upl = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
-            double msdp = 0, msseed = 0, mstb = 0, msext = 0; uint64_t extCells = 0, extLaunches = 0;
+            double msdp = 0, msseed = 0, mstb = 0, msext = 0, mslk = 0; uint64_t extCells = 0, extLaunches = 0;
             for (Pipe &d : pipes) {
                 ya_get_counters(d.ctx, &c);
                 seed += d.tSeed; dp += d.tDp; host += d.tHost; upl += d.tUpload; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
                 msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback; launches += c.launches; probes += c.probes; hits += c.hits;
-                fragsAll += c.frags_all; msext += c.ms_ext; extCells += c.ext_cells; extLaunches += c.ext_launches;
+                fragsAll += c.frags_all; msext += c.ms_ext; mslk += c.ms_lookup; extCells += c.ext_cells; extLaunches += c.ext_launches;
             }
             fprintf(stderr, "{\"pass\": %d, \"reads\": %llu, \"align_s\": %.5f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"read_parse_s\": %.5f, "
                     "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
                     "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
                     "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d, \"pipes\": %d, "
-                    "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu}\n",
+                    "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu, \"dev_ms_lookup\": %.4f}\n",
                     pass, (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), tRead, upl, tWrite, seed, dp, host,
                     (unsigned long long)jobs, (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb,
                     (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads,
-                    nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches);
+                    nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches, mslk);
         }
     }
     extern uint64_t gAlignProf[4];
