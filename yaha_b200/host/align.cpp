@@ -14,6 +14,7 @@
 // clumps of a read are posted together, then all first extensions, and only the (rare) careful
 // re-extensions of split pieces are demand driven.
 #include <algorithm>
+#include <stdlib.h>
 #include "host.hpp"
 
 namespace yh {
@@ -401,6 +402,7 @@ static int scoreClump(const Env &E, ReadCtx &rc, Clump *c)             // AlignH
 }
 
 uint64_t gAlignProf[4];
+static const bool kAlignProf = getenv("YAHA_B200_PROF") != nullptr;
 static inline uint64_t rdtsc_() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
 void postProcessClumps(const Env &E, ReadCtx &rc)                       // QueryMatch.c:306-331
 {
@@ -416,7 +418,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         alignPrepare(E, rc, *old[k], gaps[k]);
         for (auto &g : gaps[k]) any |= g.needDp;
     }
-    gAlignProf[0] += rdtsc_() - q0;
+    if (kAlignProf) gAlignProf[0] += rdtsc_() - q0;
     if (any) dpWait(rc);
     q0 = rdtsc_();
     // phase 2: splice, collapse, perfect-extend and post the first extensions
@@ -440,7 +442,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         extendPerfect(E, rc, c, true, true, scores[k], xs[k]);
         any |= xs[k].doB || xs[k].doF;
     }
-    gAlignProf[1] += rdtsc_() - q0;
+    if (kAlignProf) gAlignProf[1] += rdtsc_() - q0;
     if (any) dpWait(rc);
     q0 = rdtsc_();
     // phase 3: apply every extension first (answers of a round are only valid until this fiber
@@ -451,7 +453,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         extendApply(E, rc, *c, xs[k], false, scores[k]);
         c->set(kAligned, true);
     }
-    gAlignProf[2] += rdtsc_() - q0;
+    if (kAlignProf) gAlignProf[2] += rdtsc_() - q0;
     q0 = rdtsc_();
     for (size_t k = 0; k < old.size(); k++) {
         Clump *c = old[k];
@@ -459,7 +461,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         if (c->is(kScored)) rc.clumps.push_back(c);
         else delete c;
     }
-    gAlignProf[3] += rdtsc_() - q0;
+    if (kAlignProf) gAlignProf[3] += rdtsc_() - q0;
 }
 
 }  // namespace yh

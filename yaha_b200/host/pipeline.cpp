@@ -101,6 +101,7 @@ DpAnswer dpGet(ReadCtx &rc, DpFuture fu)
 }
 
 static std::atomic<uint64_t> gProf[8];
+static const bool kProf = getenv("YAHA_B200_PROF") != nullptr;     // phase cycle counters are off unless asked for
 static inline uint64_t rdtsc() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
 static void readMain(const Env &E, ReadCtx &rc)                       // body of the Query.c:306-497 loop
 {
@@ -126,7 +127,7 @@ static void readMain(const Env &E, ReadCtx &rc)                       // body of
     uint64_t t4 = rdtsc();
     for (Clump *c : rc.clumps) delete c;
     rc.clumps.clear();
-    gProf[0] += t1 - t0; gProf[1] += t2 - t1; gProf[2] += t3 - t2; gProf[3] += t4 - t3; gProf[4] += rdtsc() - t4;
+    if (kProf) { gProf[0] += t1 - t0; gProf[1] += t2 - t1; gProf[2] += t3 - t2; gProf[3] += t4 - t3; gProf[4] += rdtsc() - t4; }
 }
 
 static thread_local Fiber *tBoot;
@@ -188,7 +189,7 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     std::vector<ya_dp_job> jobs;
     std::vector<ya_dp_result> res;
     std::vector<ya_op> ops;
-    double tSeed = 0, tDp = 0, tHost = 0, tUpload = 0;
+    double tSeed = 0, tDp = 0, tHost = 0, tUpload = 0, tSetup = 0;
     uint64_t nJobs = 0, nRounds = 0;
 };
 
@@ -233,6 +234,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
     D.tSeed += nowSec() - t0;
 
     // fibers, dealt to the workers in contiguous slices
+    t0 = nowSec();
     B.fibers.clear();
     B.fibers.reserve((size_t)n);
     std::vector<Worker> workers((size_t)nThreads);
@@ -252,6 +254,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
         B.fibers.push_back(std::move(f));
     }
 
+    D.tSetup += nowSec() - t0;
     // rounds: every worker thread keeps its own fibers for the whole batch (a fiber never migrates
     // between OS threads); thread 0 runs the device call between two barriers
     std::atomic<int> live(0);
@@ -389,7 +392,7 @@ int runQueries(const Args &A0)
         const bool replaying = A.replay && pass > 0;
         if (pass > 0 && out != stdout) { out = freopen(A.ofile.c_str(), "w", out); setvbuf(out, obuf, _IOFBF, sizeof obuf); }
         writeHeader(E, out);
-        for (Pipe &p : pipes) { p.tSeed = p.tDp = p.tHost = p.tUpload = 0; p.nJobs = p.nRounds = 0; ya_counters c; ya_get_counters(p.ctx, &c); }
+        for (Pipe &p : pipes) { p.tSeed = p.tDp = p.tHost = p.tUpload = p.tSetup = 0; p.nJobs = p.nRounds = 0; ya_counters c; ya_get_counters(p.ctx, &c); }
         Flow F;
         F.maxQueued = (size_t)nPipes + 2;
         double tRead = 0, tWrite = 0;
@@ -480,11 +483,11 @@ int runQueries(const Args &A0)
         const double tAlign = nowSec() - tStart;
         if (A.verbose || A.passes > 1 || getenv("YAHA_B200_STATS")) {
             ya_counters c{};
-            double seed = 0, dp = 0, host = 0, upl = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
+            double seed = 0, dp = 0, host = 0, upl = 0, setup = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
             double msdp = 0, msseed = 0, mstb = 0, msext = 0, mslk = 0; uint64_t extCells = 0, extLaunches = 0;
             for (Pipe &d : pipes) {
                 ya_get_counters(d.ctx, &c);
-                seed += d.tSeed; dp += d.tDp; host += d.tHost; upl += d.tUpload; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
+                seed += d.tSeed; dp += d.tDp; host += d.tHost; upl += d.tUpload; setup += d.tSetup; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
                 msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback; launches += c.launches; probes += c.probes; hits += c.hits;
                 fragsAll += c.frags_all; msext += c.ms_ext; mslk += c.ms_lookup; extCells += c.ext_cells; extLaunches += c.ext_launches;
             }
@@ -492,11 +495,11 @@ int runQueries(const Args &A0)
                     "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
                     "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
                     "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d, \"pipes\": %d, "
-                    "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu, \"dev_ms_lookup\": %.4f}\n",
+                    "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu, \"dev_ms_lookup\": %.4f, \"fiber_setup_s\": %.5f}\n",
                     pass, (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), tRead, upl, tWrite, seed, dp, host,
                     (unsigned long long)jobs, (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb,
                     (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads,
-                    nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches, mslk);
+                    nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches, mslk, setup);
         }
     }
     extern uint64_t gAlignProf[4];
