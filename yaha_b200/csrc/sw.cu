@@ -668,6 +668,9 @@ static bool forbid_packed_kernel()
 
 struct PackedCfg { int G, C, W; };
 static const PackedCfg kPackedCfgs[] = {{2, 11, 21}, {4, 11, 41}};
+// Below this many jobs per launch the grid cannot fill the GPU with 8 (16) jobs per warp; the narrow
+// variants <7,6,41> / <4,6,21> put 4 (8) jobs in a warp: twice the warps, shorter macro steps.
+static const size_t kPackedNarrowBelow = 16384;
 static const int kNumPackedCfgs = sizeof(kPackedCfgs) / sizeof(kPackedCfgs[0]);
 
 template <int G, int C, int W>
@@ -711,6 +714,9 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     if ((int)lists.size() != nClasses) lists.assign((size_t)nClasses, std::vector<uint32_t>());
     for (auto &v : lists) v.clear();
     const int packedBase = 2 * kNumWaveCfgs + 1;
+    size_t nExt = 0;
+    for (int i = 0; i < n; i++) nExt += jobs[i].kind >= YA_DP_EXT_FWD;
+    const bool narrowExt = nExt < kPackedNarrowBelow, narrow21 = narrowExt, narrow41 = narrowExt;
     uint64_t tb_cells = 0, rows_ints = 0, ops_slots = 0;
     int n_live = 0;
     std::vector<uint32_t> &live_of = c->sw_live_of;   // device job index -> caller job index
@@ -754,7 +760,8 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         if (allowPacked && j.kind >= YA_DP_EXT_FWD && W <= P.maxGap && W <= P.maxIntron)
             for (int k = 0; k < kNumPackedCfgs; k++) if (kPackedCfgs[k].W == W) pcls = k;
         if (pcls >= 0) {
-            const int G = kPackedCfgs[pcls].G, C = kPackedCfgs[pcls].C, CP = (C + 3) & ~3;
+            const int G = narrowExt ? (pcls == 0 ? 4 : 7) : kPackedCfgs[pcls].G;
+            const int C = narrowExt ? 6 : kPackedCfgs[pcls].C, CP = (C + 3) & ~3;
             d.layout = 2; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * CP);
             tb_cells = (tb_cells + 7) & ~7ull;                         // 16-byte alignment for the 128-bit stores
             d.tb_off = tb_cells / 2;                                  // in 32-bit words
@@ -825,8 +832,14 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     }
     const bool anyPacked = !lists[packedBase + 0].empty() || !lists[packedBase + 1].empty();
     if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[3], st));
-    if (!lists[packedBase + 0].empty()) launch_packed<2, 11, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
-    if (!lists[packedBase + 1].empty()) launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
+    if (!lists[packedBase + 0].empty()) {
+        if (narrow21) launch_packed<4, 6, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
+        else          launch_packed<2, 11, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
+    }
+    if (!lists[packedBase + 1].empty()) {
+        if (narrow41) launch_packed<7, 6, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
+        else          launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
+    }
     if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[4], st));
     if (!lists[2 * kNumWaveCfgs].empty()) {
         int nt = (int)lists[2 * kNumWaveCfgs].size();

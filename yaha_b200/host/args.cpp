@@ -116,6 +116,7 @@ int parseArgs(int argc, char **argv, Args &a)
         else if (!strcmp(k, "-passes")) a.passes = std::max(1, parseInt(val(), "-passes"));
         else if (!strcmp(k, "-pipes")) a.pipes = std::max(1, parseInt(val(), "-pipes"));
         else if (!strcmp(k, "-replay")) a.replay = true;
+        else if (!strcmp(k, "-tpp")) a.threadsPerPipe = parseInt(val(), "-tpp");
         else { fprintf(stderr, "%s is not a valid option.\n\n", k); usage(); exit(1); }
     }
     if (index) {

@@ -369,7 +369,7 @@ int runQueries(const Args &A0)
     int pipesPerDev = std::max(1, A.pipes);
     if (nThreads < nDev * pipesPerDev) pipesPerDev = std::max(1, nThreads / nDev);
     const int nPipes = nDev * pipesPerDev;
-    const int threadsPerPipe = std::max(1, nThreads / nPipes);
+    const int threadsPerPipe = A.threadsPerPipe > 0 ? A.threadsPerPipe : std::max(1, nThreads / nPipes);
     std::vector<Pipe> pipes((size_t)nPipes);
     double tOpen = nowSec();
     for (int d = 0; d < nDev; d++) {
