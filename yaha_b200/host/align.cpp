@@ -14,6 +14,7 @@
 // clumps of a read are posted together, then all first extensions, and only the (rare) careful
 // re-extensions of split pieces are demand driven.
 #include <algorithm>
+#include <stdio.h>
 #include <stdlib.h>
 #include "host.hpp"
 
@@ -157,7 +158,7 @@ static void collapse(Clump &c)                                          // Align
 }
 
 // perfect part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:76-107)
-static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool goForw, int &score, ExtState &x)
+static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool goForw, int &score, ExtState &x, bool post = true)
 {
     const Args &A = *E.A;
     const uint8_t *q = rc.codes(c.reversed());
@@ -181,10 +182,32 @@ static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool
     }
     x.doB = goBack && x.backLen >= A.minExtLength;
     x.doF = goForw && x.forwLen >= A.minExtLength;
+    if (!post) return;                     // jobs were already posted by extendPlanEarly
     // Both DP jobs can be posted now: the backward extension never moves the fragment's end
     // (FragsClumps.inl:81-85), so the forward job's anchor is already final.
     if (x.doB) x.fb = dpSubmit(rc, YA_DP_EXT_BWD, c.reversed(), f.startRefOff - 1, 0, f.startQueryOff - 1, x.backLen);
     if (x.doF) x.ff = dpSubmit(rc, YA_DP_EXT_FWD, c.reversed(), fragERO(f) + 1, 0, f.endQueryOff + 1, x.forwLen);
+}
+
+// The first extensions of a clump (AlignHelpers.c:264) start from the outer ends of its first and
+// last fragment; the gap fills between fragments never move those ends.  So the extension jobs can be
+// posted in the SAME round as the gap fills: the perfect pre-extension is evaluated here on copies, and
+// repeated for real (same outcome) after the collapse.
+static void extendPlanEarly(const Env &E, ReadCtx &rc, Clump &c, ExtState &x)
+{
+    const Args &A = *E.A;
+    const uint8_t *q = rc.codes(c.reversed());
+    Frag f0 = c.sf.front().frag, fn = c.sf.back().frag;
+    x.backLen = (int)std::min<uint32_t>(f0.startQueryOff, f0.startRefOff);
+    if (x.backLen > 0) x.backLen -= perfectBackward(E, q, f0, x.backLen);
+    uint16_t qlen = (uint16_t)((rc.read->len() - 1) - fn.endQueryOff);
+    uint32_t rlen = E.G->maxROff - fragERO(fn);
+    x.forwLen = (int)std::min<uint32_t>(qlen, rlen);
+    if (x.forwLen > 0) x.forwLen -= perfectForward(E, q, fn, x.forwLen);
+    x.doB = x.backLen >= A.minExtLength;
+    x.doF = x.forwLen >= A.minExtLength;
+    if (x.doB) x.fb = dpSubmit(rc, YA_DP_EXT_BWD, c.reversed(), f0.startRefOff - 1, 0, f0.startQueryOff - 1, x.backLen);
+    if (x.doF) x.ff = dpSubmit(rc, YA_DP_EXT_FWD, c.reversed(), fragERO(fn) + 1, 0, fn.endQueryOff + 1, x.forwLen);
 }
 
 // SW.cpp:671-788: trim a backward extension so the running score never reaches zero
@@ -410,21 +433,22 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     std::vector<Clump *> old;
     old.swap(rc.clumps);
     std::reverse(old.begin(), old.end());                               // reference walks from the list head
-    // phase 1: everything up to the gap-fill jobs, for all clumps of the read
+    // phase 1: perfect extensions, gap-fill jobs AND the first extension jobs, for all clumps of the read
     std::vector<std::vector<GapJob>> gaps(old.size());
+    std::vector<ExtState> xs(old.size());
     bool any = false;
     for (size_t k = 0; k < old.size(); k++) {
         if (old[k]->is(kAligned)) continue;
         alignPrepare(E, rc, *old[k], gaps[k]);
         for (auto &g : gaps[k]) any |= g.needDp;
+        extendPlanEarly(E, rc, *old[k], xs[k]);
+        any |= xs[k].doB || xs[k].doF;
     }
     if (kAlignProf) gAlignProf[0] += rdtsc_() - q0;
     if (any) dpWait(rc);
     q0 = rdtsc_();
-    // phase 2: splice, collapse, perfect-extend and post the first extensions
-    std::vector<ExtState> xs(old.size());
+    // phase 2: splice the gap pieces, collapse, redo the perfect end extensions on the real fragment
     std::vector<int> scores(old.size(), 0);
-    any = false;
     for (size_t k = 0; k < old.size(); k++) {
         Clump &c = *old[k];
         if (c.is(kAligned)) continue;
@@ -439,11 +463,14 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         }
         collapse(c);
         scores[k] = c.sf.front().score;
-        extendPerfect(E, rc, c, true, true, scores[k], xs[k]);
-        any |= xs[k].doB || xs[k].doF;
+        ExtState chk = xs[k];
+        extendPerfect(E, rc, c, true, true, scores[k], chk, false);
+        if (chk.doB != xs[k].doB || chk.doF != xs[k].doF || (chk.doB && chk.backLen != xs[k].backLen) || (chk.doF && chk.forwLen != xs[k].forwLen)) {
+            fprintf(stderr, "yaha_b200: internal error: early extension plan diverged\n");
+            abort();
+        }
     }
     if (kAlignProf) gAlignProf[1] += rdtsc_() - q0;
-    if (any) dpWait(rc);
     q0 = rdtsc_();
     // phase 3: apply every extension first (answers of a round are only valid until this fiber
     // parks again), then score -- and split, which may park -- in list order
