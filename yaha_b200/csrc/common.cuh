@@ -98,7 +98,7 @@ struct ya_ctx {
     DevBuf    d_jobs, d_jobout, d_tb, d_rows, d_ops_raw, d_ops_cnt, d_ops_off, d_ops_out, d_res;
     PinBuf    h_jobs, h_res, h_ops;
     std::vector<std::vector<uint32_t>> sw_lists;      // ya_sw_batch host scratch (reused)
-    std::vector<uint32_t> sw_live_of, sw_flat;
+    std::vector<uint32_t> sw_live_of, sw_flat, sw_cnt, sw_tmp;
     std::vector<uint32_t> seed_small, seed_big;       // ya_seed_frags host scratch (segment id lists)
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

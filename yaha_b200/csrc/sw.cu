@@ -810,10 +810,19 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     YA_CUDA(c, c->d_misc.reserve((size_t)n_live * 4 + 64));
     YA_CUDA(c, c->h_res.reserve((size_t)n_live * (sizeof(ya_dp_result) + sizeof(DevJobOut)) + 64));
     YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, hj, (size_t)n_live * sizeof(DevJob), cudaMemcpyHostToDevice, st));
-    // longest jobs first inside each packed class: groups sharing a warp get similar row counts
+    // longest jobs first inside each packed class (groups sharing a warp get similar row counts):
+    // counting sort on qLen/8, descending -- a comparison sort of 20 K ids costs milliseconds here
     for (int k = 0; k < kNumPackedCfgs; k++) {
         std::vector<uint32_t> &v = lists[packedBase + k];
-        std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return hj[a].qLen != hj[b].qLen ? hj[a].qLen > hj[b].qLen : a < b; });
+        if (v.size() < 64) continue;
+        std::vector<uint32_t> &cnt = c->sw_cnt, &tmp = c->sw_tmp;
+        cnt.assign(8192 + 1, 0u);
+        for (uint32_t id : v) cnt[8191 - (hj[id].qLen >> 3)]++;
+        uint32_t run = 0;
+        for (size_t b = 0; b <= 8192; b++) { uint32_t t = cnt[b]; cnt[b] = run; run += t; }
+        tmp.resize(v.size());
+        for (uint32_t id : v) tmp[cnt[8191 - (hj[id].qLen >> 3)]++] = id;
+        v.swap(tmp);
     }
     // id lists
     std::vector<uint32_t> &flat = c->sw_flat; flat.clear(); flat.reserve(n_live);
