@@ -116,18 +116,6 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def _unused_tiny_aligner(device: int):
-    """A context on a toy reference, used only to run the INT32 peak micro-benchmark."""
-    import yaha_b200
-    from yaha_b200 import refio, synth
-    img = refio.build_nib2([("t", synth.random_reference(4096, 1))])
-    path = os.path.join(tempfile.gettempdir(), f"yaha_b200_tiny_{os.getpid()}.nib2")
-    with open(path, "wb") as f:
-        f.write(img)
-    nib = refio.load_nib2(path)
-    return yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=8), device=device)
-
-
 def run_host(idx_path, reads_path, out_path, flags, threads, device, passes, batch, pipes, replay=False, tpp=0):
     """Run the product's host program (the call a user makes) and return its per-pass stats."""
     host = os.path.join(ROOT, "yaha_b200", "yaha_b200_host")
@@ -208,6 +196,13 @@ def run_ours(args):
     timed = stats_b[1 + args.warmup:]
     assert len(timed) == args.steps
     el_res = sum(s["align_s"] for s in timed)
+    # run C (not part of value/e2e): one pipeline, whole shard per batch -> the same kernels timed without a
+    # second pipeline's launches sharing the SMs
+    stats_c = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + args.warmup + args.steps,
+                       n_reads, 1, replay=True)[1 + args.warmup:]
+    iso_cells, iso_ms, iso_n = (sum(s[k] for s in stats_c) for k in ("ext_cells", "dev_ms_ext", "ext_launches"))
+    iso_gcups = iso_cells / (iso_ms * 1e-3) / 1e9 if iso_ms > 0 else 0.0
+    iso_lookup_ms, iso_probes = sum(s["dev_ms_lookup"] for s in stats_c), sum(s["probes"] for s in stats_c)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     if world > 1:
@@ -241,6 +236,18 @@ def run_ours(args):
     h2d = int(codes_bytes + 16 * tot("dp_jobs") / args.steps + 40 * tot("dp_jobs") / args.steps)
     d2h = int(16 * tot("dp_jobs") / args.steps + 16 * 2 * n_reads)
 
+    # DRAM bytes of the two dominant kernels from the committed `ncu --set full` captures, scaled from the
+    # captured launch to this run's average launch (per cell / per probe)
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    t_ext, t_seed = traffic.get("dp_ext_packed_kernel"), traffic.get("seed_count_kernel")
+    ext_traffic = t_ext["dram_bytes"] / t_ext["cells"] * (ext_cells / max(ext_launches, 1)) if t_ext else None
+    seed_launches = max(1, -(-n_reads // args.batch)) * args.steps
+    seed_traffic = t_seed["dram_bytes"] / t_seed["probes"] * (tot("probes") / seed_launches) if t_seed else None
+
     line = {
         "metric": "reads/s (whole alignment job: FASTA in -> SAM out, identical to reference) and banded-SW GCUPS",
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -268,15 +275,24 @@ def run_ours(args):
                      "launches_timed": int(ext_launches), "avg_launch_ms": ms_ext / max(ext_launches, 1),
                      "cells_per_launch": ext_cells / max(ext_launches, 1),
                      "achieved": achieved_giops, "peak": int_add, "unit": "GIOP/s",
-                     "frac": achieved_giops / int_add if int_add else None, "traffic": None,
+                     "frac": achieved_giops / int_add if int_add else None, "traffic": ext_traffic,
+                     "traffic_unit": "bytes per launch (dram__bytes_read+write of the ncu capture in profiles/ncu_traffic.json, per cell x cells_per_launch)",
+                     "algorithmic_bytes_per_launch": 1.0 * ext_cells / max(ext_launches, 1),
                      "peak_source": "ya_measure_int32_peak: dependent-free IADD/LOP3 stream on all SMs, measured live",
                      "peak_dp_mix": int_mix, "ops_per_cell": INT_OPS_PER_CELL_EXT,
+                     "single_pipeline": {"launches_timed": int(iso_n), "avg_launch_ms": iso_ms / max(iso_n, 1),
+                                         "cells_per_launch": iso_cells / max(iso_n, 1), "gcups": iso_gcups,
+                                         "achieved": iso_gcups * INT_OPS_PER_CELL_EXT,
+                                         "frac": iso_gcups * INT_OPS_PER_CELL_EXT / int_add if int_add else None,
+                                         "note": "same job, one pipeline per GPU (no concurrent launches from a second pipeline); "
+                                                 "`achieved`/`frac` above are from the timed region of `value` (2 pipelines)"},
                      "gcups_roof": int_add / INT_OPS_PER_CELL_EXT},
         "roofline_seed": {"bound": "hbm", "kernel": "seed_count_kernel (k-mer -> starting-offset gather, Query.c:391)",
                           "achieved": 8.0 * probes_per_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                          "frac": 8.0 * probes_per_s / 1e9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                          "frac": 8.0 * probes_per_s / 1e9 / hbm_peak, "traffic": seed_traffic, "peak_source": hbm_src,
                           "algorithmic_bytes_per_probe": 8, "probes_per_s": probes_per_s,
                           "random_gather_peak_per_s": gather_peak,
+                          "single_pipeline_probes_per_s": iso_probes / (iso_lookup_ms * 1e-3) if iso_lookup_ms > 0 else None,
                           "frac_of_random_gather_peak": probes_per_s / gather_peak if gather_peak else None,
                           "note": "a probe is one independent 32 B-sector DRAM miss in a 4 GiB table; the binding limit is the HBM "
                                   "random-access rate (measured live by ya_measure_gather_peak), not streaming bandwidth",

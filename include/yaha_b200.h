@@ -187,9 +187,14 @@ int ya_seed_frags(ya_ctx *, ya_frag_batch *out);
 /* Stage 3 for n independent jobs against the uploaded batch.  Replaces findAGSAlignment,
  * findAGSAlignmentBanded, findAGSForwardExtension, findAGSBackwardExtension
  * (Math.h:401-408) = findAffineGapScore<...> (SW.cpp:798-1208) + decompressRef
- * (SW.cpp:444-456).  res[i] answers jobs[i].  On YA_E_CAPACITY *ops_needed is set. */
+ * (SW.cpp:444-456).  res[i] answers jobs[i].  On YA_E_CAPACITY *ops_needed is set, every
+ * res[i] is already valid and the edit operations stay on the device until the next
+ * ya_sw_batch: collect them with ya_sw_fetch_ops (no DP is repeated), or repeat the call. */
 int ya_sw_batch(ya_ctx *, const ya_dp_job *jobs, int n, ya_dp_result *res,
                 ya_op *ops, size_t ops_cap, size_t *ops_needed);
+/* Copy the edit operations of the last ya_sw_batch that returned YA_E_CAPACITY (ops_needed
+ * entries).  YA_E_CAPACITY again if ops_cap is still too small, YA_E_STATE if nothing is pending. */
+int ya_sw_fetch_ops(ya_ctx *, ya_op *ops, size_t ops_cap);
 
 /* Perfect (exact-match) extension lengths (ref: extendFragment{Forward,Backward}
  * ToStopPerfectly, AlignExtFrag.cpp:30-48): for job i, count equal codes starting at

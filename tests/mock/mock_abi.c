@@ -14,9 +14,34 @@ struct ya_ctx {
     const uint8_t *bases; size_t n_base_bytes; uint32_t maxROff;
     int n_reads; uint8_t *fwd, *rev; uint64_t *off;
     ya_counters ctr;
+    ya_op *pending; size_t pendingN, pendingCap;     /* ops of the last ya_sw_batch (for ya_sw_fetch_ops) */
     char err[256];
 };
 static const uint8_t comp[16] = {2, 3, 0, 1, 4, 12, 7, 6, 9, 8, 15, 11, 5, 13, 14, 10};
+
+/* MOCK_MEMO=1: answers are remembered by a hash of the request, so that repeated passes over the same
+ * reads (-passes N -replay, one thread) cost no oracle time -- used to profile the host logic alone. */
+typedef struct memo { uint64_t key; int kind; void *a; size_t na; void *b; size_t nb; void *c; size_t nc; size_t extra; struct memo *next; } memo;
+static memo *memo_head;
+static int memo_on(void) { static int v = -1; if (v < 0) v = getenv("MOCK_MEMO") != NULL; return v; }
+static uint64_t fnv(const void *p, size_t n, uint64_t h)
+{
+    const uint8_t *b = p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+static memo *memo_find(uint64_t key, int kind)
+{
+    for (memo *m = memo_head; m; m = m->next) if (m->key == key && m->kind == kind) return m;
+    return NULL;
+}
+static void *dupmem(const void *p, size_t n) { void *q = malloc(n ? n : 1); memcpy(q, p, n); return q; }
+static memo *memo_add(uint64_t key, int kind)
+{
+    memo *m = calloc(1, sizeof *m);
+    m->key = key; m->kind = kind; m->next = memo_head; memo_head = m;
+    return m;
+}
 
 ya_ctx *ya_open(int device, const ya_params *p, const uint32_t *so, size_t n_so, const uint32_t *roa, size_t n_roa,
                 const uint8_t *bases, size_t n_base_bytes, uint32_t maxROff)
@@ -33,7 +58,7 @@ ya_ctx *ya_open_build(int d, const ya_params *p, const uint8_t *b, size_t n, con
 { (void)d; (void)p; (void)b; (void)n; (void)s; (void)l; (void)ns; (void)mh; return NULL; }
 int ya_index_sizes(const ya_ctx *c, size_t *a, size_t *b) { *a = c->n_so; *b = c->n_roa; return 0; }
 int ya_index_download(ya_ctx *c, uint32_t *so, uint32_t *roa) { (void)c; (void)so; (void)roa; return YA_E_STATE; }
-void ya_close(ya_ctx *c) { if (!c) return; free(c->fwd); free(c->rev); free(c->off); free(c); }
+void ya_close(ya_ctx *c) { if (!c) return; free(c->fwd); free(c->rev); free(c->off); free(c->pending); free(c); }
 const char *ya_last_error(const ya_ctx *c) { return c ? c->err : "mock"; }
 int ya_set_params(ya_ctx *c, const ya_params *p) { c->P = *p; return 0; }
 int ya_set_stream(ya_ctx *c, void *s) { (void)c; (void)s; return 0; }
@@ -60,6 +85,17 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
 {
     size_t n_out = 0;
     int overflow = 0;
+    uint64_t key = 0;
+    if (memo_on()) {
+        key = fnv(c->off, (c->n_reads + 1) * sizeof(uint64_t), 14695981039346656037ull);
+        key = fnv(c->fwd, c->n_reads ? c->off[c->n_reads] : 0, key);
+        memo *m = memo_find(key, 1);
+        if (m && m->extra <= out->frags_cap) {
+            memcpy(out->strands, m->a, m->na); memcpy(out->frags, m->b, m->nb); memcpy(out->region, m->c, m->nc);
+            out->n_frags = m->extra;
+            return 0;
+        }
+    }
     for (int seg = 0; seg < 2 * c->n_reads; seg++) {
         int r = seg >> 1;
         int L = (int)(c->off[r + 1] - c->off[r]);
@@ -90,6 +126,13 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     }
     if (overflow) { out->frags_needed = n_out; return YA_E_CAPACITY; }
     out->n_frags = n_out;
+    if (memo_on()) {
+        memo *m = memo_add(key, 1);
+        m->na = 2 * (size_t)c->n_reads * sizeof(ya_strand_frags); m->a = dupmem(out->strands, m->na);
+        m->nb = n_out * sizeof(ya_frag); m->b = dupmem(out->frags, m->nb);
+        m->nc = n_out * 4; m->c = dupmem(out->region, m->nc);
+        m->extra = n_out;
+    }
     return 0;
 }
 
@@ -97,6 +140,17 @@ int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res, ya_o
 {
     size_t used = 0;
     int overflow = 0;
+    c->pendingN = 0;
+    uint64_t key = 0;
+    if (memo_on()) {
+        key = fnv(jobs, (size_t)n * sizeof(ya_dp_job), 14695981039346656037ull);
+        memo *m = memo_find(key, 2);
+        if (m && m->extra <= ops_cap) {
+            memcpy(res, m->a, m->na); memcpy(ops, m->b, m->nb);
+            if (ops_needed) *ops_needed = m->extra;
+            return 0;
+        }
+    }
     ya_op *tmp = malloc(70000 * sizeof(ya_op));
     for (int i = 0; i < n; i++) {
         const ya_dp_job *j = &jobs[i];
@@ -105,12 +159,29 @@ int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res, ya_o
         int score = orc_dp(&c->P, c->bases, c->maxROff, codes, j->kind, j->rOff, j->rLen, j->qOff, j->qLen, &aq, &ar, tmp, 70000, &no, &cells);
         res[i].score = score; res[i].addedQLen = (uint16_t)aq; res[i].addedRLen = (uint16_t)ar; res[i].ops_off = (uint32_t)used; res[i].ops_n = (uint32_t)no;
         if (used + no <= ops_cap) memcpy(ops + used, tmp, no * sizeof(ya_op)); else overflow = 1;
+        if (used + no > c->pendingCap) { c->pendingCap = 2 * (used + no) + 1024; c->pending = realloc(c->pending, c->pendingCap * sizeof(ya_op)); }
+        memcpy(c->pending + used, tmp, no * sizeof(ya_op));
         used += no;
         c->ctr.dp_cells += cells; c->ctr.dp_jobs++;
     }
     free(tmp);
     if (ops_needed) *ops_needed = used;
+    if (overflow) c->pendingN = used;
+    if (memo_on()) {
+        memo *m = memo_add(key, 2);
+        m->na = (size_t)n * sizeof(ya_dp_result); m->a = dupmem(res, m->na);
+        m->nb = used * sizeof(ya_op); m->b = dupmem(c->pending, m->nb);
+        m->extra = used;
+    }
     return overflow ? YA_E_CAPACITY : 0;
+}
+
+int ya_sw_fetch_ops(ya_ctx *c, ya_op *ops, size_t ops_cap)
+{
+    if (c->pendingN == 0) return YA_E_STATE;
+    if (ops_cap < c->pendingN) return YA_E_CAPACITY;
+    memcpy(ops, c->pending, c->pendingN * sizeof(ya_op));
+    return 0;
 }
 
 int ya_perfect_ext(ya_ctx *c, const ya_dp_job *jobs, int n, uint16_t *count)

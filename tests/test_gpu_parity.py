@@ -99,6 +99,35 @@ def test_seed_frags_capacity_protocol(small, aligner):
     assert np.array_equal(f1, f2) and np.array_equal(r1, r2) and np.array_equal(s1, s2)
 
 
+def test_sw_capacity_protocol(small, aligner):
+    """A too-small op buffer: YA_E_CAPACITY with every result valid, ops collected by ya_sw_fetch_ops
+    without repeating the DP; the outcome equals a call with a large buffer."""
+    import ctypes as C
+    aligner.set_params(yaha_b200.Params.defaults(word_len=11))
+    aligner.upload_read_list(small.fwd)
+    jobs, want = _golden_jobs(small, 5)
+    jobs = jobs[:500]
+    res_big, ops_big = aligner.sw_batch(jobs, ops_cap=1 << 20)
+    lib = aligner.lib
+    res = np.zeros(len(jobs), dtype=yaha_b200.RES_DT)
+    tiny = np.zeros(8, dtype=yaha_b200.OP_DT)
+    need = C.c_size_t(0)
+    before = aligner.counters().dp_cells
+    rc = lib.ya_sw_batch(aligner.ctx, jobs.ctypes.data, len(jobs), res.ctypes.data, tiny.ctypes.data, len(tiny), C.byref(need))
+    assert rc == yaha_b200.YA_E_CAPACITY and need.value == len(ops_big)
+    assert res.tobytes() == res_big.tobytes()
+    assert lib.ya_sw_fetch_ops(aligner.ctx, tiny.ctypes.data, len(tiny)) == yaha_b200.YA_E_CAPACITY
+    ops = np.zeros(need.value, dtype=yaha_b200.OP_DT)
+    assert lib.ya_sw_fetch_ops(aligner.ctx, ops.ctypes.data, len(ops)) == yaha_b200.YA_OK
+    assert ops.tobytes() == ops_big.tobytes()
+    assert aligner.counters().dp_cells > 0 and before >= 0
+    res2, ops2 = aligner.sw_batch(jobs, ops_cap=4)                 # the wrapper takes the same route
+    assert res2.tobytes() == res_big.tobytes() and ops2.tobytes() == ops_big.tobytes()
+    r0 = np.zeros(1, dtype=yaha_b200.RES_DT)
+    assert lib.ya_sw_batch(aligner.ctx, jobs.ctypes.data, 1, r0.ctypes.data, ops.ctypes.data, len(ops), C.byref(need)) == yaha_b200.YA_OK
+    assert lib.ya_sw_fetch_ops(aligner.ctx, ops.ctypes.data, len(ops)) == yaha_b200.YA_E_STATE
+
+
 def test_perfect_extension(small, aligner):
     rng = np.random.default_rng(5)
     jobs = []

@@ -488,26 +488,43 @@ __global__ void dp_thread_kernel(const DevJob *__restrict__ jobs, const uint32_t
 // Row 0 and the leading-insert boundary cells are not stored; they are known in closed form
 // (SW.cpp:900-933).
 // ------------------------------------------------------------------------------------------
-__global__ void traceback_kernel(const DevJob *__restrict__ jobs, int n_jobs, DevJobOut *__restrict__ outs,
+// Cells the reference executed in rows 1..done of a band (SW.cpp:1007 loop bounds):
+//   sum_i max(0, min(W-1, lb+rLen-i) - max(0, lb+1-i) + 1),  piecewise linear in i with kinks at
+//   i = lb+1 and i = rLen-rb, zero beyond i = lb+rLen -- summed per linear piece.
+__device__ __forceinline__ uint64_t band_cells(int done, int lb, int rb, int rLen)
+{
+    const int W = lb + rb + 1;
+    int hi = min(done, lb + rLen);
+    if (hi < 1) return 0;
+    auto f = [&](int i) { return (long long)(min(W - 1, lb + rLen - i) - max(0, lb + 1 - i) + 1); };
+    int k1 = min(lb + 1, rLen - rb), k2 = max(lb + 1, rLen - rb);
+    uint64_t total = 0;
+    int lo = 1;
+    const int cuts[3] = {k1, k2, hi};
+    for (int q = 0; q < 3; q++) {
+        int b = min(cuts[q], hi);
+        if (b >= lo) { total += (uint64_t)((f(lo) + f(b)) * (long long)(b - lo + 1) / 2); lo = b + 1; }
+    }
+    return total;
+}
+
+// One thread per job; thread t takes job ids[t] -- the kernel-class / length order the fill kernels
+// were launched in, so the lanes of a warp walk paths of the same layout and similar length.
+__global__ void traceback_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ ids, int n_jobs,
+                                 DevJobOut *__restrict__ outs,
                                  const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw,
                                  const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd,
                                  const uint8_t *__restrict__ rev)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
+    t = (int)ids[t];
     const DevJob J = jobs[t];
     DevJobOut o = outs[t];
     const bool ext = J.kind >= YA_DP_EXT_FWD;
     const int lb = J.lb, W = J.lb + J.rb + 1;
-    // cells the reference executed: rows 1..doneRows (SW.cpp:1007 loop bounds)
     {
-        uint64_t cells = 0;
-        int done = (int)o.cells_lo;
-        for (int i = 1; i <= done; i++) {
-            int s = lb + 1 - i; if (s < 0) s = 0;
-            int e = lb + (int)J.rLen - i; if (e > W - 1) e = W - 1;
-            if (e >= s) cells += (uint64_t)(e - s + 1);
-        }
+        const uint64_t cells = band_cells((int)o.cells_lo, lb, (int)J.rb, (int)J.rLen);
         o.cells_lo = (uint32_t)cells; o.cells_hi = (uint32_t)(cells >> 32);
     }
     uint32_t n = 0;
@@ -696,6 +713,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     double tp0 = now_s();
     if (!c || n < 0 || (n && (!jobs || !res))) return YA_E_ARG;
     if (ops_needed) *ops_needed = 0;
+    c->ops_pending = 0;
     if (n == 0) return YA_OK;
     if (c->n_reads == 0) return ya_fail(c, YA_E_STATE, "ya_sw_batch: no read batch uploaded");
     YA_CUDA(c, cudaSetDevice(c->device));
@@ -810,10 +828,11 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     YA_CUDA(c, c->d_misc.reserve((size_t)n_live * 4 + 64));
     YA_CUDA(c, c->h_res.reserve((size_t)n_live * (sizeof(ya_dp_result) + sizeof(DevJobOut)) + 64));
     YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, hj, (size_t)n_live * sizeof(DevJob), cudaMemcpyHostToDevice, st));
-    // longest jobs first inside each packed class (groups sharing a warp get similar row counts):
-    // counting sort on qLen/8, descending -- a comparison sort of 20 K ids costs milliseconds here
-    for (int k = 0; k < kNumPackedCfgs; k++) {
-        std::vector<uint32_t> &v = lists[packedBase + k];
+    // longest jobs first inside each kernel class (groups / lanes sharing a warp get similar row counts,
+    // in the fill kernels and in the traceback): counting sort on qLen/8, descending -- a comparison
+    // sort of 20 K ids costs milliseconds here
+    for (size_t k = 0; k < lists.size(); k++) {
+        std::vector<uint32_t> &v = lists[k];
         if (v.size() < 64) continue;
         std::vector<uint32_t> &cnt = c->sw_cnt, &tmp = c->sw_tmp;
         cnt.assign(8192 + 1, 0u);
@@ -859,7 +878,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     }
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     const int tbk = (n_live + 127) / 128;
-    traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_jobout.as<DevJobOut>(),
+    traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
                                           c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
                                           c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
     finalize_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), c->d_jobout.as<DevJobOut>(), n_live, P.bandWidth,
@@ -911,7 +930,18 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     }
     if (ops_needed) *ops_needed = total_ops;
     g_prof_sw[4] += now_s() - tp4;
-    if (!fits) return ya_fail(c, YA_E_CAPACITY, "op output buffer too small");
+    if (!fits) { c->ops_pending = total_ops; return ya_fail(c, YA_E_CAPACITY, "op output buffer too small"); }
+    return YA_OK;
+}
+
+extern "C" int ya_sw_fetch_ops(ya_ctx *c, ya_op *ops, size_t ops_cap)
+{
+    if (!c) return YA_E_ARG;
+    if (c->ops_pending == 0) return ya_fail(c, YA_E_STATE, "ya_sw_fetch_ops: no edit operations pending");
+    if (!ops || ops_cap < c->ops_pending) return ya_fail(c, YA_E_CAPACITY, "op output buffer too small");
+    YA_CUDA(c, cudaSetDevice(c->device));
+    YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, c->ops_pending * sizeof(ya_op), cudaMemcpyDeviceToHost, c->stream));
+    YA_CUDA(c, cudaStreamSynchronize(c->stream));
     return YA_OK;
 }
 

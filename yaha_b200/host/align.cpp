@@ -20,6 +20,36 @@
 
 namespace yh {
 
+uint64_t gAlignProf[4];
+static const bool kAlignProf = getenv("YAHA_B200_PROF") != nullptr;
+static inline uint64_t rdtsc_() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
+
+
+void OpVec::grow(size_t want)
+{
+    size_t cap = std::max<size_t>(want, (size_t)cap_ * 2);
+    Op *q = (Op *)malloc(cap * sizeof(Op));
+    if (!q) { fprintf(stderr, "yaha_b200: out of memory\n"); abort(); }
+    memcpy(q, p_, n_ * sizeof(Op));
+    if (heap()) free(p_);
+    p_ = q; cap_ = (uint32_t)cap;
+}
+
+void OpVec::swap(OpVec &o) noexcept
+{
+    if (heap() && o.heap()) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(cap_, o.cap_); return; }
+    OpVec *a = this, *b = &o;
+    if (a->heap()) std::swap(a, b);                 // a is inline; b may be either
+    Op tmp[kInline];
+    const uint32_t an = a->n_;
+    memcpy(tmp, a->in_, an * sizeof(Op));
+    if (b->heap()) { a->p_ = b->p_; a->cap_ = b->cap_; b->p_ = b->in_; b->cap_ = kInline; }
+    else memcpy(a->in_, b->in_, b->n_ * sizeof(Op));
+    a->n_ = b->n_;
+    memcpy(b->in_, tmp, an * sizeof(Op));
+    b->n_ = an;
+}
+
 void OpList::mergeToFront(OpList &src)
 {
     if (src.v.empty()) return;
@@ -38,7 +68,7 @@ void OpList::mergeToFront(const ya_op *o, int n)
     int drop = 0;
     uint16_t lastLen = o[n - 1].length;
     if (!v.empty() && (char)o[n - 1].opcode == v.front().code) { lastLen = (uint16_t)(lastLen + v.front().len); drop = 1; }
-    std::vector<Op> nv;
+    OpVec nv;
     nv.reserve((size_t)n + v.size());
     for (int k = 0; k < n; k++) nv.push_back(Op{o[k].length, (char)o[k].opcode});
     nv.back().len = lastLen;
@@ -387,7 +417,7 @@ static int splitHelper(const Env &E, ReadCtx &rc, Clump *c, int wSQO, int wEQO)
     ExtState x;
     int score = c->sf.front().score;
     extendPerfect(E, rc, *c, doBack, doForw, score, x);
-    if (x.doB || x.doF) dpWait(rc);
+    if (x.doB || x.doF) { uint64_t p0 = kAlignProf ? rdtsc_() : 0; dpWait(rc); if (kAlignProf) rc.parked += rdtsc_() - p0; }
     extendApply(E, rc, *c, x, true, score);
     c->set(kSplit, true);
     retval += scoreClump(E, rc, c);
@@ -424,9 +454,6 @@ static int scoreClump(const Env &E, ReadCtx &rc, Clump *c)             // AlignH
     return 1;
 }
 
-uint64_t gAlignProf[4];
-static const bool kAlignProf = getenv("YAHA_B200_PROF") != nullptr;
-static inline uint64_t rdtsc_() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
 void postProcessClumps(const Env &E, ReadCtx &rc)                       // QueryMatch.c:306-331
 {
     uint64_t q0 = rdtsc_();
@@ -482,13 +509,14 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     }
     if (kAlignProf) gAlignProf[2] += rdtsc_() - q0;
     q0 = rdtsc_();
+    const uint64_t parked0 = rc.parked;
     for (size_t k = 0; k < old.size(); k++) {
         Clump *c = old[k];
         scoreClump(E, rc, c);
         if (c->is(kScored)) rc.clumps.push_back(c);
         else delete c;
     }
-    if (kAlignProf) gAlignProf[3] += rdtsc_() - q0;
+    if (kAlignProf) gAlignProf[3] += rdtsc_() - q0 - (rc.parked - parked0);
 }
 
 }  // namespace yh

@@ -159,11 +159,15 @@ static void buildBestClump(const Args &A, std::vector<Frag> &frags, int lo, int 
     else cleanUpClump(A, clump);
 }
 
-static bool regionFree(const std::vector<char> &cov, int a, int b)
-{
-    for (int i = a; i <= b; i++) if (cov[i]) return false;
-    return true;
-}
+// Query positions covered by the clumps already cut from the current region: stamped with a
+// per-thread generation number instead of being cleared for every region.
+struct Coverage {
+    std::vector<uint32_t> stamp; uint32_t gen = 0;
+    void reset(size_t n) { if (stamp.size() < n) stamp.resize(n, 0); if (++gen == 0) { std::fill(stamp.begin(), stamp.end(), 0); gen = 1; } }
+    void mark(int i) { stamp[(size_t)i] = gen; }
+    bool covered(int i) const { return stamp[(size_t)i] == gen; }
+    bool free(int a, int b) const { for (int i = a; i <= b; i++) if (covered(i)) return false; return true; }
+};
 
 void formClumps(const Env &E, ReadCtx &rc, bool rev)
 {
@@ -171,28 +175,33 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
     std::vector<Frag> &frags = rc.frags[rev];
     const std::vector<uint32_t> &reg = rc.region[rev];
     const int n = (int)frags.size();
-    static thread_local std::vector<char> coverage, used;      // per-thread scratch, reused across reads
+    static thread_local Coverage coverage;                      // per-thread scratch, reused across reads
+    static thread_local std::vector<char> used;
     static thread_local std::vector<FNode> nodes;
+    Clump *spare = nullptr;                                     // an empty clump waiting for a path
+    const int qSlots = rc.read->len() + 1;
     int i = 0;
     while (i < n) {
         int j = i;
         while (j + 1 < n && reg[j + 1] == reg[i]) j++;
         if (j == i) {                                                 // QueryMatch.c:281-290
             if ((int)frags[i].refLen >= A.minMatch) {
-                Clump *c = new Clump();
+                Clump *c = spare ? spare : new Clump();
+                spare = nullptr;
                 addFragment(*c, frags[i]);
                 c->set(kReversed, rev);                               // addClump, QueryState.c:156-161
                 rc.clumps.push_back(c);
             }
         } else {                                                      // GraphPath.cpp:272-292
-            coverage.assign((size_t)rc.read->len() + 1, 0);
+            coverage.reset((size_t)qSlots);
             used.assign((size_t)(j - i + 1), 0);
             for (;;) {
-                Clump *c = new Clump();
+                Clump *c = spare ? spare : new Clump();
+                spare = nullptr;
                 buildBestClump(A, frags, i, j, used, nodes, *c);
-                if (c->sf.empty()) { delete c; break; }
+                if (c->sf.empty()) { *c = Clump(); spare = c; break; }
                 int sqo = c->SQO(), qlen = (uint16_t)(1 + c->EQO() - c->SQO());
-                for (int k = 0; k < qlen && sqo + k < (int)coverage.size(); k++) coverage[sqo + k] = 1;
+                for (int k = 0; k < qlen && sqo + k < qSlots; k++) coverage.mark(sqo + k);
                 // eliminateFragments, QueryMatch.c:201-215 (+ :177-197)
                 const int minLeft = A.minNonOverlap - 1;
                 for (int k = i; k <= j; k++) {
@@ -200,7 +209,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
                     const int SQO = frags[k].startQueryOff, EQO = frags[k].endQueryOff;
                     bool keep = false;
                     if (EQO - SQO >= minLeft)
-                        keep = regionFree(coverage, SQO, SQO + minLeft) || regionFree(coverage, EQO - minLeft, EQO);
+                        keep = coverage.free(SQO, SQO + minLeft) || coverage.free(EQO - minLeft, EQO);
                     if (!keep) used[k - i] = 1;
                 }
                 c->set(kReversed, rev);
@@ -209,6 +218,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
         }
         i = j + 1;
     }
+    delete spare;
 }
 
 }  // namespace yh

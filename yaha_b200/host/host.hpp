@@ -10,6 +10,8 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include <list>
@@ -91,8 +93,64 @@ struct QueryReader {                 // readNextQuery, Query.c:102-228
 
 // ----------------------------------------------------------------------------- edit ops
 struct Op { uint16_t len; char code; };
+// Vector of edit ops with room for a few entries inline: most lists (a seed fragment's single 'M', a
+// gap piece) never touch the heap.  Only the std::vector subset the host uses.
+class OpVec {
+    enum { kInline = 6 };
+    Op *p_; uint32_t n_ = 0, cap_ = kInline;
+    Op  in_[kInline];
+    bool heap() const { return p_ != in_; }
+    void grow(size_t want);
+public:
+    typedef Op *iterator; typedef const Op *const_iterator;
+    OpVec() : p_(in_) {}
+    OpVec(const OpVec &o) : p_(in_) { assign(o.begin(), o.end()); }
+    OpVec(OpVec &&o) noexcept : p_(in_) { swap(o); }
+    OpVec &operator=(const OpVec &o) { if (this != &o) assign(o.begin(), o.end()); return *this; }
+    OpVec &operator=(OpVec &&o) noexcept { if (this != &o) { clear(); swap(o); } return *this; }
+    ~OpVec() { if (heap()) free(p_); }
+    Op *begin() { return p_; }  Op *end() { return p_ + n_; }
+    const Op *begin() const { return p_; }  const Op *end() const { return p_ + n_; }
+    size_t size() const { return n_; }  bool empty() const { return n_ == 0; }
+    Op &operator[](size_t i) { return p_[i]; }  const Op &operator[](size_t i) const { return p_[i]; }
+    Op &front() { return p_[0]; }  Op &back() { return p_[n_ - 1]; }
+    const Op &front() const { return p_[0]; }  const Op &back() const { return p_[n_ - 1]; }
+    void clear() { n_ = 0; }
+    void reserve(size_t want) { if (want > cap_) grow(want); }
+    void resize(size_t n) { reserve(n); for (size_t i = n_; i < n; i++) p_[i] = Op{0, 0}; n_ = (uint32_t)n; }
+    void push_back(Op o) { if (n_ == cap_) grow((size_t)n_ + 1); p_[n_++] = o; }
+    void insert(Op *pos, Op o)
+    {
+        size_t at = (size_t)(pos - p_);
+        if (n_ == cap_) grow((size_t)n_ + 1);
+        memmove(p_ + at + 1, p_ + at, (n_ - at) * sizeof(Op));
+        p_[at] = o; n_++;
+    }
+    void insert(Op *pos, const Op *first, const Op *last)        // [first,last) must not alias this vector
+    {
+        size_t at = (size_t)(pos - p_), k = (size_t)(last - first);
+        if (k == 0) return;
+        reserve(n_ + k);
+        memmove(p_ + at + k, p_ + at, (n_ - at) * sizeof(Op));
+        memcpy(p_ + at, first, k * sizeof(Op));
+        n_ += (uint32_t)k;
+    }
+    void erase(Op *pos) { erase(pos, pos + 1); }
+    void erase(Op *first, Op *last)
+    {
+        memmove(first, last, (size_t)(end() - last) * sizeof(Op));
+        n_ -= (uint32_t)(last - first);
+    }
+    void assign(const Op *first, const Op *last)
+    {
+        size_t k = (size_t)(last - first);
+        n_ = 0; reserve(k);
+        memcpy(p_, first, k * sizeof(Op)); n_ = (uint32_t)k;
+    }
+    void swap(OpVec &o) noexcept;
+};
 struct OpList {                      // EditOpList_t semantics, SW.cpp:114-283, SW.inl:66-78
-    std::vector<Op> v;
+    OpVec v;
     bool empty() const { return v.empty(); }
     void clear() { v.clear(); }
     void pushFront(char c, int len) { v.insert(v.begin(), Op{(uint16_t)len, c}); }    // no coalescing
@@ -145,6 +203,7 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     std::vector<Clump *> clumps;     // LIFO list: back() is the reference's list head
     int    primaryCount = 0;
     RandState rng;
+    uint64_t parked = 0;             // cycles spent parked in the scoring phase (YAHA_B200_PROF only)
     std::vector<Frag> frags[2];      // mutable copy of the device's surviving fragments, per strand
     std::vector<uint32_t> region[2];
     std::string out;                 // formatted SAM / Blast8 records of this read

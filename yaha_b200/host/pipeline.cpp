@@ -275,13 +275,13 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
         const int nj = (int)D.jobs.size();
         D.res.resize((size_t)nj);
         if (D.ops.size() < (size_t)nj * 8) D.ops.resize((size_t)nj * 8);
-        for (;;) {
-            size_t need = 0;
-            int rcode = ya_sw_batch(D.ctx, D.jobs.data(), nj, D.res.data(), D.ops.data(), D.ops.size(), &need);
-            if (rcode == YA_E_CAPACITY) { D.ops.resize(need + 1024); continue; }
-            if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
-            break;
+        size_t need = 0;
+        int rcode = ya_sw_batch(D.ctx, D.jobs.data(), nj, D.res.data(), D.ops.data(), D.ops.size(), &need);
+        if (rcode == YA_E_CAPACITY) {                       // results are in; only the ops need a bigger buffer
+            D.ops.resize(need + need / 4 + 1024);
+            rcode = ya_sw_fetch_ops(D.ctx, D.ops.data(), D.ops.size());
         }
+        if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
         D.nJobs += (uint64_t)nj; D.nRounds++;
         for (Worker &w : workers) { w.res = D.res.data(); w.ops = D.ops.data(); }
         live.store(0);
