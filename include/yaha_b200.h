@@ -175,6 +175,11 @@ int ya_set_params(ya_ctx *, const ya_params *);
  * that the caller's CUDA events bracket the kernels.  NULL restores the library's stream. */
 int ya_set_stream(ya_ctx *, void *cuda_stream);
 
+/* Page-locked host memory for the buffers handed to the calls below (optional: any host pointer
+ * works, page-locked ones are copied by DMA without an intermediate staging copy).  NULL on failure. */
+void *ya_host_alloc(size_t bytes);
+void  ya_host_free(void *p);
+
 /* Make a batch of reads resident on the device (replaces the per-read buffers filled by
  * readNextQuery, Query.c:161-168).  Stays valid until the next ya_reads_upload. */
 int ya_reads_upload(ya_ctx *, const ya_read_batch *);

@@ -66,6 +66,9 @@ int ya_get_counters(ya_ctx *c, ya_counters *o) { *o = c->ctr; memset(&c->ctr, 0,
 int ya_measure_int32_peak(ya_ctx *c, double *a, double *b) { (void)c; *a = *b = 0; return 0; }
 int ya_measure_gather_peak(ya_ctx *c, double *a) { (void)c; *a = 0; return 0; }
 
+void *ya_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void ya_host_free(void *p) { free(p); }
+
 int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
 {
     free(c->fwd); free(c->rev); free(c->off);

@@ -175,15 +175,16 @@ def test_dp_full_size(big):
     def per_job(mask, w=None):
         return np.bincount(owner[mask], weights=(ln if w is None else w)[mask], minlength=n).astype(np.int64)
     m, r_, i_, d_ = per_job(isM), per_job(isR), per_job(isI), per_job(isD)
-    assert np.array_equal(m + r_ + i_, res["addedQLen"].astype(np.int64))
-    assert np.array_equal(m + r_ + d_, res["addedRLen"].astype(np.int64))
+    glob = jobs["kind"] <= yaha_b200.DP_BANDED
+    ext = ~glob
+    # extensions report what they added; global jobs consume exactly their rectangle (added* stay 0)
+    assert np.array_equal((m + r_ + i_)[ext], res["addedQLen"].astype(np.int64)[ext])
+    assert np.array_equal((m + r_ + d_)[ext], res["addedRLen"].astype(np.int64)[ext])
+    assert np.array_equal((m + r_ + i_)[glob], jobs["qLen"].astype(np.int64)[glob])
+    assert np.array_equal((m + r_ + d_)[glob], jobs["rLen"].astype(np.int64)[glob])
     gaps = np.bincount(owner[isI | isD], minlength=n)
     score = P.MScore * m - P.RCost * r_ - P.GOCost * gaps - P.GECost * (i_ + d_)
     assert np.array_equal(score, res["score"].astype(np.int64))
-    glob = jobs["kind"] <= yaha_b200.DP_BANDED
-    assert np.array_equal(res["addedQLen"][glob], jobs["qLen"][glob].astype(res["addedQLen"].dtype))
-    assert np.array_equal(res["addedRLen"][glob], jobs["rLen"][glob].astype(res["addedRLen"].dtype))
-    ext = ~glob
     assert np.all(res["score"][ext] >= 0)
     assert np.all(res["addedQLen"][ext].astype(np.int64) <= jobs["qLen"][ext])
     sameowner = owner[1:] == owner[:-1]

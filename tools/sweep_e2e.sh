@@ -1,0 +1,14 @@
+#!/bin/bash
+# e2e sweep on the GPU box: pipelines x threads-per-pipeline x batch, with and without device turns
+D=/tmp/yaha_b200_bench_cfg3
+python bench.py --no-cpu-baseline --steps 1 --warmup 3 > /dev/null 2>&1
+X=$D/ref.X15_01_65525S; Q=$D/reads_rank0.fa
+for lock in 0 1; do
+for cfg in "5000 4 8" "5000 4 4" "5000 3 5" "5000 2 8" "10000 2 8" "2500 4 8" "2500 8 4" "5000 4 6" "4000 5 6"; do
+  set -- $cfg
+  if [ $lock = 0 ]; then export YA_NO_GPU_LOCK=1; else unset YA_NO_GPU_LOCK; fi
+  r=$(yaha_b200/yaha_b200_host -x $X -q $Q -osh /tmp/sweep.sam -t 16 -batch $1 -pipes $2 -tpp $3 -passes 9 -BW 10 -G 100 2>&1 | grep '"pass"' | tail -6 | python -c "
+import sys,json
+v=[json.loads(l)['reads_per_s'] for l in sys.stdin]; print(int(sum(v)/len(v)), int(min(v)), int(max(v)))")
+  echo "lock=$lock batch=$1 pipes=$2 tpp=$3 : $r"
+done; done

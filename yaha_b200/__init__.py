@@ -69,7 +69,7 @@ class Counters(C.Structure):
 
 
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
-           "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_get_counters",
+           "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_host_alloc", "ya_host_free", "ya_get_counters",
            "ya_measure_int32_peak", "ya_measure_gather_peak")
 
 _lib = None
@@ -105,6 +105,10 @@ def load_library() -> C.CDLL:
     lib.ya_seed_frags.argtypes = [vp, C.POINTER(_FragBatch)]
     lib.ya_sw_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ya_sw_fetch_ops.argtypes = [vp, vp, C.c_size_t]
+    lib.ya_host_alloc.restype = vp
+    lib.ya_host_alloc.argtypes = [C.c_size_t]
+    lib.ya_host_free.restype = None
+    lib.ya_host_free.argtypes = [vp]
     lib.ya_perfect_ext.argtypes = [vp, vp, C.c_int, vp]
     lib.ya_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.ya_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/yaha_b200.h"
@@ -69,6 +70,17 @@ struct DevJobOut {
     int32_t  maxi, maxj;  // traceback start (band coordinates)
     uint32_t n_ops;       // filled by the traceback kernel
     uint32_t cells_lo, cells_hi;   // 64-bit cell count split (avoids alignment padding)
+};
+
+// One device phase at a time per GPU: the pipelines of a process take turns for their
+// launch..sync sections instead of time-slicing the SMs (each finishes sooner, and the CUDA-event
+// timings of a kernel are not stretched by another pipeline's launches).  YA_NO_GPU_LOCK=1 disables.
+std::mutex &ya_device_mutex(int device);
+bool ya_device_turns();
+struct DeviceTurn {
+    std::unique_lock<std::mutex> lk;
+    explicit DeviceTurn(int device) : lk(ya_device_mutex(device), std::defer_lock) { if (ya_device_turns()) lk.lock(); }
+    void done() { if (lk.owns_lock()) lk.unlock(); }
 };
 
 struct ya_ctx {

@@ -159,6 +159,25 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
     return c;
 }
 
+extern "C" void *ya_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void ya_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+std::mutex &ya_device_mutex(int device)
+{
+    static std::mutex mu[64];
+    return mu[(unsigned)device & 63u];
+}
+bool ya_device_turns()
+{
+    static const bool on = getenv("YA_NO_GPU_LOCK") == nullptr;
+    return on;
+}
+
 extern "C" ya_ctx *ya_open_shared(const ya_ctx *src)
 {
     if (!src) { g_open_err = "ya_open_shared: null source"; return nullptr; }

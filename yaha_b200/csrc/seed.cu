@@ -423,6 +423,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     }
     h_po[n_seg] = (uint32_t)acc;
     const uint32_t n_probes = (uint32_t)acc;
+    DeviceTurn turn(c->device);                 // held to the end of the call (results are copied back last)
     YA_CUDA(c, c->d_seg_probe_off.reserve(((size_t)n_seg + 1) * 4));
     YA_CUDA(c, c->d_cnt.reserve((size_t)n_probes * 4 + 16));
     YA_CUDA(c, c->d_soff.reserve((size_t)n_probes * 4 + 16));

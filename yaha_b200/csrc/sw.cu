@@ -817,6 +817,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     if (n_live == 0) return YA_OK;
     double tp1 = now_s(); g_prof_sw[0] += tp1 - tp0;
 
+    DeviceTurn turn(c->device);
     YA_CUDA(c, c->d_jobs.reserve((size_t)n_live * sizeof(DevJob)));
     YA_CUDA(c, c->d_jobout.reserve((size_t)n_live * sizeof(DevJobOut)));
     YA_CUDA(c, c->d_tb.reserve(tb_cells * 2 + 64));
@@ -905,6 +906,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaStreamSynchronize(st));
     YA_CUDA(c, cudaGetLastError());
+    turn.done();
     double tp4 = now_s(); g_prof_sw[3] += tp4 - tp3;
     float ms0 = 0, ms1 = 0;
     cudaEventElapsedTime(&ms0, c->ev[0], c->ev[1]);

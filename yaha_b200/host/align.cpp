@@ -461,25 +461,29 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     old.swap(rc.clumps);
     std::reverse(old.begin(), old.end());                               // reference walks from the list head
     // phase 1: perfect extensions, gap-fill jobs AND the first extension jobs, for all clumps of the read
-    std::vector<std::vector<GapJob>> gaps(old.size());
-    std::vector<ExtState> xs(old.size());
+    struct PerClump { ExtState x; int score = 0; size_t gapLo = 0, gapHi = 0; };
+    std::vector<PerClump> pc(old.size());
+    std::vector<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
+    gaps.reserve(4 * old.size() + 8);
     bool any = false;
     for (size_t k = 0; k < old.size(); k++) {
         if (old[k]->is(kAligned)) continue;
-        alignPrepare(E, rc, *old[k], gaps[k]);
-        for (auto &g : gaps[k]) any |= g.needDp;
-        extendPlanEarly(E, rc, *old[k], xs[k]);
-        any |= xs[k].doB || xs[k].doF;
+        pc[k].gapLo = gaps.size();
+        alignPrepare(E, rc, *old[k], gaps);
+        pc[k].gapHi = gaps.size();
+        for (size_t g = pc[k].gapLo; g < pc[k].gapHi; g++) any |= gaps[g].needDp;
+        extendPlanEarly(E, rc, *old[k], pc[k].x);
+        any |= pc[k].x.doB || pc[k].x.doF;
     }
     if (kAlignProf) gAlignProf[0] += rdtsc_() - q0;
     if (any) dpWait(rc);
     q0 = rdtsc_();
     // phase 2: splice the gap pieces, collapse, redo the perfect end extensions on the real fragment
-    std::vector<int> scores(old.size(), 0);
     for (size_t k = 0; k < old.size(); k++) {
         Clump &c = *old[k];
         if (c.is(kAligned)) continue;
-        for (auto &g : gaps[k]) {
+        for (size_t gi = pc[k].gapLo; gi < pc[k].gapHi; gi++) {
+            GapJob &g = gaps[gi];
             if (g.needDp) {
                 const DpAnswer r = dpGet(rc, g.fut);
                 g.piece.score = r.score;
@@ -489,10 +493,11 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
             c.sf.insert(std::next(g.after), std::move(g.piece));
         }
         collapse(c);
-        scores[k] = c.sf.front().score;
-        ExtState chk = xs[k];
-        extendPerfect(E, rc, c, true, true, scores[k], chk, false);
-        if (chk.doB != xs[k].doB || chk.doF != xs[k].doF || (chk.doB && chk.backLen != xs[k].backLen) || (chk.doF && chk.forwLen != xs[k].forwLen)) {
+        pc[k].score = c.sf.front().score;
+        ExtState chk = pc[k].x;
+        extendPerfect(E, rc, c, true, true, pc[k].score, chk, false);
+        if (chk.doB != pc[k].x.doB || chk.doF != pc[k].x.doF || (chk.doB && chk.backLen != pc[k].x.backLen) ||
+            (chk.doF && chk.forwLen != pc[k].x.forwLen)) {
             fprintf(stderr, "yaha_b200: internal error: early extension plan diverged\n");
             abort();
         }
@@ -504,7 +509,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     for (size_t k = 0; k < old.size(); k++) {
         Clump *c = old[k];
         if (c->is(kAligned)) continue;
-        extendApply(E, rc, *c, xs[k], false, scores[k]);
+        extendApply(E, rc, *c, pc[k].x, false, pc[k].score);
         c->set(kAligned, true);
     }
     if (kAlignProf) gAlignProf[2] += rdtsc_() - q0;

@@ -93,7 +93,7 @@ struct FNode {                       // fGraphNode, GraphPath.cpp:65-79 (16-bit 
     uint16_t SQO, EQO;
 };
 
-static void buildBestClump(const Args &A, std::vector<Frag> &frags, int lo, int hi, std::vector<char> &used,
+static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, std::vector<char> &used,
                            std::vector<FNode> &nodes, Clump &clump)   // GraphPath.cpp:161-270
 {
     nodes.clear();
@@ -172,9 +172,9 @@ struct Coverage {
 void formClumps(const Env &E, ReadCtx &rc, bool rev)
 {
     const Args &A = *E.A;
-    std::vector<Frag> &frags = rc.frags[rev];
-    const std::vector<uint32_t> &reg = rc.region[rev];
-    const int n = (int)frags.size();
+    Frag *frags = rc.frags[rev];
+    const uint32_t *reg = rc.region[rev];
+    const int n = rc.nFrags[rev];
     static thread_local Coverage coverage;                      // per-thread scratch, reused across reads
     static thread_local std::vector<char> used;
     static thread_local std::vector<FNode> nodes;

@@ -204,9 +204,11 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     int    primaryCount = 0;
     RandState rng;
     uint64_t parked = 0;             // cycles spent parked in the scoring phase (YAHA_B200_PROF only)
-    std::vector<Frag> frags[2];      // mutable copy of the device's surviving fragments, per strand
-    std::vector<uint32_t> region[2];
-    std::string out;                 // formatted SAM / Blast8 records of this read
+    Frag  *frags[2] = {nullptr, nullptr};        // the device's surviving fragments of each strand, in the
+    const uint32_t *region[2] = {nullptr, nullptr};  // pipeline's result buffers (edited in place)
+    int    nFrags[2] = {0, 0};
+    std::string *out = nullptr;      // the worker's output buffer; this read's records are [outOff, outOff+outLen)
+    size_t outOff = 0, outLen = 0;
     const uint8_t *codes(bool rev) const { return rev ? read->rcode.data() : read->fcode.data(); }
     const std::string &chars(bool rev) const { return rev ? read->rev : read->fwd; }
 };

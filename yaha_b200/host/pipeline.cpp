@@ -71,7 +71,10 @@ struct Worker {
 struct Batch {
     uint64_t seq = 0;
     std::vector<Read> reads;
-    std::vector<std::unique_ptr<Fiber>> fibers;
+    std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous
+    int nFibers = 0;
+    struct alignas(64) OutBuf { std::string s; };   // (own cache line: every append updates the size)
+    std::vector<OutBuf> outBufs;          // formatted records, one buffer per worker thread
 };
 
 DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen)
@@ -178,17 +181,41 @@ struct StackPool {
 };
 static StackPool gStacks;
 
+// Growable array in page-locked memory (ya_host_alloc): what the device copies into and out of.
+template <class T> struct PinnedVec {
+    T *p = nullptr; size_t n = 0, cap = 0;
+    PinnedVec() {}
+    PinnedVec(const PinnedVec &) = delete;
+    PinnedVec &operator=(const PinnedVec &) = delete;
+    ~PinnedVec() { ya_host_free(p); }
+    T *data() { return p; }
+    size_t size() const { return n; }
+    T &operator[](size_t i) { return p[i]; }
+    void resize(size_t want)                   // contents are kept; new elements are not initialised
+    {
+        if (want > cap) {
+            size_t nc = std::max(want, cap + cap / 2);
+            T *q = (T *)ya_host_alloc(nc * sizeof(T));
+            if (!q) { fprintf(stderr, "yaha_b200: cannot allocate %zu bytes of page-locked memory\n", nc * sizeof(T)); exit(1); }
+            if (n) memcpy(q, p, n * sizeof(T));
+            ya_host_free(p);
+            p = q; cap = nc;
+        }
+        n = want;
+    }
+};
+
 struct Pipe {                              // one batch pipeline: a ya_ctx plus reusable host buffers
     ya_ctx *ctx = nullptr;
     int device = 0;
-    std::vector<ya_strand_frags> strands;
-    std::vector<ya_frag> frags;
-    std::vector<uint32_t> region;
-    std::vector<uint8_t> codes;
-    std::vector<uint64_t> offs;
+    PinnedVec<ya_strand_frags> strands;
+    PinnedVec<ya_frag> frags;
+    PinnedVec<uint32_t> region;
+    PinnedVec<uint8_t> codes;
+    PinnedVec<uint64_t> offs;
     std::vector<ya_dp_job> jobs;
-    std::vector<ya_dp_result> res;
-    std::vector<ya_op> ops;
+    PinnedVec<ya_dp_result> res;
+    PinnedVec<ya_op> ops;
     double tSeed = 0, tDp = 0, tHost = 0, tUpload = 0, tSetup = 0;
     uint64_t nJobs = 0, nRounds = 0;
 };
@@ -235,23 +262,35 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
 
     // fibers, dealt to the workers in contiguous slices
     t0 = nowSec();
-    B.fibers.clear();
-    B.fibers.reserve((size_t)n);
+    B.fibers.reset(new Fiber[(size_t)n]);
+    B.nFibers = n;
+    B.outBufs.clear();
+    B.outBufs.resize((size_t)nThreads);
     std::vector<Worker> workers((size_t)nThreads);
-    for (int t = 0; t < nThreads; t++) workers[(size_t)t].E = &E;
+    for (int t = 0; t < nThreads; t++) {
+        workers[(size_t)t].E = &E;
+        const int lo = (int)((int64_t)t * n / nThreads), hi = (int)((int64_t)(t + 1) * n / nThreads);
+        workers[(size_t)t].fibers.reserve((size_t)(hi - lo) + 1);
+        size_t bytes = 0;
+        for (int i = lo; i < hi; i++) bytes += B.reads[(size_t)i].fcode.size();
+        B.outBufs[(size_t)t].s.reserve(2 * bytes + 512 * (size_t)(hi - lo) + 4096);
+    }
     for (int i = 0; i < n; i++) {
-        std::unique_ptr<Fiber> f(new Fiber());
+        Fiber *f = &B.fibers[(size_t)i];
         f->stack = gStacks.get();
-        Worker &w = workers[(size_t)((int64_t)i * nThreads / n)];
+        const int t = (int)(((int64_t)i * nThreads) / n);
+        Worker &w = workers[(size_t)t];
         f->w = &w;
-        f->rc.owner = f.get(); f->rc.idx = i; f->rc.read = &B.reads[(size_t)i];
+        f->rc.owner = f; f->rc.idx = i; f->rc.read = &B.reads[(size_t)i];
+        f->rc.out = &B.outBufs[(size_t)t].s;
+        f->rc.clumps.reserve(8);
         for (int st = 0; st < 2; st++) {
             const ya_strand_frags &s = D.strands[(size_t)2 * i + st];
-            f->rc.frags[st].assign(D.frags.begin() + s.first, D.frags.begin() + s.first + s.n_frags);
-            f->rc.region[st].assign(D.region.begin() + s.first, D.region.begin() + s.first + s.n_frags);
+            f->rc.frags[st] = D.frags.data() + s.first;
+            f->rc.region[st] = D.region.data() + s.first;
+            f->rc.nFrags[st] = (int)s.n_frags;
         }
-        w.fibers.push_back(f.get());
-        B.fibers.push_back(std::move(f));
+        w.fibers.push_back(f);
     }
 
     D.tSetup += nowSec() - t0;
@@ -312,7 +351,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
         for (auto &x : th) x.join();
         pthread_barrier_destroy(&bar);
     }
-    for (auto &f : B.fibers) { gStacks.put(f->stack); f->stack = nullptr; }
+    for (int i = 0; i < n; i++) { gStacks.put(B.fibers[(size_t)i].stack); B.fibers[(size_t)i].stack = nullptr; }
 }
 
 // bounded, ordered hand-off between reader, pipelines and writer
@@ -472,10 +511,14 @@ int runQueries(const Args &A0)
                 F.done.erase(next);
             }
             double w0 = nowSec();
-            if (!replaying) for (auto &f : b->fibers) fwrite(f->rc.out.data(), 1, f->rc.out.size(), out);
+            if (!replaying)
+                for (int i = 0; i < b->nFibers; i++) {
+                    const ReadCtx &rc = b->fibers[(size_t)i].rc;
+                    if (rc.outLen) fwrite(rc.out->data() + rc.outOff, 1, rc.outLen, out);
+                }
             nReads += b->reads.size();
             tWrite += nowSec() - w0;
-            if (A.replay) { b->fibers.clear(); cache.push_back(std::move(b)); }
+            if (A.replay) { b->fibers.reset(); b->nFibers = 0; b->outBufs.clear(); cache.push_back(std::move(b)); }
         }
         reader.join();
         for (auto &t : pth) t.join();

@@ -57,7 +57,7 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
 {
     const Args &A = *E.A;
     const Genome &G = *E.G;
-    std::string &o = rc.out;
+    std::string &o = *rc.out;
     const Frag &f0 = c.sf.front().frag, &fn = c.sf.back().frag;
     uint32_t sStart = f0.startRefOff, sEnd = fragERO(fn);
     int si = G.findSeq(sStart);
@@ -67,7 +67,6 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
     const std::string &q = rc.chars(c.reversed());
     const int L = rc.read->len();
     if (A.outputSAM) {
-        o.reserve(o.size() + 2 * (size_t)L + 512);
         o += rc.read->id;
         o += c.reversed() ? "\t16\t" : "\t0\t";
         o += BS.name;
@@ -140,7 +139,9 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
 
 void formatClumps(const Env &E, ReadCtx &rc)
 {
+    rc.outOff = rc.out->size();
     for (int k = (int)rc.clumps.size() - 1; k >= 0; k--) formatClump(E, rc, *rc.clumps[k]);   // from the list head
+    rc.outLen = rc.out->size() - rc.outOff;
 }
 
 }  // namespace yh
