@@ -190,7 +190,8 @@ def run_ours(args):
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
     # run B: parsed reads replayed from host memory, SAM formatted but not written -> value, stage times and
-    # the kernel rooflines.  Larger batches (device-efficient launches: 20 K extension jobs per launch).
+    # the kernel rooflines.  Large batches: 20 K extension jobs per launch keep the DP kernel fed (smaller batches on
+    # more pipelines -- `--batch 5000 --pipes 4` -- give ~20 % more reads/s but latency-bound, half-empty launches).
     stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + args.warmup + args.steps,
                        args.batch, args.pipes, replay=True)
     timed = stats_b[1 + args.warmup:]

@@ -178,6 +178,9 @@ struct ExtState { int backLen = 0, forwLen = 0; DpFuture fb, ff; bool doB = fals
 static void collapse(Clump &c)                                          // AlignHelpers.c:274-300
 {
     int total = 0;
+    size_t nOps = c.ops.v.size();
+    for (auto &s : c.sf) nOps += s.ops.v.size();
+    c.ops.v.reserve(nOps);
     for (auto &s : c.sf) { total += s.score; c.ops.mergeToBack(s.ops); }
     SFrag &s0 = c.sf.front();
     const Frag fn = c.sf.back().frag;
@@ -464,7 +467,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     struct PerClump { ExtState x; int score = 0; size_t gapLo = 0, gapHi = 0; };
     std::vector<PerClump> pc(old.size());
     std::vector<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
-    gaps.reserve(4 * old.size() + 8);
+    gaps.reserve(std::min<size_t>(4 * old.size() + 4, 960 / sizeof(GapJob)));   // (stays a small-bin allocation)
     bool any = false;
     for (size_t k = 0; k < old.size(); k++) {
         if (old[k]->is(kAligned)) continue;

@@ -93,12 +93,22 @@ struct FNode {                       // fGraphNode, GraphPath.cpp:65-79 (16-bit 
     uint16_t SQO, EQO;
 };
 
-static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, std::vector<char> &used,
+// A set of small integers (query positions covered by the clumps already cut from a region; the
+// region's consumed fragments) stamped with a generation number instead of being cleared per region.
+struct Coverage {
+    std::vector<uint32_t> stamp; uint32_t gen = 0;
+    void reset(size_t n) { if (stamp.size() < n) stamp.resize(n, 0); if (++gen == 0) { std::fill(stamp.begin(), stamp.end(), 0); gen = 1; } }
+    void mark(int i) { stamp[(size_t)i] = gen; }
+    bool covered(int i) const { return stamp[(size_t)i] == gen; }
+    bool free(int a, int b) const { for (int i = a; i <= b; i++) if (covered(i)) return false; return true; }
+};
+
+static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, const Coverage &used,
                            std::vector<FNode> &nodes, Clump &clump)   // GraphPath.cpp:161-270
 {
     nodes.clear();
     for (int i = lo; i <= hi; i++) {
-        if (used[i - lo]) continue;
+        if (used.covered(i - lo)) continue;
         Frag &f = frags[i];
         FNode n; n.prev = -1; n.pathLength = 1; n.frag = &f; n.diag = fragDiag(f);
         n.nodeLength = (int16_t)f.refLen; n.bestScore = (int16_t)(n.nodeLength * A.MScore);
@@ -159,16 +169,6 @@ static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, std::vect
     else cleanUpClump(A, clump);
 }
 
-// Query positions covered by the clumps already cut from the current region: stamped with a
-// per-thread generation number instead of being cleared for every region.
-struct Coverage {
-    std::vector<uint32_t> stamp; uint32_t gen = 0;
-    void reset(size_t n) { if (stamp.size() < n) stamp.resize(n, 0); if (++gen == 0) { std::fill(stamp.begin(), stamp.end(), 0); gen = 1; } }
-    void mark(int i) { stamp[(size_t)i] = gen; }
-    bool covered(int i) const { return stamp[(size_t)i] == gen; }
-    bool free(int a, int b) const { for (int i = a; i <= b; i++) if (covered(i)) return false; return true; }
-};
-
 void formClumps(const Env &E, ReadCtx &rc, bool rev)
 {
     const Args &A = *E.A;
@@ -176,7 +176,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
     const uint32_t *reg = rc.region[rev];
     const int n = rc.nFrags[rev];
     static thread_local Coverage coverage;                      // per-thread scratch, reused across reads
-    static thread_local std::vector<char> used;
+    static thread_local Coverage used;
     static thread_local std::vector<FNode> nodes;
     Clump *spare = nullptr;                                     // an empty clump waiting for a path
     const int qSlots = rc.read->len() + 1;
@@ -194,7 +194,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
             }
         } else {                                                      // GraphPath.cpp:272-292
             coverage.reset((size_t)qSlots);
-            used.assign((size_t)(j - i + 1), 0);
+            used.reset((size_t)(j - i + 1));
             for (;;) {
                 Clump *c = spare ? spare : new Clump();
                 spare = nullptr;
@@ -205,12 +205,12 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
                 // eliminateFragments, QueryMatch.c:201-215 (+ :177-197)
                 const int minLeft = A.minNonOverlap - 1;
                 for (int k = i; k <= j; k++) {
-                    if (used[k - i]) continue;
+                    if (used.covered(k - i)) continue;
                     const int SQO = frags[k].startQueryOff, EQO = frags[k].endQueryOff;
                     bool keep = false;
                     if (EQO - SQO >= minLeft)
                         keep = coverage.free(SQO, SQO + minLeft) || coverage.free(EQO - minLeft, EQO);
-                    if (!keep) used[k - i] = 1;
+                    if (!keep) used.mark(k - i);
                 }
                 c->set(kReversed, rev);
                 rc.clumps.push_back(c);
