@@ -104,7 +104,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.5)
 
     def summary(self):
         if not self.rows:
@@ -182,16 +182,16 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     # run A: the job exactly as a user runs it (FASTA parsed, SAM written) -> e2e.  Tuned for the latency
-    # of a 20 K-read job: small batches on 4 overlapping pipelines, worker threads 2x oversubscribed.
-    e2e_tpp = max(1, threads // 2)
+    # of a 20 K-read job: small batches on 8 overlapping pipelines served by one pool of worker threads.
+    e2e_tpp = 0                      # shared worker pool of `threads` workers serves every pipeline
     stats_a = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, args.warmup + args.steps,
                        args.e2e_batch, args.e2e_pipes, tpp=e2e_tpp)
     timed_a = stats_a[args.warmup:]
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
     # run B: parsed reads replayed from host memory, SAM formatted but not written -> value, stage times and
-    # the kernel rooflines.  Large batches: 20 K extension jobs per launch keep the DP kernel fed (smaller batches on
-    # more pipelines -- `--batch 5000 --pipes 4` -- give ~20 % more reads/s but latency-bound, half-empty launches).
+    # the kernel rooflines (kernels of up to 8 pipelines share the SMs here, which stretches their event timings;
+    # run C below times the same kernels alone).
     stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + args.warmup + args.steps,
                        args.batch, args.pipes, replay=True)
     timed = stats_b[1 + args.warmup:]
@@ -257,8 +257,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD_DESC[wl], "reads_per_gpu": n_reads, "read_len": rl, "error": err,
                    "flags": REF_FLAGS[wl], "host_threads_per_gpu": threads,
                    "l2": "inputs larger than L2 (4.3 GB index gathers; reads re-uploaded every step)",
-                   "value_run": {"batch_reads": args.batch, "pipelines_per_gpu": args.pipes, "threads_per_pipeline": threads // args.pipes},
-                   "e2e_run": {"batch_reads": args.e2e_batch, "pipelines_per_gpu": args.e2e_pipes, "threads_per_pipeline": e2e_tpp},
+                   "value_run": {"batch_reads": args.batch, "pipelines_per_gpu": args.pipes, "worker_pool_threads": threads},
+                   "e2e_run": {"batch_reads": args.e2e_batch, "pipelines_per_gpu": args.e2e_pipes, "worker_pool_threads": threads},
                    "value_excludes": "FASTA parsing and SAM fwrite (reads replayed from host memory; the 10 MB/step H2D of "
                                      "read codes is still inside); e2e includes everything",
                    "setup_s": round(t_setup, 2)},
@@ -412,10 +412,10 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=20000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=10000, help="reads per device batch")
-    ap.add_argument("--pipes", type=int, default=2, help="concurrent batch pipelines per GPU")
+    ap.add_argument("--batch", type=int, default=2500, help="reads per device batch")
+    ap.add_argument("--pipes", type=int, default=8, help="concurrent batch pipelines per GPU")
     ap.add_argument("--e2e-batch", type=int, default=2500, help="reads per device batch in the e2e run")
-    ap.add_argument("--e2e-pipes", type=int, default=4, help="pipelines per GPU in the e2e run")
+    ap.add_argument("--e2e-pipes", type=int, default=8, help="pipelines per GPU in the e2e run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

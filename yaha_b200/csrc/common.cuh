@@ -20,7 +20,7 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 2 + 256;        // generous: a re-allocation (cudaFree) synchronises the whole device
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -38,7 +38,7 @@ struct PinBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + bytes / 2 + 256;        // generous: a re-allocation (cudaFree) synchronises the whole device
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -72,11 +72,20 @@ struct DevJobOut {
     uint32_t cells_lo, cells_hi;   // 64-bit cell count split (avoids alignment padding)
 };
 
-// One device phase at a time per GPU: the pipelines of a process take turns for their
-// launch..sync sections instead of time-slicing the SMs (each finishes sooner, and the CUDA-event
-// timings of a kernel are not stretched by another pipeline's launches).  YA_NO_GPU_LOCK=1 disables.
+// YA_GPU_LOCK=1: one device phase at a time per GPU -- the pipelines of a process take turns for their
+// launch..sync sections instead of sharing the SMs (CUDA-event timings of a kernel are then not stretched
+// by another pipeline's launches).  Off by default: most calls are bound by launch and serial-chain latency,
+// and overlapping them is worth more than clean timings.
 std::mutex &ya_device_mutex(int device);
 bool ya_device_turns();
+// Waits for a stream the way YA_SYNC asks.  Default "nap": poll cudaStreamQuery and sleep ~20 us between
+// polls -- the thread driving a context shares the machine with the host's worker threads, so it must not
+// burn a core while the device works.  "yield" polls with sched_yield; "spin" / "block" are the driver's own
+// cudaStreamSynchronize (with cudaDeviceScheduleBlockingSync for "block").
+cudaError_t ya_stream_wait(cudaStream_t st);
+cudaError_t ya_event_wait(cudaEvent_t ev);
+std::mutex &ya_bulk_mutex(int device);
+
 struct DeviceTurn {
     std::unique_lock<std::mutex> lk;
     explicit DeviceTurn(int device) : lk(ya_device_mutex(device), std::defer_lock) { if (ya_device_turns()) lk.lock(); }
@@ -87,6 +96,7 @@ struct ya_ctx {
     int          device = -1;
     ya_params    P{};
     cudaStream_t own_stream = nullptr;
+    cudaStream_t bulk_stream = nullptr;   // lowest priority: DP calls with many jobs
     cudaStream_t stream = nullptr;
     std::string  err;
     // index + genome (device resident)

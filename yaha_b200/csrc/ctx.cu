@@ -5,6 +5,9 @@
 // (Query.c:161-168: forward + reverse-complement code buffers) with one batched upload plus
 // a device kernel that derives the reverse-complement strand.
 #include "common.cuh"
+#include <sched.h>
+#include <sys/prctl.h>
+#include <time.h>
 #include <algorithm>
 
 static thread_local std::string g_open_err;
@@ -59,6 +62,11 @@ static ya_ctx *open_common(int device, const ya_params *params)
     }
     if (cudaSetDevice(device) != cudaSuccess) { g_open_err = "cudaSetDevice failed"; return nullptr; }
     {
+        // YA_SYNC=block: the thread that drives a context sleeps in its stream synchronisations (see ya_stream_wait)
+        const char *e = getenv("YA_SYNC");
+        if (e && strcmp(e, "block") == 0) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+    }
+    {
         // Every hot access of this library is a random gather (starting-offset table, ROA lists,
         // back-pointer walk): ask L2 to fetch 32 B sectors instead of whole 128 B lines so that a
         // probe costs one DRAM sector, not four (measured: 4.85 sectors/probe at the default).
@@ -69,7 +77,12 @@ static ya_ctx *open_common(int device, const ya_params *params)
     ya_ctx *c = new ya_ctx();
     c->device = device;
     c->P = *params;
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // Two streams: latency-critical work (read upload, seed stage, DP calls with few jobs) runs at the highest
+    // priority so that its small kernels are not queued behind another pipeline's bulk DP launches.
+    int prLeast = 0, prGreatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest);
+    if (cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prGreatest) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->bulk_stream, cudaStreamNonBlocking, prLeast) != cudaSuccess) {
         g_open_err = "cudaStreamCreate failed"; delete c; return nullptr;
     }
     c->stream = c->own_stream;
@@ -167,6 +180,49 @@ extern "C" void *ya_host_alloc(size_t bytes)
 }
 extern "C" void ya_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+static int ya_sync_mode()
+{
+    // 0 nap (default): poll, sleeping ~20 us between polls (timer slack lowered for this thread)
+    // 1 the driver's own synchronisation ("spin", or "block" with cudaDeviceScheduleBlockingSync)
+    // 2 yield: poll and sched_yield between polls
+    static const int mode = [] {
+        const char *e = getenv("YA_SYNC");
+        if (!e) return 0;
+        if (strcmp(e, "spin") == 0 || strcmp(e, "block") == 0) return 1;
+        if (strcmp(e, "yield") == 0) return 2;
+        return 0;
+    }();
+    return mode;
+}
+template <class Query> static cudaError_t ya_poll(Query q)
+{
+    static const long nap_ns = [] { const char *e = getenv("YA_NAP_US"); return (long)(e ? atoi(e) : 20) * 1000L; }();
+    const int mode = ya_sync_mode();
+    static thread_local bool slackSet = false;
+    if (mode == 0 && !slackSet) { prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0); slackSet = true; }
+    for (int polls = 0;; polls++) {
+        cudaError_t e = q();
+        if (e != cudaErrorNotReady) return e;
+        if (mode == 2 || polls < 4) sched_yield();
+        else { struct timespec ts = {0, nap_ns}; nanosleep(&ts, nullptr); }
+    }
+}
+cudaError_t ya_stream_wait(cudaStream_t st)
+{
+    if (ya_sync_mode() == 1) return cudaStreamSynchronize(st);
+    return ya_poll([st] { return cudaStreamQuery(st); });
+}
+cudaError_t ya_event_wait(cudaEvent_t ev)
+{
+    if (ya_sync_mode() == 1) return cudaEventSynchronize(ev);
+    return ya_poll([ev] { return cudaEventQuery(ev); });
+}
+std::mutex &ya_bulk_mutex(int device)
+{
+    static std::mutex mu[64];
+    return mu[(unsigned)device & 63u];
+}
+
 std::mutex &ya_device_mutex(int device)
 {
     static std::mutex mu[64];
@@ -174,7 +230,7 @@ std::mutex &ya_device_mutex(int device)
 }
 bool ya_device_turns()
 {
-    static const bool on = getenv("YA_NO_GPU_LOCK") == nullptr;
+    static const bool on = getenv("YA_GPU_LOCK") != nullptr;      // off by default: contexts of one device overlap their phases
     return on;
 }
 
@@ -209,6 +265,7 @@ extern "C" void ya_close(ya_ctx *c)
     for (PinBuf *b : pins) b->release();
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->bulk_stream) cudaStreamDestroy(c->bulk_stream);
     delete c;
 }
 
@@ -261,7 +318,7 @@ extern "C" int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
         c->ctr.launches++;
         YA_CUDA(c, cudaGetLastError());
     }
-    YA_CUDA(c, cudaStreamSynchronize(c->stream));
+    YA_CUDA(c, ya_stream_wait(c->stream));
     return YA_OK;
 }
 

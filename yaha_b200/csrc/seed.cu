@@ -451,7 +451,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     }
     uint32_t *h_seg_eff = c->h_stage.as<uint32_t>();
     YA_CUDA(c, cudaMemcpyAsync(h_seg_eff, d_seg_eff, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
-    YA_CUDA(c, cudaStreamSynchronize(st));
+    YA_CUDA(c, ya_stream_wait(st));
     c->ctr.probes += n_probes;
     { float msl = 0; cudaEventElapsedTime(&msl, c->ev[3], c->ev[4]); c->ctr.ms_lookup += msl; }
 
@@ -511,7 +511,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
                     seg_sort_kernel<8192, 256><<<(unsigned)big.size(), 256, 8192 * 8, st>>>(ka, d_sko, d_big, (int)big.size());
                     c->ctr.launches++;
                 }
-                YA_CUDA(c, cudaStreamSynchronize(st));              // the id vectors are reused by the next chunk
+                YA_CUDA(c, ya_stream_wait(st));              // the id vectors are reused by the next chunk
             } else {
                 int segbits = 1; while ((1 << segbits) < cseg) segbits++;
                 rc = ya_radix_sort_u64(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
@@ -531,7 +531,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             if (rc != YA_OK) return rc;
             uint32_t nf = 0;
             YA_CUDA(c, cudaMemcpyAsync(&nf, d_tot, 4, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, ya_stream_wait(st));
             c->ctr.frags_all += nf;
             YA_CUDA(c, c->d_frags_all.reserve((size_t)nf * sizeof(FragRaw)));
             YA_CUDA(c, c->d_frag_seg.reserve((size_t)nf * 2 + 16));
@@ -558,7 +558,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             if (rc != YA_OK) return rc;
             uint32_t nreg = 0;
             YA_CUDA(c, cudaMemcpyAsync(&nreg, d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, ya_stream_wait(st));
             YA_CUDA(c, c->d_regstart.reserve(((size_t)nreg + 1) * 4));
             uint32_t *rstart = c->d_regstart.as<uint32_t>();
             region_start_kernel<<<fb, 256, 0, st>>>(rflag, ridx, nf, rstart, nreg);
@@ -568,7 +568,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             if (rc != YA_OK) return rc;
             uint32_t nkeep = 0;
             YA_CUDA(c, cudaMemcpyAsync(&nkeep, d_tot + 2, 4, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, ya_stream_wait(st));
             YA_CUDA(c, c->d_frags_out.reserve((size_t)nkeep * sizeof(ya_frag) + 16));
             YA_CUDA(c, c->d_region_out.reserve((size_t)nkeep * 4 + 16));
             compact_kernel<<<fb, 256, 0, st>>>(raw, eqo, rflag, ridx, keep, kidx, seg_first, nf,
@@ -588,7 +588,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             // strands of this chunk come back with chunk-relative `first`; fix up on the host
             YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
                                        cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, ya_stream_wait(st));
             for (int s = s0; s < s1; s++) {
                 ya_strand_frags &v = out->strands[s];
                 v.first = v.n_frags ? (uint32_t)(v.first + out_base) : (uint32_t)out_base;
@@ -597,7 +597,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
         } else {
             YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
                                        cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, cudaStreamSynchronize(st));
+            YA_CUDA(c, ya_stream_wait(st));
             for (int s = s0; s < s1; s++) out->strands[s].first = (uint32_t)out_base;
         }
         s0 = s1;

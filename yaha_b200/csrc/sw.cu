@@ -717,6 +717,12 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     if (n == 0) return YA_OK;
     if (c->n_reads == 0) return ya_fail(c, YA_E_STATE, "ya_sw_batch: no read batch uploaded");
     YA_CUDA(c, cudaSetDevice(c->device));
+    // bulk calls go to the low-priority stream (unless the caller installed its own stream)
+    struct StreamSwap {
+        ya_ctx *c; cudaStream_t saved;
+        StreamSwap(ya_ctx *c_, bool bulk) : c(c_), saved(c_->stream) { if (bulk && c->stream == c->own_stream && c->bulk_stream) c->stream = c->bulk_stream; }
+        ~StreamSwap() { c->stream = saved; }
+    } streamSwap(c, n >= 2048);
     cudaStream_t st = c->stream;
     const ya_params &P = c->P;
     const int bw2 = 2 * P.bandWidth;
@@ -860,6 +866,12 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
             launch_wave_cfg(c, k, false, d_ids + start[kNumWaveCfgs + k], (int)lists[kNumWaveCfgs + k].size(), K);
     }
     const bool anyPacked = !lists[packedBase + 0].empty() || !lists[packedBase + 1].empty();
+    // Bulk extension launches of the contexts sharing a device run one at a time (they would only time-slice
+    // the SMs), which also keeps their CUDA-event timing free of another pipeline's bulk kernel.
+    static const bool bulkExclusive = [] { const char *e = getenv("YA_BULK_EXCLUSIVE"); return !e || atoi(e) != 0; }();
+    const size_t nPackedAll = lists[packedBase + 0].size() + lists[packedBase + 1].size();
+    std::unique_lock<std::mutex> bulkTurn(ya_bulk_mutex(c->device), std::defer_lock);
+    if (anyPacked && bulkExclusive && nPackedAll >= 2048) bulkTurn.lock();
     if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[3], st));
     if (!lists[packedBase + 0].empty()) {
         if (narrow21) launch_packed<4, 6, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
@@ -870,6 +882,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         else          launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
     }
     if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[4], st));
+    if (bulkTurn.owns_lock()) { YA_CUDA(c, ya_event_wait(c->ev[4])); bulkTurn.unlock(); }
     if (!lists[2 * kNumWaveCfgs].empty()) {
         int nt = (int)lists[2 * kNumWaveCfgs].size();
         dp_thread_kernel<<<(nt + 63) / 64, 64, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids + start[2 * kNumWaveCfgs], nt,
@@ -890,7 +903,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     if (rc != YA_OK) return rc;
     uint32_t total_ops = 0;
     YA_CUDA(c, cudaMemcpyAsync(&total_ops, d_tot, 4, cudaMemcpyDeviceToHost, st));
-    YA_CUDA(c, cudaStreamSynchronize(st));
+    YA_CUDA(c, ya_stream_wait(st));
     double tp3 = now_s(); g_prof_sw[2] += tp3 - tp2;
     YA_CUDA(c, c->d_ops_out.reserve((size_t)total_ops * sizeof(ya_op) + 64));
     compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
@@ -904,7 +917,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     const bool fits = total_ops <= ops_cap && (total_ops == 0 || ops != nullptr);
     if (fits && total_ops)
         YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
-    YA_CUDA(c, cudaStreamSynchronize(st));
+    YA_CUDA(c, ya_stream_wait(st));
     YA_CUDA(c, cudaGetLastError());
     turn.done();
     double tp4 = now_s(); g_prof_sw[3] += tp4 - tp3;
@@ -943,7 +956,7 @@ extern "C" int ya_sw_fetch_ops(ya_ctx *c, ya_op *ops, size_t ops_cap)
     if (!ops || ops_cap < c->ops_pending) return ya_fail(c, YA_E_CAPACITY, "op output buffer too small");
     YA_CUDA(c, cudaSetDevice(c->device));
     YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, c->ops_pending * sizeof(ya_op), cudaMemcpyDeviceToHost, c->stream));
-    YA_CUDA(c, cudaStreamSynchronize(c->stream));
+    YA_CUDA(c, ya_stream_wait(c->stream));
     return YA_OK;
 }
 
@@ -976,7 +989,7 @@ extern "C" int ya_perfect_ext(ya_ctx *c, const ya_dp_job *jobs, int n, uint16_t 
         c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), c->d_res.as<uint16_t>());
     c->ctr.launches++;
     YA_CUDA(c, cudaMemcpyAsync(count, c->d_res.p, (size_t)n * 2, cudaMemcpyDeviceToHost, c->stream));
-    YA_CUDA(c, cudaStreamSynchronize(c->stream));
+    YA_CUDA(c, ya_stream_wait(c->stream));
     YA_CUDA(c, cudaGetLastError());
     return YA_OK;
 }

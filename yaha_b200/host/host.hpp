@@ -44,7 +44,7 @@ struct Args {                       // AlignmentArgs_t, Math.h:257-334; defaults
     int   firstDev = 0;             // -dev D  : first CUDA device ordinal
     int   passes = 1;               // -passes N: repeat the whole job N times (bench.py), one stats line per pass
     int   pipes = 2;                // -pipes P : concurrent batch pipelines per device (overlap host and device phases)
-    int   threadsPerPipe = 0;       // -tpp N   : worker threads per pipeline (0 = threads / pipelines); may oversubscribe
+    int   threadsPerPipe = 0;       // -tpp N   : size of the shared worker pool when it should differ from -t (may oversubscribe)
     bool  replay = false;           // -replay  : passes after the first reuse the parsed reads and skip the SAM fwrite
     bool  query = false, index = true;
     void  postProcess(bool queryMode);           // AlignArgs.c:108-169

@@ -49,37 +49,46 @@ __asm__(
     "  ret\n"
     ".size yh_switch,.-yh_switch\n");
 
-struct Worker;
+struct Slot;
 struct Fiber {
     void *sp = nullptr;                   // saved stack pointer while not running
     void *stack = nullptr;
     bool done = false, started = false;
     ReadCtx rc;
-    Worker *w = nullptr;
+    Slot *w = nullptr;
 };
 
-struct Worker {
+// Page-locked result arrays of one ya_sw_batch call.  A block stays alive until every slot served by the
+// call has run its next pass (the fibers' DpAnswer views point into it).
+struct ResultBlock;
+
+// One worker thread's share of one batch: its fibers, the jobs they posted in the current pass and the
+// answers of the previous device call.  A fiber never migrates between OS threads.
+struct Slot {
     void *mainSp = nullptr;
     std::vector<Fiber *> fibers;
-    std::vector<ya_dp_job> jobs;          // posted in the current round
-    const ya_dp_result *res = nullptr;    // previous round's results (this worker's jobs start at ansBase)
+    int lo = 0, hi = 0;                   // this slot's reads of the batch: [lo, hi)
+    std::vector<ya_dp_job> jobs;          // posted in the current pass
+    const ya_dp_result *res = nullptr;    // answers (this slot's jobs start at ansBase)
     const ya_op *ops = nullptr;
-    size_t ansBase = 0, ansCount = 0;
+    size_t ansBase = 0;
+    ResultBlock *block = nullptr;         // the block res/ops point into (released after the next pass)
     const Env *E = nullptr;
+    bool set = false;                     // fibers created
 };
 
 struct Batch {
     uint64_t seq = 0;
     std::vector<Read> reads;
-    std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous
-    int nFibers = 0;
+    std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous (kept when the batch object is recycled)
+    int nFibers = 0, fiberCap = 0;
     struct alignas(64) OutBuf { std::string s; };   // (own cache line: every append updates the size)
     std::vector<OutBuf> outBufs;          // formatted records, one buffer per worker thread
 };
 
 DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen)
 {
-    Worker *w = ((Fiber *)rc.owner)->w;
+    Slot *w = ((Fiber *)rc.owner)->w;
     ya_dp_job j;
     j.rOff = rOff; j.read = (uint32_t)rc.idx; j.rLen = (uint16_t)rLen; j.qOff = (uint16_t)qOff; j.qLen = (uint16_t)qLen;
     j.kind = (uint8_t)kind; j.strand = rev ? 1 : 0;
@@ -96,7 +105,7 @@ void dpWait(ReadCtx &rc)
 
 DpAnswer dpGet(ReadCtx &rc, DpFuture fu)
 {
-    Worker *w = ((Fiber *)rc.owner)->w;
+    Slot *w = ((Fiber *)rc.owner)->w;
     const ya_dp_result &r = w->res[w->ansBase + (size_t)fu.slot];
     DpAnswer a;
     a.score = r.score; a.addedQ = r.addedQLen; a.addedR = r.addedRLen; a.ops = w->ops + r.ops_off; a.n = (int)r.ops_n;
@@ -143,8 +152,8 @@ static void fiberEntry()
     __builtin_trap();                     // a finished fiber is never resumed
 }
 
-// run every unfinished fiber of this worker until it parks or finishes; returns #unfinished
-static int workerRound(Worker &w)
+// run every unfinished fiber of this slot until it parks or finishes; returns #unfinished
+static int slotPass(Slot &w)
 {
     int live = 0;
     for (Fiber *f : w.fibers) {
@@ -191,18 +200,24 @@ template <class T> struct PinnedVec {
     T *data() { return p; }
     size_t size() const { return n; }
     T &operator[](size_t i) { return p[i]; }
-    void resize(size_t want)                   // contents are kept; new elements are not initialised
+    void resize(size_t want, bool keep = true)   // new elements are not initialised
     {
         if (want > cap) {
             size_t nc = std::max(want, cap + cap / 2);
             T *q = (T *)ya_host_alloc(nc * sizeof(T));
             if (!q) { fprintf(stderr, "yaha_b200: cannot allocate %zu bytes of page-locked memory\n", nc * sizeof(T)); exit(1); }
-            if (n) memcpy(q, p, n * sizeof(T));
+            if (n && keep) memcpy(q, p, n * sizeof(T));
             ya_host_free(p);
             p = q; cap = nc;
         }
         n = want;
     }
+};
+
+struct ResultBlock {
+    PinnedVec<ya_dp_result> res;
+    PinnedVec<ya_op> ops;
+    std::atomic<int> users{0};
 };
 
 struct Pipe {                              // one batch pipeline: a ya_ctx plus reusable host buffers
@@ -214,10 +229,29 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     PinnedVec<uint8_t> codes;
     PinnedVec<uint64_t> offs;
     std::vector<ya_dp_job> jobs;
-    PinnedVec<ya_dp_result> res;
-    PinnedVec<ya_op> ops;
+    std::vector<std::unique_ptr<ResultBlock>> blocks;      // every result block this pipeline ever made
+    std::vector<ResultBlock *> freeBlocks;
+    std::mutex blkMu;
+    size_t capJobs = 0, capOps = 0;       // capacity every result block is grown to
+    // hand-off between the worker threads and this pipeline's device thread, for the batch in flight
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> published;           // slots whose pass ended with posted jobs
+    int slotsDone = 0, running = 0;       // slots with no unfinished fiber / slots inside a pass
     double tSeed = 0, tDp = 0, tHost = 0, tUpload = 0, tSetup = 0;
     uint64_t nJobs = 0, nRounds = 0;
+
+    ResultBlock *acquireBlock()
+    {
+        std::lock_guard<std::mutex> g(blkMu);
+        if (!freeBlocks.empty()) { ResultBlock *b = freeBlocks.back(); freeBlocks.pop_back(); return b; }
+        blocks.emplace_back(new ResultBlock());
+        return blocks.back().get();
+    }
+    void releaseBlock(ResultBlock *b)
+    {
+        if (b->users.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(blkMu); freeBlocks.push_back(b); }
+    }
 };
 
 static void die(ya_ctx *c, const char *what)
@@ -231,125 +265,226 @@ static double nowSec()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Align one batch on one pipeline with `nThreads` host workers.  Results land in each read's rc.out.
-static void processBatch(const Env &E, Pipe &D, Batch &B, int nThreads)
+// YA_TRACE=<file>: every phase of every thread as one line "kind who batch t0_us t1_us extra" (timeline debugging)
+struct TraceEv { char kind; int who; int batch; double t0, t1; int extra; };
+static const char *kTracePath = getenv("YA_TRACE");
+static std::mutex gTraceMu;
+static std::vector<TraceEv> gTrace;
+static inline void traceEv(char kind, int who, int batch, double t0, double t1, int extra = 0)
+{
+    if (!kTracePath) return;
+    std::lock_guard<std::mutex> g(gTraceMu);
+    gTrace.push_back(TraceEv{kind, who, batch, t0, t1, extra});
+}
+static void traceDump()
+{
+    if (!kTracePath || gTrace.empty()) return;
+    FILE *f = fopen(kTracePath, "w");
+    if (!f) return;
+    for (const TraceEv &e : gTrace) fprintf(f, "%c %d %d %.1f %.1f %d\n", e.kind, e.who, e.batch, e.t0 * 1e6, e.t1 * 1e6, e.extra);
+    fclose(f);
+}
+
+// ----------------------------------------------------------------------------- worker pool
+// -t N persistent worker threads shared by every pipeline.  A task is "run one pass over your fibers
+// of that batch": worker t always serves slot t, so a fiber stays on one OS thread for its whole life.
+struct Task { Pipe *pipe; Batch *batch; Slot *slot; int t; };
+struct PoolWorker {
+    std::mutex mu; std::condition_variable cv;
+    std::deque<Task> q; bool stop = false;
+    std::thread th;
+};
+
+static void runSlotPass(const Task &t)
+{
+    Pipe &D = *t.pipe; Slot &s = *t.slot; Batch &B = *t.batch;
+    const double h0 = nowSec();
+    if (!s.set) {                                                       // first pass: this slot's fibers
+        s.set = true;
+        s.fibers.reserve((size_t)(s.hi - s.lo));
+        size_t bytes = 0;
+        for (int i = s.lo; i < s.hi; i++) bytes += B.reads[(size_t)i].fcode.size();
+        B.outBufs[(size_t)t.t].s.reserve(2 * bytes + 512 * (size_t)(s.hi - s.lo) + 4096);
+        for (int i = s.lo; i < s.hi; i++) {
+            Fiber *f = &B.fibers[(size_t)i];
+            f->stack = gStacks.get();
+            f->w = &s;
+            f->sp = nullptr; f->done = false; f->started = false;     // (the fiber object may be a recycled one)
+            f->rc.clumps.clear(); f->rc.primaryCount = 0; f->rc.parked = 0; f->rc.outOff = 0; f->rc.outLen = 0;
+            f->rc.owner = f; f->rc.idx = i; f->rc.read = &B.reads[(size_t)i];
+            f->rc.out = &B.outBufs[(size_t)t.t].s;
+            f->rc.clumps.reserve(8);
+            for (int st = 0; st < 2; st++) {
+                const ya_strand_frags &sf = D.strands[(size_t)2 * i + st];
+                f->rc.frags[st] = D.frags.data() + sf.first;
+                f->rc.region[st] = D.region.data() + sf.first;
+                f->rc.nFrags[st] = (int)sf.n_frags;
+            }
+            s.fibers.push_back(f);
+        }
+    }
+    const int live = slotPass(s);
+    if (s.block) { D.releaseBlock(s.block); s.block = nullptr; }      // the answers of the previous call are consumed
+    const double dt = nowSec() - h0;
+    traceEv('H', t.t, (int)B.seq, h0, h0 + dt, live);
+    std::lock_guard<std::mutex> lk(D.mu);
+    D.tHost += dt;
+    D.running--;
+    if (!s.jobs.empty()) D.published.push_back(t.t);
+    else {
+        if (live != 0) { fprintf(stderr, "yaha_b200: internal error: parked fibers without jobs\n"); exit(1); }
+        D.slotsDone++;
+    }
+    D.cv.notify_one();
+}
+
+struct WorkerPool {
+    std::vector<std::unique_ptr<PoolWorker>> w;
+    void start(int n)
+    {
+        for (int t = 0; t < n; t++) {
+            w.emplace_back(new PoolWorker());
+            PoolWorker *me = w.back().get();
+            me->th = std::thread([me]() {
+                for (;;) {
+                    Task t;
+                    {
+                        std::unique_lock<std::mutex> lk(me->mu);
+                        me->cv.wait(lk, [&] { return !me->q.empty() || me->stop; });
+                        if (me->q.empty()) return;
+                        t = me->q.front(); me->q.pop_front();
+                    }
+                    runSlotPass(t);
+                }
+            });
+        }
+    }
+    void post(const Task &t)
+    {
+        PoolWorker &p = *w[(size_t)t.t];
+        { std::lock_guard<std::mutex> lk(p.mu); p.q.push_back(t); }
+        p.cv.notify_one();
+    }
+    void stop()
+    {
+        for (auto &p : w) { { std::lock_guard<std::mutex> lk(p->mu); p->stop = true; } p->cv.notify_one(); }
+        for (auto &p : w) p->th.join();
+        w.clear();
+    }
+    int size() const { return (int)w.size(); }
+};
+
+// After the first slot of a batch has published its jobs the device thread waits this long (at most)
+// for the slots still inside a pass, so that one ya_sw_batch serves many slots.
+static int coalesceMicros()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("YA_COALESCE_US"); v = e ? atoi(e) : 200; }
+    return v;
+}
+
+// Align one batch on one pipeline.  This thread drives the device (stages 1+2, then one ya_sw_batch per
+// group of published slots); the shared workers run the fibers.  Results land in each read's rc.out.
+static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
 {
     const int n = (int)B.reads.size();
     if (n == 0) return;
     double t0 = nowSec();
-    D.offs.resize((size_t)n + 1);
+    D.offs.resize((size_t)n + 1, false);
     size_t total = 0;
     for (int i = 0; i < n; i++) { D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fcode.size(); }
     D.offs[(size_t)n] = total;
-    D.codes.resize(total);
+    D.codes.resize(total, false);
     for (int i = 0; i < n; i++) memcpy(D.codes.data() + D.offs[(size_t)i], B.reads[(size_t)i].fcode.data(), B.reads[(size_t)i].fcode.size());
     ya_read_batch rb; rb.n_reads = n; rb.codes = D.codes.data(); rb.offsets = D.offs.data();
     if (ya_reads_upload(D.ctx, &rb) != YA_OK) die(D.ctx, "ya_reads_upload");
     D.tUpload += nowSec() - t0;
+    traceEv('U', D.device, (int)B.seq, t0, nowSec());
     t0 = nowSec();
     // stages 1+2
-    D.strands.resize((size_t)2 * n);
-    if (D.frags.size() < (size_t)64 * n) { D.frags.resize((size_t)64 * n); D.region.resize((size_t)64 * n); }
+    D.strands.resize((size_t)2 * n, false);
+    if (D.frags.size() < (size_t)64 * n) { D.frags.resize((size_t)64 * n, false); D.region.resize((size_t)64 * n, false); }
     ya_frag_batch fb;
     for (;;) {
         fb.frags_cap = D.frags.size(); fb.strands = D.strands.data(); fb.frags = D.frags.data(); fb.region = D.region.data();
         int rcode = ya_seed_frags(D.ctx, &fb);
-        if (rcode == YA_E_CAPACITY) { D.frags.resize(fb.frags_needed + 1024); D.region.resize(fb.frags_needed + 1024); continue; }
+        if (rcode == YA_E_CAPACITY) { D.frags.resize(fb.frags_needed + 1024, false); D.region.resize(fb.frags_needed + 1024, false); continue; }
         if (rcode != YA_OK) die(D.ctx, "ya_seed_frags");
         break;
     }
     D.tSeed += nowSec() - t0;
+    traceEv('S', D.device, (int)B.seq, t0, nowSec());
 
-    // fibers, dealt to the workers in contiguous slices
+    // fibers: contiguous slices of the batch, one slot per worker thread (set up by the worker itself)
     t0 = nowSec();
-    B.fibers.reset(new Fiber[(size_t)n]);
+    const int nW = pool.size();
+    if (B.fiberCap < n) { B.fibers.reset(new Fiber[(size_t)n]); B.fiberCap = n; }
     B.nFibers = n;
-    B.outBufs.clear();
-    B.outBufs.resize((size_t)nThreads);
-    std::vector<Worker> workers((size_t)nThreads);
-    for (int t = 0; t < nThreads; t++) {
-        workers[(size_t)t].E = &E;
-        const int lo = (int)((int64_t)t * n / nThreads), hi = (int)((int64_t)(t + 1) * n / nThreads);
-        workers[(size_t)t].fibers.reserve((size_t)(hi - lo) + 1);
-        size_t bytes = 0;
-        for (int i = lo; i < hi; i++) bytes += B.reads[(size_t)i].fcode.size();
-        B.outBufs[(size_t)t].s.reserve(2 * bytes + 512 * (size_t)(hi - lo) + 4096);
-    }
-    for (int i = 0; i < n; i++) {
-        Fiber *f = &B.fibers[(size_t)i];
-        f->stack = gStacks.get();
-        const int t = (int)(((int64_t)i * nThreads) / n);
-        Worker &w = workers[(size_t)t];
-        f->w = &w;
-        f->rc.owner = f; f->rc.idx = i; f->rc.read = &B.reads[(size_t)i];
-        f->rc.out = &B.outBufs[(size_t)t].s;
-        f->rc.clumps.reserve(8);
-        for (int st = 0; st < 2; st++) {
-            const ya_strand_frags &s = D.strands[(size_t)2 * i + st];
-            f->rc.frags[st] = D.frags.data() + s.first;
-            f->rc.region[st] = D.region.data() + s.first;
-            f->rc.nFrags[st] = (int)s.n_frags;
+    if ((int)B.outBufs.size() != nW) { B.outBufs.clear(); B.outBufs.resize((size_t)nW); }
+    for (auto &ob : B.outBufs) ob.s.clear();
+    std::vector<Slot> slots((size_t)nW);
+    {
+        std::lock_guard<std::mutex> lk(D.mu);
+        D.published.clear(); D.slotsDone = 0; D.running = 0;
+        for (int t = 0; t < nW; t++) {
+            Slot &s = slots[(size_t)t];
+            s.E = &E;
+            s.lo = (int)((int64_t)t * n / nW); s.hi = (int)((int64_t)(t + 1) * n / nW);
+            if (s.hi > s.lo) D.running++; else D.slotsDone++;
         }
-        w.fibers.push_back(f);
     }
-
+    for (int t = 0; t < nW; t++)
+        if (slots[(size_t)t].hi > slots[(size_t)t].lo) pool.post(Task{&D, &B, &slots[(size_t)t], t});
     D.tSetup += nowSec() - t0;
-    // rounds: every worker thread keeps its own fibers for the whole batch (a fiber never migrates
-    // between OS threads); thread 0 runs the device call between two barriers
-    std::atomic<int> live(0);
-    bool finished = false;
-    auto deviceRound = [&]() {
-        double h1 = nowSec();
-        D.jobs.clear();
-        for (Worker &w : workers) {
-            w.ansBase = D.jobs.size(); w.ansCount = w.jobs.size();
-            D.jobs.insert(D.jobs.end(), w.jobs.begin(), w.jobs.end());
-            w.jobs.clear();
+
+    std::vector<int> take;
+    for (;;) {
+        take.clear();
+        {
+            std::unique_lock<std::mutex> lk(D.mu);
+            D.cv.wait(lk, [&] { return !D.published.empty() || D.slotsDone == nW; });
+            if (D.published.empty()) break;                            // every fiber has finished
+            if (D.running > 0 && coalesceMicros() > 0)
+                D.cv.wait_for(lk, std::chrono::microseconds(coalesceMicros()), [&] { return D.running == 0; });
+            take.swap(D.published);
         }
-        if (D.jobs.empty()) {
-            if (live.load() != 0) { fprintf(stderr, "yaha_b200: internal error: parked fibers without jobs\n"); exit(1); }
-            finished = true;
-            return;
+        const double h1 = nowSec();
+        D.jobs.clear();
+        for (int t : take) {
+            Slot &s = slots[(size_t)t];
+            s.ansBase = D.jobs.size();
+            D.jobs.insert(D.jobs.end(), s.jobs.begin(), s.jobs.end());
+            s.jobs.clear();
         }
         const int nj = (int)D.jobs.size();
-        D.res.resize((size_t)nj);
-        if (D.ops.size() < (size_t)nj * 8) D.ops.resize((size_t)nj * 8);
+        // Every block of a pipeline has the pipeline-wide capacity (monotonic): re-pinning host memory in the
+        // middle of a run stalls the whole process (cudaFreeHost / cudaHostAlloc synchronise the device).
+        D.capJobs = std::max(D.capJobs, std::max((size_t)nj + (size_t)nj / 2, (size_t)12 * (size_t)n));
+        D.capOps = std::max(D.capOps, 8 * D.capJobs);
+        ResultBlock *blk = D.acquireBlock();
+        blk->users.store((int)take.size());
+        if (blk->res.size() < D.capJobs) blk->res.resize(D.capJobs, false);
+        if (blk->ops.size() < D.capOps) blk->ops.resize(D.capOps, false);
         size_t need = 0;
-        int rcode = ya_sw_batch(D.ctx, D.jobs.data(), nj, D.res.data(), D.ops.data(), D.ops.size(), &need);
+        int rcode = ya_sw_batch(D.ctx, D.jobs.data(), nj, blk->res.data(), blk->ops.data(), blk->ops.size(), &need);
         if (rcode == YA_E_CAPACITY) {                       // results are in; only the ops need a bigger buffer
-            D.ops.resize(need + need / 4 + 1024);
-            rcode = ya_sw_fetch_ops(D.ctx, D.ops.data(), D.ops.size());
+            D.capOps = std::max(D.capOps, need + need / 2 + 1024);
+            blk->ops.resize(D.capOps, false);
+            rcode = ya_sw_fetch_ops(D.ctx, blk->ops.data(), blk->ops.size());
         }
         if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
         D.nJobs += (uint64_t)nj; D.nRounds++;
-        for (Worker &w : workers) { w.res = D.res.data(); w.ops = D.ops.data(); }
-        live.store(0);
         D.tDp += nowSec() - h1;
-    };
-    if (nThreads == 1) {
-        while (!finished) {
-            double h0 = nowSec();
-            live += workerRound(workers[0]);
-            D.tHost += nowSec() - h0;
-            deviceRound();
+        traceEv('D', (int)take.size(), (int)B.seq, h1, nowSec(), nj);
+        {
+            std::lock_guard<std::mutex> lk(D.mu);
+            D.running += (int)take.size();
         }
-    } else {
-        pthread_barrier_t bar;
-        pthread_barrier_init(&bar, nullptr, (unsigned)nThreads);
-        std::vector<std::thread> th;
-        for (int t = 0; t < nThreads; t++)
-            th.emplace_back([&, t]() {
-                for (;;) {
-                    double h0 = nowSec();
-                    live += workerRound(workers[(size_t)t]);
-                    pthread_barrier_wait(&bar);
-                    if (t == 0) { D.tHost += nowSec() - h0; deviceRound(); }
-                    pthread_barrier_wait(&bar);
-                    if (finished) break;
-                }
-            });
-        for (auto &x : th) x.join();
-        pthread_barrier_destroy(&bar);
+        for (int t : take) {
+            Slot &s = slots[(size_t)t];
+            s.res = blk->res.data(); s.ops = blk->ops.data(); s.block = blk;
+            pool.post(Task{&D, &B, &s, t});
+        }
     }
     for (int i = 0; i < n; i++) { gStacks.put(B.fibers[(size_t)i].stack); B.fibers[(size_t)i].stack = nullptr; }
 }
@@ -405,10 +540,10 @@ int runQueries(const Args &A0)
     }
     ya_params P = A.deviceParams();
     const int nDev = std::max(1, A.gpus);
-    int pipesPerDev = std::max(1, A.pipes);
-    if (nThreads < nDev * pipesPerDev) pipesPerDev = std::max(1, nThreads / nDev);
+    const int pipesPerDev = std::max(1, A.pipes);
     const int nPipes = nDev * pipesPerDev;
-    const int threadsPerPipe = A.threadsPerPipe > 0 ? A.threadsPerPipe : std::max(1, nThreads / nPipes);
+    WorkerPool pool;                                                    // -t worker threads, shared by all pipelines
+    pool.start(A.threadsPerPipe > 0 ? std::min(A.threadsPerPipe, 4 * nproc) : nThreads);   // (-tpp N: explicit pool size, may oversubscribe)
     std::vector<Pipe> pipes((size_t)nPipes);
     double tOpen = nowSec();
     for (int d = 0; d < nDev; d++) {
@@ -427,6 +562,7 @@ int runQueries(const Args &A0)
     tOpen = nowSec() - tOpen;
 
     std::vector<std::unique_ptr<Batch>> cache;                          // -replay: parsed batches of pass 0
+    std::vector<std::unique_ptr<Batch>> spare;                          // written batches, refilled by the reader (strings keep their capacity)
     for (int pass = 0; pass < std::max(1, A.passes); pass++) {
         const bool replaying = A.replay && pass > 0;
         if (pass > 0 && out != stdout) { out = freopen(A.ofile.c_str(), "w", out); setvbuf(out, obuf, _IOFBF, sizeof obuf); }
@@ -458,13 +594,21 @@ int runQueries(const Args &A0)
                 bool eof = false;
                 while (!eof) {
                     double r0 = nowSec();
-                    std::unique_ptr<Batch> b(new Batch());
-                    b->reads.reserve((size_t)A.batchReads);
-                    while ((int)b->reads.size() < A.batchReads) {
-                        b->reads.emplace_back();
-                        if (!qr.next(b->reads.back())) { b->reads.pop_back(); eof = true; break; }
+                    std::unique_ptr<Batch> b;
+                    {
+                        std::lock_guard<std::mutex> lk(F.mu);
+                        if (!spare.empty()) { b = std::move(spare.back()); spare.pop_back(); }
                     }
+                    if (!b) { b.reset(new Batch()); b->reads.reserve((size_t)A.batchReads); }
+                    size_t k = 0;                                       // Read objects of a recycled batch are refilled in place
+                    while ((int)k < A.batchReads) {
+                        if (k == b->reads.size()) b->reads.emplace_back();
+                        if (!qr.next(b->reads[k])) { eof = true; break; }
+                        k++;
+                    }
+                    b->reads.resize(k);
                     tRead += nowSec() - r0;
+                    traceEv('P', 0, (int)seq, r0, nowSec());
                     if (b->reads.empty()) break;
                     b->seq = seq++;
                     std::unique_lock<std::mutex> lk(F.mu);
@@ -492,7 +636,7 @@ int runQueries(const Args &A0)
                         F.in.pop_front();
                         F.cvSpace.notify_one();
                     }
-                    processBatch(E, pipes[(size_t)p], *b, threadsPerPipe);
+                    processBatch(E, pipes[(size_t)p], *b, pool);
                     std::lock_guard<std::mutex> lk(F.mu);
                     uint64_t s = b->seq;
                     F.done[s] = std::move(b);
@@ -518,19 +662,22 @@ int runQueries(const Args &A0)
                 }
             nReads += b->reads.size();
             tWrite += nowSec() - w0;
-            if (A.replay) { b->fibers.reset(); b->nFibers = 0; b->outBufs.clear(); cache.push_back(std::move(b)); }
+            traceEv('W', 0, (int)b->seq, w0, nowSec());
+            if (A.replay) cache.push_back(std::move(b));
+            else { std::lock_guard<std::mutex> lk(F.mu); spare.push_back(std::move(b)); }
         }
         reader.join();
         for (auto &t : pth) t.join();
         fflush(out);
         const double tAlign = nowSec() - tStart;
+        traceEv('A', pass, 0, tStart, tStart + tAlign);
         if (A.verbose || A.passes > 1 || getenv("YAHA_B200_STATS")) {
             ya_counters c{};
             double seed = 0, dp = 0, host = 0, upl = 0, setup = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
             double msdp = 0, msseed = 0, mstb = 0, msext = 0, mslk = 0; uint64_t extCells = 0, extLaunches = 0;
             for (Pipe &d : pipes) {
                 ya_get_counters(d.ctx, &c);
-                seed += d.tSeed; dp += d.tDp; host += d.tHost; upl += d.tUpload; setup += d.tSetup; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
+                seed += d.tSeed; dp += d.tDp; host += d.tHost / std::max(1, pool.size()); upl += d.tUpload; setup += d.tSetup; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
                 msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback; launches += c.launches; probes += c.probes; hits += c.hits;
                 fragsAll += c.frags_all; msext += c.ms_ext; mslk += c.ms_lookup; extCells += c.ext_cells; extLaunches += c.ext_launches;
             }
@@ -552,6 +699,8 @@ int runQueries(const Args &A0)
         fprintf(stderr, "prof Mcycles: formClumps %.1f postProcess(incl. parked time) %.1f oqc %.1f format %.1f free %.1f\n", gProf[0] / 1e6,
                 gProf[1] / 1e6, gProf[2] / 1e6, gProf[3] / 1e6, gProf[4] / 1e6);
     if (out != stdout) fclose(out); else fflush(out);
+    pool.stop();
+    traceDump();
     for (int p = nPipes - 1; p >= 0; p--) ya_close(pipes[(size_t)p].ctx);      // shared contexts before their owners
     return 0;
 }
