@@ -20,7 +20,7 @@ struct DevBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 2 + 256;        // generous: a re-allocation (cudaFree) synchronises the whole device
+        size_t want = 2 * bytes + 256;                // generous: a re-allocation (cudaFree) synchronises the whole device
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -38,7 +38,7 @@ struct PinBuf {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 2 + 256;        // generous: a re-allocation (cudaFree) synchronises the whole device
+        size_t want = 2 * bytes + 256;                // generous: a re-allocation (cudaFree) synchronises the whole device
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;

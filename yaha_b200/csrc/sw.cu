@@ -596,6 +596,113 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, const uint32_t
     outs[t] = o;
 }
 
+// Warp-cooperative traceback: one warp per job.  The walk itself is sequential, but its two costs are not:
+//   * back-pointer fetches -- lane k reads the cell k rows further up the current column, so a stretch of up to
+//     32 match/replace steps (which stay in one band column) costs ONE round of loads instead of 32 dependent ones;
+//   * match vs replace along that stretch (the packed layout does not store it) -- 32 query/reference code pairs
+//     are compared at once and the mismatch mask is cut into runs with bit scans.
+// Gap steps (one cell = one whole run of the gap, its length is in the cell) take one iteration each.
+// Emits exactly the runs of traceback_kernel (same walking order, same merging of equal neighbours).
+__global__ void __launch_bounds__(128)
+traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ ids, int n_jobs,
+                      DevJobOut *__restrict__ outs, const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw,
+                      const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev)
+{
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = (int)(threadIdx.x & 31);
+    if (warp >= n_jobs) return;
+    const unsigned full = 0xffffffffu;
+    const int t = (int)ids[warp];
+    const DevJob J = jobs[t];
+    DevJobOut o = outs[t];
+    const bool ext = J.kind >= YA_DP_EXT_FWD;
+    const int lb = J.lb, W = J.lb + J.rb + 1;
+    {
+        const uint64_t cells = band_cells((int)o.cells_lo, lb, (int)J.rb, (int)J.rLen);
+        o.cells_lo = (uint32_t)cells; o.cells_hi = (uint32_t)(cells >> 32);
+    }
+    uint32_t n = 0;
+    if (!(ext && o.score <= 0)) {
+        ya_op *out = ops_raw + J.ops_off;
+        const int layout = J.layout, C = J.colsPerLane, CP = (C + 3) & ~3;
+        const uint16_t *mytb = tb + (layout == 2 ? 0 : J.tb_off);
+        const uint32_t *w32 = reinterpret_cast<const uint32_t *>(tb) + J.tb_off;       // layout 2 only
+        const bool bwd = J.kind == YA_DP_EXT_BWD;
+        const uint8_t *codes = J.strand ? rev : fwd;
+        int y = o.maxi, x = o.maxj;
+        int prev = -1; uint32_t run = 0;
+        int guard = (int)J.qLen + (int)J.rLen + 8;
+        auto emit = [&](int op, uint32_t len) {
+            if (op != prev) {
+                if (prev >= 0) {
+                    if (lane == 0 && n < J.ops_cap) { out[n].length = (uint16_t)run; out[n].opcode = "MRDI"[prev]; out[n].pad = 0; }
+                    n++;
+                }
+                prev = op; run = len;
+            } else run += len;
+        };
+        for (;;) {
+            if (--guard < 0 || x < 0 || x > W || y < 0 || x < lb - y) { n = 0xFFFFFFF0u; prev = -1; break; }   // corrupt back-pointers
+            if (y == 0) {
+                if (x == lb) break;                                      // origin
+                emit((int)BP_D, (uint32_t)(x - lb)); x = lb;             // leading deletes (row 0 is not stored)
+                continue;
+            }
+            if (x == lb - y) { emit((int)BP_I, (uint32_t)y); x += y; y = 0; continue; }     // leading-insert boundary
+            // lane k looks at the cell k rows up in this band column
+            const int yk = y - lane;
+            const bool valid = yk >= 1 && x > lb - yk;
+            uint32_t op = BP_D, len = 1;
+            if (valid) {
+                if (layout == 2) {
+                    const int sk = yk + x / C;
+                    const size_t widx = (size_t)((sk - 1) >> 2) * J.stride + (size_t)((x / C) * CP + (x % C));
+                    const uint32_t b = (w32[widx] >> (8 * (3 - ((sk - 1) & 3)))) & 0xFFu;
+                    len = (b & 63u) + 1u;
+                    if ((b >> 6) == 1u) op = BP_D;
+                    else if ((b >> 6) == 2u) op = BP_I;
+                    else {
+                        const int qc = codes[bwd ? J.qIdx - (uint32_t)(yk - 1) : J.qIdx + (uint32_t)(yk - 1)];
+                        const int ri = yk - lb - 1 + x;
+                        const int rcode = nib(bases, bwd ? J.rOff - (uint32_t)ri : J.rOff + (uint32_t)ri);
+                        op = (qc == rcode) ? BP_M : BP_R;
+                    }
+                } else {
+                    const size_t row = layout ? (size_t)(yk + x / C) : (size_t)yk;
+                    const uint32_t c = mytb[row * J.stride + x];
+                    op = c >> 14; len = c & 0x3FFFu;
+                }
+            }
+            const bool diag = valid && op <= BP_R;
+            const unsigned dmask = __ballot_sync(full, diag);
+            if (!(dmask & 1u)) {                                         // a gap cell: its whole run in one step
+                const uint32_t op0 = __shfl_sync(full, op, 0), len0 = __shfl_sync(full, len, 0);
+                emit((int)op0, len0);
+                if (op0 == BP_D) x -= (int)len0; else { y -= (int)len0; x += (int)len0; }
+                continue;
+            }
+            const int p = (dmask == full) ? 32 : (__ffs((int)~dmask) - 1);                 // leading match/replace steps
+            unsigned rmask = __ballot_sync(full, diag && op == BP_R);
+            if (p < 32) rmask &= (1u << p) - 1u;
+            for (int done = 0; done < p;) {                              // cut the mismatch mask into runs
+                const unsigned bit = (rmask >> done) & 1u;
+                const unsigned rest = (bit ? ~rmask : rmask) >> done;    // first position where the type changes
+                int r = rest ? (__ffs((int)rest) - 1) : 32;
+                if (r > p - done) r = p - done;
+                emit(bit ? (int)BP_R : (int)BP_M, (uint32_t)r);
+                done += r;
+            }
+            y -= p;
+            guard -= p - 1;
+        }
+        if (prev >= 0) {
+            if (lane == 0 && n < J.ops_cap) { out[n].length = (uint16_t)run; out[n].opcode = "MRDI"[prev]; out[n].pad = 0; }
+            n++;
+        }
+    }
+    if (lane == 0) { o.n_ops = n; outs[t] = o; }
+}
+
 __global__ void finalize_kernel(const DevJob *__restrict__ jobs, const DevJobOut *__restrict__ outs, int n_jobs,
                                 int BW, ya_dp_result *__restrict__ res, uint32_t *__restrict__ ops_cnt)
 {
@@ -892,9 +999,15 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     }
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     const int tbk = (n_live + 127) / 128;
-    traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
-                                          c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
-                                          c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
+    static const bool tbThread = [] { const char *e = getenv("YA_TB"); return e && strcmp(e, "thread") == 0; }();
+    if (tbThread)
+        traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
+                                              c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
+                                              c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
+    else
+        traceback_warp_kernel<<<(n_live + 3) / 4, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
+                                                                 c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
+                                                                 c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
     finalize_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), c->d_jobout.as<DevJobOut>(), n_live, P.bandWidth,
                                          c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
     c->ctr.launches += 2;
