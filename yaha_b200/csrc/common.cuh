@@ -12,17 +12,21 @@
 #define YA_WORST (-(0x7fffff00))      // "minus infinity" of the reference DP (SW.cpp:356)
 
 // Device-resident growable buffer (never shrinks; reused across batches).
+void ya_note_alloc(const char *kind, size_t old_bytes, size_t new_bytes, double t0);   // YA_ALLOC_LOG=1: one stderr line per growth
+double ya_now();
 struct DevBuf {
     void  *p = nullptr;
     size_t cap = 0;
     cudaError_t reserve(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        const double t0 = ya_now(); const size_t old = cap;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = 2 * bytes + 256;                // generous: a re-allocation (cudaFree) synchronises the whole device
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
+        ya_note_alloc("device", old, want, t0);
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -36,11 +40,13 @@ struct PinBuf {
     cudaError_t reserve(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        const double t0 = ya_now(); const size_t old = cap;
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = 2 * bytes + 256;                // generous: a re-allocation (cudaFree) synchronises the whole device
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
+        ya_note_alloc("pinned", old, want, t0);
         return e;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }

@@ -175,10 +175,19 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
 extern "C" void *ya_host_alloc(size_t bytes)
 {
     void *p = nullptr;
+    const double t0 = ya_now();
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    ya_note_alloc("host_alloc", 0, bytes, t0);
     return p;
 }
-extern "C" void ya_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void ya_host_free(void *p) { if (p) { const double t0 = ya_now(); cudaFreeHost(p); ya_note_alloc("host_free", 0, 0, t0); } }
+
+double ya_now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+void ya_note_alloc(const char *kind, size_t old_bytes, size_t new_bytes, double t0)
+{
+    static const bool on = getenv("YA_ALLOC_LOG") != nullptr;
+    if (on) fprintf(stderr, "ya_alloc %s %zu -> %zu bytes, %.3f ms, at %.6f\n", kind, old_bytes, new_bytes, (ya_now() - t0) * 1e3, ya_now());
+}
 
 static int ya_sync_mode()
 {

@@ -148,9 +148,6 @@ static void readToChar(QueryReader::Buf &B, FILE *f, int target, bool afterNewli
 bool QueryReader::next(Read &r)
 {
     Buf &B = *buf;
-    static uint8_t codeTab[256];
-    static bool tabReady = false;
-    if (!tabReady) { for (int c = 0; c < 256; c++) codeTab[c] = (uint8_t)codeOfChar(c < 128 ? c : 0); tabReady = true; }
     for (;;) {
         r.id.clear(); r.fwd.clear(); r.qual.clear();
         int idChars = 0;
@@ -220,15 +217,99 @@ bool QueryReader::next(Read &r)
         }
         if (fail) continue;
         if (n == 0) return false;                    // end of input (or an empty record, as in the reference)
-        // forward codes now (the device upload needs them); the reverse-complement strand is derived
-        // later, in parallel, by the worker that owns the read (Read::finish)
-        r.fcode.resize((size_t)n);
-        const unsigned char *src = (const unsigned char *)r.fwd.data();
-        uint8_t *fc = r.fcode.data();
-        for (int i = 0; i < n; i++) fc[i] = codeTab[src[i]];
+        // codes are derived later, off the reader thread: forward by the pipeline that uploads the batch
+        // (Read::encode), reverse-complement by the worker that owns the read (Read::finish)
+        r.fcode.clear();
         r.rcode.clear(); r.rev.clear();
         return true;
     }
+}
+
+bool RecordSlicer::open(const std::string &path, std::string &err)
+{
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) { err = "Failure to open input file: " + path + ".  Error number:" + std::to_string(errno); return false; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { err = "Failure to stat input file: " + path; ::close(fd); return false; }
+    len = (size_t)st.st_size; pos = 0; done = true; base = nullptr;
+    if (len > 0) {
+        void *m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (m == MAP_FAILED) { err = "Failure to map input file: " + path; ::close(fd); return false; }
+        madvise(m, len, MADV_SEQUENTIAL);
+        base = (const char *)m;
+        pos = 1;                                     // the first character is taken as the first marker (QueryReader::open)
+        done = false;
+    }
+    ::close(fd);
+    return true;
+}
+
+void RecordSlicer::close()
+{
+    if (base) munmap((void *)base, len);
+    base = nullptr; len = pos = 0; done = true;
+}
+
+bool RecordSlicer::next(const char *&s, size_t &n)
+{
+    if (done) return false;
+    if (pos > len) { done = true; return false; }
+    s = base + pos;
+    const char *bk = (const char *)memchr(s, '>', len - pos);
+    n = bk ? (size_t)(bk - s) : len - pos;
+    pos += n + 1;
+    // a record without sequence characters ends the input (Query.c:222): id line, then nothing but newlines
+    const char *nl = (const char *)memchr(s, '\n', n);
+    size_t q = nl ? (size_t)(nl - s) + 1 : n;
+    while (q < n && s[q] == '\n') q++;
+    if (q >= n) { done = true; return false; }
+    return true;
+}
+
+int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen)
+{
+    r.id.clear(); r.fwd.clear(); r.qual.clear(); r.fcode.clear(); r.rcode.clear(); r.rev.clear();
+    const char *nl = (const char *)memchr(s, '\n', n);
+    const size_t idLen = nl ? (size_t)(nl - s) : n;
+    const size_t keep = idLen < 200 ? idLen : 200;
+    r.id.assign(s, keep);
+    for (size_t k = 0; k < keep; k++) if (r.id[k] == ' ') r.id[k] = '_';
+    if (idLen > 200)
+        fprintf(stderr, "Warning, Query Id length of %d exceeds maximum length %d.  Id will be truncated.\n", (int)idLen, 200);
+    size_t p = nl ? idLen + 1 : n;
+    bool fail = false;
+    while (p < n) {
+        const char *nl2 = (const char *)memchr(s + p, '\n', n - p);
+        const size_t l = nl2 ? (size_t)(nl2 - (s + p)) : n - p;
+        if ((int)(r.fwd.size() + l) > maxLen) {
+            r.fwd.append(s + p, (size_t)maxLen - r.fwd.size());
+            fprintf(stderr, "Warning.  Query sequence exceeds maximum length of %d.  Query will be skipped.\n", maxLen);
+            fail = true;
+            break;
+        }
+        r.fwd.append(s + p, l);
+        p += l;
+        if (nl2) p++;
+    }
+    const int m = (int)r.fwd.size();
+    if (m > 0 && m < wordLen) {
+        fprintf(stderr, "Query length must be at least wordlen bases long. Query will be skipped.\n");
+        fail = true;
+    }
+    return (fail || m == 0) ? 0 : 1;
+}
+
+void Read::encode()                                 // Query.c:161-163 (codeOfChar per base)
+{
+    static uint8_t codeTab[256];
+    static const bool tabReady = [] { for (int c = 0; c < 256; c++) codeTab[c] = (uint8_t)codeOfChar(c < 128 ? c : 0); return true; }();
+    (void)tabReady;
+    const size_t n = fwd.size();
+    if (fcode.size() == n) return;
+    fcode.resize(n);
+    const unsigned char *src = (const unsigned char *)fwd.data();
+    uint8_t *fc = fcode.data();
+    for (size_t i = 0; i < n; i++) fc[i] = codeTab[src[i]];
 }
 
 void Read::finish()                                 // Query.c:164-167

@@ -81,6 +81,7 @@ struct Read {
     std::string qual;                // FASTQ only
     std::vector<uint8_t> fcode, rcode;
     int len() const { return (int)fwd.size(); }
+    void encode();                   // derive fcode from fwd (idempotent)
     void finish();                   // derive rcode / rev from fcode (idempotent)
 };
 struct QueryReader {                 // readNextQuery, Query.c:102-228
@@ -90,6 +91,18 @@ struct QueryReader {                 // readNextQuery, Query.c:102-228
     bool next(Read &r);                                        // false at EOF
     void close();
 };
+
+// FASTA input cut into records without parsing them: the reader thread only finds the '>' markers (a record
+// ends at the next marker wherever it stands, Query.c:137-158), the pipeline that takes the batch parses its
+// records (parseFastaRecord) -- so parsing runs on as many threads as there are pipelines.
+struct RecordSlicer {
+    const char *base = nullptr; size_t len = 0, pos = 0; bool done = true;
+    bool open(const std::string &path, std::string &err);      // maps the file; the first character is the first marker
+    bool next(const char *&s, size_t &n);                      // false at end of input or at an empty record (Query.c:222)
+    void close();
+};
+// 1: r filled; 0: record skipped with the reference's warning (too long / shorter than wordLen / empty)
+int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen);
 
 // ----------------------------------------------------------------------------- edit ops
 struct Op { uint16_t len; char code; };

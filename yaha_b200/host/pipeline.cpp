@@ -80,6 +80,7 @@ struct Slot {
 struct Batch {
     uint64_t seq = 0;
     std::vector<Read> reads;
+    std::vector<std::pair<const char *, size_t>> slices;   // FASTA records still to be parsed (by the pipeline that takes the batch)
     std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous (kept when the batch object is recycled)
     int nFibers = 0, fiberCap = 0;
     struct alignas(64) OutBuf { std::string s; };   // (own cache line: every append updates the size)
@@ -387,12 +388,23 @@ static int coalesceMicros()
 // group of published slots); the shared workers run the fibers.  Results land in each read's rc.out.
 static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
 {
-    const int n = (int)B.reads.size();
-    if (n == 0) return;
     double t0 = nowSec();
+    if (!B.slices.empty()) {                                            // FASTA records cut by the reader, parsed here
+        size_t k = 0;
+        for (const auto &sl : B.slices) {
+            if (k == B.reads.size()) B.reads.emplace_back();            // (Read objects of a recycled batch are refilled in place)
+            k += (size_t)parseFastaRecord(sl.first, sl.second, B.reads[k], E.A->maxQueryLength, E.A->wordLen);
+        }
+        B.reads.resize(k);
+        B.slices.clear();
+        traceEv('p', D.device, (int)B.seq, t0, nowSec());
+    }
+    const int n = (int)B.reads.size();
+    B.nFibers = 0;
+    if (n == 0) return;
     D.offs.resize((size_t)n + 1, false);
     size_t total = 0;
-    for (int i = 0; i < n; i++) { D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fcode.size(); }
+    for (int i = 0; i < n; i++) { B.reads[(size_t)i].encode(); D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fcode.size(); }
     D.offs[(size_t)n] = total;
     D.codes.resize(total, false);
     for (int i = 0; i < n; i++) memcpy(D.codes.data() + D.offs[(size_t)i], B.reads[(size_t)i].fcode.data(), B.reads[(size_t)i].fcode.size());
@@ -459,8 +471,18 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         const int nj = (int)D.jobs.size();
         // Every block of a pipeline has the pipeline-wide capacity (monotonic): re-pinning host memory in the
         // middle of a run stalls the whole process (cudaFreeHost / cudaHostAlloc synchronise the device).
-        D.capJobs = std::max(D.capJobs, std::max((size_t)nj + (size_t)nj / 2, (size_t)12 * (size_t)n));
-        D.capOps = std::max(D.capOps, 8 * D.capJobs);
+        if (D.capJobs == 0) D.capJobs = (size_t)16 * (size_t)n;        // ~8 jobs per read is typical; doubled when exceeded
+        if ((size_t)nj > D.capJobs) D.capJobs = 2 * (size_t)nj;
+        D.capOps = std::max(D.capOps, 32 * D.capJobs);
+        if (D.blocks.empty()) {                                        // first call of this pipeline: pin a few blocks up front
+            std::lock_guard<std::mutex> g(D.blkMu);
+            for (int k = 0; k < 6; k++) {
+                D.blocks.emplace_back(new ResultBlock());
+                D.blocks.back()->res.resize(D.capJobs, false);
+                D.blocks.back()->ops.resize(D.capOps, false);
+                D.freeBlocks.push_back(D.blocks.back().get());
+            }
+        }
         ResultBlock *blk = D.acquireBlock();
         blk->users.store((int)take.size());
         if (blk->res.size() < D.capJobs) blk->res.resize(D.capJobs, false);
@@ -468,7 +490,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         size_t need = 0;
         int rcode = ya_sw_batch(D.ctx, D.jobs.data(), nj, blk->res.data(), blk->ops.data(), blk->ops.size(), &need);
         if (rcode == YA_E_CAPACITY) {                       // results are in; only the ops need a bigger buffer
-            D.capOps = std::max(D.capOps, need + need / 2 + 1024);
+            D.capOps = std::max(D.capOps, 2 * need + 1024);
             blk->ops.resize(D.capOps, false);
             rcode = ya_sw_fetch_ops(D.ctx, blk->ops.data(), blk->ops.size());
         }
@@ -576,6 +598,7 @@ int runQueries(const Args &A0)
         replayIn.swap(cache);
         const double tStart = nowSec();
 
+        RecordSlicer slicerToClose;
         std::thread reader([&]() {
             uint64_t seq = 0;
             if (replaying) {
@@ -588,11 +611,37 @@ int runQueries(const Args &A0)
                 }
             } else {
                 QueryReader qr;
+                RecordSlicer sl;
                 std::string e2;
-                if (!qr.open(A.qfile, e2)) { fprintf(stderr, "%s\n", e2.c_str()); exit(1); }
+                const bool sliced = !A.fastq && getenv("YA_SEQ_READER") == nullptr;
+                if (!(sliced ? sl.open(A.qfile, e2) : qr.open(A.qfile, e2))) { fprintf(stderr, "%s\n", e2.c_str()); exit(1); }
                 qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
                 bool eof = false;
-                while (!eof) {
+                while (sliced && !eof) {                                  // FASTA: cut records here, parse them in the pipelines
+                    double r0 = nowSec();
+                    std::unique_ptr<Batch> b;
+                    {
+                        std::lock_guard<std::mutex> lk(F.mu);
+                        if (!spare.empty()) { b = std::move(spare.back()); spare.pop_back(); }
+                    }
+                    if (!b) { b.reset(new Batch()); b->reads.reserve((size_t)A.batchReads); }
+                    b->slices.clear();
+                    const char *rs; size_t rn;
+                    while ((int)b->slices.size() < A.batchReads) {
+                        if (!sl.next(rs, rn)) { eof = true; break; }
+                        b->slices.emplace_back(rs, rn);
+                    }
+                    tRead += nowSec() - r0;
+                    traceEv('P', 0, (int)seq, r0, nowSec());
+                    if (b->slices.empty()) { std::lock_guard<std::mutex> lk(F.mu); spare.push_back(std::move(b)); break; }
+                    b->seq = seq++;
+                    std::unique_lock<std::mutex> lk(F.mu);
+                    F.cvSpace.wait(lk, [&] { return F.in.size() < F.maxQueued; });
+                    F.in.push_back(std::move(b));
+                    F.cvIn.notify_one();
+                }
+                if (sliced) slicerToClose = sl;                             // unmapped after the pipelines have parsed every record
+                while (!sliced && !eof) {
                     double r0 = nowSec();
                     std::unique_ptr<Batch> b;
                     {
@@ -616,7 +665,7 @@ int runQueries(const Args &A0)
                     F.in.push_back(std::move(b));
                     F.cvIn.notify_one();
                 }
-                qr.close();
+                if (!sliced) qr.close();
             }
             std::lock_guard<std::mutex> lk(F.mu);
             F.readerDone = true; F.produced = seq;
@@ -668,6 +717,7 @@ int runQueries(const Args &A0)
         }
         reader.join();
         for (auto &t : pth) t.join();
+        slicerToClose.close();
         fflush(out);
         const double tAlign = nowSec() - tStart;
         traceEv('A', pass, 0, tStart, tStart + tAlign);
