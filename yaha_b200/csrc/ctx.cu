@@ -15,20 +15,16 @@ static thread_local std::string g_open_err;
 // complement of a 4-bit code (Math.c:155: fourBitCompCodes)
 __constant__ uint8_t c_comp[16] = {2, 3, 0, 1, 4, 12, 7, 6, 9, 8, 15, 11, 5, 13, 14, 10};
 
+// Reverse-complement strand of every read (Query.c:164-167): one warp per read, both accesses coalesced.
 __global__ void revcomp_kernel(const uint8_t *__restrict__ fwd, uint8_t *__restrict__ rev,
                                const uint64_t *__restrict__ off, int n_reads, uint64_t total)
 {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    for (; i < total; i += step) {
-        // find read r with off[r] <= i < off[r+1]
-        int lo = 0, hi = n_reads;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (off[mid] <= i) lo = mid; else hi = mid;
-        }
-        uint64_t s = off[lo], e = off[lo + 1];
-        rev[s + (e - 1 - i)] = c_comp[fwd[i] & 15];
+    const int lane = threadIdx.x & 31;
+    const int warps = (int)((gridDim.x * blockDim.x) >> 5);
+    (void)total;
+    for (int r = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_reads; r += warps) {
+        const uint64_t s = off[r], e = off[r + 1];
+        for (uint64_t i = s + lane; i < e; i += 32) rev[s + (e - 1 - i)] = c_comp[fwd[i] & 15];
     }
 }
 
@@ -321,7 +317,7 @@ extern "C" int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
     YA_CUDA(c, cudaMemcpyAsync(c->d_read_off.p, b->offsets, (size_t)(b->n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     if (total) {
         YA_CUDA(c, cudaMemcpyAsync(c->d_codes_fwd.p, b->codes, total, cudaMemcpyHostToDevice, c->stream));
-        int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+        int blocks = (b->n_reads + 7) / 8; if (blocks > 148 * 16) blocks = 148 * 16;
         revcomp_kernel<<<blocks, 256, 0, c->stream>>>(c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
                                                      c->d_read_off.as<uint64_t>(), b->n_reads, total);
         c->ctr.launches++;

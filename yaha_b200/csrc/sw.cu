@@ -746,7 +746,7 @@ __global__ void compact_ops_kernel(const DevJob *__restrict__ jobs, int n_jobs, 
 // host side
 // ------------------------------------------------------------------------------------------
 struct WaveCfg { int G, C; };
-static const WaveCfg kWaveCfgs[] = {{8, 3}, {8, 4}, {8, 6}, {8, 8}, {16, 6}, {16, 8}, {32, 8}};
+static const WaveCfg kWaveCfgs[] = {{8, 3}, {8, 4}, {8, 6}, {8, 8}, {16, 6}, {16, 8}, {32, 8}, {32, 11}};
 static const int kNumWaveCfgs = sizeof(kWaveCfgs) / sizeof(kWaveCfgs[0]);
 
 template <int G, int C>
@@ -773,7 +773,8 @@ static void launch_wave_cfg(ya_ctx *c, int cfg, bool ext, const uint32_t *d_ids,
     case 3: launch_wave<8, 8>(c, ext, d_ids, n, K); break;
     case 4: launch_wave<16, 6>(c, ext, d_ids, n, K); break;
     case 5: launch_wave<16, 8>(c, ext, d_ids, n, K); break;
-    default: launch_wave<32, 8>(c, ext, d_ids, n, K); break;
+    case 6: launch_wave<32, 8>(c, ext, d_ids, n, K); break;
+    default: launch_wave<32, 11>(c, ext, d_ids, n, K); break;
     }
 }
 
@@ -834,6 +835,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     const ya_params &P = c->P;
     const int bw2 = 2 * P.bandWidth;
     const bool forceThread = force_thread_kernel();
+    static const int fullThreadMaxW = [] { const char *e = getenv("YA_FULL_THREAD_MAXW"); return e ? atoi(e) : 0; }();   // full-matrix jobs up to this band width stay one thread per job
     const bool allowPacked = !forbid_packed_kernel();
 
     YA_CUDA(c, c->h_jobs.reserve((size_t)n * sizeof(DevJob)));
@@ -898,7 +900,9 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
             d.tb_off = tb_cells / 2;                                  // in 32-bit words
             tb_cells += 2ull * (uint64_t)((qLen + G + 3) / 4 + 1) * d.stride;
             lists[packedBase + pcls].push_back((uint32_t)n_live);
-        } else if (!forceThread && j.kind != YA_DP_FULL) {
+        } else if (!forceThread && (j.kind != YA_DP_FULL || W > fullThreadMaxW)) {
+            // (full-matrix jobs are bands with lb = qLen, rb = rLen: the small ones stay one thread per job,
+            //  the larger ones take a lane group like a banded job -- their serial row chain is what a round waits for)
             for (int k = 0; k < kNumWaveCfgs; k++)
                 if (kWaveCfgs[k].G * kWaveCfgs[k].C >= W) { cls = k; break; }
         }
