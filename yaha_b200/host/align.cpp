@@ -460,7 +460,9 @@ static int scoreClump(const Env &E, ReadCtx &rc, Clump *c)             // AlignH
 void postProcessClumps(const Env &E, ReadCtx &rc)                       // QueryMatch.c:306-331
 {
     uint64_t q0 = rdtsc_();
-    std::vector<Clump *> old;
+    std::vector<Clump *> old;                                           // (takes the fiber's spare list: both keep their capacity)
+    old.swap(rc.scratch);
+    old.clear();
     old.swap(rc.clumps);
     std::reverse(old.begin(), old.end());                               // reference walks from the list head
     // phase 1: perfect extensions, gap-fill jobs AND the first extension jobs, for all clumps of the read
@@ -525,6 +527,8 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         else delete c;
     }
     if (kAlignProf) gAlignProf[3] += rdtsc_() - q0 - (rc.parked - parked0);
+    old.clear();
+    old.swap(rc.scratch);                                               // hand the buffer back to the fiber
 }
 
 }  // namespace yh

@@ -214,6 +214,7 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     int    idx = 0;                  // index in the batch == read id on the device
     Read  *read = nullptr;
     std::vector<Clump *> clumps;     // LIFO list: back() is the reference's list head
+    std::vector<Clump *> scratch;    // second list of the same kind (filters build their result here and swap); keeps its capacity
     int    primaryCount = 0;
     RandState rng;
     uint64_t parked = 0;             // cycles spent parked in the scoring phase (YAHA_B200_PROF only)

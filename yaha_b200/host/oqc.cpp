@@ -138,7 +138,8 @@ struct PrimaryAttr { int alignedQueryLength, numOutputSecondaries; int16_t secon
 static void filterBySimilarity(const Env &E, ReadCtx &rc, std::vector<CNode> &g, int nodeCount, int best)
 {                                                                       // GraphPath.cpp:571-692
     const Args &A = *E.A;
-    std::vector<Clump *> out;
+    std::vector<Clump *> &out = rc.scratch;
+    out.clear();
     const int primeCount = g[best].pathLength;
     std::vector<CNode> primaries((size_t)primeCount);
     std::vector<PrimaryAttr> PA((size_t)primeCount);
@@ -325,7 +326,8 @@ void postFilterRemoveDups(const Env &E, ReadCtx &rc)                    // Graph
     int k = 0;
     for (int i = n - 1; i >= 0; i--) { d[k].clump = rc.clumps[i]; d[k].SRO = rc.clumps[i]->SRO(); d[k].score = rc.clumps[i]->totScore; k++; }
     qsort(d.data(), (size_t)n, sizeof(DupElem), cmpDup);                // the C library's qsort, like the reference
-    std::vector<Clump *> out;
+    std::vector<Clump *> &out = rc.scratch;
+    out.clear();
     for (int i = 0; i < n; i++) {
         Clump *c1 = d[i].clump;
         if (!c1) continue;
