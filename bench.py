@@ -86,34 +86,73 @@ def make_reads(workload: str, rank: int):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region.  NVML in-process (one query costs well under a
+    millisecond); falls back to spawning nvidia-smi, which is slow enough to disturb a 20 ms step, so less often."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu: int):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.max_mhz = gpu, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu))
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(gpu: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if gpu < len(ids) and ids[gpu].isdigit():
+                return int(ids[gpu])
+        return gpu
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        if self.nvml is not None:
+            nv = self.nvml
+            while not self.stop_flag:
+                try:
+                    mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.rows.append((mhz, mask))
+                except Exception:
+                    pass
+                time.sleep(0.05)
+            return
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if len(r) >= 6:
+                    self.max_mhz = int(float(r[1]))
+                    mask = sum(b for b, v in zip(bits, r[2:6]) if v.lower().startswith("active"))
+                    self.rows.append((int(float(r[0])), mask))
             except Exception:
                 pass
-            time.sleep(0.5)
+            time.sleep(1.0)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(float(r[0])) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons,
-                "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        seen = 0
+        for _, m in self.rows:
+            seen |= m
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": [n for b, n in self.REASONS.items() if seen & b],
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def run_host(idx_path, reads_path, out_path, flags, threads, device, passes, batch, pipes, replay=False, tpp=0, env=None):
@@ -273,7 +312,10 @@ def run_ours(args):
                               "wall_seed_call": tot("seed_wall_s") / args.steps * 1e3, "wall_dp_calls": tot("dp_wall_s") / args.steps * 1e3,
                               "wall_host_logic": tot("host_wall_s") / args.steps * 1e3, "wall_parse": tot("read_parse_s") / args.steps * 1e3,
                               "wall_upload": tot("upload_s") / args.steps * 1e3, "wall_write": tot("write_s") / args.steps * 1e3},
-        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed_a],
+                "ms_per_untimed_step": [round(s["align_s"] * 1e3, 2) for s in stats_a[:extra_warm + args.warmup]]},
+        "value_ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed],
         "gpu_launches": int(tot("launches")),
         "roofline": {"bound": "int32-issue", "kernel": "dp_ext_packed_kernel",
                      "timed_region": "run C: the same 20 K-read job as one batch on one pipeline, DP rounds in lock step (every bulk "

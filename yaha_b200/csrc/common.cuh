@@ -14,6 +14,15 @@
 // Device-resident growable buffer (never shrinks; reused across batches).
 void ya_note_alloc(const char *kind, size_t old_bytes, size_t new_bytes, double t0);   // YA_ALLOC_LOG=1: one stderr line per growth
 double ya_now();
+// Stream the current thread's device scratch is (re)allocated on: set for the duration of an ABI call
+// (AllocScope).  With it DevBuf grows through the stream-ordered allocator -- cudaFree / cudaMalloc in the middle
+// of a run wait for every stream of the device and were measured at up to 355 ms under load (YA_ALLOC_LOG).
+extern thread_local cudaStream_t ya_tls_alloc_stream;
+struct AllocScope {
+    cudaStream_t saved;
+    explicit AllocScope(cudaStream_t s) : saved(ya_tls_alloc_stream) { ya_tls_alloc_stream = s; }
+    ~AllocScope() { ya_tls_alloc_stream = saved; }
+};
 struct DevBuf {
     void  *p = nullptr;
     size_t cap = 0;
@@ -21,12 +30,13 @@ struct DevBuf {
     {
         if (bytes <= cap) return cudaSuccess;
         const double t0 = ya_now(); const size_t old = cap;
-        if (p) cudaFree(p);
+        const cudaStream_t s = ya_tls_alloc_stream;
+        if (p) { if (s) cudaFreeAsync(p, s); else cudaFree(p); }
         p = nullptr; cap = 0;
-        size_t want = 2 * bytes + 256;                // generous: a re-allocation (cudaFree) synchronises the whole device
-        cudaError_t e = cudaMalloc(&p, want);
+        size_t want = 2 * bytes + 256;                // generous: growth is rare and never repeated for the same size class
+        cudaError_t e = s ? cudaMallocAsync(&p, want, s) : cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
-        ya_note_alloc("device", old, want, t0);
+        ya_note_alloc(s ? "device(async)" : "device", old, want, t0);
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }

@@ -70,6 +70,14 @@ static ya_ctx *open_common(int device, const ya_params *params)
         size_t gran = e ? (size_t)atoi(e) : 32;
         if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
     }
+    {
+        // freed scratch stays in the device's stream-ordered pool (never handed back to the driver mid-run)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     ya_ctx *c = new ya_ctx();
     c->device = device;
     c->P = *params;
@@ -178,6 +186,7 @@ extern "C" void *ya_host_alloc(size_t bytes)
 }
 extern "C" void ya_host_free(void *p) { if (p) { const double t0 = ya_now(); cudaFreeHost(p); ya_note_alloc("host_free", 0, 0, t0); } }
 
+thread_local cudaStream_t ya_tls_alloc_stream = nullptr;
 double ya_now() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 void ya_note_alloc(const char *kind, size_t old_bytes, size_t new_bytes, double t0)
 {
@@ -301,6 +310,7 @@ extern "C" int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
     if (!c || !b || b->n_reads < 0 || (b->n_reads && (!b->codes || !b->offsets))) return YA_E_ARG;
     YA_CUDA(c, cudaSetDevice(c->device));
     if (b->n_reads > (1 << 21)) return ya_fail(c, YA_E_ARG, "at most 2^21 reads per batch");
+    AllocScope allocScope(c->stream);
     c->n_reads = b->n_reads;
     c->h_read_off.assign(b->offsets, b->offsets + b->n_reads + 1);
     if (c->h_read_off[0] != 0) return ya_fail(c, YA_E_ARG, "offsets[0] must be 0");

@@ -411,6 +411,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     out->n_frags = 0; out->frags_needed = 0;
     if (n_reads == 0) return YA_OK;
     cudaStream_t st = c->stream;
+    AllocScope allocScope(st);
 
     // probe offsets per segment
     std::vector<uint32_t> h_po((size_t)n_seg + 1);

@@ -832,6 +832,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         ~StreamSwap() { c->stream = saved; }
     } streamSwap(c, n >= 2048);
     cudaStream_t st = c->stream;
+    AllocScope allocScope(st);
     const ya_params &P = c->P;
     const int bw2 = 2 * P.bandWidth;
     const bool forceThread = force_thread_kernel();
