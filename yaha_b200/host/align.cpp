@@ -27,13 +27,55 @@ static inline uint64_t rdtsc_() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=
 
 void OpVec::grow(size_t want)
 {
-    size_t cap = std::max<size_t>(want, (size_t)cap_ * 2);
-    Op *q = (Op *)malloc(cap * sizeof(Op));
-    if (!q) { fprintf(stderr, "yaha_b200: out of memory\n"); abort(); }
+    size_t cap = 8;                                                     // power of two: exactly one pool block
+    while (cap < want || cap < (size_t)cap_ * 2) cap *= 2;
+    Op *q = (Op *)TlsPool::get(cap * sizeof(Op));
     memcpy(q, p_, n_ * sizeof(Op));
-    if (heap()) free(p_);
+    if (heap()) TlsPool::put(p_, (size_t)cap_ * sizeof(Op));
     p_ = q; cap_ = (uint32_t)cap;
 }
+
+#ifdef YH_NO_POOL
+void *TlsPool::get(size_t bytes) { void *p = malloc(bytes ? bytes : 1); if (!p) { fprintf(stderr, "yaha_b200: out of memory\n"); abort(); } return p; }
+void  TlsPool::put(void *p, size_t) { free(p); }
+#else
+namespace {
+struct PoolState {
+    enum { kMinShift = 5, kClasses = 12, kSlab = 1 << 20 };            // 32 B .. 64 KB
+    void *freeList[kClasses] = {};
+    char *slab = nullptr; size_t left = 0;
+};
+thread_local PoolState tPool;
+inline int poolClass(size_t bytes)
+{
+    if (bytes <= 32) return 0;
+    return 64 - __builtin_clzll((unsigned long long)(bytes - 1)) - PoolState::kMinShift;
+}
+}
+void *TlsPool::get(size_t bytes)
+{
+    const int k = poolClass(bytes);
+    if (k >= PoolState::kClasses) { void *p = malloc(bytes); if (!p) { fprintf(stderr, "yaha_b200: out of memory\n"); abort(); } return p; }
+    PoolState &P = tPool;
+    if (void *p = P.freeList[k]) { P.freeList[k] = *(void **)p; return p; }
+    const size_t sz = (size_t)32 << k;
+    if (P.left < sz) {
+        P.slab = (char *)malloc(PoolState::kSlab);                         // (never returned: the pool lives as long as its thread)
+        if (!P.slab) { fprintf(stderr, "yaha_b200: out of memory\n"); abort(); }
+        P.left = PoolState::kSlab;
+    }
+    void *p = P.slab;
+    P.slab += sz; P.left -= sz;
+    return p;
+}
+void TlsPool::put(void *p, size_t bytes)
+{
+    const int k = poolClass(bytes);
+    if (k >= PoolState::kClasses) { free(p); return; }
+    *(void **)p = tPool.freeList[k];
+    tPool.freeList[k] = p;
+}
+#endif
 
 void OpVec::swap(OpVec &o) noexcept
 {
@@ -128,7 +170,7 @@ static int perfectBackward(const Env &E, const uint8_t *q, Frag &f, int len)    
 }
 
 // ---- phase 1 of alignClump: perfect extensions between neighbours, "nM" lists, post gap jobs
-struct GapJob { std::list<SFrag>::iterator after; SFrag piece; DpFuture fut; bool needDp; };
+struct GapJob { SFragList::iterator after; SFrag piece; DpFuture fut; bool needDp; };
 
 static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, std::vector<GapJob> &gaps)
 {

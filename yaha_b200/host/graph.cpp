@@ -42,7 +42,7 @@ static void insertFragment(Clump &c, Frag &f1)                        // AlignHe
 
 static void cleanUpClump(const Args &A, Clump &c)                     // AlignHelpers.c:92-193
 {
-    typedef std::list<SFrag>::iterator It;
+    typedef SFragList::iterator It;
     const It END = c.sf.end();
     It s1 = c.sf.begin();
     It s2 = (s1 == END) ? END : std::next(s1);

@@ -104,6 +104,25 @@ struct RecordSlicer {
 // 1: r filled; 0: record skipped with the reference's warning (too long / shorter than wordLen / empty)
 int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen);
 
+// ----------------------------------------------------------------------------- small-block pool
+// Per-thread free lists of power-of-two blocks (32 B .. 64 KB), carved from slabs that are never handed back.
+// A read makes ~60 short-lived allocations (list nodes of the fragment pieces, clumps, op arrays); a read's fiber
+// stays on one worker thread, so get/put never lock and never reach the C library's arena bookkeeping
+// (measured: malloc/free/consolidate/trim were ~35 % of the host time before).  -DYH_NO_POOL: plain malloc (ASan).
+struct TlsPool {
+    static void *get(size_t bytes);
+    static void  put(void *p, size_t bytes);
+};
+template <class T> struct PoolAllocator {
+    typedef T value_type;
+    PoolAllocator() noexcept {}
+    template <class U> PoolAllocator(const PoolAllocator<U> &) noexcept {}
+    T *allocate(size_t n) { return (T *)TlsPool::get(n * sizeof(T)); }
+    void deallocate(T *p, size_t n) noexcept { TlsPool::put(p, n * sizeof(T)); }
+    template <class U> bool operator==(const PoolAllocator<U> &) const noexcept { return true; }
+    template <class U> bool operator!=(const PoolAllocator<U> &) const noexcept { return false; }
+};
+
 // ----------------------------------------------------------------------------- edit ops
 struct Op { uint16_t len; char code; };
 // Vector of edit ops with room for a few entries inline: most lists (a seed fragment's single 'M', a
@@ -121,7 +140,7 @@ public:
     OpVec(OpVec &&o) noexcept : p_(in_) { swap(o); }
     OpVec &operator=(const OpVec &o) { if (this != &o) assign(o.begin(), o.end()); return *this; }
     OpVec &operator=(OpVec &&o) noexcept { if (this != &o) { clear(); swap(o); } return *this; }
-    ~OpVec() { if (heap()) free(p_); }
+    ~OpVec() { if (heap()) TlsPool::put(p_, (size_t)cap_ * sizeof(Op)); }
     Op *begin() { return p_; }  Op *end() { return p_ + n_; }
     const Op *begin() const { return p_; }  const Op *end() const { return p_ + n_; }
     size_t size() const { return n_; }  bool empty() const { return n_ == 0; }
@@ -187,10 +206,13 @@ inline unsigned calcGapU(uint32_t lo, uint32_t hi) { return hi > lo ? (hi - lo) 
 inline unsigned calcOverlapU(uint32_t lo, uint32_t hi) { return lo >= hi ? (lo - hi) + 1 : 0; }
 
 struct SFrag { Frag frag; int score = 0; OpList ops; };              // SFragment_t, Math.h:469-477
+typedef std::list<SFrag, PoolAllocator<SFrag>> SFragList;
 enum { kReversed = 1, kFormed = 2, kAligned = 4, kScored = 8, kSplit = 16, kPrimary = 32 };   // FragsClumps.inl:221-226
 struct Clump {                       // Clump_t, Math.h:511-527
     OpList ops;
-    std::list<SFrag> sf;
+    SFragList sf;
+    static void *operator new(size_t n) { return TlsPool::get(n); }
+    static void operator delete(void *p, size_t n) { TlsPool::put(p, n); }
     uint16_t totScore = 0, totLength = 0, matchedBases = 0, mismatchedBases = 0, gapBases = 0;
     uint16_t numSecondaries = 0, matchedPrimary = 0;
     uint8_t  status = 0, mapQuality = 255;

@@ -237,6 +237,7 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     // hand-off between the worker threads and this pipeline's device thread, for the batch in flight
     std::mutex mu;
     std::condition_variable cv;
+    std::vector<Slot> slots;              // one per worker thread, reused from batch to batch (vectors keep their capacity)
     std::vector<int> published;           // slots whose pass ended with posted jobs
     int slotsDone = 0, running = 0;       // slots with no unfinished fiber / slots inside a pass
     double tSeed = 0, tDp = 0, tHost = 0, tUpload = 0, tSetup = 0;
@@ -434,12 +435,14 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     B.nFibers = n;
     if ((int)B.outBufs.size() != nW) { B.outBufs.clear(); B.outBufs.resize((size_t)nW); }
     for (auto &ob : B.outBufs) ob.s.clear();
-    std::vector<Slot> slots((size_t)nW);
+    if ((int)D.slots.size() != nW) D.slots = std::vector<Slot>((size_t)nW);
+    std::vector<Slot> &slots = D.slots;
     {
         std::lock_guard<std::mutex> lk(D.mu);
         D.published.clear(); D.slotsDone = 0; D.running = 0;
         for (int t = 0; t < nW; t++) {
             Slot &s = slots[(size_t)t];
+            s.fibers.clear(); s.jobs.clear(); s.res = nullptr; s.ops = nullptr; s.ansBase = 0; s.block = nullptr; s.set = false;
             s.E = &E;
             s.lo = (int)((int64_t)t * n / nW); s.hi = (int)((int64_t)(t + 1) * n / nW);
             if (s.hi > s.lo) D.running++; else D.slotsDone++;
