@@ -40,6 +40,20 @@ def test_output_order_independent_of_threads_and_batch(small, mock_host, tmp_pat
         assert H.sam_lines(open(out).read()) == want
 
 
+def test_sliced_and_sequential_fasta_readers_agree(small, mock_host, tmp_path):
+    # FASTA is cut into records by the reader and parsed by the pipelines (RecordSlicer / parseFastaRecord);
+    # YA_SEQ_READER=1 keeps the sequential reader of the FASTQ path.  Both must give the reference's records,
+    # including the odd inputs (CRLF, over-long, too-short, empty and multi-line records, '>' inside a line).
+    for reads, golden in (("weird.fa", "out_weird.sam.gz"), ("reads.fa", "out_bw5.sam.gz")):
+        want = H.expected(small, golden)
+        extra = ["-BW", "5", "-G", "50"] if reads == "reads.fa" else []
+        for k, env in enumerate(({}, {"YA_SEQ_READER": "1"})):
+            out = str(tmp_path / f"r{k}.sam")
+            cmd = [mock_host, "-x", small.idx_path, "-q", os.path.join(small.dir, reads), "-osh", out, "-t", "2", "-batch", "41"] + extra
+            subprocess.run(cmd, check=True, capture_output=True, timeout=600, env=dict(os.environ, **env))
+            assert H.sam_lines(open(out).read()) == want, (reads, env)
+
+
 def test_cli_errors_match_reference_behaviour(small, mock_host):
     # missing -x for query mode, bad flag, bad bool: message + non-zero exit like Main.c
     p = subprocess.run([mock_host, "-q", "x.fa"], capture_output=True, text=True)

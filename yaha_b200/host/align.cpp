@@ -172,7 +172,7 @@ static int perfectBackward(const Env &E, const uint8_t *q, Frag &f, int len)    
 // ---- phase 1 of alignClump: perfect extensions between neighbours, "nM" lists, post gap jobs
 struct GapJob { SFragList::iterator after; SFrag piece; DpFuture fut; bool needDp; };
 
-static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, std::vector<GapJob> &gaps)
+static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps)
 {
     const Args &A = *E.A;
     const bool rev = c.reversed();
@@ -509,8 +509,8 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     std::reverse(old.begin(), old.end());                               // reference walks from the list head
     // phase 1: perfect extensions, gap-fill jobs AND the first extension jobs, for all clumps of the read
     struct PerClump { ExtState x; int score = 0; size_t gapLo = 0, gapHi = 0; };
-    std::vector<PerClump> pc(old.size());
-    std::vector<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
+    PVec<PerClump> pc(old.size());
+    PVec<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
     gaps.reserve(std::min<size_t>(4 * old.size() + 4, 960 / sizeof(GapJob)));   // (stays a small-bin allocation)
     bool any = false;
     for (size_t k = 0; k < old.size(); k++) {

@@ -123,6 +123,8 @@ template <class T> struct PoolAllocator {
     template <class U> bool operator!=(const PoolAllocator<U> &) const noexcept { return false; }
 };
 
+template <class T> using PVec = std::vector<T, PoolAllocator<T>>;      // short-lived per-read arrays
+
 // ----------------------------------------------------------------------------- edit ops
 struct Op { uint16_t len; char code; };
 // Vector of edit ops with room for a few entries inline: most lists (a seed fragment's single 'M', a

@@ -83,7 +83,7 @@ static int scoreForLength(const OpList &l, int length, const Args &A)  // GraphP
     return AGS;
 }
 
-static int accurateOverlapScore(std::vector<CNode> &g, int left, int right, int overlap, const Args &A, bool *rightBest)
+static int accurateOverlapScore(PVec<CNode> &g, int left, int right, int overlap, const Args &A, bool *rightBest)
 {                                                                       // GraphPath.cpp:744-800
     const CNode &R = g[right];
     int rightScore = R.reversed ? scoreForLength<false>(R.clump->ops, overlap, A) : scoreForLength<true>(R.clump->ops, overlap, A);
@@ -101,7 +101,7 @@ static int accurateOverlapScore(std::vector<CNode> &g, int left, int right, int 
     return pathScore;
 }
 
-static void cacheQlenReverse(std::vector<CNode> &g, int left, int right, int overlap, bool rightBest)   // :802-826
+static void cacheQlenReverse(PVec<CNode> &g, int left, int right, int overlap, bool rightBest)   // :802-826
 {
     CNode &R = g[right];
     if (rightBest) {
@@ -118,7 +118,7 @@ static void cacheQlenReverse(std::vector<CNode> &g, int left, int right, int ove
     } else R.qLenInOQC = (uint16_t)((1 + R.EQO - R.SQO) - overlap);
 }
 
-static int cacheQlenPath(std::vector<CNode> &g, int right, const Args &A)     // GraphPath.cpp:841-867
+static int cacheQlenPath(PVec<CNode> &g, int right, const Args &A)     // GraphPath.cpp:841-867
 {
     CNode &R = g[right];
     int qLen = 1 + R.EQO - R.SQO;
@@ -135,14 +135,14 @@ static int cacheQlenPath(std::vector<CNode> &g, int right, const Args &A)     //
 
 struct PrimaryAttr { int alignedQueryLength, numOutputSecondaries; int16_t secondScore, thirdScore; };
 
-static void filterBySimilarity(const Env &E, ReadCtx &rc, std::vector<CNode> &g, int nodeCount, int best)
+static void filterBySimilarity(const Env &E, ReadCtx &rc, PVec<CNode> &g, int nodeCount, int best)
 {                                                                       // GraphPath.cpp:571-692
     const Args &A = *E.A;
     std::vector<Clump *> &out = rc.scratch;
     out.clear();
     const int primeCount = g[best].pathLength;
-    std::vector<CNode> primaries((size_t)primeCount);
-    std::vector<PrimaryAttr> PA((size_t)primeCount);
+    PVec<CNode> primaries((size_t)primeCount);
+    PVec<PrimaryAttr> PA((size_t)primeCount);
     int pi = primeCount - 1;
     for (int p = best; p >= 0; p = g[p].prev) {
         primaries[pi] = g[p];
@@ -212,7 +212,7 @@ void postFilterBySimilarity(const Env &E, ReadCtx &rc)                  // Graph
         rc.primaryCount = 1;
         return;
     }
-    std::vector<CNode> g((size_t)nodeCount);
+    PVec<CNode> g((size_t)nodeCount);
     const int L = rc.read->len();
     int cnt = 0;
     for (int k = nodeCount - 1; k >= 0; k--) {                          // walk from the list head
@@ -322,7 +322,7 @@ void postFilterRemoveDups(const Env &E, ReadCtx &rc)                    // Graph
     (void)E;
     const int n = (int)rc.clumps.size();
     if (n < 2) return;
-    std::vector<DupElem> d((size_t)n);
+    PVec<DupElem> d((size_t)n);
     int k = 0;
     for (int i = n - 1; i >= 0; i--) { d[k].clump = rc.clumps[i]; d[k].SRO = rc.clumps[i]->SRO(); d[k].score = rc.clumps[i]->totScore; k++; }
     qsort(d.data(), (size_t)n, sizeof(DupElem), cmpDup);                // the C library's qsort, like the reference
