@@ -5,6 +5,8 @@
 // (Query.c:161-168: forward + reverse-complement code buffers) with one batched upload plus
 // a device kernel that derives the reverse-complement strand.
 #include "common.cuh"
+#include <condition_variable>
+#include <mutex>
 #include <sched.h>
 #include <sys/prctl.h>
 #include <time.h>

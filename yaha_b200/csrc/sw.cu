@@ -978,9 +978,9 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
             launch_wave_cfg(c, k, false, d_ids + start[kNumWaveCfgs + k], (int)lists[kNumWaveCfgs + k].size(), K);
     }
     const bool anyPacked = !lists[packedBase + 0].empty() || !lists[packedBase + 1].empty();
-    // Bulk extension launches of the contexts sharing a device run one at a time (they would only time-slice
-    // the SMs), which also keeps their CUDA-event timing free of another pipeline's bulk kernel.
-    static const bool bulkExclusive = [] { const char *e = getenv("YA_BULK_EXCLUSIVE"); return !e || atoi(e) != 0; }();
+    // YA_BULK_EXCLUSIVE=1: bulk extension launches of the contexts sharing a device run one at a time, which keeps
+    // their CUDA-event timing free of another pipeline's bulk kernel (costs one more wait per bulk call).
+    static const bool bulkExclusive = [] { const char *e = getenv("YA_BULK_EXCLUSIVE"); return e && atoi(e) != 0; }();   // off by default
     const size_t nPackedAll = lists[packedBase + 0].size() + lists[packedBase + 1].size();
     std::unique_lock<std::mutex> bulkTurn(ya_bulk_mutex(c->device), std::defer_lock);
     if (anyPacked && bulkExclusive && nPackedAll >= 2048) bulkTurn.lock();
