@@ -255,3 +255,45 @@ def test_device_index_build_is_bit_identical(small):
     # a k-mer above the limit must be reported, not approximated
     with pytest.raises(yaha_b200.YahaError):
         yaha_b200.Aligner(small.nib, None, yaha_b200.Params.defaults(word_len=11), device=0, build_max_hits=1)
+
+
+_AB_SNIPPET = r"""
+import sys, os
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import yaha_b200, support as S
+from conftest import Small
+small = Small({tmp!r})
+out = []
+for bw, gap in ((5, 50), (10, 100)):
+    al = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11, bw=bw, max_gap=gap), device=0)
+    al.upload_read_list(small.fwd)
+    jobs = []
+    for rec in S.parse_dump(small.dump(bw), "D"):
+        _, k, qid, st, roff, rlen, qoff, qlen, score, aq, ar, ops = rec
+        jobs.append((roff, small.read_id[qid], rlen, qoff, qlen, S.KIND_OF_CHAR[k], st))
+    res, ops = al.sw_batch(np.array(jobs, dtype=yaha_b200.JOB_DT))
+    out.append(res.tobytes()); out.append(np.asarray(ops).tobytes())
+    al.close()
+open({dst!r}, "wb").write(b"".join(out))
+"""
+
+
+@pytest.mark.gpu
+def test_kernel_variants_agree_bytewise(small, tmp_path):
+    """The environment switches select kernels per process, so each variant runs in its own interpreter on the
+    reference's DP calls: warp-per-job vs thread-per-job traceback, full-matrix gap fills on the wavefront kernel
+    vs one thread per job.  Results (scores, lengths, op arrays) must be byte-identical."""
+    import subprocess
+    import sys
+    blobs = {}
+    for name, env in (("default", {}), ("tb_thread", {"YA_TB": "thread"}), ("full_thread", {"YA_FULL_THREAD_MAXW": "100000"})):
+        dst = str(tmp_path / f"{name}.bin")
+        code = _AB_SNIPPET.format(root=S.ROOT, tmp=str(tmp_path / f"small_{name}"), dst=dst)
+        os.makedirs(str(tmp_path / f"small_{name}"), exist_ok=True)
+        p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        blobs[name] = open(dst, "rb").read()
+    assert blobs["default"] == blobs["tb_thread"]
+    assert blobs["default"] == blobs["full_thread"]
+    assert len(blobs["default"]) > 100000

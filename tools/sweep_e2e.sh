@@ -1,14 +1,12 @@
 #!/bin/bash
-# e2e sweep on the GPU box: pipelines x threads-per-pipeline x batch, with and without device turns
 D=/tmp/yaha_b200_bench_cfg3
 python bench.py --no-cpu-baseline --steps 1 --warmup 3 > /dev/null 2>&1
 X=$D/ref.X15_01_65525S; Q=$D/reads_rank0.fa
-for lock in 0 1; do
-for cfg in "5000 4 8" "5000 4 4" "5000 3 5" "5000 2 8" "10000 2 8" "2500 4 8" "2500 8 4" "5000 4 6" "4000 5 6"; do
-  set -- $cfg
-  if [ $lock = 0 ]; then export YA_NO_GPU_LOCK=1; else unset YA_NO_GPU_LOCK; fi
-  r=$(yaha_b200/yaha_b200_host -x $X -q $Q -osh /tmp/sweep.sam -t 16 -batch $1 -pipes $2 -tpp $3 -passes 9 -BW 10 -G 100 2>&1 | grep '"pass"' | tail -6 | python -c "
+one() { lab=$1; shift
+  yaha_b200/yaha_b200_host -x $X -q $Q -osh /tmp/sweep.sam -t 16 -BW 10 -G 100 "$@" > /tmp/one.log 2>&1
+  grep '"pass"' /tmp/one.log | tail -20 | python -c "
 import sys,json
-v=[json.loads(l)['reads_per_s'] for l in sys.stdin]; print(int(sum(v)/len(v)), int(min(v)), int(max(v)))")
-  echo "lock=$lock batch=$1 pipes=$2 tpp=$3 : $r"
-done; done
+v=[json.loads(l) for l in sys.stdin]; n=len(v); r=sorted(x['align_s']*1e3 for x in v)
+print('$lab', 'median ms', round(r[n//2],2), 'mean', round(sum(r)/n,2), 'min', round(r[0],2), 'max', round(r[-1],2), 'host_ms', round(1e3*sum(x['host_wall_s'] for x in v)/n,2), 'rounds', v[-1]['dp_rounds'])"; }
+for cfg in "2500 8" "1250 8" "1250 16" "1667 12" "2000 10" "3334 6" "1000 20"; do set -- $cfg; one "e2e batch=$1 pipes=$2" -batch $1 -pipes $2 -passes 30; done
+for cfg in "2500 8" "1250 16" "1667 12"; do set -- $cfg; one "replay batch=$1 pipes=$2" -batch $1 -pipes $2 -passes 30 -replay; done

@@ -347,7 +347,11 @@ struct WorkerPool {
         for (int t = 0; t < n; t++) {
             w.emplace_back(new PoolWorker());
             PoolWorker *me = w.back().get();
-            me->th = std::thread([me]() {
+            me->th = std::thread([me, t]() {
+                if (getenv("YA_PIN")) {                                  // experiment: one worker per core
+                    cpu_set_t set; CPU_ZERO(&set); CPU_SET(t % get_nprocs(), &set);
+                    pthread_setaffinity_np(pthread_self(), sizeof set, &set);
+                }
                 for (;;) {
                     Task t;
                     {
