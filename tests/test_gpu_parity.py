@@ -273,7 +273,11 @@ for bw, gap in ((5, 50), (10, 100)):
         _, k, qid, st, roff, rlen, qoff, qlen, score, aq, ar, ops = rec
         jobs.append((roff, small.read_id[qid], rlen, qoff, qlen, S.KIND_OF_CHAR[k], st))
     res, ops = al.sw_batch(np.array(jobs, dtype=yaha_b200.JOB_DT))
-    out.append(res.tobytes()); out.append(np.asarray(ops).tobytes())
+    ops = np.asarray(ops)
+    for i in range(len(res)):            # (placement of a job's runs in ops[] is arbitrary: serialise per job)
+        o, n = int(res[i]["ops_off"]), int(res[i]["ops_n"])
+        out.append(np.array([res[i]["score"], res[i]["addedQLen"], res[i]["addedRLen"], n], dtype=np.int64).tobytes())
+        out.append(ops[o:o + n].tobytes())
     al.close()
 open({dst!r}, "wb").write(b"".join(out))
 """

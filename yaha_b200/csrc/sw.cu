@@ -606,7 +606,8 @@ __global__ void traceback_kernel(const DevJob *__restrict__ jobs, const uint32_t
 __global__ void __launch_bounds__(128)
 traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ ids, int n_jobs,
                       DevJobOut *__restrict__ outs, const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw,
-                      const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev)
+                      const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev,
+                      int BW, ya_dp_result *__restrict__ res, uint32_t *__restrict__ ops_cnt)
 {
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = (int)(threadIdx.x & 31);
@@ -701,6 +702,19 @@ traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restric
         }
     }
     if (lane == 0) { o.n_ops = n; outs[t] = o; }
+    // result record, fused (finalize_kernel of the thread-per-job path); the run count goes to the scan that
+    // places every job's runs in job order
+    if (lane == 0) {
+        ya_dp_result r;
+        uint32_t keep = (n >= 0xFFFFFFF0u) ? 0u : n;                     // traceback error marker: reported by the host
+        if (ext) {
+            if (o.score <= 0) { r.score = 0; r.addedQLen = 0; r.addedRLen = 0; keep = 0; }                  // SW.cpp:525,1102
+            else { r.score = o.score; r.addedQLen = (uint16_t)o.maxi; r.addedRLen = (uint16_t)(o.maxi + (o.maxj - 2 * BW)); }   // SW.cpp:1109-1110
+        } else { r.score = o.score; r.addedQLen = 0; r.addedRLen = 0; }
+        r.ops_n = keep; r.ops_off = 0;
+        res[t] = r;
+        ops_cnt[t] = keep;
+    }
 }
 
 __global__ void finalize_kernel(const DevJob *__restrict__ jobs, const DevJobOut *__restrict__ outs, int n_jobs,
@@ -728,15 +742,18 @@ __global__ void finalize_kernel(const DevJob *__restrict__ jobs, const DevJobOut
 
 // Copies each job's runs to their compact position.  Walking order is end -> start; forward and
 // global jobs are reversed into genome order, backward extensions already are (SW.cpp:1184-1185).
+// (runs that would not fit ops_out_cap are not written: the host sees total > capacity and runs the kernel again
+//  on a larger array)
 __global__ void compact_ops_kernel(const DevJob *__restrict__ jobs, int n_jobs, const uint32_t *__restrict__ ops_off,
                                    ya_dp_result *__restrict__ res, const ya_op *__restrict__ ops_raw,
-                                   ya_op *__restrict__ ops_out)
+                                   ya_op *__restrict__ ops_out, uint32_t ops_out_cap)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_jobs) return;
     const DevJob J = jobs[t];
     uint32_t n = res[t].ops_n, o = ops_off[t];
     res[t].ops_off = o;
+    if ((uint64_t)o + n > (uint64_t)ops_out_cap) return;
     const ya_op *src = ops_raw + J.ops_off;
     const bool keepOrder = J.kind == YA_DP_EXT_BWD;
     for (uint32_t k = 0; k < n; k++) ops_out[o + k] = keepOrder ? src[k] : src[n - 1 - k];
@@ -1005,37 +1022,95 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     const int tbk = (n_live + 127) / 128;
     static const bool tbThread = [] { const char *e = getenv("YA_TB"); return e && strcmp(e, "thread") == 0; }();
-    if (tbThread)
+    uint32_t *d_tot = c->d_ops_cnt.as<uint32_t>() + n_live;      // spare word after the counts
+    ya_dp_result *hres = c->h_res.as<ya_dp_result>();
+    DevJobOut *hout = (DevJobOut *)(hres + n_live);
+    uint32_t *h_total = (uint32_t *)(hout + n_live);              // (page-locked: a pageable target would stage the copy)
+    uint32_t total_ops = 0;
+    bool fits = false;
+    // the three-kernel epilogue (result records, scan of the run counts, compaction) with a sync in the middle for the total
+    auto epilogueKernels = [&]() -> int {
+        finalize_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), c->d_jobout.as<DevJobOut>(), n_live, P.bandWidth,
+                                             c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
+        c->ctr.launches++;
+        int rc = ya_exclusive_scan_u32(c, c->d_ops_cnt.as<uint32_t>(), c->d_ops_off.as<uint32_t>(), (size_t)n_live, d_tot);
+        if (rc != YA_OK) return rc;
+        YA_CUDA(c, cudaMemcpyAsync(h_total, d_tot, 4, cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, ya_stream_wait(st));
+        total_ops = *h_total;
+        YA_CUDA(c, c->d_ops_out.reserve((size_t)total_ops * sizeof(ya_op) + 64));
+        compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
+                                                c->d_res.as<ya_dp_result>(), c->d_ops_raw.as<ya_op>(), c->d_ops_out.as<ya_op>(),
+                                                (uint32_t)std::min<size_t>(c->d_ops_out.cap / sizeof(ya_op), 0xFFFFFFFFu));
+        c->ctr.launches++;
+        return YA_OK;
+    };
+    double tp3 = tp2;
+    if (tbThread) {
         traceback_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
                                               c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
                                               c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
-    else
+        c->ctr.launches++;
+        int rc = epilogueKernels();
+        if (rc != YA_OK) return rc;
+        tp3 = now_s(); g_prof_sw[2] += tp3 - tp2;
+        YA_CUDA(c, cudaEventRecord(c->ev[2], st));
+        YA_CUDA(c, cudaMemcpyAsync(hres, c->d_res.p, (size_t)n_live * sizeof(ya_dp_result), cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, cudaMemcpyAsync(hout, c->d_jobout.p, (size_t)n_live * sizeof(DevJobOut), cudaMemcpyDeviceToHost, st));
+        fits = total_ops <= ops_cap && (total_ops == 0 || ops != nullptr);
+        if (fits && total_ops)
+            YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, ya_stream_wait(st));
+    } else {
+        // warp-per-job traceback with the result records fused in, then scan + compaction without a host round
+        // trip: ONE synchronisation per call.  The compact run array is sized for 32 runs per job up front and the
+        // first 24 per job are copied back speculatively together with the results.
+        const size_t capDev = std::max<size_t>((size_t)32 * (size_t)n_live + 1024, c->d_ops_out.cap / sizeof(ya_op));
+        YA_CUDA(c, c->d_ops_out.reserve(capDev * sizeof(ya_op)));
+        const size_t devCap = std::min<size_t>(c->d_ops_out.cap / sizeof(ya_op), 0xFFFFFFFFu);
         traceback_warp_kernel<<<(n_live + 3) / 4, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
                                                                  c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
-                                                                 c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>());
-    finalize_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), c->d_jobout.as<DevJobOut>(), n_live, P.bandWidth,
-                                         c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
-    c->ctr.launches += 2;
-    uint32_t *d_tot = c->d_ops_cnt.as<uint32_t>() + n_live;      // spare word after the counts
-    int rc = ya_exclusive_scan_u32(c, c->d_ops_cnt.as<uint32_t>(), c->d_ops_off.as<uint32_t>(), (size_t)n_live, d_tot);
-    if (rc != YA_OK) return rc;
-    uint32_t total_ops = 0;
-    YA_CUDA(c, cudaMemcpyAsync(&total_ops, d_tot, 4, cudaMemcpyDeviceToHost, st));
-    YA_CUDA(c, ya_stream_wait(st));
-    double tp3 = now_s(); g_prof_sw[2] += tp3 - tp2;
-    YA_CUDA(c, c->d_ops_out.reserve((size_t)total_ops * sizeof(ya_op) + 64));
-    compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
-                                            c->d_res.as<ya_dp_result>(), c->d_ops_raw.as<ya_op>(), c->d_ops_out.as<ya_op>());
-    c->ctr.launches++;
-    YA_CUDA(c, cudaEventRecord(c->ev[2], st));
-    ya_dp_result *hres = c->h_res.as<ya_dp_result>();
-    DevJobOut *hout = (DevJobOut *)(hres + n_live);
-    YA_CUDA(c, cudaMemcpyAsync(hres, c->d_res.p, (size_t)n_live * sizeof(ya_dp_result), cudaMemcpyDeviceToHost, st));
-    YA_CUDA(c, cudaMemcpyAsync(hout, c->d_jobout.p, (size_t)n_live * sizeof(DevJobOut), cudaMemcpyDeviceToHost, st));
-    const bool fits = total_ops <= ops_cap && (total_ops == 0 || ops != nullptr);
-    if (fits && total_ops)
-        YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
-    YA_CUDA(c, ya_stream_wait(st));
+                                                                 c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
+                                                                 P.bandWidth, c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
+        c->ctr.launches++;
+        {
+            int rc = ya_exclusive_scan_u32(c, c->d_ops_cnt.as<uint32_t>(), c->d_ops_off.as<uint32_t>(), (size_t)n_live, d_tot);
+            if (rc != YA_OK) return rc;
+        }
+        compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
+                                                c->d_res.as<ya_dp_result>(), c->d_ops_raw.as<ya_op>(), c->d_ops_out.as<ya_op>(),
+                                                (uint32_t)devCap);
+        c->ctr.launches++;
+        YA_CUDA(c, cudaEventRecord(c->ev[2], st));
+        YA_CUDA(c, cudaMemcpyAsync(h_total, d_tot, 4, cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, cudaMemcpyAsync(hres, c->d_res.p, (size_t)n_live * sizeof(ya_dp_result), cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, cudaMemcpyAsync(hout, c->d_jobout.p, (size_t)n_live * sizeof(DevJobOut), cudaMemcpyDeviceToHost, st));
+        const size_t guess = ops ? std::min<size_t>(std::min<size_t>((size_t)24 * (size_t)n_live + 256, devCap), ops_cap) : 0;
+        if (guess) YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, guess * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, ya_stream_wait(st));
+        tp3 = now_s(); g_prof_sw[2] += tp3 - tp2;
+        total_ops = *h_total;
+        if ((size_t)total_ops > devCap) {
+            // more runs than the compact array holds (rare at 32 per job): compact again into a larger array
+            YA_CUDA(c, c->d_ops_out.reserve((size_t)total_ops * sizeof(ya_op) + 64));
+            compact_ops_kernel<<<tbk, 128, 0, st>>>(c->d_jobs.as<DevJob>(), n_live, c->d_ops_off.as<uint32_t>(),
+                                                    c->d_res.as<ya_dp_result>(), c->d_ops_raw.as<ya_op>(), c->d_ops_out.as<ya_op>(),
+                                                    (uint32_t)std::min<size_t>(c->d_ops_out.cap / sizeof(ya_op), 0xFFFFFFFFu));
+            c->ctr.launches++;
+            YA_CUDA(c, cudaMemcpyAsync(hres, c->d_res.p, (size_t)n_live * sizeof(ya_dp_result), cudaMemcpyDeviceToHost, st));
+            fits = total_ops <= ops_cap && (total_ops == 0 || ops != nullptr);
+            if (fits && total_ops)
+                YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, (size_t)total_ops * sizeof(ya_op), cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, ya_stream_wait(st));
+        } else {
+            fits = total_ops <= ops_cap && (total_ops == 0 || ops != nullptr);
+            if (fits && (size_t)total_ops > guess) {                  // the speculative copy was too short: fetch the rest
+                YA_CUDA(c, cudaMemcpyAsync(ops + guess, c->d_ops_out.as<ya_op>() + guess, ((size_t)total_ops - guess) * sizeof(ya_op),
+                                           cudaMemcpyDeviceToHost, st));
+                YA_CUDA(c, ya_stream_wait(st));
+            }
+        }
+    }
     YA_CUDA(c, cudaGetLastError());
     turn.done();
     double tp4 = now_s(); g_prof_sw[3] += tp4 - tp3;
