@@ -170,7 +170,8 @@ static int perfectBackward(const Env &E, const uint8_t *q, Frag &f, int len)    
 }
 
 // ---- phase 1 of alignClump: perfect extensions between neighbours, "nM" lists, post gap jobs
-struct GapJob { SFragList::iterator after; SFrag piece; DpFuture fut; bool needDp; };
+// a gap between two neighbouring pieces of a clump: either one op known in closed form, or a DP job
+struct GapJob { SFragList::iterator after; DpFuture fut; int score; uint16_t len; char code; bool needDp; };
 
 static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps)
 {
@@ -184,46 +185,60 @@ static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps
         gap -= perfectForward(E, q, s1->frag, gap);
         s1 = s2;
     }
-    for (auto &s : c.sf) {                                             // AlignHelpers.c:241-246
-        int ql = fragQLen(s.frag);
-        s.ops.pushFront('M', ql);
-        s.score = A.MScore * ql;
-    }
+    for (auto &s : c.sf) s.score = A.MScore * fragQLen(s.frag);       // AlignHelpers.c:241-246 (the "nM" op list is written at assembly)
     for (auto a = c.sf.begin(); std::next(a) != c.sf.end(); ++a) {    // AlignHelpers.c:251-261 + AlignExtFrag.cpp:164-234
         const Frag &f1 = a->frag, &f2 = std::next(a)->frag;
         uint16_t qGap = (uint16_t)calcGap(f1.endQueryOff, f2.startQueryOff);
         uint16_t rGap = (uint16_t)calcGapU(fragERO(f1), f2.startRefOff);
         if (qGap == 0 && rGap == 0) continue;
-        GapJob g; g.after = a; g.needDp = false;
-        Frag &nf = g.piece.frag;
-        nf.hitCount = 0;
-        nf.startQueryOff = (uint16_t)(f1.endQueryOff + 1);
-        nf.endQueryOff = (uint16_t)(f2.startQueryOff - 1);
-        nf.startRefOff = fragERO(f1) + 1;
-        fragSetERO(nf, f2.startRefOff - 1);
-        if (qGap == 0) { g.piece.ops.pushFront('D', rGap); g.piece.score = -(A.GOCost + rGap * A.GECost); }
-        else if (rGap == 0) { g.piece.ops.pushFront('I', qGap); g.piece.score = -(A.GOCost + qGap * A.GECost); }
-        else if (rGap == 1 && qGap == 1) { g.piece.ops.pushFront('R', 1); g.piece.score = -A.RCost; }
+        GapJob g; g.after = a; g.needDp = false; g.score = 0; g.len = 0; g.code = 0;
+        const uint16_t gSQO = (uint16_t)(f1.endQueryOff + 1);
+        const uint32_t gSRO = fragERO(f1) + 1;
+        if (qGap == 0) { g.code = 'D'; g.len = rGap; g.score = -(A.GOCost + rGap * A.GECost); }
+        else if (rGap == 0) { g.code = 'I'; g.len = qGap; g.score = -(A.GOCost + qGap * A.GECost); }
+        else if (rGap == 1 && qGap == 1) { g.code = 'R'; g.len = 1; g.score = -A.RCost; }
         else {
             int lenDiff = std::abs((int)qGap - (int)rGap);
             bool banded = lenDiff + A.bandWidth * 2 + 1 < (int)rGap;
             g.needDp = true;
-            g.fut = dpSubmit(rc, banded ? YA_DP_BANDED : YA_DP_FULL, rev, nf.startRefOff, rGap, nf.startQueryOff, qGap);
+            g.fut = dpSubmit(rc, banded ? YA_DP_BANDED : YA_DP_FULL, rev, gSRO, rGap, gSQO, qGap);
         }
-        gaps.push_back(std::move(g));
+        gaps.push_back(g);
     }
 }
 
 // ---- phase 2: splice the gap pieces, collapse, perfect-extend the ends, post both extensions
 struct ExtState { int backLen = 0, forwLen = 0; DpFuture fb, ff; bool doB = false, doF = false; };
 
-static void collapse(Clump &c)                                          // AlignHelpers.c:274-300
+// alignClump's splice + collapseSFragments (AlignHelpers.c:251-300) in one pass: the reference inserts a piece per
+// gap into the fragment list and then concatenates all op lists with mergeEOLToBack (equal codes coalesce at the
+// junctions, SW.cpp:207-261).  Here the runs go straight into the clump's list in the same order -- seed piece
+// ("nM"), its gap (closed form or the DP answer), next seed piece ... -- with the same junction rule.
+static inline void appendRun(OpVec &v, char code, uint16_t len, bool junction)
+{
+    if (junction && !v.empty() && v.back().code == code) v.back().len = (uint16_t)(v.back().len + len);
+    else v.push_back(Op{len, code});
+}
+static void assemble(ReadCtx &rc, Clump &c, PVec<GapJob> &gaps, size_t gapLo, size_t gapHi)
 {
     int total = 0;
-    size_t nOps = c.ops.v.size();
-    for (auto &s : c.sf) nOps += s.ops.v.size();
-    c.ops.v.reserve(nOps);
-    for (auto &s : c.sf) { total += s.score; c.ops.mergeToBack(s.ops); }
+    OpVec &v = c.ops.v;
+    size_t gi = gapLo;
+    for (auto it = c.sf.begin(); it != c.sf.end(); ++it) {
+        appendRun(v, 'M', (uint16_t)fragQLen(it->frag), true);
+        total += it->score;
+        if (gi < gapHi && gaps[gi].after == it) {
+            const GapJob &g = gaps[gi++];
+            if (g.needDp) {
+                const DpAnswer r = dpGet(rc, g.fut);
+                total += r.score;
+                for (int q = 0; q < r.n; q++) appendRun(v, (char)r.ops[q].opcode, r.ops[q].length, q == 0);   // (only the junction coalesces)
+            } else {
+                total += g.score;
+                appendRun(v, g.code, g.len, true);
+            }
+        }
+    }
     SFrag &s0 = c.sf.front();
     const Frag fn = c.sf.back().frag;
     s0.frag.endQueryOff = fn.endQueryOff;
@@ -511,7 +526,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     struct PerClump { ExtState x; int score = 0; size_t gapLo = 0, gapHi = 0; };
     PVec<PerClump> pc(old.size());
     PVec<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
-    gaps.reserve(std::min<size_t>(4 * old.size() + 4, 960 / sizeof(GapJob)));   // (stays a small-bin allocation)
+    gaps.reserve(16 * old.size() + 8);
     bool any = false;
     for (size_t k = 0; k < old.size(); k++) {
         if (old[k]->is(kAligned)) continue;
@@ -529,17 +544,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     for (size_t k = 0; k < old.size(); k++) {
         Clump &c = *old[k];
         if (c.is(kAligned)) continue;
-        for (size_t gi = pc[k].gapLo; gi < pc[k].gapHi; gi++) {
-            GapJob &g = gaps[gi];
-            if (g.needDp) {
-                const DpAnswer r = dpGet(rc, g.fut);
-                g.piece.score = r.score;
-                g.piece.ops.v.resize((size_t)r.n);
-                for (int q = 0; q < r.n; q++) g.piece.ops.v[(size_t)q] = Op{r.ops[q].length, (char)r.ops[q].opcode};
-            }
-            c.sf.insert(std::next(g.after), std::move(g.piece));
-        }
-        collapse(c);
+        assemble(rc, c, gaps, pc[k].gapLo, pc[k].gapHi);
         pc[k].score = c.sf.front().score;
         ExtState chk = pc[k].x;
         extendPerfect(E, rc, c, true, true, pc[k].score, chk, false);

@@ -93,14 +93,27 @@ struct FNode {                       // fGraphNode, GraphPath.cpp:65-79 (16-bit 
     uint16_t SQO, EQO;
 };
 
-// A set of small integers (query positions covered by the clumps already cut from a region; the
-// region's consumed fragments) stamped with a generation number instead of being cleared per region.
+// The region's consumed fragments, stamped with a generation number instead of being cleared per region.
 struct Coverage {
     std::vector<uint32_t> stamp; uint32_t gen = 0;
     void reset(size_t n) { if (stamp.size() < n) stamp.resize(n, 0); if (++gen == 0) { std::fill(stamp.begin(), stamp.end(), 0); gen = 1; } }
     void mark(int i) { stamp[(size_t)i] = gen; }
     bool covered(int i) const { return stamp[(size_t)i] == gen; }
-    bool free(int a, int b) const { for (int i = a; i <= b; i++) if (covered(i)) return false; return true; }
+};
+// Query positions covered by the clumps already cut from a region (the reference keeps one flag per position,
+// QueryMatch.c:177-197): a handful of intervals, so "is [a,b] untouched" is a few comparisons, not a scan.
+struct CoveredSpans {
+    struct Span { int lo, hi; };
+    Span sp[8]; int n = 0;
+    std::vector<Span> more;                                          // beyond 8 clumps per region (rare)
+    void reset() { n = 0; more.clear(); }
+    void mark(int lo, int hi) { if (hi < lo) return; if (n < 8) sp[n++] = Span{lo, hi}; else more.push_back(Span{lo, hi}); }
+    bool free(int a, int b) const
+    {
+        for (int k = 0; k < n; k++) if (sp[k].lo <= b && a <= sp[k].hi) return false;
+        for (const Span &x : more) if (x.lo <= b && a <= x.hi) return false;
+        return true;
+    }
 };
 
 static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, const Coverage &used,
@@ -175,7 +188,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
     Frag *frags = rc.frags[rev];
     const uint32_t *reg = rc.region[rev];
     const int n = rc.nFrags[rev];
-    static thread_local Coverage coverage;                      // per-thread scratch, reused across reads
+    CoveredSpans coverage;
     static thread_local Coverage used;
     static thread_local std::vector<FNode> nodes;
     Clump *spare = nullptr;                                     // an empty clump waiting for a path
@@ -193,7 +206,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
                 rc.clumps.push_back(c);
             }
         } else {                                                      // GraphPath.cpp:272-292
-            coverage.reset((size_t)qSlots);
+            coverage.reset();
             used.reset((size_t)(j - i + 1));
             for (;;) {
                 Clump *c = spare ? spare : new Clump();
@@ -201,7 +214,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
                 buildBestClump(A, frags, i, j, used, nodes, *c);
                 if (c->sf.empty()) { *c = Clump(); spare = c; break; }
                 int sqo = c->SQO(), qlen = (uint16_t)(1 + c->EQO() - c->SQO());
-                for (int k = 0; k < qlen && sqo + k < qSlots; k++) coverage.mark(sqo + k);
+                coverage.mark(sqo, std::min(sqo + qlen - 1, qSlots - 1));
                 // eliminateFragments, QueryMatch.c:201-215 (+ :177-197)
                 const int minLeft = A.minNonOverlap - 1;
                 for (int k = i; k <= j; k++) {
