@@ -223,6 +223,9 @@ static void assemble(ReadCtx &rc, Clump &c, PVec<GapJob> &gaps, size_t gapLo, si
 {
     int total = 0;
     OpVec &v = c.ops.v;
+    size_t nOps = v.size() + c.sf.size() + (gapHi - gapLo);
+    for (size_t k = gapLo; k < gapHi; k++) if (gaps[k].needDp) nOps += (size_t)dpGet(rc, gaps[k].fut).n;
+    v.reserve(nOps + 4);                                               // (+ the two extensions' junction runs and clips usually fit too)
     size_t gi = gapLo;
     for (auto it = c.sf.begin(); it != c.sf.end(); ++it) {
         appendRun(v, 'M', (uint16_t)fragQLen(it->frag), true);

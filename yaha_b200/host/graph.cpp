@@ -17,11 +17,19 @@ static const int kWorst = -(0x7fffff00);
 
 void disposeClump(Clump *c) { delete c; }
 
+static const uint8_t *gPrefetchBases = nullptr;                       // genome bytes (set once per run): see addFragment
 static void addFragment(Clump &c, const Frag &f)                      // AlignHelpers.c:48-56
 {
+    // the alignment phase that follows compares bases just outside both ends of every piece (perfect extensions,
+    // AlignExtFrag.cpp:30-48): ask for those genome lines now, they are cache misses in a 50 MB .. 1.5 GB array
+    if (gPrefetchBases) {
+        __builtin_prefetch(gPrefetchBases + ((f.startRefOff - 1u) >> 1));
+        __builtin_prefetch(gPrefetchBases + ((f.startRefOff + f.refLen) >> 1));
+    }
     c.matchedBases = (uint16_t)(c.matchedBases + f.refLen);
-    SFrag s; s.frag = f; s.frag.hitCount = 0;
-    c.sf.push_front(std::move(s));
+    c.sf.emplace_front();
+    SFrag &s = c.sf.front();
+    s.frag = f; s.frag.hitCount = 0;
 }
 
 static void insertFragment(Clump &c, Frag &f1)                        // AlignHelpers.c:60-90
@@ -130,10 +138,18 @@ static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, const Cov
     }
     const int nc = (int)nodes.size();
     if (nc == 0) return;
-    std::sort(nodes.begin(), nodes.end(), [](const FNode &a, const FNode &b) {
+    auto before = [](const FNode &a, const FNode &b) {
         if (a.SQO != b.SQO) return a.SQO < b.SQO;
-        return a.diag < b.diag;                                      // GraphPath.cpp:148-159
-    });
+        return a.diag < b.diag;                                      // GraphPath.cpp:148-159 (a total order: keys are distinct)
+    };
+    if (nc <= 24) {                                                  // the usual case: plain insertion sort
+        for (int a = 1; a < nc; a++) {
+            const FNode x = nodes[a];
+            int b = a - 1;
+            while (b >= 0 && before(x, nodes[b])) { nodes[b + 1] = nodes[b]; b--; }
+            nodes[b + 1] = x;
+        }
+    } else std::sort(nodes.begin(), nodes.end(), before);
     int bestScore = kWorst, best = -1;
     const uint32_t maxGap = (uint32_t)A.maxGap;
     for (int i = 0; i < nc; i++) {
@@ -185,6 +201,7 @@ static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, const Cov
 void formClumps(const Env &E, ReadCtx &rc, bool rev)
 {
     const Args &A = *E.A;
+    gPrefetchBases = E.G->bases;
     Frag *frags = rc.frags[rev];
     const uint32_t *reg = rc.region[rev];
     const int n = rc.nFrags[rev];

@@ -247,8 +247,9 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     int    nFrags[2] = {0, 0};
     std::string *out = nullptr;      // the worker's output buffer; this read's records are [outOff, outOff+outLen)
     size_t outOff = 0, outLen = 0;
-    const uint8_t *codes(bool rev) const { return rev ? read->rcode.data() : read->fcode.data(); }
-    const std::string &chars(bool rev) const { return rev ? read->rev : read->fwd; }
+    // the reverse-complement strand is derived the first time something asks for it (about half of the reads never do)
+    const uint8_t *codes(bool rev) const { if (rev) read->finish(); return rev ? read->rcode.data() : read->fcode.data(); }
+    const std::string &chars(bool rev) const { if (rev) read->finish(); return rev ? read->rev : read->fwd; }
 };
 
 // Implemented by the scheduler (pipeline.cpp); callable from inside a read fiber.

@@ -120,7 +120,6 @@ static void readMain(const Env &E, ReadCtx &rc)                       // body of
 {
     uint64_t t0 = rdtsc();
     const Args &A = *E.A;
-    rc.read->finish();
     {                                                                  // generateRandomSeed, QueryState.c:172-187
         const std::vector<uint8_t> &c = rc.read->fcode;
         size_t q = 0;

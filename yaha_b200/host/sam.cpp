@@ -67,36 +67,46 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
     const std::string &q = rc.chars(c.reversed());
     const int L = rc.read->len();
     if (A.outputSAM) {
-        o += rc.read->id;
-        o += c.reversed() ? "\t16\t" : "\t0\t";
-        o += BS.name;
-        o += '\t'; appendUInt(o, sStart + 1); o += '\t'; appendUInt(o, (unsigned)c.mapQuality); o += '\t';
         OpList &list = c.ops;
         int clip = L - 1 - f0.endQueryOff;
         if (clip > 0) list.pushBack(A.hardClip ? 'H' : 'S', clip);
         clip = f0.startQueryOff;
         if (clip > 0) list.pushFront(A.hardClip ? 'H' : 'S', clip);
+        // the record is written through a raw cursor into space reserved for its largest possible size
+        // (CIGAR <= 12 characters per run, MD <= 2 per reference base + 11 per run)
+        const size_t base = o.size();
+        size_t refBases = 0;
+        for (const Op &op : list.v) if (op.code != 'I') refBases += op.len;
+        const size_t bound = 512 + rc.read->id.size() + BS.name.size() + 24 * list.v.size() + 2 * (size_t)L + 2 * refBases;
+        o.resize(base + bound);
+        char *w = &o[base];
+        auto putS = [&](const char *z, size_t n) { memcpy(w, z, n); w += n; };
+        auto putU = [&](unsigned v) { char buf[12]; int n = 0; do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *w++ = buf[--n]; };
+        auto putI = [&](int v) { if (v < 0) { *w++ = '-'; putU((unsigned)(-(long)v)); } else putU((unsigned)v); };
+        putS(rc.read->id.data(), rc.read->id.size());
+        if (c.reversed()) putS("\t16\t", 4); else putS("\t0\t", 3);
+        putS(BS.name.data(), BS.name.size());
+        *w++ = '\t'; putU(sStart + 1); *w++ = '\t'; putU((unsigned)c.mapQuality); *w++ = '\t';
         int matches = 0;
         for (const Op &op : list.v) {
             if (op.code == 'M' || op.code == 'R') { matches += op.len; continue; }
-            if (matches > 0) { appendInt(o, matches); o += 'M'; matches = 0; }
-            appendInt(o, (int)op.len); o += op.code;
+            if (matches > 0) { putI(matches); *w++ = 'M'; matches = 0; }
+            putI((int)op.len); *w++ = op.code;
         }
-        if (matches > 0) { appendInt(o, matches); o += 'M'; }
-        o += "\t*\t0\t0\t";
+        if (matches > 0) { putI(matches); *w++ = 'M'; }
+        putS("\t*\t0\t0\t", 7);
         int qs = 0, qe = L - 1;
         if (A.hardClip) { qs = f0.startQueryOff; qe = fn.endQueryOff; }
-        if (qe >= qs) o.append(q, (size_t)qs, (size_t)(qe - qs + 1));
-        o += '\t';
+        if (qe >= qs) putS(q.data() + qs, (size_t)(qe - qs + 1));
+        *w++ = '\t';
         if (A.fastq) {
             const std::string &ql = rc.read->qual;
-            if (c.reversed()) for (int i = qe; i >= qs; i--) o += ql[(size_t)i];
-            else if (qe >= qs) o.append(ql, (size_t)qs, (size_t)(qe - qs + 1));
-        } else o += '*';
-        o += '\t';
-        o += "AS:i:"; appendInt(o, (int)c.totScore);
-        o += "\tNM:i:"; appendInt(o, (int)c.gapBases + (int)c.mismatchedBases);
-        o += "\tMD:Z:";
+            if (c.reversed()) for (int i = qe; i >= qs; i--) *w++ = ql[(size_t)i];
+            else if (qe >= qs) putS(ql.data() + qs, (size_t)(qe - qs + 1));
+        } else *w++ = '*';
+        putS("\tAS:i:", 6); putI((int)c.totScore);
+        putS("\tNM:i:", 6); putI((int)c.gapBases + (int)c.mismatchedBases);
+        putS("\tMD:Z:", 6);
         matches = 0;
         char prev = 'U';
         uint32_t ro = f0.startRefOff;
@@ -107,26 +117,29 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
             }
             if (op.code == 'M') { matches += op.len; ro += op.len; }
             else if (op.code == 'R') {
-                if (matches > 0) { appendInt(o, matches); matches = 0; }
-                if (prev == 'D') o += '0';
-                for (int i = 0; i < op.len; i++) o += kCharOfCode[G.code(ro + (uint32_t)i)];
+                if (matches > 0) { putI(matches); matches = 0; }
+                if (prev == 'D') *w++ = '0';
+                for (int i = 0; i < op.len; i++) *w++ = kCharOfCode[G.code(ro + (uint32_t)i)];
                 ro += op.len;
             } else if (op.code == 'D') {
-                if (matches > 0) { appendInt(o, matches); matches = 0; }
-                o += '^';
-                for (int i = 0; i < op.len; i++) o += kCharOfCode[G.code(ro + (uint32_t)i)];
+                if (matches > 0) { putI(matches); matches = 0; }
+                *w++ = '^';
+                for (int i = 0; i < op.len; i++) *w++ = kCharOfCode[G.code(ro + (uint32_t)i)];
                 ro += op.len;
             }
             prev = op.code;
         }
-        if (matches > 0) appendInt(o, matches);
-        appendf(o, "\tYF:H:%02X", (unsigned)c.status);
+        if (matches > 0) putI(matches);
+        putS("\tYF:H:", 6);
+        { static const char hex[] = "0123456789ABCDEF"; const unsigned st = (unsigned)c.status; *w++ = hex[(st >> 4) & 15]; *w++ = hex[st & 15]; }
         if (A.OQC) {
-            o += "\tYI:i:"; appendInt(o, (int)c.matchedPrimary);
-            o += "\tYP:i:"; appendInt(o, rc.primaryCount);
-            if (c.is(kPrimary)) { o += "\tYS:i:"; appendInt(o, (int)c.numSecondaries); }
+            putS("\tYI:i:", 6); putI((int)c.matchedPrimary);
+            putS("\tYP:i:", 6); putI(rc.primaryCount);
+            if (c.is(kPrimary)) { putS("\tYS:i:", 6); putI((int)c.numSecondaries); }
         }
-        o += '\n';
+        *w++ = '\n';
+        if ((size_t)(w - &o[base]) > bound) { fprintf(stderr, "yaha_b200: internal error: SAM record larger than its bound\n"); abort(); }
+        o.resize((size_t)(w - &o[0]));
     }
     if (A.outputBlast8) {                                                       // AlignOutput.c:307-318
         o += rc.read->id; o += '\t'; o += BS.name;
