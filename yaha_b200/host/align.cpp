@@ -171,23 +171,24 @@ static int perfectBackward(const Env &E, const uint8_t *q, Frag &f, int len)    
 
 // ---- phase 1 of alignClump: perfect extensions between neighbours, "nM" lists, post gap jobs
 // a gap between two neighbouring pieces of a clump: either one op known in closed form, or a DP job
-struct GapJob { SFragList::iterator after; DpFuture fut; int score; uint16_t len; char code; bool needDp; };
+struct GapJob { int after; DpFuture fut; int score; uint16_t len; char code; bool needDp; };   // after: index of the piece to its left
 
 static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps)
 {
     const Args &A = *E.A;
     const bool rev = c.reversed();
     const uint8_t *q = rc.codes(rev);
-    auto s1 = c.sf.begin();
-    for (auto s2 = std::next(s1); s2 != c.sf.end(); ++s2) {          // AlignHelpers.c:226-237
-        int gap = (int)std::min(calcGap(s1->frag.endQueryOff, s2->frag.startQueryOff), calcGapU(fragERO(s1->frag), s2->frag.startRefOff));
-        gap -= perfectBackward(E, q, s2->frag, gap);
-        gap -= perfectForward(E, q, s1->frag, gap);
-        s1 = s2;
+    PVec<Frag> &p = c.path;
+    const int np = (int)p.size();
+    for (int k = 1; k < np; k++) {                                    // AlignHelpers.c:226-237
+        Frag &l = p[(size_t)k - 1], &r = p[(size_t)k];
+        int gap = (int)std::min(calcGap(l.endQueryOff, r.startQueryOff), calcGapU(fragERO(l), r.startRefOff));
+        gap -= perfectBackward(E, q, r, gap);
+        gap -= perfectForward(E, q, l, gap);
     }
-    for (auto &s : c.sf) s.score = A.MScore * fragQLen(s.frag);       // AlignHelpers.c:241-246 (the "nM" op list is written at assembly)
-    for (auto a = c.sf.begin(); std::next(a) != c.sf.end(); ++a) {    // AlignHelpers.c:251-261 + AlignExtFrag.cpp:164-234
-        const Frag &f1 = a->frag, &f2 = std::next(a)->frag;
+    // (AlignHelpers.c:241-246: every piece is "nM" with score n * MScore -- written at assembly)
+    for (int a = 0; a + 1 < np; a++) {                                // AlignHelpers.c:251-261 + AlignExtFrag.cpp:164-234
+        const Frag &f1 = p[(size_t)a], &f2 = p[(size_t)a + 1];
         uint16_t qGap = (uint16_t)calcGap(f1.endQueryOff, f2.startQueryOff);
         uint16_t rGap = (uint16_t)calcGapU(fragERO(f1), f2.startRefOff);
         if (qGap == 0 && rGap == 0) continue;
@@ -219,17 +220,19 @@ static inline void appendRun(OpVec &v, char code, uint16_t len, bool junction)
     if (junction && !v.empty() && v.back().code == code) v.back().len = (uint16_t)(v.back().len + len);
     else v.push_back(Op{len, code});
 }
-static void assemble(ReadCtx &rc, Clump &c, PVec<GapJob> &gaps, size_t gapLo, size_t gapHi)
+static void assemble(const Args &A, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps, size_t gapLo, size_t gapHi)
 {
     int total = 0;
     OpVec &v = c.ops.v;
-    size_t nOps = v.size() + c.sf.size() + (gapHi - gapLo);
+    const PVec<Frag> &p = c.path;
+    size_t nOps = v.size() + p.size() + (gapHi - gapLo);
     for (size_t k = gapLo; k < gapHi; k++) if (gaps[k].needDp) nOps += (size_t)dpGet(rc, gaps[k].fut).n;
     v.reserve(nOps + 4);                                               // (+ the two extensions' junction runs and clips usually fit too)
     size_t gi = gapLo;
-    for (auto it = c.sf.begin(); it != c.sf.end(); ++it) {
-        appendRun(v, 'M', (uint16_t)fragQLen(it->frag), true);
-        total += it->score;
+    for (int it = 0; it < (int)p.size(); it++) {
+        const int ql = fragQLen(p[(size_t)it]);
+        appendRun(v, 'M', (uint16_t)ql, true);
+        total += A.MScore * ql;
         if (gi < gapHi && gaps[gi].after == it) {
             const GapJob &g = gaps[gi++];
             if (g.needDp) {
@@ -242,12 +245,14 @@ static void assemble(ReadCtx &rc, Clump &c, PVec<GapJob> &gaps, size_t gapLo, si
             }
         }
     }
+    c.sf.emplace_back();                                               // the collapsed piece
     SFrag &s0 = c.sf.front();
-    const Frag fn = c.sf.back().frag;
+    s0.frag = p.front();
+    const Frag fn = p.back();
     s0.frag.endQueryOff = fn.endQueryOff;
     fragSetERO(s0.frag, fragERO(fn));
     s0.score = total;
-    c.sf.erase(std::next(c.sf.begin()), c.sf.end());
+    c.path.clear();
 }
 
 // perfect part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:76-107)
@@ -290,7 +295,7 @@ static void extendPlanEarly(const Env &E, ReadCtx &rc, Clump &c, ExtState &x)
 {
     const Args &A = *E.A;
     const uint8_t *q = rc.codes(c.reversed());
-    Frag f0 = c.sf.front().frag, fn = c.sf.back().frag;
+    Frag f0 = c.path.front(), fn = c.path.back();
     x.backLen = (int)std::min<uint32_t>(f0.startQueryOff, f0.startRefOff);
     if (x.backLen > 0) x.backLen -= perfectBackward(E, q, f0, x.backLen);
     uint16_t qlen = (uint16_t)((rc.read->len() - 1) - fn.endQueryOff);
@@ -547,7 +552,7 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     for (size_t k = 0; k < old.size(); k++) {
         Clump &c = *old[k];
         if (c.is(kAligned)) continue;
-        assemble(rc, c, gaps, pc[k].gapLo, pc[k].gapHi);
+        assemble(*E.A, rc, c, gaps, pc[k].gapLo, pc[k].gapHi);
         pc[k].score = c.sf.front().score;
         ExtState chk = pc[k].x;
         extendPerfect(E, rc, c, true, true, pc[k].score, chk, false);

@@ -27,20 +27,18 @@ static void addFragment(Clump &c, const Frag &f)                      // AlignHe
         __builtin_prefetch(gPrefetchBases + ((f.startRefOff + f.refLen) >> 1));
     }
     c.matchedBases = (uint16_t)(c.matchedBases + f.refLen);
-    c.sf.emplace_front();
-    SFrag &s = c.sf.front();
-    s.frag = f; s.frag.hitCount = 0;
+    c.path.insert(c.path.begin(), f);                                 // the reference pushes at the list head
+    c.path.front().hitCount = 0;
 }
 
 static void insertFragment(Clump &c, Frag &f1)                        // AlignHelpers.c:60-90
 {
-    if (c.sf.empty()) { addFragment(c, f1); return; }
-    SFrag &nextS = c.sf.front();
-    Frag &f2 = nextS.frag;
+    if (c.path.empty()) { addFragment(c, f1); return; }
+    Frag &f2 = c.path.front();
     int maxOverlap = (int)std::max(calcOverlap(f1.endQueryOff, f2.startQueryOff), calcOverlapU(fragERO(f1), f2.startRefOff));
     if (maxOverlap > 0) {
         int l1 = fragQLen(f1), l2 = fragQLen(f2);
-        bool chop1 = (l1 != l2) ? (l1 < l2) : (c.sf.size() == 1);
+        bool chop1 = (l1 != l2) ? (l1 < l2) : (c.path.size() == 1);
         if (chop1) { f1.endQueryOff = (uint16_t)(f1.endQueryOff - maxOverlap); f1.refLen = (uint16_t)(f1.refLen - maxOverlap); }
         else { f2.startQueryOff = (uint16_t)(f2.startQueryOff + maxOverlap); f2.startRefOff += (uint32_t)maxOverlap;
                f2.refLen = (uint16_t)(f2.refLen - maxOverlap); }
@@ -48,46 +46,52 @@ static void insertFragment(Clump &c, Frag &f1)                        // AlignHe
     addFragment(c, f1);
 }
 
+// The reference walks a linked list and unlinks fragments; here the fragments are an array, "unlinked" ones are
+// marked and squeezed out afterwards.  Within the main loop an unlinked fragment always lies between s1 and the
+// anchor, and the walk continues from the anchor, so positions that are still looked at are never marked.
 static void cleanUpClump(const Args &A, Clump &c)                     // AlignHelpers.c:92-193
 {
-    typedef SFragList::iterator It;
-    const It END = c.sf.end();
-    It s1 = c.sf.begin();
-    It s2 = (s1 == END) ? END : std::next(s1);
-    It s3 = (s2 == END) ? END : std::next(s2);
-    while (s2 != END && s3 != END) {
-        if (fragQLen(s2->frag) < A.wordLen) {
-            It anchor = s3;
-            while (fragQLen(anchor->frag) < A.wordLen && std::next(anchor) != END) ++anchor;
-            uint32_t d1 = fragDiag(s1->frag), da = fragDiag(anchor->frag);
+    PVec<Frag> &p = c.path;
+    const int END = (int)p.size();
+    bool anyGone = false;
+    uint8_t goneSmall[64];
+    PVec<uint8_t> goneBig;
+    uint8_t *gone = goneSmall;
+    if (END > 64) { goneBig.assign((size_t)END, 0); gone = goneBig.data(); } else memset(goneSmall, 0, (size_t)END);
+    int s1 = 0, s2 = (END > 0) ? 1 : END, s3 = (s2 < END) ? s2 + 1 : END;
+    while (s2 < END && s3 < END) {
+        if (fragQLen(p[(size_t)s2]) < A.wordLen) {
+            int anchor = s3;
+            while (fragQLen(p[(size_t)anchor]) < A.wordLen && anchor + 1 < END) ++anchor;
+            uint32_t d1 = fragDiag(p[(size_t)s1]), da = fragDiag(p[(size_t)anchor]);
             if (absDiff(d1, da) <= (uint32_t)A.maxGap) {
-                It del = s2;
-                while (del != anchor) {
-                    It nxt = std::next(del);
-                    uint32_t dd = fragDiag(del->frag);
+                for (int del = s2; del != anchor; del++) {
+                    uint32_t dd = fragDiag(p[(size_t)del]);
                     bool outside = (dd < d1 && dd < da) || (dd > d1 && dd > da);
-                    if (!outside || std::min(absDiff(d1, dd), absDiff(dd, da)) <= (uint32_t)A.bandWidth) c.sf.erase(del);
-                    del = nxt;
+                    if (!outside || std::min(absDiff(d1, dd), absDiff(dd, da)) <= (uint32_t)A.bandWidth) { gone[del] = 1; anyGone = true; }
                 }
             }
-            s1 = anchor; s2 = std::next(anchor);
+            s1 = anchor; s2 = anchor + 1;
         } else { s1 = s2; s2 = s3; }
-        if (s2 != END) s3 = std::next(s2);
+        if (s2 < END) s3 = s2 + 1;
+    }
+    if (anyGone) {
+        size_t w = 0;
+        for (int k = 0; k < END; k++) if (!gone[k]) p[w++] = p[(size_t)k];
+        p.resize(w);
     }
     // first and last fragments: only dropped when they abut their neighbour (AlignHelpers.c:154-192)
-    if (c.sf.empty()) return;
-    It first = c.sf.begin();
-    if (fragQLen(first->frag) < A.wordLen && std::next(first) != END) {
-        const Frag &f1 = first->frag, &f2 = std::next(first)->frag;
+    if (p.empty()) return;
+    if (fragQLen(p.front()) < A.wordLen && p.size() > 1) {
+        const Frag &f1 = p[0], &f2 = p[1];
         int qGap = (int)calcGap(f1.endQueryOff, f2.startQueryOff), rGap = (int)calcGapU(fragERO(f1), f2.startRefOff);
-        if ((qGap == 0 && rGap <= 2 * A.bandWidth) || (rGap == 0 && qGap <= 2 * A.bandWidth)) c.sf.erase(first);
+        if ((qGap == 0 && rGap <= 2 * A.bandWidth) || (rGap == 0 && qGap <= 2 * A.bandWidth)) p.erase(p.begin());
     }
-    It last = std::prev(c.sf.end());
-    if (fragQLen(last->frag) < A.wordLen) {
-        if (last == c.sf.begin()) return;
-        const Frag &f1 = std::prev(last)->frag, &f2 = last->frag;
+    if (fragQLen(p.back()) < A.wordLen) {
+        if (p.size() == 1) return;
+        const Frag &f1 = p[p.size() - 2], &f2 = p.back();
         int qGap = (int)calcGap(f1.endQueryOff, f2.startQueryOff), rGap = (int)calcGapU(fragERO(f1), f2.startRefOff);
-        if ((qGap == 0 && rGap <= 2 * A.bandWidth) || (rGap == 0 && qGap <= 2 * A.bandWidth)) c.sf.erase(last);
+        if ((qGap == 0 && rGap <= 2 * A.bandWidth) || (rGap == 0 && qGap <= 2 * A.bandWidth)) p.pop_back();
     }
 }
 
@@ -194,7 +198,7 @@ static void buildBestClump(const Args &A, Frag *frags, int lo, int hi, const Cov
         if (take) { best = i; bestScore = L.bestScore; }
     }
     for (int k = best; k >= 0; k = nodes[k].prev) insertFragment(clump, *nodes[k].frag);     // GraphPath.cpp:134-146
-    if ((int)clump.matchedBases < A.minMatch) { clump.sf.clear(); clump.ops.clear(); clump.matchedBases = 0; clump.status = 0; }
+    if ((int)clump.matchedBases < A.minMatch) { clump.path.clear(); clump.ops.clear(); clump.matchedBases = 0; clump.status = 0; }
     else cleanUpClump(A, clump);
 }
 
@@ -229,7 +233,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
                 Clump *c = spare ? spare : new Clump();
                 spare = nullptr;
                 buildBestClump(A, frags, i, j, used, nodes, *c);
-                if (c->sf.empty()) { *c = Clump(); spare = c; break; }
+                if (c->path.empty()) { *c = Clump(); spare = c; break; }
                 int sqo = c->SQO(), qlen = (uint16_t)(1 + c->EQO() - c->SQO());
                 coverage.mark(sqo, std::min(sqo + qlen - 1, qSlots - 1));
                 // eliminateFragments, QueryMatch.c:201-215 (+ :177-197)

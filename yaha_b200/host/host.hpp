@@ -212,7 +212,8 @@ typedef std::list<SFrag, PoolAllocator<SFrag>> SFragList;
 enum { kReversed = 1, kFormed = 2, kAligned = 4, kScored = 8, kSplit = 16, kPrimary = 32 };   // FragsClumps.inl:221-226
 struct Clump {                       // Clump_t, Math.h:511-527
     OpList ops;
-    SFragList sf;
+    PVec<Frag> path;                 // before alignment: the seed fragments of the clump in query order (formClumps)
+    SFragList sf;                    // after alignment: the collapsed piece (and what splitting makes of it)
     static void *operator new(size_t n) { return TlsPool::get(n); }
     static void operator delete(void *p, size_t n) { TlsPool::put(p, n); }
     uint16_t totScore = 0, totLength = 0, matchedBases = 0, mismatchedBases = 0, gapBases = 0;
@@ -221,10 +222,12 @@ struct Clump {                       // Clump_t, Math.h:511-527
     bool is(int flag) const { return (status & flag) != 0; }
     void set(int flag, bool on) { if (on) status |= flag; else status &= ~flag; }
     bool reversed() const { return is(kReversed); }
-    uint16_t SQO() const { return sf.front().frag.startQueryOff; }
-    uint16_t EQO() const { return sf.back().frag.endQueryOff; }
-    uint32_t SRO() const { return sf.front().frag.startRefOff; }
-    uint32_t ERO() const { return fragERO(sf.back().frag); }
+    const Frag &firstFrag() const { return sf.empty() ? path.front() : sf.front().frag; }
+    const Frag &lastFrag() const { return sf.empty() ? path.back() : sf.back().frag; }
+    uint16_t SQO() const { return firstFrag().startQueryOff; }
+    uint16_t EQO() const { return lastFrag().endQueryOff; }
+    uint32_t SRO() const { return firstFrag().startRefOff; }
+    uint32_t ERO() const { return fragERO(lastFrag()); }
 };
 
 struct RandState { uint32_t s[5]; uint32_t bits(); };               // Math.c:274-284
