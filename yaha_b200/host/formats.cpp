@@ -233,7 +233,8 @@ bool RecordSlicer::open(const std::string &path, std::string &err)
     if (fstat(fd, &st) != 0) { err = "Failure to stat input file: " + path; ::close(fd); return false; }
     len = (size_t)st.st_size; pos = 0; done = true; base = nullptr;
     if (len > 0) {
-        void *m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        // small inputs are mapped with their pages in place; large ones are read ahead as the slicer walks through them
+        void *m = mmap(nullptr, len, PROT_READ, MAP_PRIVATE | (len <= ((size_t)256 << 20) ? MAP_POPULATE : 0), fd, 0);
         if (m == MAP_FAILED) { err = "Failure to map input file: " + path; ::close(fd); return false; }
         madvise(m, len, MADV_SEQUENTIAL);
         base = (const char *)m;
