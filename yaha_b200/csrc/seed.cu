@@ -306,11 +306,15 @@ __global__ void frag_write_kernel(const uint64_t *__restrict__ keys, uint32_t n,
     if (i + 1 == n || flag[i + 1]) eqo[id] = (uint16_t)((k & QO_MASK) + K - 1);
 }
 
-__global__ void region_flag_kernel(const FragRaw *__restrict__ raw, uint32_t nf, uint32_t maxGap,
+// The fragment / region / survivor counts stay on the device: these kernels are launched over the upper bound
+// (the number of hits), read the real count from *d_nf and zero their flag beyond it so that the scans can run over
+// the bound as well -- no host round trip between the steps.
+__global__ void region_flag_kernel(const FragRaw *__restrict__ raw, const uint32_t *__restrict__ d_nf, uint32_t n_upper, uint32_t maxGap,
                                    uint32_t *__restrict__ rflag, uint32_t *__restrict__ seg_first)
 {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
+    const uint32_t nf = *d_nf;
+    if (f >= nf) { if (f < n_upper) rflag[f] = 0; return; }
     uint32_t head = 1;
     bool newseg = true;
     if (f > 0) {
@@ -326,21 +330,23 @@ __global__ void region_flag_kernel(const FragRaw *__restrict__ raw, uint32_t nf,
 }
 
 __global__ void region_start_kernel(const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ ridx,
-                                    uint32_t nf, uint32_t *__restrict__ rstart, uint32_t n_regions)
+                                    const uint32_t *__restrict__ d_nf, uint32_t *__restrict__ rstart,
+                                    const uint32_t *__restrict__ d_nreg)
 {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f == 0) rstart[n_regions] = nf;
+    const uint32_t nf = *d_nf;
+    if (f == 0) rstart[*d_nreg] = nf;
     if (f >= nf) return;
     if (rflag[f]) rstart[ridx[f]] = f;
 }
 
 __global__ void keep_flag_kernel(const FragRaw *__restrict__ raw, const uint16_t *__restrict__ eqo,
                                  const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ ridx,
-                                 const uint32_t *__restrict__ rstart, uint32_t nf, uint32_t minMatch,
-                                 uint32_t *__restrict__ keep)
+                                 const uint32_t *__restrict__ rstart, const uint32_t *__restrict__ d_nf, uint32_t n_upper,
+                                 uint32_t minMatch, uint32_t *__restrict__ keep)
 {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
+    if (f >= *d_nf) { if (f < n_upper) keep[f] = 0; return; }
     uint32_t rid = ridx[f] + rflag[f] - 1;
     uint32_t members = rstart[rid + 1] - rstart[rid];
     uint32_t refLen = (uint32_t)eqo[f] - raw[f].sqo + 1;
@@ -350,12 +356,12 @@ __global__ void keep_flag_kernel(const FragRaw *__restrict__ raw, const uint16_t
 __global__ void compact_kernel(const FragRaw *__restrict__ raw, const uint16_t *__restrict__ eqo,
                                const uint32_t *__restrict__ rflag, const uint32_t *__restrict__ ridx,
                                const uint32_t *__restrict__ keep, const uint32_t *__restrict__ kidx,
-                               const uint32_t *__restrict__ seg_first, uint32_t nf,
+                               const uint32_t *__restrict__ seg_first, const uint32_t *__restrict__ d_nf,
                                ya_frag *__restrict__ out, uint32_t *__restrict__ region_out,
                                ya_strand_frags *__restrict__ strands)
 {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
+    if (f >= *d_nf) return;
     FragRaw r = raw[f];
     atomicAdd(&strands[r.seg].n_frags_all, 1u);
     if (!keep[f]) return;
@@ -478,6 +484,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             YA_CUDA(c, c->d_hit_off.reserve((size_t)cprobes * 4 + 16));
             YA_CUDA(c, c->d_keys0.reserve((size_t)n_keys * 8));
             YA_CUDA(c, c->d_keys1.reserve((size_t)n_keys * 8));
+            YA_CUDA(c, c->d_regstart.reserve(std::max<size_t>(((size_t)3 * cseg + 1) * 4 + 64, ((size_t)n_keys + 2) * 4)));
             uint32_t *d_hit_off = c->d_hit_off.as<uint32_t>();
             int rc = ya_exclusive_scan_u32(c, d_cnt + probe0, d_hit_off, cprobes, nullptr);
             if (rc != YA_OK) return rc;
@@ -495,7 +502,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
                     if (e >= 2 && e <= 512) small.push_back((uint32_t)(sgi - s0));
                     else if (e > 512) big.push_back((uint32_t)(sgi - s0));
                 }
-                YA_CUDA(c, c->d_regstart.reserve(((size_t)cseg + 1) * 4 + (small.size() + big.size()) * 4 + 64));
+                // (d_regstart was sized at the top of the chunk for the id lists here and the region starts later)
                 uint32_t *d_sko = c->d_regstart.as<uint32_t>();
                 uint32_t *d_small = d_sko + cseg + 1, *d_big = d_small + small.size();
                 seg_key_off_kernel<<<(cseg + 256) / 256, 256, 0, st>>>(d_po, s0, cseg, probe0, d_hit_off, cprobes, n_keys, d_sko);
@@ -512,84 +519,82 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
                     seg_sort_kernel<8192, 256><<<(unsigned)big.size(), 256, 8192 * 8, st>>>(ka, d_sko, d_big, (int)big.size());
                     c->ctr.launches++;
                 }
-                YA_CUDA(c, ya_stream_wait(st));              // the id vectors are reused by the next chunk
+                // (no wait: a copy from pageable memory has left the host vectors when cudaMemcpyAsync returns)
             } else {
                 int segbits = 1; while ((1 << segbits) < cseg) segbits++;
                 rc = ya_radix_sort_u64(c, ka, kb, n_keys, QO_BITS, SEG_SHIFT + segbits);
                 if (rc != YA_OK) return rc;
             }
 
-            // fragments
-            YA_CUDA(c, c->d_fragflag.reserve((size_t)n_keys * 4));
-            YA_CUDA(c, c->d_fragidx.reserve((size_t)n_keys * 4));
+            // fragments, regions, survivors: every array is sized by the number of hits (>= fragments >= regions,
+            // survivors), the counts stay on the device (d_tot[0..2]) and come back with the results
+            const size_t NU = n_keys;
+            YA_CUDA(c, c->d_fragflag.reserve(NU * 4));
+            YA_CUDA(c, c->d_fragidx.reserve(std::max<size_t>(NU, (size_t)cseg) * 4));
+            YA_CUDA(c, c->d_frags_all.reserve(NU * sizeof(FragRaw)));
+            YA_CUDA(c, c->d_frag_seg.reserve(NU * 2 + 16));
+            YA_CUDA(c, c->d_regflag.reserve(NU * 4));
+            YA_CUDA(c, c->d_regidx.reserve(NU * 4));
+            YA_CUDA(c, c->d_keep.reserve(NU * 4));
+            YA_CUDA(c, c->d_keepidx.reserve(NU * 4));
+            YA_CUDA(c, c->d_frags_out.reserve(NU * sizeof(ya_frag) + 16));
+            YA_CUDA(c, c->d_region_out.reserve(NU * 4 + 16));
             uint32_t *fflag = c->d_fragflag.as<uint32_t>(), *fidx = c->d_fragidx.as<uint32_t>();
-            YA_CUDA(c, c->d_regstart.reserve(64));
             uint32_t nb = (n_keys + 255) / 256;
             frag_flag_kernel<<<nb, 256, 0, st>>>(ka, n_keys, K, fflag);
             c->ctr.launches++;
-            uint32_t *d_tot = c->d_misc.as<uint32_t>() + 2 * (size_t)n_seg;    // 4 spare words
+            uint32_t *d_tot = c->d_misc.as<uint32_t>() + 2 * (size_t)n_seg;    // 4 spare words: fragments, regions, survivors
             rc = ya_exclusive_scan_u32(c, fflag, fidx, n_keys, d_tot);
             if (rc != YA_OK) return rc;
-            uint32_t nf = 0;
-            YA_CUDA(c, cudaMemcpyAsync(&nf, d_tot, 4, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, ya_stream_wait(st));
-            c->ctr.frags_all += nf;
-            YA_CUDA(c, c->d_frags_all.reserve((size_t)nf * sizeof(FragRaw)));
-            YA_CUDA(c, c->d_frag_seg.reserve((size_t)nf * 2 + 16));
             FragRaw *raw = c->d_frags_all.as<FragRaw>();
             uint16_t *eqo = c->d_frag_seg.as<uint16_t>();
             frag_write_kernel<<<nb, 256, 0, st>>>(ka, n_keys, K, fflag, fidx, raw, eqo);
             c->ctr.launches++;
-
-            // regions (reuse the key buffers' companions for flags)
-            YA_CUDA(c, c->d_regflag.reserve((size_t)nf * 4));
-            YA_CUDA(c, c->d_regidx.reserve((size_t)nf * 4));
-            YA_CUDA(c, c->d_keep.reserve((size_t)nf * 4));
-            YA_CUDA(c, c->d_keepidx.reserve((size_t)nf * 4));
-            YA_CUDA(c, c->d_fragidx.reserve((size_t)std::max<size_t>(n_keys, cseg) * 4));
             uint32_t *rflag = c->d_regflag.as<uint32_t>(), *ridx = c->d_regidx.as<uint32_t>();
             uint32_t *keep = c->d_keep.as<uint32_t>(), *kidx = c->d_keepidx.as<uint32_t>();
-            // seg_first lives in d_hit_off (no longer needed once keys are expanded)
+            // seg_first lives in d_hit_off (no longer needed once keys are expanded); the region starts get their own array
             YA_CUDA(c, c->d_hit_off.reserve((size_t)std::max<size_t>(cprobes, cseg) * 4 + 16));
             uint32_t *seg_first = c->d_hit_off.as<uint32_t>();
-            uint32_t fb = (nf + 255) / 256;
-            region_flag_kernel<<<fb, 256, 0, st>>>(raw, nf, (uint32_t)c->P.maxGap, rflag, seg_first);
+            uint32_t *rstart = c->d_regstart.as<uint32_t>();       // (the sort's id lists that lived here are consumed by now)
+            region_flag_kernel<<<nb, 256, 0, st>>>(raw, d_tot, n_keys, (uint32_t)c->P.maxGap, rflag, seg_first);
             c->ctr.launches++;
-            rc = ya_exclusive_scan_u32(c, rflag, ridx, nf, d_tot + 1);
+            rc = ya_exclusive_scan_u32(c, rflag, ridx, n_keys, d_tot + 1);
             if (rc != YA_OK) return rc;
-            uint32_t nreg = 0;
-            YA_CUDA(c, cudaMemcpyAsync(&nreg, d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, ya_stream_wait(st));
-            YA_CUDA(c, c->d_regstart.reserve(((size_t)nreg + 1) * 4));
-            uint32_t *rstart = c->d_regstart.as<uint32_t>();
-            region_start_kernel<<<fb, 256, 0, st>>>(rflag, ridx, nf, rstart, nreg);
-            keep_flag_kernel<<<fb, 256, 0, st>>>(raw, eqo, rflag, ridx, rstart, nf, (uint32_t)c->P.minMatch, keep);
+            region_start_kernel<<<nb, 256, 0, st>>>(rflag, ridx, d_tot, rstart, d_tot + 1);
+            keep_flag_kernel<<<nb, 256, 0, st>>>(raw, eqo, rflag, ridx, rstart, d_tot, n_keys, (uint32_t)c->P.minMatch, keep);
             c->ctr.launches += 2;
-            rc = ya_exclusive_scan_u32(c, keep, kidx, nf, d_tot + 2);
+            rc = ya_exclusive_scan_u32(c, keep, kidx, n_keys, d_tot + 2);
             if (rc != YA_OK) return rc;
-            uint32_t nkeep = 0;
-            YA_CUDA(c, cudaMemcpyAsync(&nkeep, d_tot + 2, 4, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, ya_stream_wait(st));
-            YA_CUDA(c, c->d_frags_out.reserve((size_t)nkeep * sizeof(ya_frag) + 16));
-            YA_CUDA(c, c->d_region_out.reserve((size_t)nkeep * 4 + 16));
-            compact_kernel<<<fb, 256, 0, st>>>(raw, eqo, rflag, ridx, keep, kidx, seg_first, nf,
+            compact_kernel<<<nb, 256, 0, st>>>(raw, eqo, rflag, ridx, keep, kidx, seg_first, d_tot,
                                                c->d_frags_out.as<ya_frag>(), c->d_region_out.as<uint32_t>(),
                                                d_strands + s0);
             c->ctr.launches++;
             YA_CUDA(c, cudaGetLastError());
+            // results: the counts, the strand records and -- speculatively -- the first survivors (32 per read)
+            uint32_t *h_cnt = c->h_stage.as<uint32_t>() + (size_t)n_seg * 2;          // 3 words after the per-segment totals
+            YA_CUDA(c, cudaMemcpyAsync(h_cnt, d_tot, 12, cudaMemcpyDeviceToHost, st));
+            YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
+                                       cudaMemcpyDeviceToHost, st));
+            const size_t room = (!overflow && out->frags_cap > out_base) ? out->frags_cap - out_base : 0;
+            const size_t guess = std::min<size_t>(std::min<size_t>(room, NU), (size_t)16 * (size_t)cseg + 64);
+            if (guess) {
+                YA_CUDA(c, cudaMemcpyAsync(out->frags + out_base, c->d_frags_out.p, guess * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
+                YA_CUDA(c, cudaMemcpyAsync(out->region + out_base, c->d_region_out.p, guess * 4, cudaMemcpyDeviceToHost, st));
+            }
+            YA_CUDA(c, ya_stream_wait(st));
+            const uint32_t nf = h_cnt[0], nkeep = h_cnt[2];
+            c->ctr.frags_all += nf;
             c->ctr.frags_out += nkeep;
             if (!overflow && out_base + nkeep <= out->frags_cap) {
-                if (nkeep) {
-                    YA_CUDA(c, cudaMemcpyAsync(out->frags + out_base, c->d_frags_out.p, (size_t)nkeep * sizeof(ya_frag),
-                                               cudaMemcpyDeviceToHost, st));
-                    YA_CUDA(c, cudaMemcpyAsync(out->region + out_base, c->d_region_out.p, (size_t)nkeep * 4,
-                                               cudaMemcpyDeviceToHost, st));
+                if ((size_t)nkeep > guess) {                              // the speculative copy was too short: fetch the rest
+                    YA_CUDA(c, cudaMemcpyAsync(out->frags + out_base + guess, c->d_frags_out.as<ya_frag>() + guess,
+                                               ((size_t)nkeep - guess) * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
+                    YA_CUDA(c, cudaMemcpyAsync(out->region + out_base + guess, c->d_region_out.as<uint32_t>() + guess,
+                                               ((size_t)nkeep - guess) * 4, cudaMemcpyDeviceToHost, st));
+                    YA_CUDA(c, ya_stream_wait(st));
                 }
             } else overflow = true;
             // strands of this chunk come back with chunk-relative `first`; fix up on the host
-            YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
-                                       cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, ya_stream_wait(st));
             for (int s = s0; s < s1; s++) {
                 ya_strand_frags &v = out->strands[s];
                 v.first = v.n_frags ? (uint32_t)(v.first + out_base) : (uint32_t)out_base;
