@@ -189,6 +189,37 @@ int ya_reads_upload(ya_ctx *, const ya_read_batch *);
  * singleton filter of processFragmentsGapped (Math.h:555, QueryMatch.c:224-303). */
 int ya_seed_frags(ya_ctx *, ya_frag_batch *out);
 
+/* ---- Next row N1: fragments -> clumps of seed fragments on the device.
+ * Replaces, for the batch ya_seed_frags has just processed, the region loop of processFragmentsGapped
+ * (QueryMatch.c:224-303), processFragmentRangeUsingGraph / buildBestClumpFromFragmentRange
+ * (GraphPath.cpp:161-292), eliminateFragments (QueryMatch.c:170-215) and addFragment / insertFragment /
+ * cleanUpClump (AlignHelpers.c:48-193).  One thread per strand runs yaha_b200/csrc/form_clumps.h -- the
+ * same source the host program compiles for its own formClumps.
+ * Output, per strand s (index 2*r + strand as in ya_frag_batch): clumps
+ * clumps[clump_first[s] .. clump_first[s] + clump_count[s]) in the reference's creation order; a clump's
+ * fragments (query order, after overlap chops and clean-up) are path[rec.first .. rec.first + rec.n).
+ * Capacities: clumps and path hold at most as many entries as ya_seed_frags returned fragments. ---- */
+typedef struct ya_clump_rec {
+    uint32_t first;        /* first fragment of the clump in path[]                              */
+    uint16_t n;            /* fragments in the clump                                              */
+    uint16_t matchedBases; /* Clump_t.matchedBases after addFragment (16-bit, as in the reference) */
+} ya_clump_rec;
+
+typedef struct ya_clump_batch {
+    /* parameters that ya_params does not carry (AlignmentArgs_t.maxDesert, .minNonOverlap)      */
+    int32_t       maxDesert, minNonOverlap;
+    /* capacity, set by the caller: entries in clumps[] and in path[] (>= ya_frag_batch.n_frags) */
+    size_t        cap;
+    /* outputs */
+    uint32_t     *clump_first;   /* [2*n_reads]                                                  */
+    uint32_t     *clump_count;   /* [2*n_reads]                                                  */
+    ya_clump_rec *clumps;        /* [cap]                                                        */
+    ya_frag      *path;          /* [cap]                                                        */
+    size_t        n_clumps, n_path;
+} ya_clump_batch;
+
+int ya_form_clumps(ya_ctx *, ya_clump_batch *out);
+
 /* Stage 3 for n independent jobs against the uploaded batch.  Replaces findAGSAlignment,
  * findAGSAlignmentBanded, findAGSForwardExtension, findAGSBackwardExtension
  * (Math.h:401-408) = findAffineGapScore<...> (SW.cpp:798-1208) + decompressRef

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../../oracle/oracle.h"
+#include "../../yaha_b200/csrc/form_clumps.h"
 
 struct ya_ctx {
     ya_params P;
@@ -14,6 +15,7 @@ struct ya_ctx {
     const uint8_t *bases; size_t n_base_bytes; uint32_t maxROff;
     int n_reads; uint8_t *fwd, *rev; uint64_t *off;
     ya_counters ctr;
+    const ya_frag_batch *last_seed;                   /* outputs of the last ya_seed_frags (caller's buffers) */
     ya_op *pending; size_t pendingN, pendingCap;     /* ops of the last ya_sw_batch (for ya_sw_fetch_ops) */
     char err[256];
 };
@@ -96,9 +98,11 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
         if (m && m->extra <= out->frags_cap) {
             memcpy(out->strands, m->a, m->na); memcpy(out->frags, m->b, m->nb); memcpy(out->region, m->c, m->nc);
             out->n_frags = m->extra;
+            c->last_seed = out;
             return 0;
         }
     }
+    c->last_seed = NULL;
     for (int seg = 0; seg < 2 * c->n_reads; seg++) {
         int r = seg >> 1;
         int L = (int)(c->off[r + 1] - c->off[r]);
@@ -129,12 +133,41 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     }
     if (overflow) { out->frags_needed = n_out; return YA_E_CAPACITY; }
     out->n_frags = n_out;
+    c->last_seed = out;
     if (memo_on()) {
         memo *m = memo_add(key, 1);
         m->na = 2 * (size_t)c->n_reads * sizeof(ya_strand_frags); m->a = dupmem(out->strands, m->na);
         m->nb = n_out * sizeof(ya_frag); m->b = dupmem(out->frags, m->nb);
         m->nc = n_out * 4; m->c = dupmem(out->region, m->nc);
         m->extra = n_out;
+    }
+    return 0;
+}
+
+/* the same source the device kernel runs (yaha_b200/csrc/form_clumps.h), one strand after the other */
+int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
+{
+    const ya_frag_batch *fb = c->last_seed;
+    out->n_clumps = out->n_path = 0;
+    if (!fb) return YA_E_STATE;
+    if (fb->n_frags > out->cap) return YA_E_CAPACITY;
+    fc_params P;
+    P.wordLen = c->P.wordLen; P.maxGap = c->P.maxGap; P.maxDesert = out->maxDesert; P.minMatch = c->P.minMatch;
+    P.minNonOverlap = out->minNonOverlap; P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.MScore = c->P.MScore;
+    for (int s = 0; s < 2 * c->n_reads; s++) {
+        const ya_strand_frags *sf = &fb->strands[s];
+        const uint32_t n = sf->n_frags, first = n ? sf->first : 0;
+        out->clump_first[s] = first; out->clump_count[s] = 0;
+        if (!n) continue;
+        ya_frag *work = malloc(n * sizeof(ya_frag)), *tmp = malloc(n * sizeof(ya_frag));
+        fc_node *nodes = malloc(n * sizeof(fc_node));
+        uint8_t *used = malloc(2 * (size_t)n);
+        memcpy(work, fb->frags + first, n * sizeof(ya_frag));
+        const int L = (int)(c->off[(s >> 1) + 1] - c->off[s >> 1]);
+        const int nc = fc_form_clumps(&P, work, fb->region + first, (int)n, L, nodes, used, tmp, out->path + first, out->clumps + first);
+        for (int k = 0; k < nc; k++) { out->clumps[first + k].first += first; out->n_path += out->clumps[first + k].n; }
+        out->clump_count[s] = (uint32_t)nc; out->n_clumps += (size_t)nc;
+        free(work); free(tmp); free(nodes); free(used);
     }
     return 0;
 }

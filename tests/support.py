@@ -61,7 +61,8 @@ def oracle():
     if _oracle is not None:
         return _oracle
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_dp.c", "oracle_seed.c", "oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_dp.c", "oracle_seed.c", "oracle_clumps.c", "oracle.h")]
+    srcs.append(os.path.join(ROOT, "yaha_b200", "csrc", "form_clumps.h"))
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
     lib = C.CDLL(so)
@@ -81,6 +82,8 @@ def oracle():
     lib.orc_perfect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int]
     lib.orc_encode.restype = None
     lib.orc_encode.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.orc_form_clumps.restype = C.c_int
+    lib.orc_form_clumps.argtypes = [C.c_int] * 9 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _oracle = lib
     return lib
 

@@ -301,3 +301,37 @@ def test_kernel_variants_agree_bytewise(small, tmp_path):
     assert blobs["default"] == blobs["tb_thread"]
     assert blobs["default"] == blobs["full_thread"]
     assert len(blobs["default"]) > 100000
+
+
+def test_device_clumps_match_cpu_build_of_the_same_source(small, aligner):
+    """Row N1: ya_form_clumps (one thread per strand running csrc/form_clumps.h) against the CPU build of the same
+    source (oracle/oracle_clumps.c) on the fragments the device itself produced -- clump by clump, fragment by
+    fragment.  The source is pinned through the host program (it is its formClumps; golden SAMs)."""
+    import ctypes as C
+    lib = S.oracle()
+    for bw, gap, desert, mno in ((5, 50, 50, 25), (10, 100, 50, 25), (5, 50, 10, 40)):
+        aligner.set_params(yaha_b200.Params.defaults(word_len=11, bw=bw, max_gap=gap))
+        strands, frags, region = aligner.seed_frags()
+        first, count, clumps, path = aligner.form_clumps(len(frags), max_desert=desert, min_non_overlap=mno)
+        n_checked = 0
+        for s in range(len(strands)):
+            n, f0 = int(strands[s]["n_frags"]), int(strands[s]["first"])
+            if n == 0:
+                assert count[s] == 0
+                continue
+            assert count[s] != 0xFFFFFFFF
+            L = len(small.fwd[s >> 1])
+            fr = np.ascontiguousarray(frags[f0:f0 + n]); rg = np.ascontiguousarray(region[f0:f0 + n])
+            opath = np.zeros(n, dtype=yaha_b200.FRAG_DT); ocl = np.zeros(n, dtype=yaha_b200.CLUMP_DT)
+            nc = lib.orc_form_clumps(11, gap, desert, 25, mno, bw, 5, 2, 1, S.ptr(fr), S.ptr(rg), n, L, S.ptr(opath), S.ptr(ocl))
+            assert nc == int(count[s]), (s, nc, int(count[s]))
+            c0 = int(first[s])
+            for k in range(nc):
+                mine, want = clumps[c0 + k], ocl[k]
+                assert int(mine["n"]) == int(want["n"]) and int(mine["matchedBases"]) == int(want["matchedBases"]), (s, k)
+                a = path[int(mine["first"]):int(mine["first"]) + int(mine["n"])]
+                b = opath[int(want["first"]):int(want["first"]) + int(want["n"])]
+                assert a.tobytes() == b.tobytes(), (s, k)
+                n_checked += 1
+        assert n_checked > 300
+    aligner.set_params(yaha_b200.Params.defaults(word_len=11))

@@ -34,6 +34,17 @@ def test_sam_independent_of_threads_and_batch(small, tmp_path):
         assert H.sam_lines(open(out).read()) == want
 
 
+def test_sam_same_with_clumps_on_host_or_device(small, tmp_path):
+    """Row N1 switch: fragments -> clumps on the device (default) or by the workers (YA_HOST_CLUMPS=1)."""
+    want = H.expected(small, "out_bw10.sam.gz")
+    for k, env in enumerate(({}, {"YA_HOST_CLUMPS": "1"})):
+        out = str(tmp_path / f"c{k}.sam")
+        cmd = H.command(HOST, small, "reads.fa", "-osh", out, ["-BW", "10", "-G", "100"], threads=3)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert H.sam_lines(open(out).read()) == want, env
+
+
 def test_sam_identical_on_10k_long_reads(tmp_path):
     """BASELINE configs[0] shape at reduced reference size, against the reference binary when it is
     on this box (oracle/_ref travels with the snapshot): 1 Mbp, 2 000 x 1000 bp reads at 2 %."""

@@ -61,6 +61,14 @@ class _FragBatch(C.Structure):
                 ("region", C.c_void_p), ("n_frags", C.c_size_t), ("frags_needed", C.c_size_t)]
 
 
+class _ClumpBatch(C.Structure):
+    _fields_ = [("maxDesert", C.c_int32), ("minNonOverlap", C.c_int32), ("cap", C.c_size_t), ("clump_first", C.c_void_p),
+                ("clump_count", C.c_void_p), ("clumps", C.c_void_p), ("path", C.c_void_p), ("n_clumps", C.c_size_t), ("n_path", C.c_size_t)]
+
+
+CLUMP_DT = np.dtype([("first", np.uint32), ("n", np.uint16), ("matchedBases", np.uint16)])
+
+
 class Counters(C.Structure):
     _fields_ = [("probes", C.c_uint64), ("hits", C.c_uint64), ("frags_all", C.c_uint64), ("frags_out", C.c_uint64),
                 ("dp_jobs", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_seed", C.c_double), ("ms_dp", C.c_double),
@@ -69,7 +77,7 @@ class Counters(C.Structure):
 
 
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
-           "ya_reads_upload", "ya_seed_frags", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_host_alloc", "ya_host_free", "ya_get_counters",
+           "ya_reads_upload", "ya_seed_frags", "ya_form_clumps", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_host_alloc", "ya_host_free", "ya_get_counters",
            "ya_measure_int32_peak", "ya_measure_gather_peak")
 
 _lib = None
@@ -103,6 +111,7 @@ def load_library() -> C.CDLL:
     lib.ya_set_stream.argtypes = [vp, vp]
     lib.ya_reads_upload.argtypes = [vp, C.POINTER(_ReadBatch)]
     lib.ya_seed_frags.argtypes = [vp, C.POINTER(_FragBatch)]
+    lib.ya_form_clumps.argtypes = [vp, C.POINTER(_ClumpBatch)]
     lib.ya_sw_batch.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.ya_sw_fetch_ops.argtypes = [vp, vp, C.c_size_t]
     lib.ya_host_alloc.restype = vp
@@ -218,6 +227,18 @@ class Aligner:
                 continue
             self._check(rc)
             return strands, frags[:fb.n_frags], region[:fb.n_frags]
+
+    def form_clumps(self, n_frags: int, max_desert: int = 50, min_non_overlap: int = 25):
+        """Row N1 for the batch seed_frags() has just processed -> (clump_first[2n], clump_count[2n], clumps, path)."""
+        n = self.n_reads
+        cap = max(16, int(n_frags))
+        first = np.zeros(2 * n, dtype=np.uint32)
+        count = np.zeros(2 * n, dtype=np.uint32)
+        clumps = np.zeros(cap, dtype=CLUMP_DT)
+        path = np.zeros(cap, dtype=FRAG_DT)
+        cb = _ClumpBatch(max_desert, min_non_overlap, cap, first.ctypes.data, count.ctypes.data, clumps.ctypes.data, path.ctypes.data, 0, 0)
+        self._check(self.lib.ya_form_clumps(self.ctx, C.byref(cb)))
+        return first, count, clumps, path
 
     def sw_batch(self, jobs: np.ndarray, ops_cap: int | None = None):
         """Stage 3 for a structured array of JOB_DT -> (results RES_DT[n], ops OP_DT[total])."""

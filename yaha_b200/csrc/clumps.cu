@@ -1,0 +1,89 @@
+// clumps.cu -- SURVEY.md section 8f, row N1: fragments -> clumps of seed fragments on the device.
+//
+// ya_form_clumps runs yaha_b200/csrc/form_clumps.h (the region loop of processFragmentsGapped, the fragment
+// graph of buildBestClumpFromFragmentRange, insertFragment's overlap chops, cleanUpClump, eliminateFragments:
+// QueryMatch.c:170-303, GraphPath.cpp:161-292, AlignHelpers.c:48-193) with one thread per strand on the
+// survivors ya_seed_frags left on the device.  The work per strand is a few thousand scalar, branchy
+// instructions (a dozen fragments, an O(n^2) chain DP with the reference's tie rules): it is bound by the
+// divergence of 32 unrelated strands per warp, not by memory -- 40 K strands keep every SM busy for a fraction
+// of a millisecond, which is what takes this step off the host's worker threads.  Strands with more than
+// kMaxStrandFrags fragments (repeat-rich loci, where the quadratic chain would make one thread the whole
+// kernel) are left to the host: their clump count comes back as 0xFFFFFFFF.
+#include "common.cuh"
+#include "form_clumps.h"
+
+static const uint32_t kMaxStrandFrags = 192;
+
+__global__ void __launch_bounds__(128)
+form_clumps_kernel(const ya_strand_frags *__restrict__ strands, int n_seg, const uint64_t *__restrict__ read_off,
+                   const ya_frag *__restrict__ frags, const uint32_t *__restrict__ region, fc_params P,
+                   ya_frag *__restrict__ work, fc_node *__restrict__ nodes, uint8_t *__restrict__ used, ya_frag *__restrict__ tmp,
+                   ya_frag *__restrict__ path, ya_clump_rec *__restrict__ clumps, uint32_t *__restrict__ count,
+                   uint32_t *__restrict__ first_out)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const ya_strand_frags sf = strands[s];
+    const uint32_t n = sf.n_frags;
+    const uint32_t first = n ? sf.first : 0;
+    first_out[s] = first;
+    if (n == 0) { count[s] = 0; return; }
+    if (n > kMaxStrandFrags) { count[s] = 0xFFFFFFFFu; return; }
+    const int readLen = (int)(read_off[(s >> 1) + 1] - read_off[s >> 1]);
+    ya_frag *w = work + first;
+    for (uint32_t k = 0; k < n; k++) w[k] = frags[first + k];          // the graph edits fragments in place: work on a copy
+    const int nc = fc_form_clumps(&P, w, region + first, (int)n, readLen, nodes + first, used + 2 * (size_t)first, tmp + first,
+                                  path + first, clumps + first);
+    for (int k = 0; k < nc; k++) clumps[first + k].first += first;      // path indices absolute
+    count[s] = (uint32_t)nc;
+}
+
+extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
+{
+    if (!c || !out || !out->clump_first || !out->clump_count) return YA_E_ARG;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    out->n_clumps = 0; out->n_path = 0;
+    const int n_seg = 2 * c->n_reads;
+    if (n_seg == 0) return YA_OK;
+    if (c->seed_chunks != 1) return ya_fail(c, YA_E_STATE, "ya_form_clumps: needs the survivors of a single-chunk ya_seed_frags call on the device");
+    const size_t nk = c->seed_nkeep;
+    if (nk > out->cap || (nk && (!out->clumps || !out->path))) return ya_fail(c, YA_E_CAPACITY, "clump output buffers too small");
+    cudaStream_t st = c->stream;
+    AllocScope allocScope(st);
+    YA_CUDA(c, c->d_fc_count.reserve((size_t)n_seg * 8 + 64));
+    uint32_t *d_count = c->d_fc_count.as<uint32_t>(), *d_first = d_count + n_seg;
+    YA_CUDA(c, c->d_fc_work.reserve(nk * sizeof(ya_frag) + 64));
+    YA_CUDA(c, c->d_fc_tmp.reserve(nk * sizeof(ya_frag) + 64));
+    YA_CUDA(c, c->d_fc_path.reserve(nk * sizeof(ya_frag) + 64));
+    YA_CUDA(c, c->d_fc_nodes.reserve(nk * sizeof(fc_node) + 64));
+    YA_CUDA(c, c->d_fc_used.reserve(nk * 2 + 64));
+    YA_CUDA(c, c->d_fc_clumps.reserve(nk * sizeof(ya_clump_rec) + 64));
+    fc_params P;
+    P.wordLen = c->P.wordLen; P.maxGap = c->P.maxGap; P.maxDesert = out->maxDesert; P.minMatch = c->P.minMatch;
+    P.minNonOverlap = out->minNonOverlap; P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.MScore = c->P.MScore;
+    YA_CUDA(c, cudaEventRecord(c->ev[0], st));
+    form_clumps_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(c->d_strand_out.as<ya_strand_frags>(), n_seg, c->d_read_off.as<uint64_t>(),
+        c->d_frags_out.as<ya_frag>(), c->d_region_out.as<uint32_t>(), P, c->d_fc_work.as<ya_frag>(), c->d_fc_nodes.as<fc_node>(),
+        c->d_fc_used.as<uint8_t>(), c->d_fc_tmp.as<ya_frag>(), c->d_fc_path.as<ya_frag>(), c->d_fc_clumps.as<ya_clump_rec>(), d_count, d_first);
+    c->ctr.launches++;
+    YA_CUDA(c, cudaEventRecord(c->ev[1], st));
+    YA_CUDA(c, cudaMemcpyAsync(out->clump_count, d_count, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(out->clump_first, d_first, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
+    if (nk) {
+        YA_CUDA(c, cudaMemcpyAsync(out->clumps, c->d_fc_clumps.p, nk * sizeof(ya_clump_rec), cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, cudaMemcpyAsync(out->path, c->d_fc_path.p, nk * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
+    }
+    YA_CUDA(c, ya_stream_wait(st));
+    YA_CUDA(c, cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->ctr.ms_seed += ms;
+    size_t nc = 0, np = 0;
+    for (int s = 0; s < n_seg; s++) {
+        const uint32_t k = out->clump_count[s];
+        if (k == 0xFFFFFFFFu) continue;
+        nc += k;
+        for (uint32_t q = 0; q < k; q++) np += out->clumps[out->clump_first[s] + q].n;
+    }
+    out->n_clumps = nc; out->n_path = np;
+    return YA_OK;
+}

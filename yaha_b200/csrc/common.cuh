@@ -131,6 +131,9 @@ struct ya_ctx {
     DevBuf    d_seg_probe_off, d_cnt, d_soff, d_hit_off, d_keys0, d_keys1, d_scan_tmp, d_hist;
     DevBuf    d_fragflag, d_fragidx, d_frags_all, d_frag_seg, d_regflag, d_regidx, d_regstart,
               d_keep, d_keepidx, d_frags_out, d_region_out, d_strand_out, d_misc;
+    DevBuf    d_fc_count, d_fc_work, d_fc_tmp, d_fc_path, d_fc_nodes, d_fc_used, d_fc_clumps;   // ya_form_clumps
+    int       seed_chunks = 0;          // chunks of the last ya_seed_frags call (its survivors stay on the device when 1)
+    size_t    seed_nkeep = 0;           // survivors of that call
     PinBuf    h_stage, h_stage2, h_stage3;
     // dp stage scratch
     DevBuf    d_jobs, d_jobout, d_tb, d_rows, d_ops_raw, d_ops_cnt, d_ops_off, d_ops_out, d_res;

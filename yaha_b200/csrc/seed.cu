@@ -465,6 +465,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     // chunk plan: <= 2^16 reads and <= MAX_KEYS hits per chunk (segment id fits 17 bits)
     const uint64_t MAX_KEYS = 1ull << 28;
     size_t out_base = 0;          // survivors written so far (device-side running offset)
+    c->seed_chunks = 0; c->seed_nkeep = 0;
     bool overflow = false;
     int s0 = 0;
     while (s0 < n_seg) {
@@ -606,8 +607,10 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             YA_CUDA(c, ya_stream_wait(st));
             for (int s = s0; s < s1; s++) out->strands[s].first = (uint32_t)out_base;
         }
+        c->seed_chunks++;
         s0 = s1;
     }
+    c->seed_nkeep = out_base;
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     YA_CUDA(c, cudaEventSynchronize(c->ev[1]));
     float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);

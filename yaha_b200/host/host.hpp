@@ -248,6 +248,9 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     Frag  *frags[2] = {nullptr, nullptr};        // the device's surviving fragments of each strand, in the
     const uint32_t *region[2] = {nullptr, nullptr};  // pipeline's result buffers (edited in place)
     int    nFrags[2] = {0, 0};
+    const ya_clump_rec *devClumps[2] = {nullptr, nullptr};   // clumps formed on the device (ya_form_clumps), or null
+    const Frag *devPath[2] = {nullptr, nullptr};
+    int    nDevClumps[2] = {0, 0};
     std::string *out = nullptr;      // the worker's output buffer; this read's records are [outOff, outOff+outLen)
     size_t outOff = 0, outLen = 0;
     // the reverse-complement strand is derived the first time something asks for it (about half of the reads never do)

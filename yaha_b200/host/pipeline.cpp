@@ -228,6 +228,10 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     PinnedVec<uint32_t> region;
     PinnedVec<uint8_t> codes;
     PinnedVec<uint64_t> offs;
+    PinnedVec<uint32_t> clumpFirst, clumpCount;     // ya_form_clumps outputs (clumps of seed fragments made on the device)
+    PinnedVec<ya_clump_rec> clumpRecs;
+    PinnedVec<ya_frag> clumpPath;
+    bool devClumps = false;               // the batch in flight has them
     std::vector<ya_dp_job> jobs;
     std::vector<std::unique_ptr<ResultBlock>> blocks;      // every result block this pipeline ever made
     std::vector<ResultBlock *> freeBlocks;
@@ -320,6 +324,12 @@ static void runSlotPass(const Task &t)
                 f->rc.frags[st] = D.frags.data() + sf.first;
                 f->rc.region[st] = D.region.data() + sf.first;
                 f->rc.nFrags[st] = (int)sf.n_frags;
+                const size_t seg = (size_t)2 * i + st;
+                if (D.devClumps && D.clumpCount[seg] != 0xFFFFFFFFu) {
+                    f->rc.devClumps[st] = D.clumpRecs.data() + D.clumpFirst[seg];
+                    f->rc.nDevClumps[st] = (int)D.clumpCount[seg];
+                    f->rc.devPath[st] = D.clumpPath.data();
+                } else { f->rc.devClumps[st] = nullptr; f->rc.nDevClumps[st] = 0; f->rc.devPath[st] = nullptr; }
             }
             s.fibers.push_back(f);
         }
@@ -427,6 +437,21 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         if (rcode == YA_E_CAPACITY) { D.frags.resize(fb.frags_needed + 1024, false); D.region.resize(fb.frags_needed + 1024, false); continue; }
         if (rcode != YA_OK) die(D.ctx, "ya_seed_frags");
         break;
+    }
+    // fragments -> clumps of seed fragments on the device (row N1); strands it leaves out (very many fragments)
+    // and everything when YA_HOST_CLUMPS is set are done by the worker that owns the read
+    static const bool hostClumps = getenv("YA_HOST_CLUMPS") != nullptr;
+    D.devClumps = false;
+    if (!hostClumps) {
+        const size_t cap = std::max<size_t>(fb.n_frags, 16);
+        D.clumpFirst.resize((size_t)2 * n, false); D.clumpCount.resize((size_t)2 * n, false);
+        if (D.clumpRecs.size() < cap) { D.clumpRecs.resize(cap + cap / 2, false); D.clumpPath.resize(cap + cap / 2, false); }
+        ya_clump_batch cb;
+        cb.maxDesert = E.A->maxDesert; cb.minNonOverlap = E.A->minNonOverlap; cb.cap = D.clumpRecs.size();
+        cb.clump_first = D.clumpFirst.data(); cb.clump_count = D.clumpCount.data(); cb.clumps = D.clumpRecs.data(); cb.path = D.clumpPath.data();
+        const int rcode = ya_form_clumps(D.ctx, &cb);
+        if (rcode == YA_OK) D.devClumps = true;
+        else if (rcode != YA_E_STATE) die(D.ctx, "ya_form_clumps");            // (YA_E_STATE: survivors not on the device -> host path)
     }
     D.tSeed += nowSec() - t0;
     traceEv('S', D.device, (int)B.seq, t0, nowSec());
