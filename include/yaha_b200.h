@@ -220,6 +220,43 @@ typedef struct ya_clump_batch {
 
 int ya_form_clumps(ya_ctx *, ya_clump_batch *out);
 
+/* ---- First phase of alignClump on the device, for the clumps ya_form_clumps has just made: perfect extensions
+ * between neighbouring seed fragments (AlignHelpers.c:226-237, AlignExtFrag.cpp:30-48), the dispatch of
+ * makeAndAlignSFragmentToFillGap for every gap (closed form: pure D / pure I / 1x1 R; else a banded or full DP job,
+ * AlignExtFrag.cpp:164-234) and the plan of the two end extensions (AlignExtFrag.cpp:64-107).  Same source as the
+ * host program's own phase 1 (yaha_b200/csrc/prepare_clumps.h).  Records are indexed like ya_clump_batch:
+ * prep[k] belongs to clumps[k]; its gaps are gaps[prep[k].gap_first .. + n_gaps); path[] holds the clumps'
+ * fragments after the perfect extensions (same positions as ya_clump_batch.path).  jobs[] is ready for
+ * ya_sw_batch; gap and extension records carry the index of their job (0xFFFFFFFF: none). ---- */
+typedef struct ya_gap_rec {
+    uint32_t job;          /* index into jobs[], or 0xFFFFFFFF for a closed-form gap                  */
+    int32_t  score;        /* closed form: score of the piece                                          */
+    uint16_t after;        /* the gap follows fragment `after` of its clump                            */
+    uint16_t len;          /* closed form: run length                                                  */
+    uint8_t  code;         /* closed form: 'D', 'I' or 'R'                                             */
+    uint8_t  pad; uint16_t pad2;
+} ya_gap_rec;
+
+typedef struct ya_prep_rec {
+    uint32_t gap_first;
+    uint32_t jobB, jobF;   /* backward / forward extension job, 0xFFFFFFFF when shorter than minExtLength */
+    uint16_t n_gaps;
+    uint16_t backLen, forwLen;   /* lengths left for the DP after the perfect pre-extension             */
+    uint16_t pad;
+} ya_prep_rec;
+
+typedef struct ya_prep_batch {
+    size_t       cap;        /* entries in prep[], gaps[], path[] (>= ya_frag_batch.n_frags)            */
+    size_t       jobs_cap;   /* entries in jobs[] (3 * cap always suffices)                             */
+    ya_prep_rec *prep;
+    ya_gap_rec  *gaps;
+    ya_frag     *path;
+    ya_dp_job   *jobs;
+    size_t       n_jobs;
+} ya_prep_batch;
+
+int ya_prepare_clumps(ya_ctx *, ya_prep_batch *out);
+
 /* Stage 3 for n independent jobs against the uploaded batch.  Replaces findAGSAlignment,
  * findAGSAlignmentBanded, findAGSForwardExtension, findAGSBackwardExtension
  * (Math.h:401-408) = findAffineGapScore<...> (SW.cpp:798-1208) + decompressRef

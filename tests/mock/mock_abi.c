@@ -8,6 +8,7 @@
 #include <string.h>
 #include "../../oracle/oracle.h"
 #include "../../yaha_b200/csrc/form_clumps.h"
+#include "../../yaha_b200/csrc/prepare_clumps.h"
 
 struct ya_ctx {
     ya_params P;
@@ -15,7 +16,8 @@ struct ya_ctx {
     const uint8_t *bases; size_t n_base_bytes; uint32_t maxROff;
     int n_reads; uint8_t *fwd, *rev; uint64_t *off;
     ya_counters ctr;
-    const ya_frag_batch *last_seed;                   /* outputs of the last ya_seed_frags (caller's buffers) */
+    ya_clump_batch last_clumps_v; int has_clumps;     /* descriptor of the last ya_form_clumps outputs (caller's buffers) */
+    ya_frag_batch last_seed_v; int has_seed;          /* descriptor of the last ya_seed_frags outputs (caller's buffers) */
     ya_op *pending; size_t pendingN, pendingCap;     /* ops of the last ya_sw_batch (for ya_sw_fetch_ops) */
     char err[256];
 };
@@ -98,11 +100,11 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
         if (m && m->extra <= out->frags_cap) {
             memcpy(out->strands, m->a, m->na); memcpy(out->frags, m->b, m->nb); memcpy(out->region, m->c, m->nc);
             out->n_frags = m->extra;
-            c->last_seed = out;
+            c->last_seed_v = *out; c->has_seed = 1;
             return 0;
         }
     }
-    c->last_seed = NULL;
+    c->has_seed = 0; c->has_clumps = 0;
     for (int seg = 0; seg < 2 * c->n_reads; seg++) {
         int r = seg >> 1;
         int L = (int)(c->off[r + 1] - c->off[r]);
@@ -133,7 +135,7 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     }
     if (overflow) { out->frags_needed = n_out; return YA_E_CAPACITY; }
     out->n_frags = n_out;
-    c->last_seed = out;
+    c->last_seed_v = *out; c->has_seed = 1;
     if (memo_on()) {
         memo *m = memo_add(key, 1);
         m->na = 2 * (size_t)c->n_reads * sizeof(ya_strand_frags); m->a = dupmem(out->strands, m->na);
@@ -147,9 +149,10 @@ int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
 /* the same source the device kernel runs (yaha_b200/csrc/form_clumps.h), one strand after the other */
 int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
 {
-    const ya_frag_batch *fb = c->last_seed;
+    const ya_frag_batch *fb = &c->last_seed_v;
     out->n_clumps = out->n_path = 0;
-    if (!fb) return YA_E_STATE;
+    c->has_clumps = 0;
+    if (!c->has_seed) return YA_E_STATE;
     if (fb->n_frags > out->cap) return YA_E_CAPACITY;
     fc_params P;
     P.wordLen = c->P.wordLen; P.maxGap = c->P.maxGap; P.maxDesert = out->maxDesert; P.minMatch = c->P.minMatch;
@@ -169,6 +172,37 @@ int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
         out->clump_count[s] = (uint32_t)nc; out->n_clumps += (size_t)nc;
         free(work); free(tmp); free(nodes); free(used);
     }
+    c->last_clumps_v = *out; c->has_clumps = 1;
+    return 0;
+}
+
+int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
+{
+    const ya_clump_batch *cb = &c->last_clumps_v;
+    out->n_jobs = 0;
+    if (!c->has_clumps) return YA_E_STATE;
+    pc_params P;
+    P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.RCost = c->P.RCost; P.MScore = c->P.MScore;
+    P.minExtLength = c->P.minExtLength; P.maxROff = c->maxROff;
+    uint32_t nj = 0;
+    for (int s = 0; s < 2 * c->n_reads; s++) {
+        const uint32_t nc = cb->clump_count[s], c0 = cb->clump_first[s];
+        if (nc == 0 || nc == 0xFFFFFFFFu) continue;
+        const uint32_t r = (uint32_t)(s >> 1);
+        const int L = (int)(c->off[r + 1] - c->off[r]);
+        const uint8_t *q = ((s & 1) ? c->rev : c->fwd) + c->off[r];
+        for (uint32_t k = 0; k < nc; k++) {
+            const ya_clump_rec rec = cb->clumps[c0 + k];
+            memcpy(out->path + rec.first, cb->path + rec.first, rec.n * sizeof(ya_frag));
+            ya_prep_rec pr;
+            pr.gap_first = rec.first;
+            pc_prepare_clump(&P, c->bases, q, L, r, s & 1, out->path + rec.first, (int)rec.n, out->gaps + rec.first, out->jobs, &nj,
+                             (uint32_t)out->jobs_cap, &pr);
+            out->prep[c0 + k] = pr;
+        }
+    }
+    if (nj > out->jobs_cap) return YA_E_CAPACITY;
+    out->n_jobs = nj;
     return 0;
 }
 

@@ -54,6 +54,17 @@ def test_sliced_and_sequential_fasta_readers_agree(small, mock_host, tmp_path):
             assert H.sam_lines(open(out).read()) == want, (reads, env)
 
 
+def test_clumps_and_alignment_phase_one_on_device_or_host(small, mock_host, tmp_path):
+    # the mock runs csrc/form_clumps.h and csrc/prepare_clumps.h behind ya_form_clumps / ya_prepare_clumps, the very
+    # sources the device kernels compile; the switches move either step back into the worker threads
+    want = H.expected(small, "out_bw10.sam.gz")
+    for k, env in enumerate(({}, {"YA_HOST_PREP": "1"}, {"YA_HOST_CLUMPS": "1"})):
+        out = str(tmp_path / f"d{k}.sam")
+        cmd = H.command(mock_host, small, "reads.fa", "-osh", out, ["-BW", "10", "-G", "100"], threads=3)
+        subprocess.run(cmd, check=True, capture_output=True, timeout=600, env=dict(os.environ, **env))
+        assert H.sam_lines(open(out).read()) == want, env
+
+
 def test_cli_errors_match_reference_behaviour(small, mock_host):
     # missing -x for query mode, bad flag, bad bool: message + non-zero exit like Main.c
     p = subprocess.run([mock_host, "-q", "x.fa"], capture_output=True, text=True)

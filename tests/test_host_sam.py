@@ -35,9 +35,10 @@ def test_sam_independent_of_threads_and_batch(small, tmp_path):
 
 
 def test_sam_same_with_clumps_on_host_or_device(small, tmp_path):
-    """Row N1 switch: fragments -> clumps on the device (default) or by the workers (YA_HOST_CLUMPS=1)."""
+    """Row N1 switches: fragments -> clumps and the first phase of their alignment on the device (default), the
+    alignment phase by the workers (YA_HOST_PREP=1), or both by the workers (YA_HOST_CLUMPS=1)."""
     want = H.expected(small, "out_bw10.sam.gz")
-    for k, env in enumerate(({}, {"YA_HOST_CLUMPS": "1"})):
+    for k, env in enumerate(({}, {"YA_HOST_PREP": "1"}, {"YA_HOST_CLUMPS": "1"})):
         out = str(tmp_path / f"c{k}.sam")
         cmd = H.command(HOST, small, "reads.fa", "-osh", out, ["-BW", "10", "-G", "100"], threads=3)
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))

@@ -11,6 +11,7 @@
 // kernel) are left to the host: their clump count comes back as 0xFFFFFFFF.
 #include "common.cuh"
 #include "form_clumps.h"
+#include "prepare_clumps.h"
 
 static const uint32_t kMaxStrandFrags = 192;
 
@@ -43,6 +44,7 @@ extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
     if (!c || !out || !out->clump_first || !out->clump_count) return YA_E_ARG;
     YA_CUDA(c, cudaSetDevice(c->device));
     out->n_clumps = 0; out->n_path = 0;
+    c->fc_valid = false;
     const int n_seg = 2 * c->n_reads;
     if (n_seg == 0) return YA_OK;
     if (c->seed_chunks != 1) return ya_fail(c, YA_E_STATE, "ya_form_clumps: needs the survivors of a single-chunk ya_seed_frags call on the device");
@@ -50,7 +52,7 @@ extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
     if (nk > out->cap || (nk && (!out->clumps || !out->path))) return ya_fail(c, YA_E_CAPACITY, "clump output buffers too small");
     cudaStream_t st = c->stream;
     AllocScope allocScope(st);
-    YA_CUDA(c, c->d_fc_count.reserve((size_t)n_seg * 8 + 64));
+    YA_CUDA(c, c->d_fc_count.reserve((size_t)n_seg * 8 + 64));     // counts, firsts and (tail) the job counter of ya_prepare_clumps
     uint32_t *d_count = c->d_fc_count.as<uint32_t>(), *d_first = d_count + n_seg;
     YA_CUDA(c, c->d_fc_work.reserve(nk * sizeof(ya_frag) + 64));
     YA_CUDA(c, c->d_fc_tmp.reserve(nk * sizeof(ya_frag) + 64));
@@ -85,5 +87,89 @@ extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
         for (uint32_t q = 0; q < k; q++) np += out->clumps[out->clump_first[s] + q].n;
     }
     out->n_clumps = nc; out->n_path = np;
+    c->fc_valid = true;
+    return YA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// First phase of alignClump for those clumps (prepare_clumps.h), one thread per strand.
+__global__ void __launch_bounds__(128)
+prepare_clumps_kernel(int n_seg, const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ count,
+                      const uint32_t *__restrict__ first, const ya_clump_rec *__restrict__ clumps, const ya_frag *__restrict__ path_in,
+                      const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev, pc_params P,
+                      ya_frag *__restrict__ path, ya_gap_rec *__restrict__ gaps, ya_prep_rec *__restrict__ prep,
+                      ya_dp_job *__restrict__ jobs, uint32_t *__restrict__ n_jobs, uint32_t jobs_cap)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const uint32_t nc = count[s];
+    if (nc == 0 || nc == 0xFFFFFFFFu) return;
+    const uint32_t r = (uint32_t)(s >> 1);
+    const int strand = s & 1;
+    const uint64_t base = read_off[r];
+    const int readLen = (int)(read_off[r + 1] - base);
+    const uint8_t *q = (strand ? rev : fwd) + base;
+    const uint32_t c0 = first[s];
+    for (uint32_t k = 0; k < nc; k++) {
+        const ya_clump_rec rec = clumps[c0 + k];
+        for (uint32_t f = 0; f < rec.n; f++) path[rec.first + f] = path_in[rec.first + f];
+        ya_prep_rec pr;
+        pr.gap_first = rec.first;
+        pc_prepare_clump(&P, bases, q, readLen, r, strand, path + rec.first, (int)rec.n, gaps + rec.first, jobs, n_jobs, jobs_cap, &pr);
+        prep[c0 + k] = pr;
+    }
+}
+
+extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
+{
+    if (!c || !out) return YA_E_ARG;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    out->n_jobs = 0;
+    const int n_seg = 2 * c->n_reads;
+    if (n_seg == 0) return YA_OK;
+    if (!c->fc_valid) return ya_fail(c, YA_E_STATE, "ya_prepare_clumps: call ya_form_clumps first");
+    const size_t nk = c->seed_nkeep;
+    if (nk == 0) return YA_OK;
+    if (nk > out->cap || !out->prep || !out->gaps || !out->path || !out->jobs) return ya_fail(c, YA_E_CAPACITY, "prepare output buffers too small");
+    cudaStream_t st = c->stream;
+    AllocScope allocScope(st);
+    const size_t jobsCap = std::min<size_t>(out->jobs_cap, 3 * nk + 16);
+    YA_CUDA(c, c->d_pc_path.reserve(nk * sizeof(ya_frag) + 64));
+    YA_CUDA(c, c->d_pc_gaps.reserve(nk * sizeof(ya_gap_rec) + 64));
+    YA_CUDA(c, c->d_pc_prep.reserve(nk * sizeof(ya_prep_rec) + 64));
+    YA_CUDA(c, c->d_pc_jobs.reserve(jobsCap * sizeof(ya_dp_job) + 64));
+    YA_CUDA(c, c->h_stage3.reserve(64));
+    uint32_t *d_count = c->d_fc_count.as<uint32_t>(), *d_first = d_count + n_seg;
+    uint32_t *d_njobs = d_first + n_seg;                               // (d_fc_count has a spare tail)
+    YA_CUDA(c, cudaMemsetAsync(d_njobs, 0, 4, st));
+    pc_params P;
+    P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.RCost = c->P.RCost; P.MScore = c->P.MScore;
+    P.minExtLength = c->P.minExtLength; P.maxROff = c->maxROff;
+    YA_CUDA(c, cudaEventRecord(c->ev[0], st));
+    prepare_clumps_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(n_seg, c->d_read_off.as<uint64_t>(), d_count, d_first,
+        c->d_fc_clumps.as<ya_clump_rec>(), c->d_fc_path.as<ya_frag>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), P,
+        c->d_pc_path.as<ya_frag>(), c->d_pc_gaps.as<ya_gap_rec>(), c->d_pc_prep.as<ya_prep_rec>(), c->d_pc_jobs.as<ya_dp_job>(), d_njobs,
+        (uint32_t)jobsCap);
+    c->ctr.launches++;
+    YA_CUDA(c, cudaEventRecord(c->ev[1], st));
+    uint32_t *h_n = c->h_stage3.as<uint32_t>();
+    YA_CUDA(c, cudaMemcpyAsync(h_n, d_njobs, 4, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(out->prep, c->d_pc_prep.p, nk * sizeof(ya_prep_rec), cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(out->gaps, c->d_pc_gaps.p, nk * sizeof(ya_gap_rec), cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(out->path, c->d_pc_path.p, nk * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
+    // jobs: speculatively 8 per read, the rest after the count is known
+    const size_t guess = std::min<size_t>(jobsCap, (size_t)8 * (size_t)c->n_reads + 64);
+    YA_CUDA(c, cudaMemcpyAsync(out->jobs, c->d_pc_jobs.p, guess * sizeof(ya_dp_job), cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, ya_stream_wait(st));
+    YA_CUDA(c, cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->ctr.ms_seed += ms;
+    const size_t nj = *h_n;
+    if (nj > jobsCap) return ya_fail(c, YA_E_CAPACITY, "prepare: more DP jobs than the job buffer holds");
+    if (nj > guess) {
+        YA_CUDA(c, cudaMemcpyAsync(out->jobs + guess, c->d_pc_jobs.as<ya_dp_job>() + guess, (nj - guess) * sizeof(ya_dp_job), cudaMemcpyDeviceToHost, st));
+        YA_CUDA(c, ya_stream_wait(st));
+    }
+    out->n_jobs = nj;
     return YA_OK;
 }

@@ -536,7 +536,28 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     PVec<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
     gaps.reserve(16 * old.size() + 8);
     bool any = false;
-    for (size_t k = 0; k < old.size(); k++) {
+    bool allDev = true;                                                 // phase 1 of every clump already done on the device?
+    for (size_t k = 0; k < old.size(); k++) if (!old[k]->is(kAligned) && !old[k]->prep) { allDev = false; break; }
+    for (size_t k = 0; allDev && k < old.size(); k++) {
+        // ya_prepare_clumps ran this phase (same source: csrc/prepare_clumps.h) and the pipeline already has the
+        // answers of its jobs: futures are indices into that first result block
+        Clump &c = *old[k];
+        if (c.is(kAligned)) continue;
+        const ya_prep_rec &pr = *c.prep;
+        pc[k].gapLo = gaps.size();
+        for (int g = 0; g < (int)pr.n_gaps; g++) {
+            const ya_gap_rec &gr = c.gapBase[pr.gap_first + (uint32_t)g];
+            GapJob gj; gj.after = gr.after; gj.needDp = gr.job != 0xFFFFFFFFu; gj.fut.slot = gj.needDp ? (int)gr.job : -1;
+            gj.score = gr.score; gj.len = gr.len; gj.code = (char)gr.code;
+            gaps.push_back(gj);
+        }
+        pc[k].gapHi = gaps.size();
+        ExtState &x = pc[k].x;
+        x.backLen = pr.backLen; x.forwLen = pr.forwLen;
+        x.doB = pr.jobB != 0xFFFFFFFFu; x.doF = pr.jobF != 0xFFFFFFFFu;
+        x.fb.slot = x.doB ? (int)pr.jobB : -1; x.ff.slot = x.doF ? (int)pr.jobF : -1;
+    }
+    for (size_t k = 0; !allDev && k < old.size(); k++) {
         if (old[k]->is(kAligned)) continue;
         pc[k].gapLo = gaps.size();
         alignPrepare(E, rc, *old[k], gaps);
@@ -558,7 +579,8 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         extendPerfect(E, rc, c, true, true, pc[k].score, chk, false);
         if (chk.doB != pc[k].x.doB || chk.doF != pc[k].x.doF || (chk.doB && chk.backLen != pc[k].x.backLen) ||
             (chk.doF && chk.forwLen != pc[k].x.forwLen)) {
-            fprintf(stderr, "yaha_b200: internal error: early extension plan diverged\n");
+            fprintf(stderr, "yaha_b200: internal error: early extension plan diverged (planned doB %d doF %d back %d forw %d; now doB %d doF %d back %d forw %d; device-prepared %d)\n",
+                    (int)pc[k].x.doB, (int)pc[k].x.doF, pc[k].x.backLen, pc[k].x.forwLen, (int)chk.doB, (int)chk.doF, chk.backLen, chk.forwLen, c.prep != nullptr);
             abort();
         }
     }

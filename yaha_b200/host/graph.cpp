@@ -20,7 +20,8 @@ static fc_params clumpParams(const Args &A)
 }
 
 // Clump objects from clump records: the clumps of a strand in creation order (addClump, QueryState.c:156-161)
-static void makeClumps(const Env &E, ReadCtx &rc, bool rev, const ya_clump_rec *recs, int nClumps, const Frag *path)
+static void makeClumps(const Env &E, ReadCtx &rc, bool rev, const ya_clump_rec *recs, int nClumps, const Frag *path,
+                       const ya_prep_rec *prep = nullptr, const ya_gap_rec *gapBase = nullptr)
 {
     const uint8_t *bases = E.G->bases;
     for (int k = 0; k < nClumps; k++) {
@@ -29,6 +30,7 @@ static void makeClumps(const Env &E, ReadCtx &rc, bool rev, const ya_clump_rec *
         c->path.assign(p, p + recs[k].n);
         c->matchedBases = recs[k].matchedBases;
         c->set(kReversed, rev);
+        if (prep) { c->prep = prep + k; c->gapBase = gapBase; }
         // the alignment phase that follows compares bases just outside both ends of every piece (perfect extensions,
         // AlignExtFrag.cpp:30-48): ask for those genome lines now, they are cache misses in a 50 MB .. 1.5 GB array
         for (int q = 0; q < (int)recs[k].n; q++) {
@@ -43,7 +45,7 @@ void formClumps(const Env &E, ReadCtx &rc, bool rev)
 {
     const int n = rc.nFrags[rev];
     if (rc.devClumps[rev]) {                                    // formed on the device (ya_form_clumps)
-        makeClumps(E, rc, rev, rc.devClumps[rev], rc.nDevClumps[rev], rc.devPath[rev]);
+        makeClumps(E, rc, rev, rc.devClumps[rev], rc.nDevClumps[rev], rc.devPath[rev], rc.devPrep[rev], rc.devGaps);
         return;
     }
     if (n == 0) return;

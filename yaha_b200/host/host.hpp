@@ -213,6 +213,8 @@ enum { kReversed = 1, kFormed = 2, kAligned = 4, kScored = 8, kSplit = 16, kPrim
 struct Clump {                       // Clump_t, Math.h:511-527
     OpList ops;
     PVec<Frag> path;                 // before alignment: the seed fragments of the clump in query order (formClumps)
+    const ya_prep_rec *prep = nullptr;   // phase 1 of the alignment done on the device (ya_prepare_clumps): plan + gaps
+    const ya_gap_rec *gapBase = nullptr;
     SFragList sf;                    // after alignment: the collapsed piece (and what splitting makes of it)
     static void *operator new(size_t n) { return TlsPool::get(n); }
     static void operator delete(void *p, size_t n) { TlsPool::put(p, n); }
@@ -251,6 +253,8 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     const ya_clump_rec *devClumps[2] = {nullptr, nullptr};   // clumps formed on the device (ya_form_clumps), or null
     const Frag *devPath[2] = {nullptr, nullptr};
     int    nDevClumps[2] = {0, 0};
+    const ya_prep_rec *devPrep[2] = {nullptr, nullptr};             // ... and prepared there (ya_prepare_clumps), or null
+    const ya_gap_rec *devGaps = nullptr;
     std::string *out = nullptr;      // the worker's output buffer; this read's records are [outOff, outOff+outLen)
     size_t outOff = 0, outLen = 0;
     // the reverse-complement strand is derived the first time something asks for it (about half of the reads never do)

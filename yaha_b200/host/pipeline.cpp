@@ -232,6 +232,12 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     PinnedVec<ya_clump_rec> clumpRecs;
     PinnedVec<ya_frag> clumpPath;
     bool devClumps = false;               // the batch in flight has them
+    PinnedVec<ya_prep_rec> prepRecs;      // ya_prepare_clumps outputs (phase 1 of the alignment done on the device)
+    PinnedVec<ya_gap_rec> gapRecs;
+    PinnedVec<ya_frag> prepPath;
+    PinnedVec<ya_dp_job> prepJobs;
+    bool devPrep = false;
+    ResultBlock *firstBlock = nullptr;    // answers of the device-made jobs: every slot's first pass reads them
     std::vector<ya_dp_job> jobs;
     std::vector<std::unique_ptr<ResultBlock>> blocks;      // every result block this pipeline ever made
     std::vector<ResultBlock *> freeBlocks;
@@ -328,8 +334,10 @@ static void runSlotPass(const Task &t)
                 if (D.devClumps && D.clumpCount[seg] != 0xFFFFFFFFu) {
                     f->rc.devClumps[st] = D.clumpRecs.data() + D.clumpFirst[seg];
                     f->rc.nDevClumps[st] = (int)D.clumpCount[seg];
-                    f->rc.devPath[st] = D.clumpPath.data();
-                } else { f->rc.devClumps[st] = nullptr; f->rc.nDevClumps[st] = 0; f->rc.devPath[st] = nullptr; }
+                    f->rc.devPath[st] = D.devPrep ? D.prepPath.data() : D.clumpPath.data();
+                    f->rc.devPrep[st] = D.devPrep ? D.prepRecs.data() + D.clumpFirst[seg] : nullptr;
+                    f->rc.devGaps = D.devPrep ? D.gapRecs.data() : nullptr;
+                } else { f->rc.devClumps[st] = nullptr; f->rc.nDevClumps[st] = 0; f->rc.devPath[st] = nullptr; f->rc.devPrep[st] = nullptr; }
             }
             s.fibers.push_back(f);
         }
@@ -453,8 +461,55 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         if (rcode == YA_OK) D.devClumps = true;
         else if (rcode != YA_E_STATE) die(D.ctx, "ya_form_clumps");            // (YA_E_STATE: survivors not on the device -> host path)
     }
+    // ... and the first phase of their alignment (perfect extensions between seed fragments, gap dispatch, extension
+    // plan): the jobs come back ready for ya_sw_batch, which this thread runs before any worker has touched the batch
+    static const bool hostPrep = getenv("YA_HOST_PREP") != nullptr;
+    D.devPrep = false; D.firstBlock = nullptr;
+    size_t nPrepJobs = 0;
+    if (D.devClumps && !hostPrep) {
+        const size_t cap = D.clumpRecs.size();
+        if (D.prepRecs.size() < cap) { D.prepRecs.resize(cap, false); D.gapRecs.resize(cap, false); D.prepPath.resize(cap, false); D.prepJobs.resize(3 * cap + 16, false); }
+        ya_prep_batch pb;
+        pb.cap = cap; pb.jobs_cap = D.prepJobs.size(); pb.prep = D.prepRecs.data(); pb.gaps = D.gapRecs.data(); pb.path = D.prepPath.data();
+        pb.jobs = D.prepJobs.data(); pb.n_jobs = 0;
+        if (ya_prepare_clumps(D.ctx, &pb) != YA_OK) die(D.ctx, "ya_prepare_clumps");
+        D.devPrep = true;
+        nPrepJobs = pb.n_jobs;
+    }
     D.tSeed += nowSec() - t0;
     traceEv('S', D.device, (int)B.seq, t0, nowSec());
+
+    // one ya_sw_batch for `nj` jobs into a result block with `users` readers
+    auto callDp = [&](const ya_dp_job *jobs, int nj, int users) -> ResultBlock * {
+        // Every block of a pipeline has the pipeline-wide capacity (monotonic): re-pinning host memory in the
+        // middle of a run stalls the whole process (cudaFreeHost / cudaHostAlloc synchronise the device).
+        if (D.capJobs == 0) D.capJobs = (size_t)16 * (size_t)n;        // ~8 jobs per read is typical; doubled when exceeded
+        if ((size_t)nj > D.capJobs) D.capJobs = 2 * (size_t)nj;
+        D.capOps = std::max(D.capOps, 32 * D.capJobs);
+        if (D.blocks.empty()) {                                        // first call of this pipeline: pin a few blocks up front
+            std::lock_guard<std::mutex> g(D.blkMu);
+            for (int k = 0; k < 6; k++) {
+                D.blocks.emplace_back(new ResultBlock());
+                D.blocks.back()->res.resize(D.capJobs, false);
+                D.blocks.back()->ops.resize(D.capOps, false);
+                D.freeBlocks.push_back(D.blocks.back().get());
+            }
+        }
+        ResultBlock *blk = D.acquireBlock();
+        blk->users.store(users);
+        if (blk->res.size() < D.capJobs) blk->res.resize(D.capJobs, false);
+        if (blk->ops.size() < D.capOps) blk->ops.resize(D.capOps, false);
+        size_t need = 0;
+        int rcode = ya_sw_batch(D.ctx, jobs, nj, blk->res.data(), blk->ops.data(), blk->ops.size(), &need);
+        if (rcode == YA_E_CAPACITY) {                       // results are in; only the ops need a bigger buffer
+            D.capOps = std::max(D.capOps, 2 * need + 1024);
+            blk->ops.resize(D.capOps, false);
+            rcode = ya_sw_fetch_ops(D.ctx, blk->ops.data(), blk->ops.size());
+        }
+        if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
+        D.nJobs += (uint64_t)nj; D.nRounds++;
+        return blk;
+    };
 
     // fibers: contiguous slices of the batch, one slot per worker thread (set up by the worker itself)
     t0 = nowSec();
@@ -476,9 +531,21 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
             if (s.hi > s.lo) D.running++; else D.slotsDone++;
         }
     }
+    D.tSetup += nowSec() - t0;
+    if (D.devPrep && nPrepJobs > 0) {                                   // the DP round the device prepared: before any worker runs
+        const double h1 = nowSec();
+        int users = 0;
+        for (int t = 0; t < nW; t++) users += slots[(size_t)t].hi > slots[(size_t)t].lo;
+        ResultBlock *blk = callDp(D.prepJobs.data(), (int)nPrepJobs, users);
+        for (int t = 0; t < nW; t++) {
+            Slot &s = slots[(size_t)t];
+            if (s.hi > s.lo) { s.res = blk->res.data(); s.ops = blk->ops.data(); s.ansBase = 0; s.block = blk; }
+        }
+        D.tDp += nowSec() - h1;
+        traceEv('D', users, (int)B.seq, h1, nowSec(), (int)nPrepJobs);
+    }
     for (int t = 0; t < nW; t++)
         if (slots[(size_t)t].hi > slots[(size_t)t].lo) pool.post(Task{&D, &B, &slots[(size_t)t], t});
-    D.tSetup += nowSec() - t0;
 
     std::vector<int> take;
     for (;;) {
@@ -500,33 +567,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
             s.jobs.clear();
         }
         const int nj = (int)D.jobs.size();
-        // Every block of a pipeline has the pipeline-wide capacity (monotonic): re-pinning host memory in the
-        // middle of a run stalls the whole process (cudaFreeHost / cudaHostAlloc synchronise the device).
-        if (D.capJobs == 0) D.capJobs = (size_t)16 * (size_t)n;        // ~8 jobs per read is typical; doubled when exceeded
-        if ((size_t)nj > D.capJobs) D.capJobs = 2 * (size_t)nj;
-        D.capOps = std::max(D.capOps, 32 * D.capJobs);
-        if (D.blocks.empty()) {                                        // first call of this pipeline: pin a few blocks up front
-            std::lock_guard<std::mutex> g(D.blkMu);
-            for (int k = 0; k < 6; k++) {
-                D.blocks.emplace_back(new ResultBlock());
-                D.blocks.back()->res.resize(D.capJobs, false);
-                D.blocks.back()->ops.resize(D.capOps, false);
-                D.freeBlocks.push_back(D.blocks.back().get());
-            }
-        }
-        ResultBlock *blk = D.acquireBlock();
-        blk->users.store((int)take.size());
-        if (blk->res.size() < D.capJobs) blk->res.resize(D.capJobs, false);
-        if (blk->ops.size() < D.capOps) blk->ops.resize(D.capOps, false);
-        size_t need = 0;
-        int rcode = ya_sw_batch(D.ctx, D.jobs.data(), nj, blk->res.data(), blk->ops.data(), blk->ops.size(), &need);
-        if (rcode == YA_E_CAPACITY) {                       // results are in; only the ops need a bigger buffer
-            D.capOps = std::max(D.capOps, 2 * need + 1024);
-            blk->ops.resize(D.capOps, false);
-            rcode = ya_sw_fetch_ops(D.ctx, blk->ops.data(), blk->ops.size());
-        }
-        if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
-        D.nJobs += (uint64_t)nj; D.nRounds++;
+        ResultBlock *blk = callDp(D.jobs.data(), nj, (int)take.size());
         D.tDp += nowSec() - h1;
         traceEv('D', (int)take.size(), (int)B.seq, h1, nowSec(), nj);
         {
