@@ -1,5 +1,6 @@
 #!/bin/bash
-# What pipeline count suits a rank that owns only 4 (or 8) cores?  (taskset confines the whole host process)
+# Throughput of a rank that owns only 4 or 8 cores (taskset confines the whole host process), with the fragment graph
+# and phase 1 of the alignment on the device (default) or in the worker threads (YA_HOST_CLUMPS=1).
 D=/tmp/yaha_b200_bench_cfg3
 python bench.py --no-cpu-baseline --steps 1 --warmup 3 > /dev/null 2>&1
 X=$D/ref.X15_01_65525S; Q=$D/reads_rank0.fa
@@ -8,11 +9,9 @@ one() { lab=$1; cpus=$2; shift; shift
   grep '"pass"' /tmp/one.log | tail -12 | python -c "
 import sys,json
 v=[json.loads(l) for l in sys.stdin]; n=len(v); r=sorted(x['align_s']*1e3 for x in v)
-print('$lab', 'median ms', round(r[n//2],2), 'mean', round(sum(r)/n,2), 'reads/s', int(20000/(sum(r)/n)*1e3), 'host_ms', round(1e3*sum(x['host_wall_s'] for x in v)/n,2))"; }
-for cfg in "8 1250" "4 1250" "3 1250" "2 1250" "2 2500" "3 2500" "4 2500"; do set -- $cfg
-  one "4 cores e2e pipes=$1 batch=$2" 0-3 -t 4 -pipes $1 -batch $2 -passes 16
+print('$lab', 'median ms', round(r[n//2],2), 'reads/s', int(20000/(sum(r)/n)*1e3), 'host_ms', round(1e3*sum(x['host_wall_s'] for x in v)/n,2))"; }
+for mode in dev host; do
+  if [ $mode = host ]; then export YA_HOST_CLUMPS=1; else unset YA_HOST_CLUMPS; fi
+  one "$mode 4 cores" 0-3 -t 4 -pipes 4 -batch 1250 -passes 16
+  one "$mode 8 cores" 0-7 -t 8 -pipes 8 -batch 1250 -passes 16
 done
-for cfg in "8 1250" "4 1250" "4 2500" "6 1250"; do set -- $cfg
-  one "8 cores e2e pipes=$1 batch=$2" 0-7 -t 8 -pipes $1 -batch $2 -passes 16
-done
-for nap in 50 100; do YA_NAP_US=$nap one "4 cores e2e pipes=3 batch=1250 nap=$nap" 0-3 -t 4 -pipes 3 -batch 1250 -passes 16; done
