@@ -492,6 +492,23 @@ static int splitHelper(const Env &E, ReadCtx &rc, Clump *c, int wSQO, int wEQO)
     return retval;
 }
 
+// the split decision of scoreClump (AlignHelpers.c:302-340), without side effects
+static int willSplit(const Args &A, const Clump *c)
+{
+    if (c->is(kScored)) return 0;
+    int AGS = 0, maxAGS = 0, matches = 0;
+    const int alignedScore = c->sf.front().score;
+    const int n = (int)c->ops.v.size();
+    for (int k = 0; k < n; k++) {
+        const Op &o = c->ops.v[k];
+        if (o.code == 'M') matches += o.len;
+        AGS += opScore(A, o);
+        if (AGS <= 0 || (AGS >= alignedScore && k != n - 1)) return 1;
+        if (AGS > maxAGS) maxAGS = AGS;
+    }
+    return matches >= A.minRawScore && maxAGS > AGS;
+}
+
 static int scoreClump(const Env &E, ReadCtx &rc, Clump *c)             // AlignHelpers.c:302-366
 {
     const Args &A = *E.A;
@@ -597,11 +614,30 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     if (kAlignProf) gAlignProf[2] += rdtsc_() - q0;
     q0 = rdtsc_();
     const uint64_t parked0 = rc.parked;
-    for (size_t k = 0; k < old.size(); k++) {
-        Clump *c = old[k];
-        scoreClump(E, rc, c);
-        if (c->is(kScored)) rc.clumps.push_back(c);
-        else delete c;
+    // Clumps are scored independently; a clump that has to be split parks for its re-extensions (splitHelper).  With
+    // several such clumps in a read -- repeat-rich reads have hundreds -- each is scored in a child fiber, so that
+    // their re-extension rounds run side by side instead of one clump after the other.  The read's clump list is
+    // put together per clump afterwards, in the order the sequential walk would have appended.
+    int nSplit = 0;
+    if (old.size() >= 2) for (size_t k = 0; k < old.size(); k++) nSplit += willSplit(*E.A, old[k]);
+    if (nSplit >= 2) {
+        struct Arg { const Env *E; ReadCtx *rc; std::vector<Clump *> *old; } arg{&E, &rc, &old};
+        std::vector<std::vector<Clump *>> outs(old.size());
+        runAsChildren(rc, (int)old.size(), [](void *p, int k) {
+            Arg &a = *(Arg *)p;
+            Clump *c = (*a.old)[(size_t)k];
+            scoreClump(*a.E, *a.rc, c);
+            if (c->is(kScored)) a.rc->clumps.push_back(c);
+            else delete c;
+        }, &arg, outs.data());
+        for (auto &o : outs) rc.clumps.insert(rc.clumps.end(), o.begin(), o.end());
+    } else {
+        for (size_t k = 0; k < old.size(); k++) {
+            Clump *c = old[k];
+            scoreClump(E, rc, c);
+            if (c->is(kScored)) rc.clumps.push_back(c);
+            else delete c;
+        }
     }
     if (kAlignProf) gAlignProf[3] += rdtsc_() - q0 - (rc.parked - parked0);
     old.clear();

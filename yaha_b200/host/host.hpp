@@ -253,6 +253,8 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     const ya_clump_rec *devClumps[2] = {nullptr, nullptr};   // clumps formed on the device (ya_form_clumps), or null
     const Frag *devPath[2] = {nullptr, nullptr};
     int    nDevClumps[2] = {0, 0};
+    void **childSp = nullptr;        // set while a child fiber of this read runs (runAsChildren): where dpWait saves it ...
+    void **parentSp = nullptr;       // ... and the read's own context it returns to
     const ya_prep_rec *devPrep[2] = {nullptr, nullptr};             // ... and prepared there (ya_prepare_clumps), or null
     const ya_gap_rec *devGaps = nullptr;
     std::string *out = nullptr;      // the worker's output buffer; this read's records are [outOff, outOff+outLen)
@@ -266,6 +268,10 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
 DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen);
 void     dpWait(ReadCtx &rc);                      // park until the round's jobs are done
 DpAnswer dpGet(ReadCtx &rc, DpFuture f);        // valid until this fiber parks again
+// Runs fn(arg, k), k = 0..n-1, as child fibers of the read's fiber: each runs until it parks in dpWait or returns;
+// when all live children are parked the read's fiber parks ONCE for all of them, so their DP requests share a round.
+// While child k runs, rc.clumps is outs[k] (what it appends to the read's clump list lands there).
+void runAsChildren(ReadCtx &rc, int n, void (*fn)(void *arg, int k), void *arg, std::vector<Clump *> *outs);
 
 // ----------------------------------------------------------------------------- algorithms
 struct Env { const Args *A; const Genome *G; };

@@ -100,6 +100,7 @@ DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int 
 
 void dpWait(ReadCtx &rc)
 {
+    if (rc.childSp) { yh_switch(rc.childSp, *rc.parentSp); return; }   // a child fiber parks into its read's fiber
     Fiber *f = (Fiber *)rc.owner;
     yh_switch(&f->sp, f->w->mainSp);
 }
@@ -581,6 +582,55 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         }
     }
     for (int i = 0; i < n; i++) { gStacks.put(B.fibers[(size_t)i].stack); B.fibers[(size_t)i].stack = nullptr; }
+}
+
+// ----------------------------------------------------------------------------- child fibers of a read
+struct ChildFiber { void *sp = nullptr; void *stack = nullptr; bool done = false, started = false; };
+struct ChildBoot { ReadCtx *rc; void (*fn)(void *, int); void *arg; int k; ChildFiber *cf; };
+static thread_local ChildBoot *tChildBoot;
+static void childEntry()
+{
+    const ChildBoot b = *tChildBoot;                 // (the boot record lives on the parent's stack: copy it first)
+    b.fn(b.arg, b.k);
+    b.cf->done = true;
+    yh_switch(&b.cf->sp, *b.rc->parentSp);
+    __builtin_trap();                                // a finished child is never resumed
+}
+
+void runAsChildren(ReadCtx &rc, int n, void (*fn)(void *, int), void *arg, std::vector<Clump *> *outs)
+{
+    PVec<ChildFiber> kids((size_t)n);
+    void *parentSp = nullptr;
+    rc.parentSp = &parentSp;
+    for (;;) {
+        int live = 0;
+        for (int k = 0; k < n; k++) {
+            ChildFiber &c = kids[(size_t)k];
+            if (c.done) continue;
+            ChildBoot boot{&rc, fn, arg, k, &c};
+            if (!c.started) {
+                c.started = true;
+                c.stack = gStacks.get();
+                uintptr_t top = ((uintptr_t)c.stack + kStackBytes) & ~(uintptr_t)15;
+                void **sp = (void **)top;
+                *--sp = nullptr;
+                *--sp = (void *)childEntry;
+                for (int q = 0; q < 6; q++) *--sp = nullptr;
+                c.sp = sp;
+                tChildBoot = &boot;
+            }
+            rc.clumps.swap(outs[k]);
+            rc.childSp = &c.sp;
+            yh_switch(&parentSp, c.sp);
+            rc.childSp = nullptr;
+            rc.clumps.swap(outs[k]);
+            if (!c.done) live++;
+        }
+        if (live == 0) break;
+        dpWait(rc);                                  // one park of the read's fiber serves every parked child
+    }
+    for (ChildFiber &c : kids) if (c.stack) gStacks.put(c.stack);
+    rc.parentSp = nullptr;
 }
 
 // bounded, ordered hand-off between reader, pipelines and writer
