@@ -3,8 +3,7 @@
 three 300 bp Alu-like elements and 40 tandem arrays, 2 500 x 1000 bp reads at 5 %.  Writes ref.fa / ref.nib2 / the index /
 reads.fa into the current directory; compare `oracle/_ref/yaha -t 1` with the host program (or tests/_build/yaha_host_mock,
 no GPU needed) on it.  r01: SAM identical in all three modes (device clumps + phase 1, YA_HOST_PREP=1, YA_HOST_CLUMPS=1);
-632 DP jobs per read and 708 DP rounds for one 2 500-read batch -- the demand-driven split re-extensions run one clump at a
-time inside a read's fiber, which is the thing to batch next on data like this."""
+632 DP jobs per read; 22 DP rounds for one 2 500-read batch since clumps that split are scored in child fibers (708 before)."""
 import sys, os, time
 sys.path.insert(0, "/root/repo")
 from yaha_b200 import refio, synth
