@@ -27,7 +27,48 @@ def gz(src, dst):
         shutil.copyfileobj(f, g)
 
 
+def chimera_reads(ref, seed, n_reads=60):
+    """Reads glued from 2-6 distant loci, each locus piece (60-110 bases either side) with a block of 44-49 substituted bases in its middle: every
+    piece becomes one clump whose score dips below zero inside, i.e. a clump that has to be SPLIT -- several per read,
+    which is what sends the host through its child-fiber scoring (host/pipeline.cpp runAsChildren)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = []
+    for r in range(n_reads):
+        pieces = []
+        for _ in range(int(rng.integers(2, 7))):
+            s = int(rng.integers(2000, len(ref) - 3000))
+            a, b = int(rng.integers(60, 111)), int(rng.integers(60, 111))
+            blk = int(rng.integers(44, 50))
+            left = ref[s:s + a]
+            mid = synth._BASES[(np.searchsorted(synth._BASES, ref[s + a:s + a + blk]) + rng.integers(1, 4, size=blk)) % 4]
+            right = ref[s + a + blk:s + a + blk + b]
+            p = np.concatenate([synth.mutate(left, 0.03, rng), mid, synth.mutate(right, 0.03, rng)])
+            if rng.integers(0, 3) == 0:
+                p = synth._COMP[p[::-1]]
+            pieces.append(p)
+        out.append((f"chim{r}", np.concatenate(pieces)))
+    return out
+
+
+def only_chimera():
+    """Adds chimera.fa.gz / out_chimera.sam.gz without touching the other goldens."""
+    tmp = tempfile.mkdtemp()
+    ref = synth.random_reference(300_000, 4242)
+    bounds = [0, 120_000, 200_003, 300_000]
+    synth.write_fasta(tmp + "/ref.fa", [(f"chr{k + 1}", ref[bounds[k]:bounds[k + 1]]) for k in range(3)])
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp)
+    synth.write_reads(tmp + "/chimera.fa", chimera_reads(ref, 17))
+    subprocess.check_call([REF + "/yaha", "-x", "ref.X11_01_65525S", "-q", "chimera.fa", "-osh", "out_chimera.sam", "-t", "1"], cwd=tmp)
+    gz(tmp + "/out_chimera.sam", OUT + "/out_chimera.sam.gz")
+    gz(tmp + "/chimera.fa", OUT + "/chimera.fa.gz")
+    shutil.rmtree(tmp)
+
+
 def main():
+    if "--only-chimera" in sys.argv:
+        only_chimera()
+        return
     os.makedirs(OUT, exist_ok=True)
     tmp = tempfile.mkdtemp()
     ref = synth.random_reference(300_000, 4242)

@@ -12,6 +12,8 @@ CASES = [
     ("out_fastq_oss.sam.gz", "reads.fq", "-oss", []),
     ("out_blast8.sam.gz", "reads.fa", "-o8", []),
     ("out_weird.sam.gz", "weird.fa", "-osh", []),
+    # reads glued from 2-6 loci whose pieces each have to be split: several splitting clumps per read (child fibers)
+    ("out_chimera.sam.gz", "chimera.fa", "-osh", []),
 ]
 
 
