@@ -81,7 +81,13 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
         o.resize(base + bound);
         char *w = &o[base];
         auto putS = [&](const char *z, size_t n) { memcpy(w, z, n); w += n; };
-        auto putU = [&](unsigned v) { char buf[12]; int n = 0; do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) *w++ = buf[--n]; };
+        auto putU = [&](unsigned v) {                                      // (CIGAR / MD numbers are mostly one or two digits)
+            if (v < 10) { *w++ = (char)('0' + v); return; }
+            if (v < 100) { *w++ = (char)('0' + v / 10); *w++ = (char)('0' + v % 10); return; }
+            char buf[12]; int n = 0;
+            do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+            while (n) *w++ = buf[--n];
+        };
         auto putI = [&](int v) { if (v < 0) { *w++ = '-'; putU((unsigned)(-(long)v)); } else putU((unsigned)v); };
         putS(rc.read->id.data(), rc.read->id.size());
         if (c.reversed()) putS("\t16\t", 4); else putS("\t0\t", 3);
