@@ -4,9 +4,9 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg3|cfg2|cfg1s]
 
 One "step" = one complete alignment of the workload's synthetic read set by the product's host
-program `yaha_b200/yaha_b200_host` (FASTA parsed -> reads uploaded -> seed lookup -> hits->fragments->
-regions -> host fragment graph -> banded affine-gap DP rounds with X-drop + traceback on the device ->
-host split/score/OQC -> SAM written).  The SAM is byte-identical to the reference's (`cpu_baseline.
+program `yaha_b200/yaha_b200_host` (FASTA cut into records and parsed -> reads uploaded -> seed lookup ->
+hits->fragments->regions -> fragment graph and first alignment phase (ya_form_clumps, ya_prepare_clumps) ->
+banded affine-gap DP rounds with X-drop + traceback on the device -> host assembly/split/score/OQC -> SAM written).  The SAM is byte-identical to the reference's (`cpu_baseline.
 sam_identical_to_reference`).  `e2e` times all of that; `value` excludes FASTA parsing, the H2D copy
 of the reads and the SAM fwrite (inputs resident).  Device stage times come from CUDA events inside the
 library (`ya_get_counters`), on the stream the kernels are launched on.
