@@ -10,6 +10,7 @@ Outputs (all gzip'd, deterministic seeds):
   dump_bw10.txt.gz            same with -BW 10 -G 100 (D and G records only)
   out_bw5.sam.gz, out_bw10.sam.gz   the reference's SAM output (-t 1)
   out_{fbs,nooqc,fastq_oss,blast8}.sam.gz   more reference outputs (-FBS Y, -OQC N, FASTQ input with -oss, -o8)
+  flag_sweep.json             digest of the reference's SAM for every flag set of tests/hostcases.py FLAG_SWEEP (--only-flag-sweep)
   files.sha256                digests of the reference-built ref.nib2 and index
 """
 import gzip, hashlib, os, shutil, subprocess, sys, tempfile
@@ -65,9 +66,34 @@ def only_chimera():
     shutil.rmtree(tmp)
 
 
+def only_flag_sweep():
+    """Writes flag_sweep.json: for every flag set of tests/hostcases.py FLAG_SWEEP the line count and sha256 of the reference's
+    SAM (reads.fa, -osh, -t 1) without its @PG line."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hostcases as H
+    tmp = tempfile.mkdtemp()
+    for name in ("ref.fa", "reads.fa"):
+        with gzip.open(f"{OUT}/{name}.gz", "rb") as f, open(f"{tmp}/{name}", "wb") as o:
+            o.write(f.read())
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp)
+    table = {}
+    for flags in H.FLAG_SWEEP:
+        subprocess.check_call([REF + "/yaha", "-x", "ref.X11_01_65525S", "-q", "reads.fa", "-osh", "o.sam", "-t", "1"] + flags, cwd=tmp,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        table[" ".join(flags)] = H.digest(H.sam_lines(open(tmp + "/o.sam").read()))
+    with open(OUT + "/flag_sweep.json", "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+        f.write("\n")
+    shutil.rmtree(tmp)
+
+
 def main():
     if "--only-chimera" in sys.argv:
         only_chimera()
+        return
+    if "--only-flag-sweep" in sys.argv:
+        only_flag_sweep()
         return
     os.makedirs(OUT, exist_ok=True)
     tmp = tempfile.mkdtemp()

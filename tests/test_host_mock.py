@@ -30,6 +30,13 @@ def test_host_logic_reproduces_reference_sam(small, mock_host, tmp_path, golden,
     assert len(got) == len(want)
 
 
+@pytest.mark.parametrize("flags", H.FLAG_SWEEP, ids=lambda f: "".join(f))
+def test_every_alignment_flag_reproduces_reference_sam(small, mock_host, tmp_path, flags):
+    # -X -M -MD -P -H -AGS -GOC -GEC -MS -RC -BP -MGDP -MNO -PRL -PSS -BW -G, alone and combined, against digests of the
+    # reference's output (golden/small/flag_sweep.json)
+    H.check_flag_sweep(mock_host, small, str(tmp_path / "o.sam"), flags)
+
+
 def test_output_order_independent_of_threads_and_batch(small, mock_host, tmp_path):
     want = H.expected(small, "out_bw5.sam.gz")
     for k, extra in enumerate((["-t", "3"], ["-batch", "37"], ["-t", "2", "-batch", "100"], ["-t", "4", "-gpus", "2", "-batch", "50", "-pipes", "2"],

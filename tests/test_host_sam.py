@@ -24,6 +24,14 @@ def test_sam_identical_to_reference(small, tmp_path, golden, reads, outflag, ext
     assert len(got) == len(want)
 
 
+@pytest.mark.parametrize("flags", H.FLAG_SWEEP, ids=lambda f: "".join(f))
+def test_every_alignment_flag_gives_reference_sam(small, tmp_path, flags):
+    """Every alignment flag of the reference's CLI, alone and combined, degenerate values included (band 0, X-drop 0, one hit
+    per k-mer, band wider than the gap cap -- parameter sets the packed kernel does not serve): digest of the SAM equals the
+    digest of the reference's (golden/small/flag_sweep.json)."""
+    H.check_flag_sweep(HOST, small, str(tmp_path / "o.sam"), flags, threads=3)
+
+
 def test_sam_independent_of_threads_and_batch(small, tmp_path):
     want = H.expected(small, "out_bw5.sam.gz")
     for k, extra in enumerate((["-t", "4"], ["-batch", "37"], ["-t", "3", "-batch", "100"])):
