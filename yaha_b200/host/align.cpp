@@ -16,9 +16,14 @@
 #include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include "host.hpp"
+#include "../csrc/assemble_clumps.h"
 
 namespace yh {
+
+static_assert(sizeof(Op) == sizeof(ya_op) && offsetof(Op, len) == offsetof(ya_op, length) && offsetof(Op, code) == offsetof(ya_op, opcode),
+              "assemble_clumps.h writes ya_op runs straight into a clump's op array");
 
 uint64_t gAlignProf[4];
 static const bool kAlignProf = getenv("YAHA_B200_PROF") != nullptr;
@@ -169,11 +174,9 @@ static int perfectBackward(const Env &E, const uint8_t *q, Frag &f, int len)    
     return n;
 }
 
-// ---- phase 1 of alignClump: perfect extensions between neighbours, "nM" lists, post gap jobs
-// a gap between two neighbouring pieces of a clump: either one op known in closed form, or a DP job
-struct GapJob { int after; DpFuture fut; int score; uint16_t len; char code; bool needDp; };   // after: index of the piece to its left
-
-static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps)
+// ---- phase 1 of alignClump: perfect extensions between neighbours, classify every gap (closed form or a posted DP job);
+// same records as ya_prepare_clumps writes (a job number is the index of the job in this pass' list)
+static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<ya_gap_rec> &gaps)
 {
     const Args &A = *E.A;
     const bool rev = c.reversed();
@@ -192,7 +195,7 @@ static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps
         uint16_t qGap = (uint16_t)calcGap(f1.endQueryOff, f2.startQueryOff);
         uint16_t rGap = (uint16_t)calcGapU(fragERO(f1), f2.startRefOff);
         if (qGap == 0 && rGap == 0) continue;
-        GapJob g; g.after = a; g.needDp = false; g.score = 0; g.len = 0; g.code = 0;
+        ya_gap_rec g; g.after = (uint16_t)a; g.job = 0xFFFFFFFFu; g.score = 0; g.len = 0; g.code = 0; g.pad = 0; g.pad2 = 0;
         const uint16_t gSQO = (uint16_t)(f1.endQueryOff + 1);
         const uint32_t gSRO = fragERO(f1) + 1;
         if (qGap == 0) { g.code = 'D'; g.len = rGap; g.score = -(A.GOCost + rGap * A.GECost); }
@@ -201,59 +204,14 @@ static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps
         else {
             int lenDiff = std::abs((int)qGap - (int)rGap);
             bool banded = lenDiff + A.bandWidth * 2 + 1 < (int)rGap;
-            g.needDp = true;
-            g.fut = dpSubmit(rc, banded ? YA_DP_BANDED : YA_DP_FULL, rev, gSRO, rGap, gSQO, qGap);
+            g.job = (uint32_t)dpSubmit(rc, banded ? YA_DP_BANDED : YA_DP_FULL, rev, gSRO, rGap, gSQO, qGap).slot;
         }
         gaps.push_back(g);
     }
 }
 
-// ---- phase 2: splice the gap pieces, collapse, perfect-extend the ends, post both extensions
+// ---- end extensions: perfect part, DP jobs, (careful) application
 struct ExtState { int backLen = 0, forwLen = 0; DpFuture fb, ff; bool doB = false, doF = false; };
-
-// alignClump's splice + collapseSFragments (AlignHelpers.c:251-300) in one pass: the reference inserts a piece per
-// gap into the fragment list and then concatenates all op lists with mergeEOLToBack (equal codes coalesce at the
-// junctions, SW.cpp:207-261).  Here the runs go straight into the clump's list in the same order -- seed piece
-// ("nM"), its gap (closed form or the DP answer), next seed piece ... -- with the same junction rule.
-static inline void appendRun(OpVec &v, char code, uint16_t len, bool junction)
-{
-    if (junction && !v.empty() && v.back().code == code) v.back().len = (uint16_t)(v.back().len + len);
-    else v.push_back(Op{len, code});
-}
-static void assemble(const Args &A, ReadCtx &rc, Clump &c, PVec<GapJob> &gaps, size_t gapLo, size_t gapHi)
-{
-    int total = 0;
-    OpVec &v = c.ops.v;
-    const PVec<Frag> &p = c.path;
-    size_t nOps = v.size() + p.size() + (gapHi - gapLo);
-    for (size_t k = gapLo; k < gapHi; k++) if (gaps[k].needDp) nOps += (size_t)dpGet(rc, gaps[k].fut).n;
-    v.reserve(nOps + 4);                                               // (+ the two extensions' junction runs and clips usually fit too)
-    size_t gi = gapLo;
-    for (int it = 0; it < (int)p.size(); it++) {
-        const int ql = fragQLen(p[(size_t)it]);
-        appendRun(v, 'M', (uint16_t)ql, true);
-        total += A.MScore * ql;
-        if (gi < gapHi && gaps[gi].after == it) {
-            const GapJob &g = gaps[gi++];
-            if (g.needDp) {
-                const DpAnswer r = dpGet(rc, g.fut);
-                total += r.score;
-                for (int q = 0; q < r.n; q++) appendRun(v, (char)r.ops[q].opcode, r.ops[q].length, q == 0);   // (only the junction coalesces)
-            } else {
-                total += g.score;
-                appendRun(v, g.code, g.len, true);
-            }
-        }
-    }
-    c.sf.emplace_back();                                               // the collapsed piece
-    SFrag &s0 = c.sf.front();
-    s0.frag = p.front();
-    const Frag fn = p.back();
-    s0.frag.endQueryOff = fn.endQueryOff;
-    fragSetERO(s0.frag, fragERO(fn));
-    s0.score = total;
-    c.path.clear();
-}
 
 // perfect part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:76-107)
 static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool goForw, int &score, ExtState &x, bool post = true)
@@ -548,96 +506,96 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
     old.swap(rc.clumps);
     std::reverse(old.begin(), old.end());                               // reference walks from the list head
     // phase 1: perfect extensions, gap-fill jobs AND the first extension jobs, for all clumps of the read
-    struct PerClump { ExtState x; int score = 0; size_t gapLo = 0, gapHi = 0; };
+    struct PerClump { const ya_gap_rec *g = nullptr; ya_prep_rec prep; size_t gapLo = 0; ya_asm_rec rec; bool assembled = false; };
     PVec<PerClump> pc(old.size());
-    PVec<GapJob> gaps;                                           // of every clump, [gapLo, gapHi) each
-    gaps.reserve(16 * old.size() + 8);
+    PVec<ya_gap_rec> gaps;                                       // host-made records of every clump, [gapLo, gapLo + n_gaps) each
     bool any = false;
     bool allDev = true;                                                 // phase 1 of every clump already done on the device?
     for (size_t k = 0; k < old.size(); k++) if (!old[k]->is(kAligned) && !old[k]->prep) { allDev = false; break; }
     for (size_t k = 0; allDev && k < old.size(); k++) {
         // ya_prepare_clumps ran this phase (same source: csrc/prepare_clumps.h) and the pipeline already has the
-        // answers of its jobs: futures are indices into that first result block
+        // answers of its jobs: the records are used where they lie, their job numbers index that first result block
         Clump &c = *old[k];
         if (c.is(kAligned)) continue;
-        const ya_prep_rec &pr = *c.prep;
-        pc[k].gapLo = gaps.size();
-        for (int g = 0; g < (int)pr.n_gaps; g++) {
-            const ya_gap_rec &gr = c.gapBase[pr.gap_first + (uint32_t)g];
-            GapJob gj; gj.after = gr.after; gj.needDp = gr.job != 0xFFFFFFFFu; gj.fut.slot = gj.needDp ? (int)gr.job : -1;
-            gj.score = gr.score; gj.len = gr.len; gj.code = (char)gr.code;
-            gaps.push_back(gj);
-        }
-        pc[k].gapHi = gaps.size();
-        ExtState &x = pc[k].x;
-        x.backLen = pr.backLen; x.forwLen = pr.forwLen;
-        x.doB = pr.jobB != 0xFFFFFFFFu; x.doF = pr.jobF != 0xFFFFFFFFu;
-        x.fb.slot = x.doB ? (int)pr.jobB : -1; x.ff.slot = x.doF ? (int)pr.jobF : -1;
+        pc[k].prep = *c.prep;
+        pc[k].g = c.gapBase + c.prep->gap_first;
     }
+    if (!allDev) gaps.reserve(16 * old.size() + 8);
     for (size_t k = 0; !allDev && k < old.size(); k++) {
         if (old[k]->is(kAligned)) continue;
         pc[k].gapLo = gaps.size();
         alignPrepare(E, rc, *old[k], gaps);
-        pc[k].gapHi = gaps.size();
-        for (size_t g = pc[k].gapLo; g < pc[k].gapHi; g++) any |= gaps[g].needDp;
-        extendPlanEarly(E, rc, *old[k], pc[k].x);
-        any |= pc[k].x.doB || pc[k].x.doF;
+        ExtState x;
+        extendPlanEarly(E, rc, *old[k], x);
+        ya_prep_rec &pr = pc[k].prep;
+        pr.gap_first = 0; pr.n_gaps = (uint16_t)(gaps.size() - pc[k].gapLo); pr.pad = 0;
+        pr.backLen = (uint16_t)x.backLen; pr.forwLen = (uint16_t)x.forwLen;
+        pr.jobB = x.doB ? (uint32_t)x.fb.slot : 0xFFFFFFFFu; pr.jobF = x.doF ? (uint32_t)x.ff.slot : 0xFFFFFFFFu;
+        for (size_t g = pc[k].gapLo; g < gaps.size(); g++) any |= gaps[g].job != 0xFFFFFFFFu;
+        any |= x.doB || x.doF;
     }
+    for (size_t k = 0; !allDev && k < old.size(); k++) pc[k].g = gaps.data() + pc[k].gapLo;
     if (kAlignProf) gAlignProf[0] += rdtsc_() - q0;
     if (any) dpWait(rc);
     q0 = rdtsc_();
-    // phase 2: splice the gap pieces, collapse, redo the perfect end extensions on the real fragment
+    // phases 2 and 3 (csrc/assemble_clumps.h): splice the gap answers between the seed pieces, collapse, perfect-extend
+    // both ends, apply both extensions, and walk the runs once for scoreClump's verdict.  The extension plan is
+    // re-derived on the collapsed fragment; a difference from phase 1's (the device's, normally) is fatal -- a
+    // built-in parity check of the device's plan on every read.
+    ac_params AP;
+    AP.GOCost = E.A->GOCost; AP.GECost = E.A->GECost; AP.RCost = E.A->RCost; AP.MScore = E.A->MScore;
+    AP.minExtLength = E.A->minExtLength; AP.minRawScore = E.A->minRawScore; AP.maxROff = E.G->maxROff; AP.minIdentity = E.A->minIdentity;
+    const ya_dp_result *res = nullptr; const ya_op *rops = nullptr;
+    dpView(rc, res, rops);
     for (size_t k = 0; k < old.size(); k++) {
         Clump &c = *old[k];
         if (c.is(kAligned)) continue;
-        assemble(*E.A, rc, c, gaps, pc[k].gapLo, pc[k].gapHi);
-        pc[k].score = c.sf.front().score;
-        ExtState chk = pc[k].x;
-        extendPerfect(E, rc, c, true, true, pc[k].score, chk, false);
-        if (chk.doB != pc[k].x.doB || chk.doF != pc[k].x.doF || (chk.doB && chk.backLen != pc[k].x.backLen) ||
-            (chk.doF && chk.forwLen != pc[k].x.forwLen)) {
-            fprintf(stderr, "yaha_b200: internal error: early extension plan diverged (planned doB %d doF %d back %d forw %d; now doB %d doF %d back %d forw %d; device-prepared %d)\n",
-                    (int)pc[k].x.doB, (int)pc[k].x.doF, pc[k].x.backLen, pc[k].x.forwLen, (int)chk.doB, (int)chk.doF, chk.backLen, chk.forwLen, c.prep != nullptr);
+        const ya_prep_rec &pr = pc[k].prep;
+        Op *out = c.ops.v.fill(ac_ops_bound((int)c.path.size(), pc[k].g, pr.n_gaps, &pr, res, rops));
+        if (ac_assemble_clump(&AP, E.G->bases, rc.codes(c.reversed()), rc.read->len(), c.path.data(), (int)c.path.size(), pc[k].g, pr.n_gaps, &pr,
+                              res, rops, reinterpret_cast<ya_op *>(out), &pc[k].rec) != 0) {
+            fprintf(stderr, "yaha_b200: internal error: early extension plan diverged (planned back %d forw %d jobs %d %d; device-prepared %d)\n",
+                    (int)pr.backLen, (int)pr.forwLen, (int)pr.jobB, (int)pr.jobF, c.prep != nullptr);
             abort();
         }
+        c.ops.v.setSize(pc[k].rec.n_ops);
+        c.sf.emplace_back();                                            // the collapsed piece
+        c.sf.front().frag = pc[k].rec.frag;
+        c.sf.front().score = pc[k].rec.score;
+        c.path.clear();
+        c.set(kAligned, true);
+        pc[k].assembled = true;
     }
     if (kAlignProf) gAlignProf[1] += rdtsc_() - q0;
-    q0 = rdtsc_();
-    // phase 3: apply every extension first (answers of a round are only valid until this fiber
-    // parks again), then score -- and split, which may park -- in list order
-    for (size_t k = 0; k < old.size(); k++) {
-        Clump *c = old[k];
-        if (c->is(kAligned)) continue;
-        extendApply(E, rc, *c, pc[k].x, false, pc[k].score);
-        c->set(kAligned, true);
-    }
-    if (kAlignProf) gAlignProf[2] += rdtsc_() - q0;
     q0 = rdtsc_();
     const uint64_t parked0 = rc.parked;
     // Clumps are scored independently; a clump that has to be split parks for its re-extensions (splitHelper).  With
     // several such clumps in a read -- repeat-rich reads have hundreds -- each is scored in a child fiber, so that
     // their re-extension rounds run side by side instead of one clump after the other.  The read's clump list is
     // put together per clump afterwards, in the order the sequential walk would have appended.
+    // the verdict of an assembled clump is already known (assemble_clumps.h walked its runs): scored, dropped, or "split"
+    auto verdict = [&](size_t k) { return pc[k].assembled ? (int)pc[k].rec.verdict : -1; };
+    auto settle = [&](size_t k) {                                       // scoreClump for clump k, appending to the read's list
+        Clump *c = old[k];
+        const int v = verdict(k);
+        if (v == YA_ASM_SCORED) {
+            const ya_asm_rec &r = pc[k].rec;
+            c->matchedBases = r.matchedBases; c->mismatchedBases = r.mismatchedBases; c->gapBases = r.gapBases;
+            c->totLength = r.totLength; c->totScore = r.totScore;
+            c->set(kScored, true);
+        } else if (v != YA_ASM_DROP) scoreClump(E, rc, c);
+        if (c->is(kScored)) rc.clumps.push_back(c);
+        else delete c;
+    };
     int nSplit = 0;
-    if (old.size() >= 2) for (size_t k = 0; k < old.size(); k++) nSplit += willSplit(*E.A, old[k]);
+    if (old.size() >= 2) for (size_t k = 0; k < old.size(); k++) nSplit += verdict(k) < 0 ? willSplit(*E.A, old[k]) : verdict(k) == YA_ASM_SPLIT;
     if (nSplit >= 2) {
-        struct Arg { const Env *E; ReadCtx *rc; std::vector<Clump *> *old; } arg{&E, &rc, &old};
+        struct Arg { decltype(settle) *fn; } arg{&settle};
         std::vector<std::vector<Clump *>> outs(old.size());
-        runAsChildren(rc, (int)old.size(), [](void *p, int k) {
-            Arg &a = *(Arg *)p;
-            Clump *c = (*a.old)[(size_t)k];
-            scoreClump(*a.E, *a.rc, c);
-            if (c->is(kScored)) a.rc->clumps.push_back(c);
-            else delete c;
-        }, &arg, outs.data());
+        runAsChildren(rc, (int)old.size(), [](void *p, int k) { (*((Arg *)p)->fn)((size_t)k); }, &arg, outs.data());
         for (auto &o : outs) rc.clumps.insert(rc.clumps.end(), o.begin(), o.end());
     } else {
-        for (size_t k = 0; k < old.size(); k++) {
-            Clump *c = old[k];
-            scoreClump(E, rc, c);
-            if (c->is(kScored)) rc.clumps.push_back(c);
-            else delete c;
-        }
+        for (size_t k = 0; k < old.size(); k++) settle(k);
     }
     if (kAlignProf) gAlignProf[3] += rdtsc_() - q0 - (rc.parked - parked0);
     old.clear();

@@ -182,6 +182,9 @@ public:
         memcpy(p_, first, k * sizeof(Op)); n_ = (uint32_t)k;
     }
     void swap(OpVec &o) noexcept;
+    // filled from outside: room for `cap` entries, then the number actually written
+    Op *fill(size_t cap) { n_ = 0; reserve(cap); return p_; }
+    void setSize(size_t n) { n_ = (uint32_t)n; }
 };
 struct OpList {                      // EditOpList_t semantics, SW.cpp:114-283, SW.inl:66-78
     OpVec v;
@@ -268,6 +271,7 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
 DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen);
 void     dpWait(ReadCtx &rc);                      // park until the round's jobs are done
 DpAnswer dpGet(ReadCtx &rc, DpFuture f);        // valid until this fiber parks again
+void     dpView(ReadCtx &rc, const ya_dp_result *&res, const ya_op *&ops);   // the round's arrays: res[slot], ops + res[slot].ops_off
 // Runs fn(arg, k), k = 0..n-1, as child fibers of the read's fiber: each runs until it parks in dpWait or returns;
 // when all live children are parked the read's fiber parks ONCE for all of them, so their DP requests share a round.
 // While child k runs, rc.clumps is outs[k] (what it appends to the read's clump list lands there).

@@ -114,6 +114,13 @@ DpAnswer dpGet(ReadCtx &rc, DpFuture fu)
     return a;
 }
 
+void dpView(ReadCtx &rc, const ya_dp_result *&res, const ya_op *&ops)
+{
+    Slot *w = ((Fiber *)rc.owner)->w;
+    res = w->res ? w->res + w->ansBase : nullptr;
+    ops = w->ops;
+}
+
 static std::atomic<uint64_t> gProf[8];
 static const bool kProf = getenv("YAHA_B200_PROF") != nullptr;     // phase cycle counters are off unless asked for
 static inline uint64_t rdtsc() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
