@@ -37,14 +37,6 @@ typedef struct ya_asm_rec {
     uint8_t  pad;
 } ya_asm_rec;
 
-FC_HD int ac_op_score(const ac_params *P, int code, int len)          /* EditOp score, AlignHelpers.c:312-328 */
-{
-    if (code == 'M') return P->MScore * len;
-    if (code == 'R') return -(P->RCost * len);
-    if (code == 'I' || code == 'D') return -(P->GOCost + P->GECost * len);
-    return 0;
-}
-
 #if defined(__CUDA_ARCH__) || !defined(__GNUC__)
 #define AC_TOUCH(P) ((void)0)
 #else
@@ -64,6 +56,8 @@ FC_HD uint32_t ac_ops_bound(int np, const ya_gap_rec *gaps, int ng, const ya_pre
     if (prep->jobF != 0xFFFFFFFFu) { const ya_dp_result *r = &res[prep->jobF]; n += r->ops_n; AC_TOUCH(rops + r->ops_off); }
     return n;
 }
+
+#define AC_SLOT(CODE) (((CODE) >> 1) & 7)      /* 'M' 6, 'R' 1, 'I' 4, 'D' 2 */
 
 #define AC_RUN(CODE, LEN, JUNCTION)                                                                     \
     do {                                                                                                \
@@ -142,15 +136,21 @@ FC_HD int ac_assemble_clump(const ac_params *P, const uint8_t *bases, const uint
 
     /* scoreClump (AlignHelpers.c:302-366): running score over the runs; a clump whose score touches zero, reaches its
      * total before the end, or ends below its maximum has to be split */
-    int AGS = 0, maxAGS = 0, matches = 0, mism = 0, ins = 0, del = 0, split = 0;
+    /* score of a run (AlignHelpers.c:312-328): M +MScore*len, R -RCost*len, I and D -(GOCost + GECost*len)
+     * (M, R, I, D -- the only codes a run carries here -- fall into four different slots under (code >> 1) & 7, so the
+     * per-code sums and the score a * len + b need no data-dependent branch) */
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mul[8] = {0, 0, 0, 0, 0, 0, 0, 0}, add[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    mul[AC_SLOT('M')] = P->MScore; mul[AC_SLOT('R')] = -P->RCost;
+    mul[AC_SLOT('I')] = mul[AC_SLOT('D')] = -P->GECost; add[AC_SLOT('I')] = add[AC_SLOT('D')] = -P->GOCost;
+    int AGS = 0, maxAGS = 0, split = 0;
     for (uint32_t k = 0; k < n; k++) {
-        const int code = out[k].opcode, len = out[k].length;
-        if (code == 'M') matches += len; else if (code == 'R') mism += len;
-        else if (code == 'I') ins += len; else if (code == 'D') del += len;
-        AGS += ac_op_score(P, code, len);
+        const int h = AC_SLOT(out[k].opcode), len = out[k].length;
+        cnt[h] += len;
+        AGS += mul[h] * len + add[h];
         if (AGS <= 0 || (AGS >= score && k != n - 1)) { split = 1; break; }
         if (AGS > maxAGS) maxAGS = AGS;
     }
+    const int matches = cnt[AC_SLOT('M')], mism = cnt[AC_SLOT('R')], ins = cnt[AC_SLOT('I')], del = cnt[AC_SLOT('D')];
     if (!split && matches >= P->minRawScore && maxAGS > AGS) split = 1;
     if (split) { rec->verdict = YA_ASM_SPLIT; return 0; }
     rec->verdict = YA_ASM_DROP;

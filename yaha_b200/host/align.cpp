@@ -565,6 +565,10 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         c.path.clear();
         c.set(kAligned, true);
         pc[k].assembled = true;
+        if (pc[k].rec.verdict == YA_ASM_SCORED) {                       // the MD tag will read the reference under every R and D run
+            const uint8_t *g0 = E.G->bases + (pc[k].rec.frag.startRefOff >> 1), *g1 = E.G->bases + (fragERO(pc[k].rec.frag) >> 1);
+            for (const uint8_t *g = g0; g <= g1; g += 64) __builtin_prefetch(g);
+        }
     }
     if (kAlignProf) gAlignProf[1] += rdtsc_() - q0;
     q0 = rdtsc_();

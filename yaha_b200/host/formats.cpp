@@ -9,6 +9,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include "host.hpp"
+#if defined(__x86_64__)
+#include <tmmintrin.h>
+#endif
 
 namespace yh {
 
@@ -313,12 +316,36 @@ void Read::encode()                                 // Query.c:161-163 (codeOfCh
     for (size_t i = 0; i < n; i++) fc[i] = codeTab[src[i]];
 }
 
+// reverse complement 16 bases per step: both tables (complement of a 4-bit code, character of a code) have 16 entries,
+// i.e. each is one byte shuffle; a third shuffle reverses the block
+#if defined(__x86_64__)
+__attribute__((target("ssse3"))) static int revcomp16(const uint8_t *f, uint8_t *rc, char *rv, int n)
+{
+    const __m128i comp = _mm_loadu_si128((const __m128i *)kCompCode);
+    const __m128i chr = _mm_loadu_si128((const __m128i *)kCharOfCode);
+    const __m128i flip = _mm_set_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    int i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(f + i)), flip);
+        const __m128i c = _mm_shuffle_epi8(comp, v);
+        _mm_storeu_si128((__m128i *)(rc + n - 16 - i), c);
+        _mm_storeu_si128((__m128i *)(rv + n - 16 - i), _mm_shuffle_epi8(chr, c));
+    }
+    return i;
+}
+#endif
+
 void Read::finish()                                 // Query.c:164-167
 {
     const int n = (int)fcode.size();
     if ((int)rcode.size() == n) return;
     rcode.resize((size_t)n); rev.resize((size_t)n);
-    for (int i = 0; i < n; i++) {
+    int i = 0;
+#if defined(__x86_64__)
+    static const bool ssse3 = __builtin_cpu_supports("ssse3");
+    if (ssse3) i = revcomp16(fcode.data(), rcode.data(), &rev[0], n);
+#endif
+    for (; i < n; i++) {
         const uint8_t cc = kCompCode[fcode[(size_t)i]];
         rcode[(size_t)(n - 1 - i)] = cc;
         rev[(size_t)(n - 1 - i)] = kCharOfCode[cc];

@@ -33,6 +33,19 @@ static inline void appendInt(std::string &s, int v)
     if (v < 0) { s.push_back('-'); appendUInt(s, (unsigned)(-(long)v)); } else appendUInt(s, (unsigned)v);
 }
 
+struct TwoDigits { char d[2]; uint8_t n; };
+static const struct TwoDigitTable {
+    TwoDigits t[100];
+    TwoDigitTable()
+    {
+        for (int v = 0; v < 100; v++) {
+            if (v < 10) { t[v].d[0] = (char)('0' + v); t[v].d[1] = '0'; t[v].n = 1; }
+            else { t[v].d[0] = (char)('0' + v / 10); t[v].d[1] = (char)('0' + v % 10); t[v].n = 2; }
+        }
+    }
+    const TwoDigits &operator[](unsigned v) const { return t[v]; }
+} kTwoDigits;
+
 void writeHeader(const Env &E, FILE *out)
 {
     const Args &A = *E.A;
@@ -81,9 +94,8 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
         o.resize(base + bound);
         char *w = &o[base];
         auto putS = [&](const char *z, size_t n) { memcpy(w, z, n); w += n; };
-        auto putU = [&](unsigned v) {                                      // (CIGAR / MD numbers are mostly one or two digits)
-            if (v < 10) { *w++ = (char)('0' + v); return; }
-            if (v < 100) { *w++ = (char)('0' + v / 10); *w++ = (char)('0' + v % 10); return; }
+        auto putU = [&](unsigned v) {                                      // (CIGAR / MD numbers are mostly one or two digits:
+            if (v < 100) { memcpy(w, kTwoDigits[v].d, 2); w += kTwoDigits[v].n; return; }   //  both bytes stored, cursor moved by 1 or 2 -- no branch on the value)
             char buf[12]; int n = 0;
             do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
             while (n) *w++ = buf[--n];
