@@ -208,6 +208,9 @@ def run_ours(args):
     out_path = os.path.join(d, f"out_rank{rank}.sam")
     ncores = os.cpu_count() or 1
     threads = max(1, ncores // world)
+    # a pipeline is a thread too (it drives the device and naps between polls): a rank that owns fewer cores than the default
+    # 8 pipelines runs one pipeline per core (the configuration tools/sweep_fewcores.sh measured: 4 cores, 4 pipelines)
+    pipes, e2e_pipes = (min(p, max(2, threads)) for p in (args.pipes, args.e2e_pipes))
 
     # roofline denominators measured live on this GPU: INT32 issue rate and the HBM random-gather rate
     # over the real 4 GiB starting-offset table (index rebuilt on the device for this, ~1 s)
@@ -225,7 +228,7 @@ def run_ours(args):
     e2e_tpp = 0                      # shared worker pool of `threads` workers serves every pipeline
     extra_warm = 5                   # (page-locked / device scratch of 8 pipelines reaches its final size in the first passes)
     stats_a = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, extra_warm + args.warmup + args.steps,
-                       args.e2e_batch, args.e2e_pipes, tpp=e2e_tpp)
+                       args.e2e_batch, e2e_pipes, tpp=e2e_tpp)
     timed_a = stats_a[extra_warm + args.warmup:]
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
@@ -233,7 +236,7 @@ def run_ours(args):
     # the kernel rooflines (kernels of up to 8 pipelines share the SMs here, which stretches their event timings;
     # run C below times the same kernels alone).
     stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + extra_warm + args.warmup + args.steps,
-                       args.batch, args.pipes, replay=True)
+                       args.batch, pipes, replay=True)
     timed = stats_b[1 + extra_warm + args.warmup:]
     assert len(timed) == args.steps
     el_res = sum(s["align_s"] for s in timed)
@@ -296,8 +299,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD_DESC[wl], "reads_per_gpu": n_reads, "read_len": rl, "error": err,
                    "flags": REF_FLAGS[wl], "host_threads_per_gpu": threads,
                    "l2": "inputs larger than L2 (4.3 GB index gathers; reads re-uploaded every step)",
-                   "value_run": {"batch_reads": args.batch, "pipelines_per_gpu": args.pipes, "worker_pool_threads": threads},
-                   "e2e_run": {"batch_reads": args.e2e_batch, "pipelines_per_gpu": args.e2e_pipes, "worker_pool_threads": threads},
+                   "value_run": {"batch_reads": args.batch, "pipelines_per_gpu": pipes, "worker_pool_threads": threads},
+                   "e2e_run": {"batch_reads": args.e2e_batch, "pipelines_per_gpu": e2e_pipes, "worker_pool_threads": threads},
                    "value_excludes": "FASTA parsing and SAM fwrite (reads replayed from host memory; the 10 MB/step H2D of "
                                      "read codes is still inside); e2e includes everything",
                    "setup_s": round(t_setup, 2)},
