@@ -12,7 +12,9 @@
 //
 // Because a DP result is a pure function of its job tuple, all gap fills of all
 // clumps of a read are posted together, then all first extensions, and only the (rare) careful
-// re-extensions of split pieces are demand driven.
+// re-extensions of split pieces are demand driven.  What follows the first DP round for a clump -- splicing the
+// answers between the seed pieces, both end extensions, scoreClump's walk -- is stated in csrc/assemble_clumps.h
+// (plain C99 over the device's records, the body of the device kernel of row N2) and called from here.
 #include <algorithm>
 #include <stdio.h>
 #include <stdlib.h>
@@ -214,7 +216,7 @@ static void alignPrepare(const Env &E, ReadCtx &rc, Clump &c, PVec<ya_gap_rec> &
 struct ExtState { int backLen = 0, forwLen = 0; DpFuture fb, ff; bool doB = false, doF = false; };
 
 // perfect part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:76-107)
-static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool goForw, int &score, ExtState &x, bool post = true)
+static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool goForw, int &score, ExtState &x)
 {
     const Args &A = *E.A;
     const uint8_t *q = rc.codes(c.reversed());
@@ -238,7 +240,6 @@ static void extendPerfect(const Env &E, ReadCtx &rc, Clump &c, bool goBack, bool
     }
     x.doB = goBack && x.backLen >= A.minExtLength;
     x.doF = goForw && x.forwLen >= A.minExtLength;
-    if (!post) return;                     // jobs were already posted by extendPlanEarly
     // Both DP jobs can be posted now: the backward extension never moves the fragment's end
     // (FragsClumps.inl:81-85), so the forward job's anchor is already final.
     if (x.doB) x.fb = dpSubmit(rc, YA_DP_EXT_BWD, c.reversed(), f.startRefOff - 1, 0, f.startQueryOff - 1, x.backLen);
@@ -316,15 +317,14 @@ static int carefulForward(const Args &A, const DpAnswer &r, OpList &list, int sc
 }
 
 // DP part of extendClumpForwardReverseTemplated (AlignExtFrag.cpp:109-143)
-static void extendApply(const Env &E, ReadCtx &rc, Clump &c, ExtState &x, bool careful, int score)
+static void extendApplyCarefully(const Env &E, ReadCtx &rc, Clump &c, ExtState &x, int score)
 {
     const Args &A = *E.A;
     Frag &f = c.sf.front().frag;
     if (x.doB) {
         const DpAnswer r = dpGet(rc, x.fb);
-        int ns, aq, ar;
-        if (careful) ns = carefulBackward(A, r, c.ops, score, aq, ar);
-        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToFront(r.ops, r.n); }
+        int aq, ar;
+        const int ns = carefulBackward(A, r, c.ops, score, aq, ar);
         if (ns > 0) {
             score += ns;
             f.startQueryOff = (uint16_t)(f.startQueryOff - aq);
@@ -333,9 +333,8 @@ static void extendApply(const Env &E, ReadCtx &rc, Clump &c, ExtState &x, bool c
     }
     if (x.doF) {
         const DpAnswer r = dpGet(rc, x.ff);
-        int ns, aq, ar;
-        if (careful) ns = carefulForward(A, r, c.ops, score, aq, ar);
-        else { ns = r.score > 0 ? r.score : 0; aq = r.addedQ; ar = r.addedR; if (ns > 0) c.ops.mergeToBack(r.ops, r.n); }
+        int aq, ar;
+        const int ns = carefulForward(A, r, c.ops, score, aq, ar);
         if (ns > 0) {
             score += ns;
             f.endQueryOff = (uint16_t)(f.endQueryOff + aq);
@@ -444,7 +443,7 @@ static int splitHelper(const Env &E, ReadCtx &rc, Clump *c, int wSQO, int wEQO)
     int score = c->sf.front().score;
     extendPerfect(E, rc, *c, doBack, doForw, score, x);
     if (x.doB || x.doF) { uint64_t p0 = kAlignProf ? rdtsc_() : 0; dpWait(rc); if (kAlignProf) rc.parked += rdtsc_() - p0; }
-    extendApply(E, rc, *c, x, true, score);
+    extendApplyCarefully(E, rc, *c, x, score);
     c->set(kSplit, true);
     retval += scoreClump(E, rc, c);
     return retval;

@@ -33,9 +33,11 @@ static void makeClumps(const Env &E, ReadCtx &rc, bool rev, const ya_clump_rec *
         if (prep) { c->prep = prep + k; c->gapBase = gapBase; }
         // the alignment phase that follows compares bases just outside both ends of every piece (perfect extensions,
         // AlignExtFrag.cpp:30-48): ask for those genome lines now, they are cache misses in a 50 MB .. 1.5 GB array
+        // (with phase 1 done on the device only the clump's two outer ends are still compared here)
         for (int q = 0; q < (int)recs[k].n; q++) {
-            __builtin_prefetch(bases + ((p[q].startRefOff - 1u) >> 1));
-            __builtin_prefetch(bases + ((p[q].startRefOff + p[q].refLen) >> 1));
+            if (prep && q != 0 && q != (int)recs[k].n - 1) continue;
+            if (!prep || q == 0) __builtin_prefetch(bases + ((p[q].startRefOff - 1u) >> 1));
+            if (!prep || q == (int)recs[k].n - 1) __builtin_prefetch(bases + ((p[q].startRefOff + p[q].refLen) >> 1));
         }
         rc.clumps.push_back(c);
     }
