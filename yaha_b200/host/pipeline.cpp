@@ -160,30 +160,6 @@ static void fiberEntry()
     __builtin_trap();                     // a finished fiber is never resumed
 }
 
-// run every unfinished fiber of this slot until it parks or finishes; returns #unfinished
-static int slotPass(Slot &w)
-{
-    int live = 0;
-    for (Fiber *f : w.fibers) {
-        if (f->done) continue;
-        if (!f->started) {
-            f->started = true;
-            // initial frame: six zeroed callee-saved registers, then the entry point as return address;
-            // the slot above keeps (%rsp + 8) 16-byte aligned at function entry as the ABI requires
-            uintptr_t top = ((uintptr_t)f->stack + kStackBytes) & ~(uintptr_t)15;
-            void **sp = (void **)top;
-            *--sp = nullptr;
-            *--sp = (void *)fiberEntry;
-            for (int k = 0; k < 6; k++) *--sp = nullptr;
-            f->sp = sp;
-            tBoot = f;
-        }
-        yh_switch(&w.mainSp, f->sp);
-        if (!f->done) live++;
-    }
-    return live;
-}
-
 struct StackPool {
     std::vector<void *> free_;
     std::mutex mu;
@@ -197,6 +173,44 @@ struct StackPool {
     void put(void *p) { std::lock_guard<std::mutex> g(mu); free_.push_back(p); }
 };
 static StackPool gStacks;
+// A fiber takes its stack when it first runs and hands it back the moment it finishes, through a per-thread LIFO: most
+// reads finish in the pass that starts them (their first DP round was made and answered on the device), so a worker
+// keeps running its fibers on the same one or two stacks -- warm in cache and TLB -- instead of touching a fresh
+// 512 KB mapping per read.  Only a fiber that parks keeps its stack across passes.
+struct StackCache {
+    std::vector<void *> v;
+    void *get() { if (!v.empty()) { void *p = v.back(); v.pop_back(); return p; } return gStacks.get(); }
+    void put(void *p) { if (v.size() < 256) v.push_back(p); else gStacks.put(p); }
+    ~StackCache() { for (void *p : v) gStacks.put(p); }
+};
+static thread_local StackCache tStacks;
+
+// run every unfinished fiber of this slot until it parks or finishes; returns #unfinished
+static int slotPass(Slot &w)
+{
+    int live = 0;
+    for (Fiber *f : w.fibers) {
+        if (f->done) continue;
+        if (!f->started) {
+            f->started = true;
+            f->stack = tStacks.get();
+            // initial frame: six zeroed callee-saved registers, then the entry point as return address;
+            // the slot above keeps (%rsp + 8) 16-byte aligned at function entry as the ABI requires
+            uintptr_t top = ((uintptr_t)f->stack + kStackBytes) & ~(uintptr_t)15;
+            void **sp = (void **)top;
+            *--sp = nullptr;
+            *--sp = (void *)fiberEntry;
+            for (int k = 0; k < 6; k++) *--sp = nullptr;
+            f->sp = sp;
+            tBoot = f;
+        }
+        yh_switch(&w.mainSp, f->sp);
+        if (!f->done) live++;
+        else { tStacks.put(f->stack); f->stack = nullptr; }
+    }
+    return live;
+}
+
 
 // Growable array in page-locked memory (ya_host_alloc): what the device copies into and out of.
 template <class T> struct PinnedVec {
@@ -326,7 +340,7 @@ static void runSlotPass(const Task &t)
         B.outBufs[(size_t)t.t].s.reserve(2 * bytes + 512 * (size_t)(s.hi - s.lo) + 4096);
         for (int i = s.lo; i < s.hi; i++) {
             Fiber *f = &B.fibers[(size_t)i];
-            f->stack = gStacks.get();
+            f->stack = nullptr;                                       // (taken when the fiber first runs, slotPass)
             f->w = &s;
             f->sp = nullptr; f->done = false; f->started = false;     // (the fiber object may be a recycled one)
             f->rc.clumps.clear(); f->rc.primaryCount = 0; f->rc.parked = 0; f->rc.outOff = 0; f->rc.outLen = 0;
@@ -588,7 +602,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
             pool.post(Task{&D, &B, &s, t});
         }
     }
-    for (int i = 0; i < n; i++) { gStacks.put(B.fibers[(size_t)i].stack); B.fibers[(size_t)i].stack = nullptr; }
+    for (int i = 0; i < n; i++) if (B.fibers[(size_t)i].stack) { gStacks.put(B.fibers[(size_t)i].stack); B.fibers[(size_t)i].stack = nullptr; }
 }
 
 // ----------------------------------------------------------------------------- child fibers of a read
@@ -617,7 +631,7 @@ void runAsChildren(ReadCtx &rc, int n, void (*fn)(void *, int), void *arg, std::
             ChildBoot boot{&rc, fn, arg, k, &c};
             if (!c.started) {
                 c.started = true;
-                c.stack = gStacks.get();
+                c.stack = tStacks.get();
                 uintptr_t top = ((uintptr_t)c.stack + kStackBytes) & ~(uintptr_t)15;
                 void **sp = (void **)top;
                 *--sp = nullptr;
@@ -632,6 +646,7 @@ void runAsChildren(ReadCtx &rc, int n, void (*fn)(void *, int), void *arg, std::
             rc.childSp = nullptr;
             rc.clumps.swap(outs[k]);
             if (!c.done) live++;
+            else if (c.stack) { tStacks.put(c.stack); c.stack = nullptr; }
         }
         if (live == 0) break;
         dpWait(rc);                                  // one park of the read's fiber serves every parked child
