@@ -211,6 +211,9 @@ def run_ours(args):
     # a pipeline is a thread too (it drives the device and naps between polls): a rank that owns fewer cores than the default
     # 8 pipelines runs one pipeline per core (the configuration tools/sweep_fewcores.sh measured: 4 cores, 4 pipelines)
     pipes, e2e_pipes = (min(p, max(2, threads)) for p in (args.pipes, args.e2e_pipes))
+    # ... and its device-driving threads nap 50 us between stream polls instead of 20 (YA_NAP_US): with 4 cores per GPU the job is
+    # bound by host CPU, not by latency, and every poll is a wake-up taken from a worker
+    few_cores_env = {"YA_NAP_US": os.environ.get("YA_NAP_US", "50")} if threads <= 4 else {}
 
     # roofline denominators measured live on this GPU: INT32 issue rate and the HBM random-gather rate
     # over the real 4 GiB starting-offset table (index rebuilt on the device for this, ~1 s)
@@ -228,7 +231,7 @@ def run_ours(args):
     e2e_tpp = 0                      # shared worker pool of `threads` workers serves every pipeline
     extra_warm = 5                   # (page-locked / device scratch of 8 pipelines reaches its final size in the first passes)
     stats_a = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, extra_warm + args.warmup + args.steps,
-                       args.e2e_batch, e2e_pipes, tpp=e2e_tpp)
+                       args.e2e_batch, e2e_pipes, tpp=e2e_tpp, env=few_cores_env)
     timed_a = stats_a[extra_warm + args.warmup:]
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
@@ -236,7 +239,7 @@ def run_ours(args):
     # the kernel rooflines (kernels of up to 8 pipelines share the SMs here, which stretches their event timings;
     # run C below times the same kernels alone).
     stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + extra_warm + args.warmup + args.steps,
-                       args.batch, pipes, replay=True)
+                       args.batch, pipes, replay=True, env=few_cores_env)
     timed = stats_b[1 + extra_warm + args.warmup:]
     assert len(timed) == args.steps
     el_res = sum(s["align_s"] for s in timed)
@@ -301,6 +304,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (4.3 GB index gathers; reads re-uploaded every step)",
                    "value_run": {"batch_reads": args.batch, "pipelines_per_gpu": pipes, "worker_pool_threads": threads},
                    "e2e_run": {"batch_reads": args.e2e_batch, "pipelines_per_gpu": e2e_pipes, "worker_pool_threads": threads},
+                   "stream_poll_nap_us": int(few_cores_env.get("YA_NAP_US", os.environ.get("YA_NAP_US", "20"))),
                    "value_excludes": "FASTA parsing and SAM fwrite (reads replayed from host memory; the 10 MB/step H2D of "
                                      "read codes is still inside); e2e includes everything",
                    "setup_s": round(t_setup, 2)},
