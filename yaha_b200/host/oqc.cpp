@@ -38,6 +38,17 @@ struct CNode {                        // cGraphNode, GraphPath.cpp:299-324
     uint8_t  reversed, seqNum;
 };
 
+static void seedRandom(ReadCtx &rc)                                     // generateRandomSeed, QueryState.c:172-187
+{
+    const std::vector<uint8_t> &c = rc.read->fcode;
+    size_t q = 0;
+    for (int i = 0; i < 5; i++) {
+        uint32_t word = 0;
+        for (int j = 0; j < 16; j++) { word = (word << 2) | (c[q] & 3u); if (++q >= c.size()) q = 0; }
+        rc.rng.s[i] = word;
+    }
+}
+
 static inline uint64_t compareKey(const CNode &n)                      // GraphPath.cpp:377-380
 {
     return (((((uint64_t)n.SQO) << 16) + ((uint16_t)-(int16_t)n.EQO)) << 16) + ((uint16_t)-n.nodeScore);
@@ -228,6 +239,7 @@ void postFilterBySimilarity(const Env &E, ReadCtx &rc)                  // Graph
         n.qLenInOQC = (uint16_t)(1 + c->EQO() - c->SQO());
         n.seqNum = (uint8_t)E.G->findSeq(n.SRO);
     }
+    seedRandom(rc);
     quickSort(g.data(), 0, cnt - 1, rc.rng);
 
     // deleteSubsumedDups, GraphPath.cpp:488-517

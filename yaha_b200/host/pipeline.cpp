@@ -128,15 +128,8 @@ static void readMain(const Env &E, ReadCtx &rc)                       // body of
 {
     uint64_t t0 = rdtsc();
     const Args &A = *E.A;
-    {                                                                  // generateRandomSeed, QueryState.c:172-187
-        const std::vector<uint8_t> &c = rc.read->fcode;
-        size_t q = 0;
-        for (int i = 0; i < 5; i++) {
-            uint32_t word = 0;
-            for (int j = 0; j < 16; j++) { word = (word << 2) | (c[q] & 3u); if (++q >= c.size()) q = 0; }
-            rc.rng.s[i] = word;
-        }
-    }
+    // (generateRandomSeed, QueryState.c:172-187: the seed is a function of the read alone and its only consumer is the tie
+    //  break of the OQC sort, so it is derived there -- seedRandom, oqc.cpp -- for the few reads that get that far)
     for (int rev = 0; rev <= 1; rev++) formClumps(E, rc, rev != 0);
     uint64_t t1 = rdtsc();
     postProcessClumps(E, rc);
