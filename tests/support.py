@@ -62,7 +62,7 @@ def oracle():
         return _oracle
     so = os.path.join(ORACLE_DIR, "liboracle.so")
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle_dp.c", "oracle_seed.c", "oracle_clumps.c", "oracle.h")]
-    srcs.append(os.path.join(ROOT, "yaha_b200", "csrc", "form_clumps.h"))
+    srcs += [os.path.join(ROOT, "yaha_b200", "csrc", h) for h in ("form_clumps.h", "prepare_clumps.h", "assemble_clumps.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "liboracle.so"], stdout=subprocess.DEVNULL)
     lib = C.CDLL(so)
