@@ -241,6 +241,34 @@ struct RandState { uint32_t s[5]; uint32_t bits(); };               // Math.c:27
 struct DpFuture { int slot = -1; };  // index into the round's job list
 struct DpAnswer { int score = 0; int addedQ = 0, addedR = 0; const ya_op *ops = nullptr; int n = 0; };   // view into the round's result arrays
 
+// Growable text buffer of one worker's formatted records.  Unlike std::string it hands out uninitialised room: a SAM record
+// is written through a raw cursor into space reserved for its largest possible size (a few KB), and value-initialising that
+// space for every record cost about a quarter of the formatting time.
+struct OutText {
+    char *p = nullptr; size_t n = 0, cap = 0;
+    OutText() {}
+    OutText(OutText &&o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    OutText &operator=(OutText &&o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+    OutText(const OutText &) = delete;
+    OutText &operator=(const OutText &) = delete;
+    ~OutText() { free(p); }
+    size_t size() const { return n; }
+    const char *data() const { return p; }
+    void clear() { n = 0; }
+    void reserve(size_t want)
+    {
+        if (want <= cap) return;
+        size_t c = cap ? cap : 4096;
+        while (c < want) c *= 2;
+        char *q = (char *)realloc(p, c);
+        if (!q) { fprintf(stderr, "yaha_b200: out of memory\n"); abort(); }
+        p = q; cap = c;
+    }
+    char *room(size_t k) { reserve(n + k); return p + n; }          // k writable bytes behind the text; commit() what was used
+    void commit(size_t k) { n += k; }
+    void append(const char *s, size_t k) { memcpy(room(k), s, k); n += k; }
+};
+
 struct ReadCtx {                     // the per-read half of QueryState_t (Math.h:587-666)
     void  *owner = nullptr;         // the fiber running this read (scheduler private)
     int    idx = 0;                  // index in the batch == read id on the device
@@ -260,7 +288,7 @@ struct ReadCtx {                     // the per-read half of QueryState_t (Math.
     void **parentSp = nullptr;       // ... and the read's own context it returns to
     const ya_prep_rec *devPrep[2] = {nullptr, nullptr};             // ... and prepared there (ya_prepare_clumps), or null
     const ya_gap_rec *devGaps = nullptr;
-    std::string *out = nullptr;      // the worker's output buffer; this read's records are [outOff, outOff+outLen)
+    OutText *out = nullptr;          // the worker's output buffer; this read's records are [outOff, outOff+outLen)
     size_t outOff = 0, outLen = 0;
     // the reverse-complement strand is derived the first time something asks for it (about half of the reads never do)
     const uint8_t *codes(bool rev) const { if (rev) read->finish(); return rev ? read->rcode.data() : read->fcode.data(); }

@@ -83,7 +83,7 @@ struct Batch {
     std::vector<std::pair<const char *, size_t>> slices;   // FASTA records still to be parsed (by the pipeline that takes the batch)
     std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous (kept when the batch object is recycled)
     int nFibers = 0, fiberCap = 0;
-    struct alignas(64) OutBuf { std::string s; };   // (own cache line: every append updates the size)
+    struct alignas(64) OutBuf { OutText s; };   // (own cache line: every append updates the size)
     std::vector<OutBuf> outBufs;          // formatted records, one buffer per worker thread
 };
 

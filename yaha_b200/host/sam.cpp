@@ -10,8 +10,8 @@
 
 namespace yh {
 
-static void appendf(std::string &s, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
-static void appendf(std::string &s, const char *fmt, ...)
+static void appendf(OutText &s, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+static void appendf(OutText &s, const char *fmt, ...)
 {
     char buf[256];
     va_list ap;
@@ -19,18 +19,6 @@ static void appendf(std::string &s, const char *fmt, ...)
     int n = vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     if (n > 0) s.append(buf, (size_t)std::min<int>(n, (int)sizeof buf - 1));
-}
-
-static inline void appendUInt(std::string &s, unsigned v)
-{
-    char buf[12];
-    int n = 0;
-    do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-    while (n) s.push_back(buf[--n]);
-}
-static inline void appendInt(std::string &s, int v)
-{
-    if (v < 0) { s.push_back('-'); appendUInt(s, (unsigned)(-(long)v)); } else appendUInt(s, (unsigned)v);
 }
 
 struct TwoDigits { char d[2]; uint8_t n; };
@@ -70,7 +58,7 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
 {
     const Args &A = *E.A;
     const Genome &G = *E.G;
-    std::string &o = *rc.out;
+    OutText &o = *rc.out;
     const Frag &f0 = c.sf.front().frag, &fn = c.sf.back().frag;
     uint32_t sStart = f0.startRefOff, sEnd = fragERO(fn);
     int si = G.findSeq(sStart);
@@ -87,12 +75,11 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
         if (clip > 0) list.pushFront(A.hardClip ? 'H' : 'S', clip);
         // the record is written through a raw cursor into space reserved for its largest possible size
         // (CIGAR <= 12 characters per run, MD <= 2 per reference base + 11 per run)
-        const size_t base = o.size();
         size_t refBases = 0;
         for (const Op &op : list.v) if (op.code != 'I') refBases += op.len;
         const size_t bound = 512 + rc.read->id.size() + BS.name.size() + 24 * list.v.size() + 2 * (size_t)L + 2 * refBases;
-        o.resize(base + bound);
-        char *w = &o[base];
+        char *const w0 = o.room(bound);
+        char *w = w0;
         auto putS = [&](const char *z, size_t n) { memcpy(w, z, n); w += n; };
         auto putU = [&](unsigned v) {                                      // (CIGAR / MD numbers are mostly one or two digits:
             if (v < 100) { memcpy(w, kTwoDigits[v].d, 2); w += kTwoDigits[v].n; return; }   //  both bytes stored, cursor moved by 1 or 2 -- no branch on the value)
@@ -156,11 +143,11 @@ static void formatClump(const Env &E, ReadCtx &rc, Clump &c)
             if (c.is(kPrimary)) { putS("\tYS:i:", 6); putI((int)c.numSecondaries); }
         }
         *w++ = '\n';
-        if ((size_t)(w - &o[base]) > bound) { fprintf(stderr, "yaha_b200: internal error: SAM record larger than its bound\n"); abort(); }
-        o.resize((size_t)(w - &o[0]));
+        if ((size_t)(w - w0) > bound) { fprintf(stderr, "yaha_b200: internal error: SAM record larger than its bound\n"); abort(); }
+        o.commit((size_t)(w - w0));
     }
     if (A.outputBlast8) {                                                       // AlignOutput.c:307-318
-        o += rc.read->id; o += '\t'; o += BS.name;
+        o.append(rc.read->id.data(), rc.read->id.size()); o.append("\t", 1); o.append(BS.name.data(), BS.name.size());
         appendf(o, "\t%4.2f\t%d\t%d\t%d", 0.8 * 100, (int)c.totLength, (int)c.mismatchedBases, (int)c.gapBases);
         if (c.reversed()) appendf(o, "\t%d\t%d\t%d\t%d\t%c", L - fn.endQueryOff, L - f0.startQueryOff, sEnd + 1, sStart + 1, '-');
         else appendf(o, "\t%d\t%d\t%d\t%d\t%c", f0.startQueryOff + 1, fn.endQueryOff + 1, sStart + 1, sEnd + 1, '+');
