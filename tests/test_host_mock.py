@@ -80,3 +80,19 @@ def test_cli_errors_match_reference_behaviour(small, mock_host):
     assert p.returncode != 0 and "is not a valid option" in p.stderr
     p = subprocess.run([mock_host, "-x", small.idx_path, "-q", "r.fa", "-OQC", "maybe"], capture_output=True, text=True)
     assert p.returncode != 0 and "is not a valid value for parameter -OQC" in p.stderr
+
+
+@pytest.mark.parametrize("word_len,skip", [(12, 3), (13, 2), (10, 1)])
+def test_other_word_lengths_and_skip_distances(small, mock_host, tmp_path, word_len, skip):
+    # -L / -S are index-time flags (Main.c:559-563 puts them into the file name): the index is made by the unmodified
+    # reference where it is built (oracle/_ref/yaha; skipped elsewhere), both programs align against that file
+    if not os.path.exists(S.REF_BIN):
+        pytest.skip("oracle/_ref/yaha not built here")
+    import shutil
+    shutil.copy(os.path.join(small.dir, "ref.fa"), tmp_path / "ref.fa")
+    subprocess.run([S.REF_BIN, "-g", "ref.fa", "-L", str(word_len), "-S", str(skip)], cwd=tmp_path, check=True, capture_output=True, timeout=600)
+    idx = str(tmp_path / f"ref.X{word_len:02d}_{skip:02d}_65525S")
+    reads = os.path.join(small.dir, "reads.fa")
+    subprocess.run([S.REF_BIN, "-x", idx, "-q", reads, "-osh", str(tmp_path / "want.sam"), "-t", "1"], check=True, capture_output=True, timeout=600)
+    subprocess.run([mock_host, "-x", idx, "-q", reads, "-osh", str(tmp_path / "got.sam"), "-t", "2"], check=True, capture_output=True, timeout=600)
+    assert H.sam_lines(open(tmp_path / "got.sam").read()) == H.sam_lines(open(tmp_path / "want.sam").read())
