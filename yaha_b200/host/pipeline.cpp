@@ -841,11 +841,20 @@ int runQueries(const Args &A0)
                 F.done.erase(next);
             }
             double w0 = nowSec();
-            if (!replaying)
+            if (!replaying) {
+                // records of consecutive reads mostly lie back to back in their worker's buffer (a slot is a run of
+                // reads formatted in order, unless a read parked): such a stretch is one fwrite
+                const char *runP = nullptr; size_t runN = 0;
                 for (int i = 0; i < b->nFibers; i++) {
                     const ReadCtx &rc = b->fibers[(size_t)i].rc;
-                    if (rc.outLen) fwrite(rc.out->data() + rc.outOff, 1, rc.outLen, out);
+                    if (!rc.outLen) continue;
+                    const char *p = rc.out->data() + rc.outOff;
+                    if (runN && p == runP + runN) { runN += rc.outLen; continue; }
+                    if (runN) fwrite(runP, 1, runN, out);
+                    runP = p; runN = rc.outLen;
                 }
+                if (runN) fwrite(runP, 1, runN, out);
+            }
             nReads += b->reads.size();
             tWrite += nowSec() - w0;
             traceEv('W', 0, (int)b->seq, w0, nowSec());
