@@ -11,6 +11,7 @@ Outputs (all gzip'd, deterministic seeds):
   out_bw5.sam.gz, out_bw10.sam.gz   the reference's SAM output (-t 1)
   out_{fbs,nooqc,fastq_oss,blast8}.sam.gz   more reference outputs (-FBS Y, -OQC N, FASTQ input with -oss, -o8)
   flag_sweep.json             digest of the reference's SAM for every flag set of tests/hostcases.py FLAG_SWEEP (--only-flag-sweep)
+  index_variants.json         sha256 of reference-built indexes for several -L / -S / -H on two references (--only-index-variants)
   files.sha256                digests of the reference-built ref.nib2 and index
 """
 import gzip, hashlib, os, shutil, subprocess, sys, tempfile
@@ -88,7 +89,36 @@ def only_flag_sweep():
     shutil.rmtree(tmp)
 
 
+INDEX_VARIANTS = [(11, 1, 65525), (11, 3, 65525), (10, 4, 65525), (9, 1, 20), (8, 2, 7), (11, 11, 65525), (11, 5, 3)]   # (-L, -S, -H)
+
+
+def only_index_variants():
+    """Writes index_variants.json: sha256 of the index files the reference builds for synth.n_rich_reference() and for the
+    golden reference with several -L / -S / -H (tests/test_formats.py rebuilds them with yaha_b200.refio)."""
+    import json
+    tmp = tempfile.mkdtemp()
+    synth.write_fasta(tmp + "/nrich.fa", synth.n_rich_reference())
+    with gzip.open(OUT + "/ref.fa.gz", "rb") as f, open(tmp + "/small.fa", "wb") as o:
+        o.write(f.read())
+    table = {}
+    for stem in ("nrich", "small"):
+        for L, S, H in INDEX_VARIANTS:
+            subprocess.check_call([REF + "/yaha", "-g", stem + ".fa", "-L", str(L), "-S", str(S), "-H", str(H)], cwd=tmp,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            name = f"{stem}.X{L:02d}_{S:02d}_{H:05d}S"
+            table[name] = hashlib.sha256(open(f"{tmp}/{name}", "rb").read()).hexdigest()
+            os.remove(f"{tmp}/{name}")
+        table[stem + ".nib2"] = hashlib.sha256(open(f"{tmp}/{stem}.nib2", "rb").read()).hexdigest()
+    with open(OUT + "/index_variants.json", "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+        f.write("\n")
+    shutil.rmtree(tmp)
+
+
 def main():
+    if "--only-index-variants" in sys.argv:
+        only_index_variants()
+        return
     if "--only-chimera" in sys.argv:
         only_chimera()
         return

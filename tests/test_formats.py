@@ -10,6 +10,50 @@ def test_nib2_and_index_match_reference_digests(small):
     assert small.idx_sha == small.sha["ref.X11_01_65525S"]
 
 
+def test_index_builder_matches_reference_for_other_word_lengths_skips_and_hit_caps(small, tmp_path):
+    # -L / -S / -H (Index.c:95-331): every `skip`-th window from the sequence start, the walk renormalised to a multiple
+    # of `skip` behind each run of non-ACGT codes, k-mer lists above -H down-sampled with the reference's generator.
+    # Digests of the files the unmodified reference writes: golden/small/index_variants.json (make_golden.py).
+    import hashlib
+    import json
+    import os
+    from yaha_b200 import synth
+    want = json.load(open(os.path.join(small.golden, "index_variants.json")))
+    nrich = refio.build_nib2(synth.n_rich_reference())
+    assert hashlib.sha256(nrich).hexdigest() == want["nrich.nib2"]
+    open(tmp_path / "nrich.nib2", "wb").write(nrich)
+    nibs = {"nrich": refio.load_nib2(str(tmp_path / "nrich.nib2")), "small": small.nib}
+    checked = 0
+    for name, digest in want.items():
+        if name.endswith(".nib2"):
+            continue
+        stem, spec = name.split(".X")
+        L, S, H = int(spec[0:2]), int(spec[3:5]), int(spec[6:11])
+        assert name == refio.index_file_name(stem, L, S, H)
+        img = refio.build_index(nibs[stem], L, max_hits=H, skip=S)
+        assert hashlib.sha256(img).hexdigest() == digest, name
+        checked += 1
+    assert checked == 14
+
+
+def test_index_creation_command(small, tmp_path):
+    # python -m yaha_b200.refio -g ref.fa -L 9 -S 2 -H 20: the reference's index mode, its file names (Main.c:559-563)
+    import hashlib
+    import json
+    import os
+    import shutil
+    import subprocess
+    import sys
+    shutil.copy(os.path.join(small.dir, "ref.fa"), tmp_path / "small.fa")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-W", "ignore", "-m", "yaha_b200.refio", "-g", "small.fa", "-L", "9", "-S", "1", "-H", "20"], cwd=tmp_path,
+                       env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-1000:]
+    want = json.load(open(os.path.join(small.golden, "index_variants.json")))
+    assert hashlib.sha256(open(tmp_path / "small.X09_01_00020S", "rb").read()).hexdigest() == want["small.X09_01_00020S"]
+    assert hashlib.sha256(open(tmp_path / "small.nib2", "rb").read()).hexdigest() == want["small.nib2"] == small.sha["ref.nib2"]
+
+
 def test_nib2_roundtrip(small):
     nib = small.nib
     assert nib.names == ["chr1", "chr2", "chr3"]

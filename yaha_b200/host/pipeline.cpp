@@ -904,8 +904,9 @@ int runQueries(const Args &A0)
 int runIndex(const Args &A)
 {
     (void)A;
-    fprintf(stderr, "yaha_b200: index creation (-g) is provided by the Python front end (yaha_b200.refio / Aligner(index=None));\n"
-                    "the alignment hot path reads the reference's .nib2 and index files unchanged.\n");
+    fprintf(stderr, "yaha_b200: index creation is provided by the Python front end, with the reference's flags and file names:\n"
+                    "    python -m yaha_b200.refio -g genome.(fa|nib2) [-L wordLen] [-S skipDist] [-H maxHits]\n"
+                    "(byte-identical .nib2 and index files; `yaha -g` works as well -- the alignment hot path reads either unchanged).\n");
     return 2;
 }
 

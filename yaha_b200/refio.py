@@ -201,26 +201,57 @@ def _rand_sample(state, inp: np.ndarray, out_len: int) -> np.ndarray:
     return inp[marked == keep_marked]
 
 
+def _indexed_positions(codes: np.ndarray, st: int, ln: int, K: int, skip: int) -> np.ndarray:
+    """Global offsets of the k-mers the reference indexes in one sequence (Index.c:95-128): from the sequence start
+    every `skip`-th window while it is free of non-ACGT codes; a window that holds one makes the walk resume at the
+    first multiple of `skip` (of the GLOBAL offset) at or behind the first good base after that run of bad codes.
+    `codes` is the whole genome's code array, one byte per base."""
+    end = st + ln - K                                   # last window start of the sequence
+    n = len(codes)
+    bad = codes > 3
+    idx = np.arange(n, dtype=np.int64)
+    big = np.int64(1) << 40
+    next_bad = np.minimum.accumulate(np.where(bad, idx, big)[::-1])[::-1]          # first bad code at or behind i
+    next_good = np.minimum.accumulate(np.where(~bad, idx, big)[::-1])[::-1]
+    out = []
+    b = st
+    while b <= end:
+        nb = int(next_bad[b]) if b < n else int(big)
+        last = min(end, nb - K)                         # windows [p, p+K) with p <= last are clean
+        if last >= b:
+            cnt = (last - b) // skip + 1
+            out.append(b + skip * np.arange(cnt, dtype=np.int64))
+            b += skip * cnt
+            if b > end or nb >= big:
+                break
+            if b + K <= nb:                             # (cannot happen: b is the first window start past `last`)
+                continue
+        # the window at b holds the bad code at nb: skip the run of bad codes, renormalise (Index.c:110-116)
+        x = nb + 1
+        x = int(next_good[x]) if x < n else int(big)
+        if x >= big:
+            break
+        b = ((x + skip - 1) // skip) * skip
+    return np.concatenate(out) if out else np.zeros(0, np.int64)
+
+
 def build_index(nib: Nib2, word_len: int, max_hits: int = 65525, skip: int = 1) -> bytes:
-    """Index image (Index.c:95-331) for a loaded .nib2.  skip (-S) must be 1."""
-    if skip != 1:
-        raise NotImplementedError("only -S 1 indexes are built here")
+    """Index image (Index.c:95-331) for a loaded .nib2, any -L / -S / -H."""
     K = word_len
+    total = int(nib.starts[-1] + nib.lengths[-1]) if len(nib.starts) else 0
+    n_codes = min(2 * len(nib.bases), total + 16)
+    allc = nib.unpack(0, n_codes)
     pos_all, hash_all = [], []
     for st, ln in zip(nib.starts, nib.lengths):
         st, ln = int(st), int(ln)
         if ln < K:
             continue
-        codes = nib.unpack(st, ln).astype(np.uint32)
-        bad = (codes > 3).astype(np.int64)
-        cb = np.concatenate([[0], np.cumsum(bad)])
-        ok = (cb[K:] - cb[:-K]) == 0                    # window free of non-ACGT (Index.c:105-128)
-        h = np.zeros(ln - K + 1, dtype=np.uint32)
+        p = _indexed_positions(allc, st, ln, K, skip)
+        h = np.zeros(len(p), dtype=np.uint32)
         for k in range(K):
-            h = (h << 2) | (codes[k:ln - K + 1 + k] & 3)
-        p = np.nonzero(ok)[0]
-        pos_all.append((p + st).astype(np.uint32))
-        hash_all.append(h[p])
+            h = (h << 2) | (allc[p + k].astype(np.uint32) & 3)
+        pos_all.append(p.astype(np.uint32))
+        hash_all.append(h)
     pos = np.concatenate(pos_all) if pos_all else np.zeros(0, np.uint32)
     hsh = np.concatenate(hash_all) if hash_all else np.zeros(0, np.uint32)
     order = np.argsort(hsh, kind="stable")              # ascending offset inside each k-mer list
@@ -257,3 +288,36 @@ def write_index(path: str, idx: Index) -> None:
         np.array([INDEX_VERSION, idx.word_len, idx.max_hits, len(idx.roa)], dtype="<u4").tofile(f)
         np.ascontiguousarray(idx.so, dtype="<u4").tofile(f)
         np.ascontiguousarray(idx.roa, dtype="<u4").tofile(f)
+
+
+def main(argv=None) -> int:
+    """`python -m yaha_b200.refio -g genome.(fa|nib2) [-L wordLen] [-S skipDist] [-H maxHits]` -- the reference's index
+    creation mode (Main.c:567-634): writes <stem>.nib2 (from FASTA input) and <stem>.X<LL>_<SS>_<HHHHH>S next to the
+    input, byte for byte the files `yaha -g` writes (defaults -L 15 -S 1 -H 65525, AlignArgs.c:48-87)."""
+    import argparse
+    import os
+    import sys
+    ap = argparse.ArgumentParser(prog="python -m yaha_b200.refio", description="yaha-compatible .nib2 and index files")
+    ap.add_argument("-g", required=True, metavar="genome.(fa|nib2)")
+    ap.add_argument("-L", type=int, default=15, metavar="wordLen")
+    ap.add_argument("-S", type=int, default=1, metavar="skipDist")
+    ap.add_argument("-H", type=int, default=65525, metavar="maxHits")
+    a = ap.parse_args(argv)
+    if not 1 <= a.S <= a.L or not 1 <= a.L <= 15:
+        print("wordLen must be 1..15 and skipDist 1..wordLen", file=sys.stderr)
+        return 1
+    stem, ext = os.path.splitext(a.g)
+    nib_path = a.g if ext == ".nib2" else stem + ".nib2"
+    if ext != ".nib2":
+        print(f"Compressing {a.g} into {nib_path}.", file=sys.stderr)
+        with open(nib_path, "wb") as f:
+            f.write(build_nib2(read_fasta(a.g)))
+    idx_path = index_file_name(stem, a.L, a.S, min(a.H, 65525))
+    print(f"Creating index file {idx_path}.", file=sys.stderr)
+    with open(idx_path, "wb") as f:
+        f.write(build_index(load_nib2(nib_path), a.L, max_hits=min(a.H, 65525), skip=a.S))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

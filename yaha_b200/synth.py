@@ -199,3 +199,23 @@ if __name__ == "__main__":
     ap.add_argument("--read-seed", type=int, default=777)
     a = ap.parse_args()
     print(make_config(a.outdir, a.ref_bases, a.reads, a.len, a.err, a.ref_seed, a.read_seed, a.seqs))
+
+
+def n_rich_reference(seed: int = 3):
+    """Five sequences (50 001, 12, 30 007, 999 and 20 000 bases) with runs of N of 1-40 bases about every 300 bases, one
+    sequence starting and one ending with N, one shorter than most word lengths: what the index builder's walk over
+    non-ACGT codes (Index.c:95-128) has to get right for every -L / -S."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for k, L in enumerate([50_001, 12, 30_007, 999, 20_000]):
+        s = random_reference(L, 50 + k).copy()
+        for _ in range(L // 300):
+            p = int(rng.integers(0, L))
+            n = int(rng.choice([1, 1, 2, 3, 5, 8, 13, 40]))
+            s[p:p + n] = ord("N")
+        if k == 2:
+            s[:7] = ord("N")
+        if k == 4:
+            s[-5:] = ord("N")
+        seqs.append((f"s{k}", s))
+    return seqs
