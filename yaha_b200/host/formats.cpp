@@ -303,6 +303,30 @@ int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen)
     return (fail || m == 0) ? 0 : 1;
 }
 
+// codeOfChar for 16 characters per step.  A letter's code depends on its low five bits only (upper and lower case agree), so
+// the 256-entry table folds into two 16-entry byte shuffles; everything that is not an ASCII letter is X (14) like the table
+// says.  The routine is compared with the table on all 256 byte values before it is first used, and left unused otherwise.
+#if defined(__x86_64__)
+__attribute__((target("ssse3"))) static size_t encode16(const unsigned char *src, uint8_t *dst, size_t n, const uint8_t *lut32)
+{
+    const __m128i lutLo = _mm_loadu_si128((const __m128i *)lut32), lutHi = _mm_loadu_si128((const __m128i *)(lut32 + 16));
+    const __m128i c20 = _mm_set1_epi8(0x20), ca = _mm_set1_epi8('a'), c25 = _mm_set1_epi8(25), c15 = _mm_set1_epi8(15);
+    const __m128i c31 = _mm_set1_epi8(31), cX = _mm_set1_epi8(14);
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m128i v = _mm_loadu_si128((const __m128i *)(src + i));
+        const __m128i t = _mm_sub_epi8(_mm_or_si128(v, c20), ca);
+        const __m128i letter = _mm_cmpeq_epi8(_mm_min_epu8(t, c25), t);            // (v | 0x20) - 'a' < 26, unsigned
+        const __m128i idx = _mm_and_si128(v, c31);
+        const __m128i high = _mm_cmpgt_epi8(idx, c15);
+        const __m128i low4 = _mm_and_si128(idx, c15);
+        const __m128i code = _mm_or_si128(_mm_andnot_si128(high, _mm_shuffle_epi8(lutLo, low4)), _mm_and_si128(high, _mm_shuffle_epi8(lutHi, low4)));
+        _mm_storeu_si128((__m128i *)(dst + i), _mm_or_si128(_mm_and_si128(letter, code), _mm_andnot_si128(letter, cX)));
+    }
+    return i;
+}
+#endif
+
 void Read::encode()                                 // Query.c:161-163 (codeOfChar per base)
 {
     static uint8_t codeTab[256];
@@ -313,7 +337,21 @@ void Read::encode()                                 // Query.c:161-163 (codeOfCh
     fcode.resize(n);
     const unsigned char *src = (const unsigned char *)fwd.data();
     uint8_t *fc = fcode.data();
-    for (size_t i = 0; i < n; i++) fc[i] = codeTab[src[i]];
+    size_t i = 0;
+#if defined(__x86_64__)
+    static uint8_t lut32[32];
+    static const bool wide = [] {
+        if (!__builtin_cpu_supports("ssse3")) return false;
+        for (int k = 0; k < 32; k++) lut32[k] = codeTab[k >= 1 && k <= 26 ? 'A' + k - 1 : 0];
+        unsigned char all[256]; uint8_t got[256];
+        for (int c = 0; c < 256; c++) all[c] = (unsigned char)c;
+        if (encode16(all, got, 256, lut32) != 256) return false;
+        for (int c = 0; c < 256; c++) if (got[c] != codeTab[c]) return false;
+        return true;
+    }();
+    if (wide) i = encode16(src, fc, n, lut32);
+#endif
+    for (; i < n; i++) fc[i] = codeTab[src[i]];
 }
 
 // reverse complement 16 bases per step: both tables (complement of a 4-bit code, character of a code) have 16 entries,
