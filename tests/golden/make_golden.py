@@ -115,7 +115,50 @@ def only_index_variants():
     shutil.rmtree(tmp)
 
 
+def only_weird_fastq():
+    """Adds weird.fq.gz / out_weird_fastq.sam.gz: FASTQ reader corner cases (Query.c:102-228) -- description after the id and on the
+    '+' line, CRLF, multi-line sequence and quality, '@' inside a quality line, quality shorter than the sequence (skipped with the
+    reference's warning), lower case, a read shorter than the word length, no final newline."""
+    tmp = tempfile.mkdtemp()
+    for name in ("ref.fa", "reads.fa"):
+        with gzip.open(f"{OUT}/{name}.gz", "rb") as f, open(f"{tmp}/{name}", "wb") as o:
+            o.write(f.read())
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = open(tmp + "/reads.fa").read().split(">")[1:8]
+    rs = [(l.split("\n", 1)[0], l.split("\n", 1)[1].replace("\n", "")) for l in lines]
+
+    def qual(n, k):
+        return "".join(chr(33 + (i * 7 + k) % 40) for i in range(n))
+    with open(tmp + "/weird.fq", "w") as f:
+        n, s = rs[0]
+        f.write(f"@{n} desc with spaces\n{s}\n+{n} again\n{qual(len(s), 1)}\n")
+        n, s = rs[1]
+        f.write(f"@{n}\r\n{s}\r\n+\r\n{qual(len(s), 2)}\r\n")
+        n, s = rs[2]
+        h, q = len(s) // 3, qual(len(s), 3)
+        f.write(f"@{n}\n{s[:h]}\n{s[h:]}\n+\n{q[:h]}\n{q[h:2 * h]}\n{q[2 * h:]}\n")
+        n, s = rs[3]
+        q = list(qual(len(s), 4))
+        q[50] = "@"
+        f.write(f"@{n}\n{s}\n+\n{''.join(q)}\n")
+        n, s = rs[4]
+        f.write(f"@{n}\n{s}\n+\n{qual(len(s) - 5, 5)}\n")
+        n, s = rs[5]
+        f.write(f"@{n}\n{s.lower()}\n+\n{qual(len(s), 6)}\n")
+        f.write("@tiny\nACGTACG\n+\nIIIIIII\n")
+        n, s = rs[6]
+        f.write(f"@{n}\n{s}\n+\n{qual(len(s), 7)}")
+    subprocess.check_call([REF + "/yaha", "-x", "ref.X11_01_65525S", "-q", "weird.fq", "-oss", "out_weird_fastq.sam", "-t", "1"], cwd=tmp,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    gz(tmp + "/out_weird_fastq.sam", OUT + "/out_weird_fastq.sam.gz")
+    gz(tmp + "/weird.fq", OUT + "/weird.fq.gz")
+    shutil.rmtree(tmp)
+
+
 def main():
+    if "--only-weird-fastq" in sys.argv:
+        only_weird_fastq()
+        return
     if "--only-index-variants" in sys.argv:
         only_index_variants()
         return

@@ -16,6 +16,8 @@ CASES = [
     ("out_weird.sam.gz", "weird.fa", "-osh", []),
     # reads glued from 2-6 loci whose pieces each have to be split: several splitting clumps per read (child fibers)
     ("out_chimera.sam.gz", "chimera.fa", "-osh", []),
+    # FASTQ reader corner cases: descriptions, CRLF, multi-line records, '@' inside quality, mismatched lengths, no final newline
+    ("out_weird_fastq.sam.gz", "weird.fq", "-oss", []),
 ]
 
 # One line per flag of the reference's alignment CLI (Main.c:187-470) that changes the result, plus combinations and
