@@ -312,7 +312,7 @@ def run_ours(args):
         "gcups_in_value_run": ext_gcups,
         "gcups_all_dp_kernels_in_value_run": gcups, "dp_cells_per_step": cells // max(args.steps, 1), "dp_jobs_per_step": tot("dp_jobs") // args.steps,
         "dp_calls_per_step": tot("dp_rounds") // args.steps,
-        "stage_ms_per_step": {"note": "value run; device_* are CUDA-event spans on each pipeline's stream (8 pipelines overlap on the device, so "
+        "stage_ms_per_step": {"note": f"value run; device_* are CUDA-event spans on each pipeline's stream ({pipes} pipelines overlap on the device, so "
                                       "the spans overlap and include queueing); wall_host_logic is worker-pool busy time per thread",
                               "device_seed": ms_seed / args.steps, "device_dp_fill": ms_dp / args.steps,
                               "device_traceback": ms_tb / args.steps,
@@ -339,7 +339,7 @@ def run_ours(args):
                      "in_value_run": {"launches_timed": int(ext_launches), "avg_launch_ms": ms_ext / max(ext_launches, 1),
                                       "cells_per_launch": ext_cells / max(ext_launches, 1), "gcups": ext_gcups,
                                       "achieved": achieved_giops, "frac": achieved_giops / int_add if int_add else None,
-                                      "note": "the throughput-tuned run feeds the device 2 500-read batches from 8 pipelines: ~4-5 K jobs per "
+                                      "note": f"the throughput-tuned run feeds the device {args.batch}-read batches from {pipes} pipelines: ~4-5 K jobs per "
                                               "launch, which is bound by one job's serial row chain (about 2 warps per scheduler), not by "
                                               "issue rate; the device is idle most of the step there, the host is the limiter"},
                      "gcups_roof": int_add / INT_OPS_PER_CELL_EXT},
