@@ -50,6 +50,7 @@ WORKLOAD_DESC = {
     "cfg2": "BASELINE configs[1]: synthetic 100 Mbp reference, 100K 100 bp reads at 5% error",
     "cfg1s": "BASELINE configs[0]: synthetic 10 Mbp reference, 10K 1000 bp reads at 2% error",
 }
+METRIC = "reads/s (whole alignment job: FASTA in -> SAM out, identical to reference)"
 INT_OPS_PER_CELL_EXT = 33      # algorithmic integer ops per extension cell
 
 
@@ -281,6 +282,10 @@ def run_ours(args):
     seed_gbs = seed_bytes / (ms_seed * 1e-3) / 1e9 if ms_seed > 0 else 0.0
     ms_lookup = tot("dev_ms_lookup")
     probes_per_s = tot("probes") / (ms_lookup * 1e-3) if ms_lookup > 0 else 0.0
+    k2_bytes = 20.0 * tot("hits") + 12.0 * tot("frags_all")
+    k2_gbs = k2_bytes / ((ms_seed - ms_lookup) * 1e-3) / 1e9 if ms_seed > ms_lookup else 0.0
+    iso_k2_ms = sum(s["dev_ms_seed"] - s["dev_ms_lookup"] for s in stats_c)
+    iso_k2_gbs = sum(20.0 * s["hits"] + 12.0 * s["frags_all"] for s in stats_c) / (iso_k2_ms * 1e-3) / 1e9 if iso_k2_ms > 0 else 0.0
     codes_bytes = sum(len(s) for _, s in reads) + 8 * (len(reads) + 1)
     h2d = int(codes_bytes + 16 * tot("dp_jobs") / args.steps + 40 * tot("dp_jobs") / args.steps)
     d2h = int(16 * tot("dp_jobs") / args.steps + 16 * 2 * n_reads)
@@ -295,7 +300,7 @@ def run_ours(args):
     t_ext, t_seed = traffic.get("dp_ext_packed_kernel"), traffic.get("seed_count_kernel")
 
     line = {
-        "metric": "reads/s (whole alignment job: FASTA in -> SAM out, identical to reference) and banded-SW GCUPS",
+        "metric": METRIC,
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": el_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -308,8 +313,8 @@ def run_ours(args):
                    "value_excludes": "FASTA parsing and SAM fwrite (reads replayed from host memory; the 10 MB/step H2D of "
                                      "read codes is still inside); e2e includes everything",
                    "setup_s": round(t_setup, 2)},
-        "gcups": iso_gcups, "gcups_kernel": "dp_ext_packed_kernel (banded X-drop extension, 92 % of all DP cells), whole-shard launches (run C)",
-        "gcups_in_value_run": ext_gcups,
+        "gcups": ext_gcups, "gcups_kernel": "dp_ext_packed_kernel (banded X-drop extension, 92 % of all DP cells), value run",
+        "gcups_isolated_run_c": iso_gcups,
         "gcups_all_dp_kernels_in_value_run": gcups, "dp_cells_per_step": cells // max(args.steps, 1), "dp_jobs_per_step": tot("dp_jobs") // args.steps,
         "dp_calls_per_step": tot("dp_rounds") // args.steps,
         "stage_ms_per_step": {"note": f"value run; device_* are CUDA-event spans on each pipeline's stream ({pipes} pipelines overlap on the device, so "
@@ -324,25 +329,39 @@ def run_ours(args):
                 "ms_per_untimed_step": [round(s["align_s"] * 1e3, 2) for s in stats_a[:extra_warm + args.warmup]]},
         "value_ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed],
         "gpu_launches": int(tot("launches")),
+        # frac is the figure of the run that produces `value` (the product's own launches); the same kernel timed alone on
+        # whole-shard launches (run C) is reported beside it as `isolated`
         "roofline": {"bound": "int32-issue", "kernel": "dp_ext_packed_kernel",
-                     "timed_region": "run C: the same 20 K-read job as one batch on one pipeline, DP rounds in lock step (every bulk "
-                                     "extension launch carries the workload's ~40 K jobs); CUDA events on the launching stream",
-                     "launches_timed": int(iso_n), "avg_launch_ms": iso_ms / max(iso_n, 1),
-                     "cells_per_launch": iso_cells / max(iso_n, 1),
-                     "achieved": iso_gcups * INT_OPS_PER_CELL_EXT, "peak": int_add, "unit": "GIOP/s",
-                     "frac": iso_gcups * INT_OPS_PER_CELL_EXT / int_add if int_add else None,
-                     "traffic": t_ext["dram_bytes"] / t_ext["cells"] * (iso_cells / max(iso_n, 1)) if t_ext else None,
+                     "timed_region": f"value run: bulk extension launches (>= 4096 jobs) of the {pipes} pipelines, CUDA events on the launching stream",
+                     "launches_timed": int(ext_launches), "avg_launch_ms": ms_ext / max(ext_launches, 1),
+                     "cells_per_launch": ext_cells / max(ext_launches, 1),
+                     "achieved": achieved_giops, "peak": int_add, "unit": "GIOP/s",
+                     "frac": achieved_giops / int_add if int_add else None,
+                     "traffic": t_ext["dram_bytes"] / t_ext["cells"] * (ext_cells / max(ext_launches, 1)) if t_ext else None,
                      "traffic_unit": "bytes per launch (dram__bytes_read+write of the ncu capture in profiles/ncu_traffic.json, per cell x cells_per_launch)",
-                     "algorithmic_bytes_per_launch": 1.0 * iso_cells / max(iso_n, 1),
-                     "peak_source": "ya_measure_int32_peak: dependent-free IADD/LOP3 stream on all SMs, measured live",
-                     "peak_dp_mix": int_mix, "ops_per_cell": INT_OPS_PER_CELL_EXT,
-                     "in_value_run": {"launches_timed": int(ext_launches), "avg_launch_ms": ms_ext / max(ext_launches, 1),
-                                      "cells_per_launch": ext_cells / max(ext_launches, 1), "gcups": ext_gcups,
-                                      "achieved": achieved_giops, "frac": achieved_giops / int_add if int_add else None,
-                                      "note": f"the throughput-tuned run feeds the device {args.batch}-read batches from {pipes} pipelines: ~4-5 K jobs per "
-                                              "launch, which is bound by one job's serial row chain (about 2 warps per scheduler), not by "
-                                              "issue rate; the device is idle most of the step there, the host is the limiter"},
-                     "gcups_roof": int_add / INT_OPS_PER_CELL_EXT},
+                     "algorithmic_bytes_per_launch": 1.0 * ext_cells / max(ext_launches, 1),
+                     "peak_source": "ya_measure_int32_peak: dependent-free IADD/LOP3 stream on all SMs, measured live (not in MEASURED_PEAKS.json, "
+                                    "which holds HBM and bf16 figures only)",
+                     "peak_dp_mix": int_mix, "ops_per_cell": INT_OPS_PER_CELL_EXT, "gcups": ext_gcups,
+                     "gcups_roof": int_add / INT_OPS_PER_CELL_EXT,
+                     "hardware_utilisation_ncu": {"alu_pipe_pct": (t_ext or {}).get("alu_pipe_pct"), "issue_active_pct": (t_ext or {}).get("issue_active_pct"),
+                                                  "thread_instructions_per_cell": (t_ext or {}).get("thread_inst_per_cell"),
+                                                  "note": "frac divides ALGORITHMIC ops (33/cell, SURVEY 8d) by an instruction rate; DPX fuses 2-3 of them "
+                                                          "per instruction, so the hardware figure is the ncu pipe utilisation of the committed capture"},
+                     "isolated": {"timed_region": "run C: the same job as one batch on one pipeline, DP rounds in lock step (every bulk extension "
+                                                  "launch carries the workload's whole first round)",
+                                  "launches_timed": int(iso_n), "avg_launch_ms": iso_ms / max(iso_n, 1),
+                                  "cells_per_launch": iso_cells / max(iso_n, 1), "gcups": iso_gcups,
+                                  "achieved": iso_gcups * INT_OPS_PER_CELL_EXT,
+                                  "frac": iso_gcups * INT_OPS_PER_CELL_EXT / int_add if int_add else None}},
+        "roofline_k2": {"bound": "hbm", "kernel": "hits -> fragments -> regions (expand_hits, segmented sort, fragment / region / survivor scans)",
+                        "timed_region": "value run: CUDA-event span of ya_seed_frags minus the seed_count_kernel span",
+                        "algorithmic_bytes": "4 B/hit ROA read + 16 B/hit (key written and read once) + 12 B/fragment (SURVEY 8d)",
+                        "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k2_gbs / hbm_peak if hbm_peak else None,
+                        "hits_per_step": tot("hits") / args.steps, "frags_per_step": tot("frags_all") / args.steps,
+                        "ms_per_step": (ms_seed - ms_lookup) / args.steps, "peak_source": hbm_src,
+                        "isolated": {"timed_region": "run C", "achieved": iso_k2_gbs, "frac": iso_k2_gbs / hbm_peak if hbm_peak else None,
+                                     "ms_per_step": iso_k2_ms / max(len(stats_c), 1)}},
         "roofline_seed": {"bound": "hbm", "kernel": "seed_count_kernel (k-mer -> starting-offset gather, Query.c:391)",
                           "timed_region": "run C (see roofline.timed_region)",
                           "achieved": 8.0 * iso_pps / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -360,7 +379,7 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl, d, idx_path, reads, min(n_reads, args.cpu_sample), out_path)
+            line["cpu_baseline"] = cpu_baseline(wl, d, idx_path, reads, min(n_reads, args.cpu_sample), out_path, min(n_reads, args.t1_sample))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -406,7 +425,7 @@ def reference_rate(wl, d, idx, reads, ncores, tag):
     return t_full, t_load, out
 
 
-def cpu_baseline(wl, d, idx, reads, sample, my_sam):
+def cpu_baseline(wl, d, idx, reads, sample, my_sam, t1_sample=0):
     ncores = os.cpu_count() or 1
     yaha = os.path.join(ROOT, "oracle", "_ref", "yaha")
     if not os.path.exists(yaha):
@@ -417,11 +436,26 @@ def cpu_baseline(wl, d, idx, reads, sample, my_sam):
            "whole_program_reads_per_s": len(sub) / t_full, "index_load_s": round(t_load, 3),
            "sample": f"{len(sub)} reads of the workload, unmodified yaha -t {ncores}; value = reads / (wall - wall of a 1-read run); "
                      f"whole-program wall {t_full:.2f} s"}
-    if sample == len(reads):
-        a = sorted(l for l in open(ref_sam) if not l.startswith("@PG"))
-        b = sorted(l for l in open(my_sam) if not l.startswith("@PG"))
-        res["sam_identical_to_reference"] = (a == b)
-        res["sam_records"] = len(a)
+    # SAM identity on every run: the reference's records for the sampled reads against the product's records for the
+    # same reads (multiset: `yaha -t N` emits reads in completion order), and once in order against `yaha -t 1`
+    names = {n for n, _ in sub}
+    mine = [l for l in open(my_sam) if not l.startswith("@PG")]           # (@PG echoes file names and -t, AlignOutput.c:50-60)
+    if len(sub) != len(reads):
+        mine = [l for l in mine if l.startswith("@") or l.split("\t", 1)[0] in names]
+    a = sorted(l for l in open(ref_sam) if not l.startswith("@PG"))
+    res["sam_identical_to_reference"] = (a == sorted(mine))
+    res["sam_records"] = len(a)
+    if t1_sample > 0:
+        q1 = os.path.join(d, "cpu_t1.fa")
+        from yaha_b200 import synth
+        synth.write_reads(q1, reads[:t1_sample])
+        out1 = os.path.join(d, "cpu_t1.sam")
+        time_reference(wl, d, idx, q1, 1, out1)
+        want = [l for l in open(out1) if not l.startswith("@PG")]
+        n1 = {n for n, _ in reads[:t1_sample]}
+        got = [l for l in mine if l.startswith("@") or l.split("\t", 1)[0] in n1] if t1_sample != len(reads) else mine
+        res["sam_identical_in_order_to_t1"] = (want == got)
+        res["sam_records_t1"] = len(want)
     return res
 
 
@@ -448,7 +482,7 @@ def run_reference(args):
             load = t_load
     tot = sum(times)
     v = len(sample) * len(times) / tot
-    line = {"impl": "reference", "metric": "reads/s (whole alignment job: FASTA in -> SAM out)", "value": v, "unit": "reads/s",
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "reads/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / len(times) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[wl], "flags": REF_FLAGS[wl], "threads": ncores,
@@ -467,7 +501,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=20000)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="reads of the workload the reference arm / cpu_baseline aligns (default: all)")
+    ap.add_argument("--t1-sample", type=int, default=20000, help="reads aligned once with `yaha -t 1` for the in-order SAM comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=2500, help="reads per device batch")
     ap.add_argument("--pipes", type=int, default=8, help="concurrent batch pipelines per GPU")

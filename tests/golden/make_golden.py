@@ -155,7 +155,36 @@ def only_weird_fastq():
     shutil.rmtree(tmp)
 
 
+def only_weird_headers():
+    """Adds weird2.fa.gz / out_weird2.sam.gz: FASTA id lines that contain the record markers themselves ('>' '+' '@'
+    inside or at the start of the description).  The reference reads an id line to its newline whatever it holds
+    (Query.c:111-135); only sequence lines end at the next '>' (Query.c:137-158)."""
+    tmp = tempfile.mkdtemp()
+    for name in ("ref.fa", "reads.fa"):
+        with gzip.open(f"{OUT}/{name}.gz", "rb") as f, open(f"{tmp}/{name}", "wb") as o:
+            o.write(f.read())
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = open(tmp + "/reads.fa").read().split(">")[10:17]
+    rs = [(l.split("\n", 1)[0], l.split("\n", 1)[1].replace("\n", "")) for l in lines]
+    with open(tmp + "/weird2.fa", "w") as f:
+        f.write(f">{rs[0][0]}\n{rs[0][1]}\n")
+        f.write(f">{rs[1][0]} desc>foo\n{rs[1][1]}\n")
+        f.write(f">>{rs[2][0]}\n{rs[2][1][:120]}\n{rs[2][1][120:]}\n")
+        f.write(f">{rs[3][0]}+plus @at >\n{rs[3][1]}\n")
+        f.write(f">{rs[4][0]}>\r\n{rs[4][1]}\r\n")
+        f.write(f">{rs[5][0]}\n{rs[5][1]}\n")
+        f.write(f">{rs[6][0]} last>one\n{rs[6][1]}")
+    subprocess.check_call([REF + "/yaha", "-x", "ref.X11_01_65525S", "-q", "weird2.fa", "-osh", "out_weird2.sam", "-t", "1"], cwd=tmp,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    gz(tmp + "/out_weird2.sam", OUT + "/out_weird2.sam.gz")
+    gz(tmp + "/weird2.fa", OUT + "/weird2.fa.gz")
+    shutil.rmtree(tmp)
+
+
 def main():
+    if "--only-weird-headers" in sys.argv:
+        only_weird_headers()
+        return
     if "--only-weird-fastq" in sys.argv:
         only_weird_fastq()
         return

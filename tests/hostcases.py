@@ -18,6 +18,8 @@ CASES = [
     ("out_chimera.sam.gz", "chimera.fa", "-osh", []),
     # FASTQ reader corner cases: descriptions, CRLF, multi-line records, '@' inside quality, mismatched lengths, no final newline
     ("out_weird_fastq.sam.gz", "weird.fq", "-oss", []),
+    # FASTA id lines holding the record markers themselves ('>' '+' '@'): an id line ends at its newline only
+    ("out_weird2.sam.gz", "weird2.fa", "-osh", []),
 ]
 
 # One line per flag of the reference's alignment CLI (Main.c:187-470) that changes the result, plus combinations and

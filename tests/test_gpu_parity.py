@@ -195,6 +195,45 @@ def test_random_jobs_against_oracle(small, aligner):
             assert _res_tuple(res, ops, i) == w, (tuple(j), (bw, gap, goc, gec, rc, ms, x))
 
 
+def test_packed_kernel_score_range_guard(small):
+    """dp_ext_packed_kernel keeps scores x256 in int32 under a -2^29 sentinel; ya_sw_batch must route a job whose
+    (rows + W + 2) * largest step cost reaches 2^20 to dp_wave_kernel (plain int32 like SW.cpp).  Long extensions with
+    costs at the top of what the reference's own arithmetic allows (GOC + GEC <= 256, SW.cpp:356) against the oracle;
+    jobs below the bound in the same batch stay on the packed kernel."""
+    b = small.nib.bases
+    n = 9000
+    packed = np.asarray(b[500:500 + n // 2 + 1])
+    codes = np.empty(2 * len(packed), np.uint8)
+    codes[0::2] = packed >> 4; codes[1::2] = packed & 15
+    exact = np.ascontiguousarray(codes[:n])                         # reference bases 1000 .. 1000 + n
+    rng = np.random.default_rng(5)
+    noisy = exact.copy()
+    hit = rng.random(n) < 0.03
+    noisy[hit] = (noisy[hit] + rng.integers(1, 4, size=int(hit.sum()))) % 4
+    reads = [exact, noisy, small.fwd[0]]
+    for (bw, gap, goc, gec, rc, ms, x) in [(5, 50, 200, 50, 250, 30, 600), (10, 100, 150, 100, 255, 100, 2000), (5, 50, 5, 2, 3, 1, 25)]:
+        P = yaha_b200.Params.defaults(word_len=11, bw=bw, max_gap=gap, goc=goc, gec=gec, rc=rc, ms=ms, x=x)
+        al = yaha_b200.Aligner(small.nib, small.idx, P, device=0)
+        al.upload_read_list(reads)
+        p = S.default_params(word_len=11, bw=bw, max_gap=gap, goc=goc, gec=gec, rc=rc, ms=ms, x=x)
+        jobs = []
+        for r in (0, 1):
+            for q0 in (0, 17, 4000, 8000):
+                jobs.append((1000 + q0, r, 0, q0, n - q0, yaha_b200.DP_EXT_FWD, 0))
+                jobs.append((1000 + n - 1 - q0, r, 0, n - 1 - q0, n - q0, yaha_b200.DP_EXT_BWD, 0))
+            jobs.append((1000 + 8900, r, 0, 8900, 100, yaha_b200.DP_EXT_FWD, 0))      # short: below the bound
+        jobs = np.array(jobs, dtype=yaha_b200.JOB_DT)
+        res, ops = al.sw_batch(jobs)
+        long_rows = 0
+        for i, j in enumerate(jobs):
+            w = S.oracle_dp(p, small.nib.bases, small.nib.max_roff, reads[int(j["read"])], int(j["kind"]), int(j["rOff"]),
+                            int(j["rLen"]), int(j["qOff"]), int(j["qLen"]))[:4]
+            assert _res_tuple(res, ops, i) == w, (tuple(j), (bw, gap, goc, gec, rc, ms, x))
+            long_rows = max(long_rows, int(res[i]["addedQLen"]))
+        assert long_rows > 4000                                    # the exact copies really run thousands of rows
+        al.close()
+
+
 def test_empty_and_degenerate_inputs(small):
     al = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11), device=0)
     # empty batch

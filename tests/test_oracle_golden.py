@@ -83,3 +83,53 @@ def test_singleton_clumps_match_reference(small):
             assert w in got_single, (qid, st, w)
         seen += len(want)
     assert seen >= 3
+
+
+@pytest.mark.parametrize("bw,gap", [(5, 50)])
+def test_multi_fragment_clumps_match_reference(small, bw, gap):
+    """Row N1 pinned independently of the SAM: the CPU build of csrc/form_clumps.h (orc_form_clumps -- the source the
+    device kernel and the host program compile) must reproduce EVERY clump the unmodified reference formed on the
+    golden reads, multi-fragment ones included: same clumps in the same creation order, same fragments after the
+    overlap chops of insertFragment and cleanUpClump (QueryMatch.c:224-303, GraphPath.cpp:161-292,
+    AlignHelpers.c:48-193).  The C records of the dump list the read's clump list (head first, LIFO:
+    QueryState.c:156-161) after each strand's processFragmentsGapped."""
+    p = _params(small, bw, gap)
+    lib = S.oracle()
+    n_multi = n_clumps = 0
+    before = {}
+    cur = None
+    for rec in S.parse_dump(small.dump(bw), "GC"):
+        if rec[0] == "G":
+            cur = rec
+            continue
+        _, qid, st, clumps = rec
+        assert cur[1] == qid and cur[2] == st
+        fr = cur[3]
+        n_before = before.get(qid, 0) if st == 1 else 0
+        new = clumps[:len(clumps) - n_before][::-1]                   # creation order
+        before[qid] = len(clumps)
+        frags = np.zeros(len(fr), dtype=S.FRAG_DT)
+        for i, (sro, sqo, eqo, rl) in enumerate(fr):
+            frags[i] = (sro, sqo, eqo, 0, rl)
+        got = []
+        if len(fr):
+            region = np.zeros(len(fr), dtype=np.uint32)
+            keep = np.zeros(len(fr), dtype=np.uint8)
+            lib.orc_regions(p, S.ptr(frags), len(fr), S.ptr(region), S.ptr(keep))
+            sel = keep.astype(bool)
+            sf, sr = np.ascontiguousarray(frags[sel]), np.ascontiguousarray(region[sel])
+            n = len(sf)
+            if n:
+                L = len(small.codes(qid, st))
+                opath = np.zeros(n, dtype=S.FRAG_DT)
+                ocl = np.zeros(n, dtype=np.dtype([("first", "<u4"), ("n", "<u2"), ("matchedBases", "<u2")]))
+                nc = lib.orc_form_clumps(p.wordLen, gap, 50, 25, 25, bw, 5, 2, 1, S.ptr(sf), S.ptr(sr), n, L, S.ptr(opath), S.ptr(ocl))
+                for k in range(nc):
+                    a = opath[int(ocl[k]["first"]):int(ocl[k]["first"]) + int(ocl[k]["n"])]
+                    got.append([(int(f["startRefOff"]), int(f["startQueryOff"]), int(f["endQueryOff"]), int(f["refLen"])) for f in a])
+        want = [list(c[1]) for c in new]
+        assert all(c[0] == st for c in new)
+        assert got == want, (qid, st, got, want)
+        n_clumps += len(want)
+        n_multi += sum(1 for w in want if len(w) > 1)
+    assert n_multi > 500 and n_clumps > n_multi

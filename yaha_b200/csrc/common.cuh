@@ -133,6 +133,7 @@ struct ya_ctx {
               d_keep, d_keepidx, d_frags_out, d_region_out, d_strand_out, d_misc;
     DevBuf    d_fc_count, d_fc_work, d_fc_tmp, d_fc_path, d_fc_nodes, d_fc_used, d_fc_clumps;   // ya_form_clumps
     DevBuf    d_pc_path, d_pc_gaps, d_pc_prep, d_pc_jobs;                                       // ya_prepare_clumps
+    bool      big_sort_attr = false;    // seg_sort_kernel<8192,256> has its 64 KB shared-memory opt-in on this context's device
     bool      fc_valid = false;         // the clumps of the last ya_form_clumps call are on the device
     int       seed_chunks = 0;          // chunks of the last ya_seed_frags call (its survivors stay on the device when 1)
     size_t    seed_nkeep = 0;           // survivors of that call

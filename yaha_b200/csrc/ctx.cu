@@ -324,6 +324,8 @@ extern "C" int ya_reads_upload(ya_ctx *c, const ya_read_batch *b)
             return ya_fail(c, YA_E_ARG, "read length must be in 0..32767 (16-bit query offsets, Math.h:104)");
     }
     uint64_t total = c->h_read_off[b->n_reads];
+    // query codes are addressed with 32-bit indices downstream (DevJob.qIdx, the probe offsets of ya_seed_frags)
+    if (total >= 0xFFFF0000ull) { c->n_reads = 0; return ya_fail(c, YA_E_ARG, "at most 2^32 - 65536 bases per batch (32-bit code offsets): split the batch"); }
     c->total_bases = total;
     YA_CUDA(c, c->d_codes_fwd.reserve(total + 64));
     YA_CUDA(c, c->d_codes_rev.reserve(total + 64));

@@ -514,8 +514,11 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
                     c->ctr.launches++;
                 }
                 if (!big.empty()) {
-                    static bool attr = false;
-                    if (!attr) { cudaFuncSetAttribute(seg_sort_kernel<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8); attr = true; }
+                    // (the opt-in to 64 KB of dynamic shared memory is per device: made once per context, which is bound to one)
+                    if (!c->big_sort_attr) {
+                        YA_CUDA(c, cudaFuncSetAttribute(seg_sort_kernel<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+                        c->big_sort_attr = true;
+                    }
                     YA_CUDA(c, cudaMemcpyAsync(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice, st));
                     seg_sort_kernel<8192, 256><<<(unsigned)big.size(), 256, 8192 * 8, st>>>(ka, d_sko, d_big, (int)big.size());
                     c->ctr.launches++;

@@ -855,6 +855,8 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     const bool forceThread = force_thread_kernel();
     static const int fullThreadMaxW = [] { const char *e = getenv("YA_FULL_THREAD_MAXW"); return e ? atoi(e) : 0; }();   // full-matrix jobs up to this band width stay one thread per job
     const bool allowPacked = !forbid_packed_kernel();
+    const int64_t packedStepCost = std::max<int64_t>(std::max<int64_t>(std::abs(P.MScore), std::abs(P.RCost)),
+                                                     (int64_t)std::abs(P.GOCost) + std::abs(P.GECost));
 
     YA_CUDA(c, c->h_jobs.reserve((size_t)n * sizeof(DevJob)));
     DevJob *hj = c->h_jobs.as<DevJob>();
@@ -908,7 +910,11 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         d.qIdx = (uint32_t)(rbase + j.qOff);
         const int W = d.lb + d.rb + 1;
         int cls = -1, pcls = -1;
-        if (allowPacked && j.kind >= YA_DP_EXT_FWD && W <= P.maxGap && W <= P.maxIntron)
+        // The packed kernel keeps scores x256 in int32 below a sentinel of -2^29: a job is eligible only while every real
+        // score (|V| <= (rows + W + 2) * largest per-step cost) and the drift of the sentinel chains (one cost per row)
+        // stay below 2^28 / 256 = 2^20; anything larger runs on dp_wave_kernel, which computes in plain int32 like SW.cpp.
+        if (allowPacked && j.kind >= YA_DP_EXT_FWD && W <= P.maxGap && W <= P.maxIntron &&
+            (int64_t)(qLen + W + 2) * packedStepCost < ((int64_t)1 << 20))
             for (int k = 0; k < kNumPackedCfgs; k++) if (kPackedCfgs[k].W == W) pcls = k;
         if (pcls >= 0) {
             const int G = narrowExt ? (pcls == 0 ? 4 : 7) : kPackedCfgs[pcls].G;
@@ -1174,10 +1180,28 @@ extern "C" int ya_perfect_ext(ya_ctx *c, const ya_dp_job *jobs, int n, uint16_t 
 {
     if (!c || n < 0 || (n && (!jobs || !count))) return YA_E_ARG;
     if (n == 0) return YA_OK;
+    if (c->n_reads == 0) return ya_fail(c, YA_E_STATE, "ya_perfect_ext: no read batch uploaded");
     YA_CUDA(c, cudaSetDevice(c->device));
+    // the walk must stay inside the read and inside the reference: clamp its length here, as the callers of
+    // extendFragment*ToStopPerfectly do with min(query room, reference room) (AlignExtFrag.cpp:76-100)
+    YA_CUDA(c, c->h_jobs.reserve((size_t)n * sizeof(ya_dp_job)));
+    ya_dp_job *hj = c->h_jobs.as<ya_dp_job>();
+    for (int i = 0; i < n; i++) {
+        ya_dp_job j = jobs[i];
+        if (j.read >= (uint32_t)c->n_reads || j.strand > 1 || (j.kind != YA_DP_EXT_FWD && j.kind != YA_DP_EXT_BWD))
+            return ya_fail(c, YA_E_ARG, "ya_perfect_ext: bad job");
+        const int L = (int)(c->h_read_off[j.read + 1] - c->h_read_off[j.read]);
+        if ((int)j.qOff >= L || j.rOff > c->maxROff) return ya_fail(c, YA_E_ARG, "ya_perfect_ext: job starts outside the read or the reference");
+        uint32_t room;
+        if (j.kind == YA_DP_EXT_BWD) room = std::min<uint32_t>((uint32_t)j.qOff + 1u, j.rOff + 1u);
+        else room = std::min<uint32_t>((uint32_t)(L - (int)j.qOff), c->maxROff - j.rOff + 1u);
+        if ((uint32_t)j.qLen > room) j.qLen = (uint16_t)room;
+        hj[i] = j;
+    }
+    AllocScope allocScope(c->stream);
     YA_CUDA(c, c->d_jobs.reserve((size_t)n * sizeof(ya_dp_job)));
     YA_CUDA(c, c->d_res.reserve((size_t)n * 2 + 64));
-    YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, jobs, (size_t)n * sizeof(ya_dp_job), cudaMemcpyHostToDevice, c->stream));
+    YA_CUDA(c, cudaMemcpyAsync(c->d_jobs.p, hj, (size_t)n * sizeof(ya_dp_job), cudaMemcpyHostToDevice, c->stream));
     perfect_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d_jobs.as<ya_dp_job>(), c->d_read_off.as<uint64_t>(), n,
         c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), c->d_res.as<uint16_t>());
     c->ctr.launches++;

@@ -28,6 +28,7 @@ static_assert(sizeof(Op) == sizeof(ya_op) && offsetof(Op, len) == offsetof(ya_op
               "assemble_clumps.h writes ya_op runs straight into a clump's op array");
 
 uint64_t gAlignProf[4];
+uint64_t gVerdictProf[8];
 static const bool kAlignProf = getenv("YAHA_B200_PROF") != nullptr;
 static inline uint64_t rdtsc_() { unsigned lo, hi; __asm__ volatile("rdtsc" : "=a"(lo), "=d"(hi)); return ((uint64_t)hi << 32) | lo; }
 
@@ -590,6 +591,13 @@ void postProcessClumps(const Env &E, ReadCtx &rc)                       // Query
         if (c->is(kScored)) rc.clumps.push_back(c);
         else delete c;
     };
+    if (kAlignProf) {
+        int ns = 0, nk = 0, nd = 0;
+        for (size_t k = 0; k < old.size(); k++) { const int v = verdict(k); ns += v == YA_ASM_SCORED; nk += v == YA_ASM_SPLIT; nd += v == YA_ASM_DROP; }
+        extern uint64_t gVerdictProf[8];
+        gVerdictProf[0]++; gVerdictProf[1] += old.size() == 0; gVerdictProf[2] += (nk == 0 && old.size() > 0); gVerdictProf[3] += (nk == 0 && ns <= 1);
+        gVerdictProf[4] += ns; gVerdictProf[5] += nk; gVerdictProf[6] += nd; gVerdictProf[7] += (nk == 0 && ns == 1);
+    }
     int nSplit = 0;
     if (old.size() >= 2) for (size_t k = 0; k < old.size(); k++) nSplit += verdict(k) < 0 ? willSplit(*E.A, old[k]) : verdict(k) == YA_ASM_SPLIT;
     if (nSplit >= 2) {

@@ -259,12 +259,15 @@ bool RecordSlicer::next(const char *&s, size_t &n)
     if (done) return false;
     if (pos > len) { done = true; return false; }
     s = base + pos;
-    const char *bk = (const char *)memchr(s, '>', len - pos);
+    // the id line runs to its newline whatever it contains (Query.c:111-135); only the sequence lines
+    // behind it end at the next marker (Query.c:137-158)
+    const char *nl = (const char *)memchr(s, '\n', len - pos);
+    const size_t idEnd = nl ? (size_t)(nl - s) + 1 : len - pos;
+    const char *bk = (const char *)memchr(s + idEnd, '>', len - pos - idEnd);
     n = bk ? (size_t)(bk - s) : len - pos;
     pos += n + 1;
     // a record without sequence characters ends the input (Query.c:222): id line, then nothing but newlines
-    const char *nl = (const char *)memchr(s, '\n', n);
-    size_t q = nl ? (size_t)(nl - s) + 1 : n;
+    size_t q = idEnd;
     while (q < n && s[q] == '\n') q++;
     if (q >= n) { done = true; return false; }
     return true;

@@ -159,9 +159,13 @@ struct StackPool {
     void *get()
     {
         { std::lock_guard<std::mutex> g(mu); if (!free_.empty()) { void *p = free_.back(); free_.pop_back(); return p; } }
-        void *p = mmap(nullptr, kStackBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-        if (p == MAP_FAILED) { fprintf(stderr, "cannot allocate fiber stack\n"); exit(1); }
-        return p;
+        // one guard page below the stack: recursion that outgrows it (splitHelper, the OQC quickSort on repeat-rich
+        // 32 kb reads) faults instead of silently writing into the neighbouring mapping
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        char *m = (char *)mmap(nullptr, kStackBytes + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (m == MAP_FAILED) { fprintf(stderr, "cannot allocate fiber stack\n"); exit(1); }
+        mprotect(m, page, PROT_NONE);
+        return m + page;
     }
     void put(void *p) { std::lock_guard<std::mutex> g(mu); free_.push_back(p); }
 };
@@ -891,6 +895,10 @@ int runQueries(const Args &A0)
     extern uint64_t gAlignProf[4];
     if (getenv("YAHA_B200_PROF")) fprintf(stderr, "prof align Mcycles: prepare %.1f collapse+ext %.1f apply %.1f score(incl parked) %.1f\n",
                                           gAlignProf[0] / 1e6, gAlignProf[1] / 1e6, gAlignProf[2] / 1e6, gAlignProf[3] / 1e6);
+    extern uint64_t gVerdictProf[8];
+    if (getenv("YAHA_B200_PROF")) fprintf(stderr, "prof verdicts: reads %llu noclumps %llu nosplit %llu nosplit&<=1scored %llu | clumps scored %llu split %llu drop %llu | reads nosplit&1scored %llu\n",
+        (unsigned long long)gVerdictProf[0], (unsigned long long)gVerdictProf[1], (unsigned long long)gVerdictProf[2], (unsigned long long)gVerdictProf[3],
+        (unsigned long long)gVerdictProf[4], (unsigned long long)gVerdictProf[5], (unsigned long long)gVerdictProf[6], (unsigned long long)gVerdictProf[7]);
     if (getenv("YAHA_B200_PROF"))
         fprintf(stderr, "prof Mcycles: formClumps %.1f postProcess(incl. parked time) %.1f oqc %.1f format %.1f free %.1f\n", gProf[0] / 1e6,
                 gProf[1] / 1e6, gProf[2] / 1e6, gProf[3] / 1e6, gProf[4] / 1e6);
