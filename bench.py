@@ -38,52 +38,105 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+HUMAN_BASES = int(float(os.environ.get("YAHA_BENCH_GBP", "3.1")) * 1e9)     # cfg4 / cfg5 reference size (scaled down on small boxes)
 WORKLOADS = {
-    # name: (ref_bases, n_reads, read_len, err, flags)
-    "cfg3": (100_000_000, 20_000, 500, 0.10, dict(bw=10, max_gap=100)),
-    "cfg2": (100_000_000, 100_000, 100, 0.05, dict()),
-    "cfg1s": (10_000_000, 10_000, 1000, 0.02, dict()),
+    # ref: "iid" = uniform ACGT, one sequence; "human" = 24 unequal sequences with an Alu-like repeat family and runs of N
+    # reads: "sim" = uniform loci, per-base errors; "sv" = reads spanning implanted deletions / inversions / insertions
+    # index_h: -H of the index build (650: over-full k-mers are down-sampled, Index.c:271-315)
+    "cfg1": dict(ref="iid", ref_bases=10_000_000, reads="sim", n_reads=10_000, read_len=1000, err=0.02, flags=[], index_h=65525,
+                 desc="BASELINE configs[0]: synthetic 10 Mbp reference, 10K 1000 bp reads at 2% error"),
+    "cfg2": dict(ref="iid", ref_bases=100_000_000, reads="sim", n_reads=100_000, read_len=100, err=0.05, flags=[], index_h=65525,
+                 desc="BASELINE configs[1]: synthetic 100 Mbp reference, 100K 100 bp reads at 5% error"),
+    "cfg3": dict(ref="iid", ref_bases=100_000_000, reads="sim", n_reads=20_000, read_len=500, err=0.10, flags=["-BW", "10", "-G", "100"],
+                 index_h=65525, desc="BASELINE configs[2]: synthetic 100 Mbp reference, 20K 500 bp reads at 10% error, -BW 10 -G 100"),
+    "cfg4": dict(ref="human", ref_bases=HUMAN_BASES, reads="sv", n_reads=1_000, read_len=10_000, err=0.0, flags=["-OQC", "Y", "-FBS", "Y"],
+                 index_h=650, desc=f"BASELINE configs[3]: synthetic {HUMAN_BASES / 1e9:.2f} Gbp reference in 24 sequences with an Alu-like family "
+                                   "(one copy per 25 kbp) and N runs, index -H 650 (down-sampled), 1K 10 kbp reads spanning implanted "
+                                   "deletions / inversions / insertions / translocated pieces at 2-5% error, -OQC Y -FBS Y"),
+    "cfg5": dict(ref="human", ref_bases=HUMAN_BASES, reads="sim", n_reads=int(os.environ.get("YAHA_BENCH_CFG5_READS", "200000")), read_len=1000, err=0.05,
+                 flags=["-H", "650", "-MD", "50"], index_h=650,
+                 desc=f"BASELINE configs[4]: same {HUMAN_BASES / 1e9:.2f} Gbp reference, 1000 bp reads at 5% error, -H 650 -MD 50; a step is a bounded "
+                      "sample of the 10M-read set"),
 }
-REF_FLAGS = {"cfg3": ["-BW", "10", "-G", "100"], "cfg2": [], "cfg1s": []}
-WORKLOAD_DESC = {
-    "cfg3": "BASELINE configs[2]: synthetic 100 Mbp reference, 20K 500 bp reads at 10% error, -BW 10 -G 100",
-    "cfg2": "BASELINE configs[1]: synthetic 100 Mbp reference, 100K 100 bp reads at 5% error",
-    "cfg1s": "BASELINE configs[0]: synthetic 10 Mbp reference, 10K 1000 bp reads at 2% error",
-}
+WORKLOADS["cfg1s"] = WORKLOADS["cfg1"]
+REF_FLAGS = {k: v["flags"] for k, v in WORKLOADS.items()}
+WORKLOAD_DESC = {k: v["desc"] for k, v in WORKLOADS.items()}
 METRIC = "reads/s (whole alignment job: FASTA in -> SAM out, identical to reference)"
 INT_OPS_PER_CELL_EXT = 33      # algorithmic integer ops per extension cell
 
 
 def cache_dir(workload: str) -> str:
-    d = os.path.join(os.environ.get("YAHA_BENCH_CACHE", tempfile.gettempdir()), f"yaha_b200_bench_{workload}")
+    w = WORKLOADS[workload]
+    tag = "human%d" % (w["ref_bases"] // 1_000_000) if w["ref"] == "human" else "iid%d" % (w["ref_bases"] // 1_000_000)
+    d = os.path.join(os.environ.get("YAHA_BENCH_CACHE", tempfile.gettempdir()), f"yaha_b200_bench_{tag}")
     os.makedirs(d, exist_ok=True)
     return d
 
 
-def make_reference(workload: str):
-    """Reference FASTA + .nib2 on disk (cached); returns (dir, Nib2)."""
+_REF_CACHE = {}
+
+
+def reference_bases(workload: str):
+    """The workload's reference as (one uint8 character array, sequence bounds); deterministic (the last one made is kept)."""
+    from yaha_b200 import synth
+    w = WORKLOADS[workload]
+    key = (w["ref"], w["ref_bases"])
+    if key not in _REF_CACHE:
+        _REF_CACHE.clear()
+        if w["ref"] == "human":
+            _REF_CACHE[key] = synth.human_like_reference(w["ref_bases"], 24, 2024)
+        else:
+            ref = synth.random_reference(w["ref_bases"], 12345)
+            _REF_CACHE[key] = (ref, np.array([0, len(ref)], dtype=np.int64))
+    return _REF_CACHE[key]
+
+
+def make_reference(workload: str, with_fasta: bool = True):
+    """Reference .nib2 (and FASTA, for `yaha -g`) on disk (cached); returns (dir, Nib2)."""
     from yaha_b200 import refio, synth
-    nb = WORKLOADS[workload][0]
     d = cache_dir(workload)
     fa, nib = os.path.join(d, "ref.fa"), os.path.join(d, "ref.nib2")
     if not os.path.exists(nib):
-        ref = synth.random_reference(nb, 12345)
-        synth.write_fasta(fa + ".tmp", [("chr1", ref)])
-        os.replace(fa + ".tmp", fa)
-        img = refio.build_nib2([("chr1", ref)])
+        ref, bounds = reference_bases(workload)
+        seqs = [(f"chr{k + 1}", ref[bounds[k]:bounds[k + 1]]) for k in range(len(bounds) - 1)]
+        if with_fasta and len(ref) <= 500_000_000:                 # (human scale: the index is built on the device, no FASTA needed)
+            synth.write_fasta(fa + ".tmp", seqs)
+            os.replace(fa + ".tmp", fa)
+        img = refio.build_nib2(seqs)
         with open(nib + ".tmp", "wb") as f:
             f.write(img)
         os.replace(nib + ".tmp", nib)
     return d, refio.load_nib2(nib)
 
 
+def index_path_of(workload: str, d: str) -> str:
+    from yaha_b200 import refio
+    return os.path.join(d, refio.index_file_name("ref", 15, 1, WORKLOADS[workload]["index_h"]))
+
+
+def ensure_device_built_index(workload: str, d: str, nib, device: int) -> str:
+    """Index file in the reference's format, built ON THE DEVICE (ya_open_build: bit-identical to `yaha -g -L 15 -S 1 -H <h>`,
+    tests/test_gpu_parity.py, tests/test_gpu_configs.py), written once per cache directory."""
+    import yaha_b200
+    from yaha_b200 import refio
+    path = index_path_of(workload, d)
+    if not os.path.exists(path):
+        h = WORKLOADS[workload]["index_h"]
+        al = yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=15, max_hits=min(650, h)), device=device, build_max_hits=h)
+        refio.write_index(path + ".tmp", al.download_index(max_hits=h))
+        os.replace(path + ".tmp", path)
+        al.close()
+    return path
+
+
 def make_reads(workload: str, rank: int):
-    """(names, list of char arrays) for this rank's shard; deterministic per rank."""
+    """(name, char array) reads of this rank's shard; deterministic per rank."""
     from yaha_b200 import synth
-    nb, n_reads, rl, err, _ = WORKLOADS[workload]
-    ref = synth.random_reference(nb, 12345)
-    reads = list(synth.simulate_reads(ref, n_reads, rl, err, 777 + 1000 * rank))
-    return reads
+    w = WORKLOADS[workload]
+    ref, _ = reference_bases(workload)
+    if w["reads"] == "sv":
+        return list(synth.sv_reads(ref, w["n_reads"], w["read_len"], 4242 + 1000 * rank))
+    return list(synth.simulate_reads(ref, w["n_reads"], w["read_len"], w["err"], 777 + 1000 * rank))
 
 
 class ClockSampler(threading.Thread):
@@ -185,22 +238,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl = args.workload
-    nb, n_reads, rl, err, flags = WORKLOADS[wl]
+    W = WORKLOADS[wl]
+    n_reads, rl, err = W["n_reads"], W["read_len"], W["err"]
     t0 = time.time()
     if rank == 0:
         d, nib = make_reference(wl)
-        # index: built on the device (bit-identical to `yaha -g`, tests/test_gpu_parity.py), written in the
-        # reference's file format for both arms
-        idx_path = os.path.join(d, refio.index_file_name("ref", 15, 1, 65525))
-        if not os.path.exists(idx_path):
-            al = yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=15), device=local)
-            refio.write_index(idx_path + ".tmp", al.download_index())
-            os.replace(idx_path + ".tmp", idx_path)
-            al.close()
+        # index: built on the device (bit-identical to `yaha -g`), written in the reference's file format for both arms
+        ensure_device_built_index(wl, d, nib, local)
     if world > 1:
         dist.barrier()
     d, nib = make_reference(wl)
-    idx_path = os.path.join(d, refio.index_file_name("ref", 15, 1, 65525))
+    idx_path = index_path_of(wl, d)
     t_setup = time.time() - t0
 
     reads = make_reads(wl, rank)
@@ -218,7 +266,7 @@ def run_ours(args):
 
     # roofline denominators measured live on this GPU: INT32 issue rate and the HBM random-gather rate
     # over the real 4 GiB starting-offset table (index rebuilt on the device for this, ~1 s)
-    probe_al = yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=15), device=local)
+    probe_al = yaha_b200.Aligner(nib, None, yaha_b200.Params.defaults(word_len=15), device=local, build_max_hits=W["index_h"])
     int_add, int_mix = probe_al.int32_peak()
     gather_peak = probe_al.gather_peak()
     probe_al.close()
@@ -385,20 +433,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ensure_index_file(wl: str, d: str, al=None) -> str:
-    """Index file on disk for the reference binary.  Built by the reference itself (`yaha -g`)
-    unless an Aligner with a device-built (bit-identical) index is at hand."""
-    from yaha_b200 import refio
-    path = os.path.join(d, refio.index_file_name("ref", 15, 1, 65525))
-    if os.path.exists(path):
-        return path
-    if al is not None:
-        idx = al.download_index()
-        refio.write_index(path + ".tmp", idx)
-        os.replace(path + ".tmp", path)
-    else:
+def ensure_index_file(wl: str, d: str) -> str:
+    """Index file on disk for the reference binary: the one our arm built on the device if it is there, else built by the
+    reference itself (`yaha -g`; only for references small enough to have a FASTA in the cache directory)."""
+    path = index_path_of(wl, d)
+    if not os.path.exists(path):
         yaha = os.path.join(ROOT, "oracle", "_ref", "yaha")
-        subprocess.check_call([yaha, "-g", "ref.fa", "-L", "15", "-S", "1"], cwd=d,
+        subprocess.check_call([yaha, "-g", "ref.fa", "-L", "15", "-S", "1", "-H", str(WORKLOADS[wl]["index_h"])], cwd=d,
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return path
 
@@ -464,13 +505,13 @@ def run_reference(args):
     if rank != 0:
         return
     wl = args.workload
-    nb, n_reads, rl, err, flags = WORKLOADS[wl]
+    n_reads = WORKLOADS[wl]["n_reads"]
     yaha = os.path.join(ROOT, "oracle", "_ref", "yaha")
     if not os.path.exists(yaha):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/yaha not built (reference sources absent)"}))
         return
     d, nib = make_reference(wl)
-    idx = ensure_index_file(wl, d, None)
+    idx = ensure_index_file(wl, d)
     reads = make_reads(wl, 0)
     sample = reads[:min(n_reads, args.cpu_sample)]
     ncores = os.cpu_count() or 1

@@ -150,13 +150,15 @@ ya_ctx *ya_open(int device, const ya_params *params,
 ya_ctx *ya_open_peer(int device, const ya_ctx *src);
 
 /* Same as ya_open, but BUILD the index on the device from the .nib2 base area instead of loading
- * an index file (replaces indexFile, Index.c:49-331, for -S 1).  seq_start/seq_len are the global
- * base offset and length of each sequence (BaseSeq.c:115-119).  The result is bit-identical to the
- * reference's file contents; ya_index_download() returns it for writing in the reference's format.
- * Fails if any k-mer occurs more than index_max_hits times (the reference then down-samples with a
- * sequential RNG, Index.c:271-315). */
+ * an index file (replaces indexFile, Index.c:49-331, for every -L / -S / -H).  seq_start/seq_len are the
+ * global base offset and length of each sequence (BaseSeq.c:115-119); index_max_hits and skip_dist are the
+ * -H and -S of `yaha -g`.  The result is bit-identical to the reference's file contents, including the
+ * down-sampling of k-mers with more than index_max_hits occurrences (Index.c:271-315: Floyd sampling from one
+ * xorshift stream, Math.c:274-343 -- the stream is sequential, so its draws are made on the host for the few
+ * over-full lists the device finds); ya_index_download() returns it for writing in the reference's format. */
 ya_ctx *ya_open_build(int device, const ya_params *params, const uint8_t *bases, size_t n_base_bytes,
-                      const uint32_t *seq_start, const uint32_t *seq_len, int n_seq, uint32_t index_max_hits);
+                      const uint32_t *seq_start, const uint32_t *seq_len, int n_seq, uint32_t index_max_hits,
+                      uint32_t skip_dist);
 int     ya_index_sizes(const ya_ctx *, size_t *n_so, size_t *n_roa);
 int     ya_index_download(ya_ctx *, uint32_t *so, uint32_t *roa);
 

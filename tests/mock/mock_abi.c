@@ -58,8 +58,8 @@ ya_ctx *ya_open(int device, const ya_params *p, const uint32_t *so, size_t n_so,
 }
 ya_ctx *ya_open_peer(int device, const ya_ctx *src) { ya_ctx *c = malloc(sizeof *c); *c = *src; c->fwd = c->rev = NULL; c->off = NULL; c->n_reads = 0; (void)device; return c; }
 ya_ctx *ya_open_shared(const ya_ctx *src) { return ya_open_peer(0, src); }
-ya_ctx *ya_open_build(int d, const ya_params *p, const uint8_t *b, size_t n, const uint32_t *s, const uint32_t *l, int ns, uint32_t mh)
-{ (void)d; (void)p; (void)b; (void)n; (void)s; (void)l; (void)ns; (void)mh; return NULL; }
+ya_ctx *ya_open_build(int d, const ya_params *p, const uint8_t *b, size_t n, const uint32_t *s, const uint32_t *l, int ns, uint32_t mh, uint32_t sk)
+{ (void)d; (void)p; (void)b; (void)n; (void)s; (void)l; (void)ns; (void)mh; (void)sk; return NULL; }
 int ya_index_sizes(const ya_ctx *c, size_t *a, size_t *b) { *a = c->n_so; *b = c->n_roa; return 0; }
 int ya_index_download(ya_ctx *c, uint32_t *so, uint32_t *roa) { (void)c; (void)so; (void)roa; return YA_E_STATE; }
 void ya_close(ya_ctx *c) { if (!c) return; free(c->fwd); free(c->rev); free(c->off); free(c->pending); free(c); }

@@ -291,9 +291,35 @@ def test_device_index_build_is_bit_identical(small):
     s2, f2, r2 = al2.seed_frags()
     al2.close()
     assert np.array_equal(f1, f2) and np.array_equal(s1, s2)
-    # a k-mer above the limit must be reported, not approximated
-    with pytest.raises(yaha_b200.YahaError):
-        yaha_b200.Aligner(small.nib, None, yaha_b200.Params.defaults(word_len=11), device=0, build_max_hits=1)
+
+
+def test_device_index_build_every_word_length_skip_and_hit_cap(small, tmp_path):
+    """Row N3: ya_open_build for every -L / -S / -H the reference was run with (golden/small/index_variants.json:
+    sha256 of the files the UNMODIFIED reference wrote for the golden reference and for an N-riddled one), i.e. the
+    -S grid with its renormalisation behind runs of non-ACGT codes (Index.c:105-128) and the down-sampling of
+    over-full k-mers with the reference's generator (Index.c:271-315, Math.c:274-343)."""
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(small.golden, "index_variants.json")))
+    nrich = refio.build_nib2(synth.n_rich_reference())
+    open(tmp_path / "nrich.nib2", "wb").write(nrich)
+    nibs = {"nrich": refio.load_nib2(str(tmp_path / "nrich.nib2")), "small": small.nib}
+    checked = sampled = 0
+    for name, digest in want.items():
+        if name.endswith(".nib2"):
+            continue
+        stem, spec = name.split(".X")
+        L, Sk, H = int(spec[0:2]), int(spec[3:5]), int(spec[6:11])
+        al = yaha_b200.Aligner(nibs[stem], None, yaha_b200.Params.defaults(word_len=L, max_hits=min(650, H)), device=0,
+                               build_max_hits=H, build_skip=Sk)
+        idx = al.download_index(max_hits=H)
+        al.close()
+        path = str(tmp_path / name)
+        refio.write_index(path, idx)
+        assert hashlib.sha256(open(path, "rb").read()).hexdigest() == digest, name
+        sampled += int(np.max(np.diff(idx.so.astype(np.int64))) == H and H < 65525)
+        checked += 1
+    assert checked == 14 and sampled >= 4
 
 
 _AB_SNIPPET = r"""

@@ -96,7 +96,7 @@ def load_library() -> C.CDLL:
     lib.ya_open.restype = vp
     lib.ya_open.argtypes = [C.c_int, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32]
     lib.ya_open_build.restype = vp
-    lib.ya_open_build.argtypes = [C.c_int, C.POINTER(Params), vp, C.c_size_t, vp, vp, C.c_int, C.c_uint32]
+    lib.ya_open_build.argtypes = [C.c_int, C.POINTER(Params), vp, C.c_size_t, vp, vp, C.c_int, C.c_uint32, C.c_uint32]
     lib.ya_index_sizes.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     lib.ya_index_download.argtypes = [vp, vp, vp]
     lib.ya_open_peer.restype = vp
@@ -134,7 +134,7 @@ class Aligner:
     """One GPU context with a resident index (`ya_ctx`)."""
 
     def __init__(self, nib2: refio.Nib2, index: "refio.Index | None", params: Params | None = None, device: int = 0,
-                 peer_of: "Aligner | None" = None, build_max_hits: int = 65525):
+                 peer_of: "Aligner | None" = None, build_max_hits: int = 65525, build_skip: int = 1):
         self.lib = load_library()
         self.nib2, self.index = nib2, index
         if params is None:
@@ -148,7 +148,7 @@ class Aligner:
             st = np.ascontiguousarray(nib2.starts, dtype=np.uint32)
             ln = np.ascontiguousarray(nib2.lengths, dtype=np.uint32)
             self.ctx = self.lib.ya_open_build(device, C.byref(params), bases.ctypes.data, len(bases),
-                                              st.ctypes.data, ln.ctypes.data, len(st), build_max_hits)
+                                              st.ctypes.data, ln.ctypes.data, len(st), build_max_hits, build_skip)
         else:
             so = np.ascontiguousarray(index.so)
             roa = np.ascontiguousarray(index.roa)

@@ -186,6 +186,74 @@ def edge_reads(ref: np.ndarray, seed: int, n_each: int = 40, read_len: int = 300
     return out
 
 
+def human_like_reference(n_bases: int, n_seqs: int = 24, seed: int = 2024, alu_sites: int | None = None,
+                         alu_len: int = 300, alu_div: float = 0.12, n_runs_per_seq: int = 2):
+    """BASELINE configs[3]/[4] reference: `n_bases` i.i.d. bases cut into `n_seqs` sequences of chromosome-like unequal
+    sizes, with an Alu-like family implanted -- ONE `alu_len`-base consensus copied to `alu_sites` uniformly random
+    places (default one per 25 kbp: 124 000 at 3.1 Gbp), every copy on a random strand with its own `alu_div`
+    substitutions -- and a few runs of N per sequence (assembly gaps).  The k-mers of the consensus occur tens of
+    thousands of times, so the index builder has to down-sample them (Index.c:271-315) and reads that touch a copy
+    produce thousands of seed hits per strand.  Returns (bases as one uint8 array, sequence bounds)."""
+    rng = np.random.default_rng(seed)
+    ref = _BASES[rng.integers(0, 4, size=n_bases, dtype=np.uint8)]
+    if alu_sites is None:
+        alu_sites = max(8, n_bases // 25_000)
+    cons = _BASES[rng.integers(0, 4, size=alu_len, dtype=np.uint8)]
+    pos = np.sort(rng.integers(0, n_bases - alu_len, size=alu_sites))
+    for a in range(0, alu_sites, 1 << 16):                           # in slabs: bounded temporaries
+        p = pos[a:a + (1 << 16)]
+        m = len(p)
+        copies = np.tile(cons, (m, 1))
+        sub = rng.random((m, alu_len)) < alu_div
+        idx = np.searchsorted(_BASES, copies[sub])
+        copies[sub] = _BASES[(idx + rng.integers(1, 4, size=int(sub.sum()))) % 4]
+        flip = rng.integers(0, 2, size=m).astype(bool)
+        copies[flip] = _COMP[copies[flip][:, ::-1]]
+        ref[(p[:, None] + np.arange(alu_len)[None, :]).ravel()] = copies.ravel()
+    w = np.linspace(2.0, 0.5, n_seqs)
+    bounds = np.concatenate([[0], np.cumsum(w / w.sum() * n_bases)]).astype(np.int64)
+    bounds[-1] = n_bases
+    for k in range(n_seqs):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        for _ in range(n_runs_per_seq):
+            ln = int(rng.integers(50, 20_000))
+            if hi - lo > 4 * ln:
+                a = int(rng.integers(lo, hi - ln))
+                ref[a:a + ln] = ord("N")
+    return ref, bounds
+
+
+def sv_reads(ref: np.ndarray, n_reads: int, read_len: int, seed: int, err_lo: float = 0.02, err_hi: float = 0.05):
+    """BASELINE configs[3] reads: `read_len`-base reads (10 kbp) of a donor that differs from the reference by one to
+    three structural variants inside the read -- a deletion (50-2000 bases missing), an inversion (300-3000 bases
+    reverse-complemented in place), a novel 300-base insertion, or a translocated piece from elsewhere -- plus 2-5 %
+    per-base errors: the split-read sets -OQC / -FBS are made for."""
+    rng = np.random.default_rng(seed)
+    L = len(ref)
+    for i in range(n_reads):
+        s = int(rng.integers(0, L - 2 * read_len))
+        w = ref[s:s + read_len + 6000].copy()
+        kinds = []
+        for _ in range(int(rng.integers(1, 4))):
+            k = int(rng.integers(0, 4))
+            at = int(rng.integers(500, read_len - 500))
+            if k == 0:
+                n = int(rng.integers(50, 2000)); w = np.concatenate([w[:at], w[at + n:]]); kinds.append(f"del{n}")
+            elif k == 1:
+                n = int(rng.integers(300, 3000)); w = np.concatenate([w[:at], _COMP[w[at:at + n][::-1]], w[at + n:]]); kinds.append(f"inv{n}")
+            elif k == 2:
+                w = np.concatenate([w[:at], _BASES[rng.integers(0, 4, size=300)], w[at:]]); kinds.append("ins300")
+            else:
+                n = int(rng.integers(500, 3000)); b = int(rng.integers(0, L - n))
+                w = np.concatenate([w[:at], ref[b:b + n], w[at:]]); kinds.append(f"tra{n}")
+        w = w[:read_len]
+        strand = int(rng.integers(0, 2))
+        if strand:
+            w = _COMP[w[::-1]]
+        w = w[w != 0] if (w == 0).any() else w                      # (_COMP of a non-ACGTN byte: none here)
+        yield f"sv{i}_{s}_{'-' if strand else '+'}_{'_'.join(kinds)}", mutate(w, float(rng.uniform(err_lo, err_hi)), rng)
+
+
 if __name__ == "__main__":
     import argparse
     ap = argparse.ArgumentParser(description=__doc__)
