@@ -131,6 +131,9 @@ typedef struct ya_counters {
     double   ms_ext;       /* device time of dp_ext_packed_kernel launches (CUDA events)      */
     uint64_t ext_launches; /* number of dp_ext_packed_kernel launches in ms_ext               */
     double   ms_lookup;    /* device time of seed_count_kernel (the SO gathers) alone         */
+    double   ms_finish;    /* device time of the assemble / finish / format kernels (ya_align_batch) */
+    uint64_t reads_finished, reads_handed_back;   /* ya_align_batch: reads done on the device / returned with status 1 */
+    uint64_t text_bytes;   /* SAM text produced on the device                                 */
 } ya_counters;
 
 typedef struct ya_ctx ya_ctx;
@@ -258,6 +261,48 @@ typedef struct ya_prep_batch {
 } ya_prep_batch;
 
 int ya_prepare_clumps(ya_ctx *, ya_prep_batch *out);
+
+/* ---- Rows N2 + N4: the whole per-read path for a batch in ONE call.  Replaces, per read, the body of
+ * the processQueries loop (Query.c:306-497) and printClumps (QueryMatch.c:333-344, AlignOutput.c:115-289): the reads go up
+ * as they stand in the query file (characters, ids); the device encodes them (Query.c:161-168), runs stages 1-3 with the
+ * jobs of the first DP round born, laid out and answered on the device, splices and scores every clump
+ * (AlignHelpers.c:251-366), runs Optimal Query Coverage / filter by similarity (GraphPath.cpp:294-1086) and writes the SAM
+ * records (AlignOutput.c:115-289) of every read it can finish, in read order, into one text buffer.
+ * A read is handed back (status 1, no text) when the reference's control flow for it leaves the straight path: a clump
+ * splitClump has to look at (AlignHelpers.c:374-579), a strand too crowded for the device's fragment graph, more scored
+ * clumps than the device's graph holds, -OQC N with several clumps.  The caller runs those reads through the calls above.
+ * ya_set_output must have been called.  On YA_E_CAPACITY (text_cap too small) text_needed is set, status / text_off are
+ * valid and the text stays on the device for ya_align_fetch_text. ---- */
+typedef struct ya_out_params {       /* the AlignmentArgs_t fields the tail of the per-read path reads (Math.h:257-334) */
+    int32_t maxDesert, minNonOverlap;                        /* fragment graph (GraphPath.cpp:161-292)          */
+    int32_t minRawScore;  float minIdentity;                 /* scoreClump thresholds (AlignHelpers.c:343-361)   */
+    int32_t OQC, FBS, OQCMinNonOverlap, BPCost, maxBPLog;    /* -OQC -FBS -MNO -BP -MGDP                        */
+    float   FBS_PSLength, FBS_PSScore;                       /* -PRL -PSS                                       */
+    int32_t hardClip, fastq;                                 /* -osh / -oss; FASTQ input (QUAL column)           */
+} ya_out_params;
+
+/* names / starts / lengths of the reference sequences (BaseSequence_t, Math.h:218-225; the @SQ lines and the RNAME column) */
+int ya_set_output(ya_ctx *, const ya_out_params *, int n_seq, const char *const *seq_names,
+                  const uint32_t *seq_start, const uint32_t *seq_len);
+
+typedef struct ya_text_batch {
+    int32_t         n_reads;
+    const char     *chars;      /* the reads' characters as in the file, concatenated                      */
+    const uint64_t *offsets;    /* n_reads+1 entries, offsets[0] == 0                                      */
+    const char     *quals;      /* FASTQ: quality characters, same offsets; NULL for FASTA                 */
+    const char     *ids;        /* ids (<= 200 characters, blanks replaced: Query.c:111-135), concatenated */
+    const uint32_t *id_off;     /* n_reads+1 entries                                                       */
+    /* outputs (caller's buffers) */
+    char           *text;       /* SAM records of the reads finished on the device, in read order          */
+    size_t          text_cap;
+    uint64_t       *text_off;   /* [n_reads+1]: read r's records are text[text_off[r] .. text_off[r+1])     */
+    uint8_t        *status;     /* [n_reads] 0: finished here (possibly without a record), 1: handed back   */
+    size_t          text_len, text_needed;
+    int32_t         n_handed_back;
+} ya_text_batch;
+
+int ya_align_batch(ya_ctx *, ya_text_batch *);
+int ya_align_fetch_text(ya_ctx *, char *text, size_t text_cap);
 
 /* Stage 3 for n independent jobs against the uploaded batch.  Replaces findAGSAlignment,
  * findAGSAlignmentBanded, findAGSForwardExtension, findAGSBackwardExtension

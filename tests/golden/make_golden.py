@@ -67,6 +67,60 @@ def only_chimera():
     shutil.rmtree(tmp)
 
 
+def multi_reads(ref, seed, n=220):
+    import numpy as np
+    """Reads glued from 2-7 clean pieces (0-2 % error: no piece has to be split) so that Optimal Query Coverage has real
+    work on reads the device finishes itself (csrc/finish_reads.h): pieces from different loci, strands and sequences,
+    pieces that overlap in the query (the tail of one locus repeated at the head of the next: accurate overlap scoring),
+    the same locus twice (duplicates), a short piece inside a long one (subsumed), equal-scoring copies (the RNG tie break
+    of the sort), secondaries that -FBS keeps."""
+    rng = np.random.default_rng(seed)
+    L = len(ref)
+    out = []
+    for i in range(n):
+        pieces, tags = [], []
+        k = int(rng.integers(2, 8))
+        prev = None
+        for j in range(k):
+            mode = int(rng.integers(0, 6))
+            ln = int(rng.integers(40, 260))
+            if mode == 0 and prev is not None:                         # same locus again (duplicate / equal keys)
+                s, ln2, st = prev
+                p = ref[s:s + ln2]
+            elif mode == 1 and prev is not None:                       # overlaps the previous piece in the reference
+                s0, ln0, st = prev
+                s = max(0, s0 + ln0 - int(rng.integers(10, 40))); p = ref[s:s + ln]
+            elif mode == 2 and prev is not None:                       # a short piece from inside the previous one
+                s0, ln0, st = prev
+                ln = max(30, ln0 // 3); s = s0 + int(rng.integers(0, max(1, ln0 - ln))); p = ref[s:s + ln]
+            else:
+                s = int(rng.integers(0, L - ln)); p = ref[s:s + ln]
+            st = int(rng.integers(0, 2))
+            prev = (s, len(p), st)
+            if st:
+                p = synth._COMP[p[::-1]]
+            pieces.append(synth.mutate(p, float(rng.choice([0.0, 0.0, 0.01, 0.02])), rng))
+            tags.append(f"{s}{'-' if st else '+'}")
+        out.append((f"multi{i}_" + "_".join(tags), np.concatenate(pieces)))
+    return out
+
+
+def only_multi():
+    """Adds multi.fa.gz / out_multi.sam.gz / out_multi_fbs.sam.gz / out_multi_mno.sam.gz."""
+    tmp = tempfile.mkdtemp()
+    with gzip.open(OUT + "/ref.fa.gz", "rb") as f, open(tmp + "/ref.fa", "wb") as o:
+        o.write(f.read())
+    ref = synth.random_reference(300_000, 4242)
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    synth.write_reads(tmp + "/multi.fa", multi_reads(ref, 23))
+    for tag, flags in (("multi", []), ("multi_fbs", ["-FBS", "Y", "-PRL", "0.5", "-PSS", "0.5"]), ("multi_mno", ["-MNO", "5", "-BP", "2", "-MGDP", "9", "-M", "15"])):
+        subprocess.check_call([REF + "/yaha", "-x", "ref.X11_01_65525S", "-q", "multi.fa", "-osh", f"out_{tag}.sam", "-t", "1"] + flags, cwd=tmp,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        gz(f"{tmp}/out_{tag}.sam", f"{OUT}/out_{tag}.sam.gz")
+    gz(tmp + "/multi.fa", OUT + "/multi.fa.gz")
+    shutil.rmtree(tmp)
+
+
 def only_flag_sweep():
     """Writes flag_sweep.json: for every flag set of tests/hostcases.py FLAG_SWEEP the line count and sha256 of the reference's
     SAM (reads.fa, -osh, -t 1) without its @PG line."""
@@ -182,6 +236,9 @@ def only_weird_headers():
 
 
 def main():
+    if "--only-multi" in sys.argv:
+        only_multi()
+        return
     if "--only-weird-headers" in sys.argv:
         only_weird_headers()
         return

@@ -20,6 +20,11 @@ CASES = [
     ("out_weird_fastq.sam.gz", "weird.fq", "-oss", []),
     # FASTA id lines holding the record markers themselves ('>' '+' '@'): an id line ends at its newline only
     ("out_weird2.sam.gz", "weird2.fa", "-osh", []),
+    # reads glued from 2-7 clean pieces (overlapping, duplicated, subsumed, equal-scoring): Optimal Query Coverage, the filter
+    # by similarity and the mapping qualities on reads the device finishes itself (csrc/finish_reads.h)
+    ("out_multi.sam.gz", "multi.fa", "-osh", []),
+    ("out_multi_fbs.sam.gz", "multi.fa", "-osh", ["-FBS", "Y", "-PRL", "0.5", "-PSS", "0.5"]),
+    ("out_multi_mno.sam.gz", "multi.fa", "-osh", ["-MNO", "5", "-BP", "2", "-MGDP", "9", "-M", "15"]),
 ]
 
 # One line per flag of the reference's alignment CLI (Main.c:187-470) that changes the result, plus combinations and

@@ -9,6 +9,9 @@
 #include "../../oracle/oracle.h"
 #include "../../yaha_b200/csrc/form_clumps.h"
 #include "../../yaha_b200/csrc/prepare_clumps.h"
+#include "../../yaha_b200/csrc/assemble_clumps.h"
+#include "../../yaha_b200/csrc/finish_reads.h"
+#include <math.h>
 
 struct ya_ctx {
     ya_params P;
@@ -20,6 +23,11 @@ struct ya_ctx {
     ya_frag_batch last_seed_v; int has_seed;          /* descriptor of the last ya_seed_frags outputs (caller's buffers) */
     ya_op *pending; size_t pendingN, pendingCap;     /* ops of the last ya_sw_batch (for ya_sw_fetch_ops) */
     char err[256];
+    /* ya_align_batch */
+    ya_out_params out; int out_set;
+    int n_seq; uint32_t *seq_start, *seq_len, *seq_name_off; char *seq_names;
+    uint32_t *bpp_dist; int n_bpp, bpp_base;
+    char *text; size_t text_pending;
 };
 static const uint8_t comp[16] = {2, 3, 0, 1, 4, 12, 7, 6, 9, 8, 15, 11, 5, 13, 14, 10};
 
@@ -56,13 +64,25 @@ ya_ctx *ya_open(int device, const ya_params *p, const uint32_t *so, size_t n_so,
     (void)device;
     return c;
 }
-ya_ctx *ya_open_peer(int device, const ya_ctx *src) { ya_ctx *c = malloc(sizeof *c); *c = *src; c->fwd = c->rev = NULL; c->off = NULL; c->n_reads = 0; (void)device; return c; }
+ya_ctx *ya_open_peer(int device, const ya_ctx *src)
+{
+    ya_ctx *c = malloc(sizeof *c); *c = *src; c->fwd = c->rev = NULL; c->off = NULL; c->n_reads = 0; (void)device;
+    c->pending = NULL; c->pendingN = c->pendingCap = 0;
+    c->out_set = 0; c->seq_start = c->seq_len = c->seq_name_off = NULL; c->seq_names = NULL; c->bpp_dist = NULL; c->text = NULL; c->text_pending = 0;
+    return c;
+}
 ya_ctx *ya_open_shared(const ya_ctx *src) { return ya_open_peer(0, src); }
 ya_ctx *ya_open_build(int d, const ya_params *p, const uint8_t *b, size_t n, const uint32_t *s, const uint32_t *l, int ns, uint32_t mh, uint32_t sk)
 { (void)d; (void)p; (void)b; (void)n; (void)s; (void)l; (void)ns; (void)mh; (void)sk; return NULL; }
 int ya_index_sizes(const ya_ctx *c, size_t *a, size_t *b) { *a = c->n_so; *b = c->n_roa; return 0; }
 int ya_index_download(ya_ctx *c, uint32_t *so, uint32_t *roa) { (void)c; (void)so; (void)roa; return YA_E_STATE; }
-void ya_close(ya_ctx *c) { if (!c) return; free(c->fwd); free(c->rev); free(c->off); free(c->pending); free(c); }
+void ya_close(ya_ctx *c)
+{
+    if (!c) return;
+    free(c->fwd); free(c->rev); free(c->off); free(c->pending);
+    free(c->seq_start); free(c->seq_len); free(c->seq_name_off); free(c->seq_names); free(c->bpp_dist); free(c->text);
+    free(c);
+}
 const char *ya_last_error(const ya_ctx *c) { return c ? c->err : "mock"; }
 int ya_set_params(ya_ctx *c, const ya_params *p) { c->P = *p; return 0; }
 int ya_set_stream(ya_ctx *c, void *s) { (void)c; (void)s; return 0; }
@@ -261,5 +281,181 @@ int ya_perfect_ext(ya_ctx *c, const ya_dp_job *jobs, int n, uint16_t *count)
         const uint8_t *codes = (jobs[i].strand ? c->rev : c->fwd) + c->off[jobs[i].read];
         count[i] = (uint16_t)orc_perfect(c->bases, codes, jobs[i].rOff, jobs[i].qOff, jobs[i].qLen, jobs[i].kind == YA_DP_EXT_BWD ? -1 : 1);
     }
+    return 0;
+}
+
+/* ---- ya_align_batch on the CPU: the same headers the device kernels compile (form_clumps.h, prepare_clumps.h,
+ * assemble_clumps.h, finish_reads.h) around the oracle's seed lookup and DP ---- */
+int ya_set_output(ya_ctx *c, const ya_out_params *o, int n_seq, const char *const *names, const uint32_t *st, const uint32_t *ln)
+{
+    c->out = *o; c->out_set = 1; c->n_seq = n_seq;
+    free(c->seq_start); free(c->seq_len); free(c->seq_name_off); free(c->seq_names); free(c->bpp_dist);
+    c->seq_start = malloc(n_seq * 4); c->seq_len = malloc(n_seq * 4); c->seq_name_off = malloc((n_seq + 1) * 4);
+    size_t tot = 0;
+    for (int i = 0; i < n_seq; i++) tot += strlen(names[i]);
+    c->seq_names = malloc(tot + 1);
+    tot = 0;
+    for (int i = 0; i < n_seq; i++) {
+        c->seq_start[i] = st[i]; c->seq_len[i] = ln[i]; c->seq_name_off[i] = (uint32_t)tot;
+        memcpy(c->seq_names + tot, names[i], strlen(names[i])); tot += strlen(names[i]);
+    }
+    c->seq_name_off[n_seq] = (uint32_t)tot;
+    /* break-point penalty steps, as the CUDA library tabulates them (GraphPath.cpp:1018-1020) */
+    int b0, b1;
+    {
+        double lg = log10(11.0); if (lg > o->maxBPLog) lg = o->maxBPLog; b0 = (int)(lg * o->BPCost + 0.5);
+        lg = log10(4294967295.0); if (lg > o->maxBPLog) lg = o->maxBPLog; b1 = (int)(lg * o->BPCost + 0.5);
+    }
+    c->bpp_base = b0; c->n_bpp = 0; c->bpp_dist = malloc((size_t)(b1 > b0 ? b1 - b0 : 1) * 4);
+    for (int b = b0 + 1; b <= b1; b++) {
+        uint64_t lo = 11, hi = 0xFFFFFFFFull;
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            double lg = log10((double)(uint32_t)mid); if (lg > o->maxBPLog) lg = o->maxBPLog;
+            if ((int)(lg * o->BPCost + 0.5) >= b) hi = mid; else lo = mid + 1;
+        }
+        c->bpp_dist[c->n_bpp++] = (uint32_t)lo;
+    }
+    return 0;
+}
+
+int ya_align_fetch_text(ya_ctx *c, char *text, size_t cap)
+{
+    if (!c->text_pending) return YA_E_STATE;
+    if (cap < c->text_pending) return YA_E_CAPACITY;
+    memcpy(text, c->text, c->text_pending);
+    return 0;
+}
+
+static int code_of_char(int ch)                                       /* Math.c:141-157 */
+{
+    static const char k[16] = {'T', 'C', 'A', 'G', 'N', 'B', 'D', 'H', 'K', 'M', 'R', 'S', 'V', 'W', 'X', 'Y'};
+    if (ch == 'U' || ch == 'u') return 0;
+    for (int i = 0; i < 16; i++) if (ch == k[i] || ch == k[i] + 32) return i;
+    return 14;
+}
+
+int ya_align_batch(ya_ctx *c, ya_text_batch *b)
+{
+    const int n = b->n_reads;
+    b->text_len = b->text_needed = 0; b->n_handed_back = 0; b->text_off[0] = 0;
+    c->text_pending = 0;
+    if (!c->out_set) return YA_E_STATE;
+    if (n == 0) return 0;
+    const uint64_t total = b->offsets[n];
+    uint8_t *codes = malloc(total + 1);
+    for (uint64_t i = 0; i < total; i++) codes[i] = (uint8_t)code_of_char((unsigned char)b->chars[i]);
+    ya_read_batch rb; rb.n_reads = n; rb.codes = codes; rb.offsets = b->offsets;
+    ya_reads_upload(c, &rb);
+    free(codes);
+    /* stages 1 + 2 */
+    ya_frag_batch fb; memset(&fb, 0, sizeof fb);
+    fb.frags_cap = (size_t)64 * n + 1024;
+    fb.strands = malloc((size_t)2 * n * sizeof(ya_strand_frags));
+    for (;;) {
+        fb.frags = malloc(fb.frags_cap * sizeof(ya_frag)); fb.region = malloc(fb.frags_cap * 4);
+        int rc = ya_seed_frags(c, &fb);
+        if (rc == YA_E_CAPACITY) { free(fb.frags); free(fb.region); fb.frags_cap = fb.frags_needed + 1024; continue; }
+        break;
+    }
+    const size_t nk = fb.n_frags, cap = nk + 16;
+    ya_clump_batch cb; memset(&cb, 0, sizeof cb);
+    cb.maxDesert = c->out.maxDesert; cb.minNonOverlap = c->out.minNonOverlap; cb.cap = cap;
+    cb.clump_first = malloc((size_t)2 * n * 4); cb.clump_count = malloc((size_t)2 * n * 4);
+    cb.clumps = malloc(cap * sizeof(ya_clump_rec)); cb.path = malloc(cap * sizeof(ya_frag));
+    ya_form_clumps(c, &cb);
+    ya_prep_batch pb; memset(&pb, 0, sizeof pb);
+    pb.cap = cap; pb.jobs_cap = 3 * cap + 16;
+    pb.prep = malloc(cap * sizeof(ya_prep_rec)); pb.gaps = malloc(cap * sizeof(ya_gap_rec)); pb.path = malloc(cap * sizeof(ya_frag));
+    pb.jobs = malloc(pb.jobs_cap * sizeof(ya_dp_job));
+    ya_prepare_clumps(c, &pb);
+    /* the first DP round */
+    ya_dp_result *res = malloc((pb.n_jobs + 1) * sizeof(ya_dp_result));
+    size_t opsCap = 64 * pb.n_jobs + 1024, need = 0;
+    ya_op *rops = malloc(opsCap * sizeof(ya_op));
+    if (ya_sw_batch(c, pb.jobs, (int)pb.n_jobs, res, rops, opsCap, &need) == YA_E_CAPACITY) {
+        opsCap = need + 16; rops = realloc(rops, opsCap * sizeof(ya_op));
+        ya_sw_fetch_ops(c, rops, opsCap);
+    }
+    /* splice + score every clump */
+    ac_params AP;
+    AP.GOCost = c->P.GOCost; AP.GECost = c->P.GECost; AP.RCost = c->P.RCost; AP.MScore = c->P.MScore; AP.minExtLength = c->P.minExtLength;
+    AP.minRawScore = c->out.minRawScore; AP.maxROff = c->maxROff; AP.minIdentity = c->out.minIdentity;
+    ya_asm_rec *recs = calloc(cap, sizeof(ya_asm_rec));
+    size_t asmCap = need + 2 * nk + 64, asmUsed = 0;
+    ya_op *asmOps = malloc(asmCap * sizeof(ya_op));
+    for (int s = 0; s < 2 * n; s++) {
+        const uint32_t nc = cb.clump_count[s], c0 = cb.clump_first[s];
+        if (nc == 0 || nc == 0xFFFFFFFFu) continue;
+        const int r = s >> 1;
+        const int L = (int)(c->off[r + 1] - c->off[r]);
+        const uint8_t *q = ((s & 1) ? c->rev : c->fwd) + c->off[r];
+        for (uint32_t k = 0; k < nc; k++) {
+            const ya_clump_rec cr = cb.clumps[c0 + k];
+            const ya_prep_rec *pr = &pb.prep[c0 + k];
+            const ya_gap_rec *g = pb.gaps + pr->gap_first;
+            const uint32_t bound = ac_ops_bound((int)cr.n, g, pr->n_gaps, pr, res, rops);
+            if (asmUsed + bound > asmCap) { fprintf(stderr, "mock: run array too small\n"); abort(); }
+            if (ac_assemble_clump(&AP, c->bases, q, L, pb.path + cr.first, (int)cr.n, g, pr->n_gaps, pr, res, rops, asmOps + asmUsed, &recs[c0 + k]) != 0) {
+                fprintf(stderr, "mock: extension plan diverged\n"); abort();
+            }
+            recs[c0 + k].ops_off = (uint32_t)asmUsed;
+            asmUsed += bound;
+        }
+    }
+    if (getenv("YA_MOCK_TRACE")) fprintf(stderr, "mock: assembled, %zu runs\n", asmUsed);
+    /* finish every read */
+    fr_params F; memset(&F, 0, sizeof F);
+    F.GOCost = c->P.GOCost; F.GECost = c->P.GECost; F.RCost = c->P.RCost; F.MScore = c->P.MScore;
+    F.OQC = c->out.OQC; F.FBS = c->out.FBS; F.OQCMinNonOverlap = c->out.OQCMinNonOverlap; F.BPCost = c->out.BPCost; F.maxBPLog = c->out.maxBPLog;
+    F.FBS_PSLength = c->out.FBS_PSLength; F.FBS_PSScore = c->out.FBS_PSScore; F.hardClip = c->out.hardClip; F.fastq = c->out.fastq;
+    F.n_seq = c->n_seq; F.seq_start = c->seq_start; F.seq_len = c->seq_len; F.seq_name_off = c->seq_name_off; F.seq_names = c->seq_names;
+    F.bpp_base = c->bpp_base; F.n_bpp = c->n_bpp; F.bpp_dist = c->bpp_dist;
+    size_t textCap = 1 << 20, textLen = 0;
+    free(c->text); c->text = malloc(textCap);
+    for (int r = 0; r < n; r++) {
+        const uint64_t base = c->off[r];
+        const int L = (int)(c->off[r + 1] - base);
+        fr_clump cl[FR_MAX_NODES];
+        int m = 0, hand = 0;
+        for (int st = 0; st < 2 && !hand; st++) {
+            const int s = 2 * r + st;
+            const uint32_t nc = cb.clump_count[s], c0 = cb.clump_first[s];
+            if (nc == 0xFFFFFFFFu) { hand = 1; break; }
+            for (uint32_t k = 0; k < nc; k++) {
+                const ya_asm_rec *a = &recs[c0 + k];
+                if (a->verdict == YA_ASM_SPLIT) { hand = 1; break; }
+                if (a->verdict != YA_ASM_SCORED) continue;
+                if (m == FR_MAX_NODES) { hand = 1; break; }
+                cl[m].rec = a; cl[m].ops = asmOps + a->ops_off; cl[m].reversed = st; m++;
+            }
+        }
+        b->text_off[r] = textLen;
+        if (getenv("YA_MOCK_TRACE")) fprintf(stderr, "mock: read %d clumps %d hand %d\n", r, m, hand);
+        if (!hand && m > 0) {
+            fr_node g[FR_MAX_NODES]; fr_out o[FR_MAX_NODES];
+            int prim = 0;
+            const int k = fr_finish_read(&F, c->fwd + base, L, cl, m, g, o, &prim);
+            if (k < 0) hand = 1;
+            for (int q = 0; q < k; q++) {
+                const size_t len = fr_format_record(&F, c->bases, b->ids + b->id_off[r], (int)(b->id_off[r + 1] - b->id_off[r]), b->chars + base,
+                                                    b->quals ? b->quals + base : NULL, c->rev + base, L, &cl[o[q].clump], &o[q], prim, NULL);
+                if (textLen + len > textCap) { textCap = 2 * (textLen + len); c->text = realloc(c->text, textCap); }
+                const size_t wrote = fr_format_record(&F, c->bases, b->ids + b->id_off[r], (int)(b->id_off[r + 1] - b->id_off[r]), b->chars + base,
+                                                      b->quals ? b->quals + base : NULL, c->rev + base, L, &cl[o[q].clump], &o[q], prim, c->text + textLen);
+                if (wrote != len) { fprintf(stderr, "mock: record length changed between the counting and the writing pass\n"); abort(); }
+                textLen += len;
+            }
+        }
+        b->status[r] = (uint8_t)hand;
+        b->n_handed_back += hand;
+    }
+    b->text_off[n] = textLen;
+    b->text_len = b->text_needed = textLen;
+    free(fb.strands); free(fb.frags); free(fb.region); free(cb.clump_first); free(cb.clump_count); free(cb.clumps); free(cb.path);
+    free(pb.prep); free(pb.gaps); free(pb.path); free(pb.jobs); free(res); free(rops); free(recs); free(asmOps);
+    c->has_seed = 0; c->has_clumps = 0;
+    if (textLen > b->text_cap) { c->text_pending = textLen; return YA_E_CAPACITY; }
+    memcpy(b->text, c->text, textLen);
     return 0;
 }

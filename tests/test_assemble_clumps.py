@@ -23,13 +23,13 @@ PREP_DT = np.dtype([("gap_first", "<u4"), ("jobB", "<u4"), ("jobF", "<u4"), ("n_
                     ("forwLen", "<u2"), ("pad", "<u2")])
 RES_DT = np.dtype([("score", "<i4"), ("addedQLen", "<u2"), ("addedRLen", "<u2"), ("ops_off", "<u4"), ("ops_n", "<u4")])
 ASM_DT = np.dtype([("frag", S.FRAG_DT), ("score", "<i4"), ("n_ops", "<u4"), ("matchedBases", "<u2"), ("mismatchedBases", "<u2"),
-                   ("gapBases", "<u2"), ("totLength", "<u2"), ("totScore", "<u2"), ("verdict", "u1"), ("pad", "u1")])
+                   ("gapBases", "<u2"), ("totLength", "<u2"), ("totScore", "<u2"), ("verdict", "u1"), ("pad", "u1"), ("ops_off", "<u4")])
 NONE = 0xFFFFFFFF
 DROP, SCORED, SPLIT = 0, 1, 2
 
 
 def test_record_layouts_match_the_abi():
-    assert (GAP_DT.itemsize, PREP_DT.itemsize, RES_DT.itemsize, S.OP_DT.itemsize, S.FRAG_DT.itemsize, ASM_DT.itemsize) == (16, 20, 16, 4, 12, 32)
+    assert (GAP_DT.itemsize, PREP_DT.itemsize, RES_DT.itemsize, S.OP_DT.itemsize, S.FRAG_DT.itemsize, ASM_DT.itemsize) == (16, 20, 16, 4, 12, 36)
 
 
 def pack(codes):

@@ -82,14 +82,14 @@ def test_baseline_config_sam_identical_in_order(bench, wl):
 
 
 def test_down_sampled_index_equals_the_reference_build(bench, tmp_path):
-    """ya_open_build with -H 650 on a repeat-rich reference (40 Mbp, one Alu-like copy per 10 kbp: hundreds of k-mers far
+    """ya_open_build with -H 650 on a repeat-rich reference (40 Mbp, one Alu-like copy per kbp: hundreds of k-mers far
     above the cap) against the file `yaha -g -H 650` writes: the sampled lists must be the reference's, entry for entry."""
     import hashlib
     import yaha_b200
     from yaha_b200 import refio, synth
     if not os.path.exists(REF):
         pytest.skip("oracle/_ref/yaha not built")
-    ref, bounds = synth.human_like_reference(40_000_000, 5, 7, alu_sites=4000)
+    ref, bounds = synth.human_like_reference(40_000_000, 5, 7, alu_sites=40000)
     seqs = [(f"chr{k + 1}", ref[bounds[k]:bounds[k + 1]]) for k in range(len(bounds) - 1)]
     synth.write_fasta(str(tmp_path / "ref.fa"), seqs)
     subprocess.check_call([REF, "-g", "ref.fa", "-L", "15", "-S", "1", "-H", "650"], cwd=str(tmp_path), stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)

@@ -73,12 +73,13 @@ class Counters(C.Structure):
     _fields_ = [("probes", C.c_uint64), ("hits", C.c_uint64), ("frags_all", C.c_uint64), ("frags_out", C.c_uint64),
                 ("dp_jobs", C.c_uint64), ("dp_cells", C.c_uint64), ("ms_seed", C.c_double), ("ms_dp", C.c_double),
                 ("ms_traceback", C.c_double), ("launches", C.c_uint64), ("ext_cells", C.c_uint64), ("ms_ext", C.c_double),
-                ("ext_launches", C.c_uint64), ("ms_lookup", C.c_double)]
+                ("ext_launches", C.c_uint64), ("ms_lookup", C.c_double), ("ms_finish", C.c_double), ("reads_finished", C.c_uint64),
+                ("reads_handed_back", C.c_uint64), ("text_bytes", C.c_uint64)]
 
 
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
            "ya_reads_upload", "ya_seed_frags", "ya_form_clumps", "ya_prepare_clumps", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_host_alloc", "ya_host_free", "ya_get_counters",
-           "ya_measure_int32_peak", "ya_measure_gather_peak")
+           "ya_measure_int32_peak", "ya_measure_gather_peak", "ya_set_output", "ya_align_batch", "ya_align_fetch_text")
 
 _lib = None
 

@@ -35,6 +35,7 @@ typedef struct ya_asm_rec {
     uint16_t matchedBases, mismatchedBases, gapBases, totLength, totScore;   /* Clump_t fields, set when SCORED      */
     uint8_t  verdict;                 /* YA_ASM_SCORED: done; YA_ASM_DROP: below -M / -P; YA_ASM_SPLIT: splitClump has to look at it */
     uint8_t  pad;
+    uint32_t ops_off;                 /* set by the caller: where the clump's runs were written (device: index into the batch's run array) */
 } ya_asm_rec;
 
 #if defined(__CUDA_ARCH__) || !defined(__GNUC__)
@@ -131,7 +132,7 @@ FC_HD int ac_assemble_clump(const ac_params *P, const uint8_t *bases, const uint
             f.refLen = (uint16_t)(f.refLen + r->addedRLen);
         }
     }
-    rec->frag = f; rec->score = score; rec->n_ops = n; rec->pad = 0;
+    rec->frag = f; rec->score = score; rec->n_ops = n; rec->pad = 0; rec->ops_off = 0;
     rec->matchedBases = rec->mismatchedBases = rec->gapBases = rec->totLength = rec->totScore = 0;
 
     /* scoreClump (AlignHelpers.c:302-366): running score over the runs; a clump whose score touches zero, reaches its

@@ -39,9 +39,10 @@ form_clumps_kernel(const ya_strand_frags *__restrict__ strands, int n_seg, const
     count[s] = (uint32_t)nc;
 }
 
-extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
+// device_only (ya_align_batch): records stay on the device, nothing is copied back and the call does not wait.
+int ya_form_clumps_impl(ya_ctx *c, ya_clump_batch *out, bool device_only)
 {
-    if (!c || !out || !out->clump_first || !out->clump_count) return YA_E_ARG;
+    if (!c || !out || (!device_only && (!out->clump_first || !out->clump_count))) return YA_E_ARG;
     YA_CUDA(c, cudaSetDevice(c->device));
     out->n_clumps = 0; out->n_path = 0;
     c->fc_valid = false;
@@ -49,7 +50,7 @@ extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
     if (n_seg == 0) return YA_OK;
     if (c->seed_chunks != 1) return ya_fail(c, YA_E_STATE, "ya_form_clumps: needs the survivors of a single-chunk ya_seed_frags call on the device");
     const size_t nk = c->seed_nkeep;
-    if (nk > out->cap || (nk && (!out->clumps || !out->path))) return ya_fail(c, YA_E_CAPACITY, "clump output buffers too small");
+    if (!device_only && (nk > out->cap || (nk && (!out->clumps || !out->path)))) return ya_fail(c, YA_E_CAPACITY, "clump output buffers too small");
     cudaStream_t st = c->stream;
     AllocScope allocScope(st);
     YA_CUDA(c, c->d_fc_count.reserve((size_t)n_seg * 8 + 64));     // counts, firsts and (tail) the job counter of ya_prepare_clumps
@@ -69,6 +70,7 @@ extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
         c->d_fc_used.as<uint8_t>(), c->d_fc_tmp.as<ya_frag>(), c->d_fc_path.as<ya_frag>(), c->d_fc_clumps.as<ya_clump_rec>(), d_count, d_first);
     c->ctr.launches++;
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
+    if (device_only) { YA_CUDA(c, cudaGetLastError()); c->fc_valid = true; return YA_OK; }
     YA_CUDA(c, cudaMemcpyAsync(out->clump_count, d_count, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaMemcpyAsync(out->clump_first, d_first, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
     if (nk) {
@@ -100,6 +102,7 @@ prepare_clumps_kernel(int n_seg, const uint64_t *__restrict__ read_off, const ui
                       ya_frag *__restrict__ path, ya_gap_rec *__restrict__ gaps, ya_prep_rec *__restrict__ prep,
                       ya_dp_job *__restrict__ jobs, uint32_t *__restrict__ n_jobs, uint32_t jobs_cap)
 {
+    // n_jobs[0]: job index allocator; n_jobs[1]: extension jobs among them (sizes the extension launch of the round)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const uint32_t nc = count[s];
@@ -117,12 +120,16 @@ prepare_clumps_kernel(int n_seg, const uint64_t *__restrict__ read_off, const ui
         pr.gap_first = rec.first;
         pc_prepare_clump(&P, bases, q, readLen, r, strand, path + rec.first, (int)rec.n, gaps + rec.first, jobs, n_jobs, jobs_cap, &pr);
         prep[c0 + k] = pr;
+        const uint32_t ne = (pr.jobB != 0xFFFFFFFFu) + (pr.jobF != 0xFFFFFFFFu);
+        if (ne) atomicAdd(n_jobs + 1, ne);
     }
 }
 
-extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
+// device_only (ya_align_batch): only the two job counts come back (out->n_jobs, *n_ext); records and jobs stay on the device.
+int ya_prepare_clumps_impl(ya_ctx *c, ya_prep_batch *out, bool device_only, size_t *n_ext)
 {
     if (!c || !out) return YA_E_ARG;
+    if (n_ext) *n_ext = 0;
     YA_CUDA(c, cudaSetDevice(c->device));
     out->n_jobs = 0;
     const int n_seg = 2 * c->n_reads;
@@ -130,10 +137,10 @@ extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
     if (!c->fc_valid) return ya_fail(c, YA_E_STATE, "ya_prepare_clumps: call ya_form_clumps first");
     const size_t nk = c->seed_nkeep;
     if (nk == 0) return YA_OK;
-    if (nk > out->cap || !out->prep || !out->gaps || !out->path || !out->jobs) return ya_fail(c, YA_E_CAPACITY, "prepare output buffers too small");
+    if (!device_only && (nk > out->cap || !out->prep || !out->gaps || !out->path || !out->jobs)) return ya_fail(c, YA_E_CAPACITY, "prepare output buffers too small");
     cudaStream_t st = c->stream;
     AllocScope allocScope(st);
-    const size_t jobsCap = std::min<size_t>(out->jobs_cap, 3 * nk + 16);
+    const size_t jobsCap = device_only ? 3 * nk + 16 : std::min<size_t>(out->jobs_cap, 3 * nk + 16);
     YA_CUDA(c, c->d_pc_path.reserve(nk * sizeof(ya_frag) + 64));
     YA_CUDA(c, c->d_pc_gaps.reserve(nk * sizeof(ya_gap_rec) + 64));
     YA_CUDA(c, c->d_pc_prep.reserve(nk * sizeof(ya_prep_rec) + 64));
@@ -141,7 +148,7 @@ extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
     YA_CUDA(c, c->h_stage3.reserve(64));
     uint32_t *d_count = c->d_fc_count.as<uint32_t>(), *d_first = d_count + n_seg;
     uint32_t *d_njobs = d_first + n_seg;                               // (d_fc_count has a spare tail)
-    YA_CUDA(c, cudaMemsetAsync(d_njobs, 0, 4, st));
+    YA_CUDA(c, cudaMemsetAsync(d_njobs, 0, 8, st));
     pc_params P;
     P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.RCost = c->P.RCost; P.MScore = c->P.MScore;
     P.minExtLength = c->P.minExtLength; P.maxROff = c->maxROff;
@@ -153,7 +160,17 @@ extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
     c->ctr.launches++;
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     uint32_t *h_n = c->h_stage3.as<uint32_t>();
-    YA_CUDA(c, cudaMemcpyAsync(h_n, d_njobs, 4, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(h_n, d_njobs, 8, cudaMemcpyDeviceToHost, st));
+    if (device_only) {
+        YA_CUDA(c, ya_stream_wait(st));
+        YA_CUDA(c, cudaGetLastError());
+        float msd = 0; cudaEventElapsedTime(&msd, c->ev[0], c->ev[1]);
+        c->ctr.ms_seed += msd;
+        if (h_n[0] > jobsCap) return ya_fail(c, YA_E_STATE, "prepare: more DP jobs than the job buffer holds");
+        out->n_jobs = h_n[0];
+        if (n_ext) *n_ext = h_n[1];
+        return YA_OK;
+    }
     YA_CUDA(c, cudaMemcpyAsync(out->prep, c->d_pc_prep.p, nk * sizeof(ya_prep_rec), cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaMemcpyAsync(out->gaps, c->d_pc_gaps.p, nk * sizeof(ya_gap_rec), cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, cudaMemcpyAsync(out->path, c->d_pc_path.p, nk * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
@@ -173,3 +190,6 @@ extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out)
     out->n_jobs = nj;
     return YA_OK;
 }
+
+extern "C" int ya_form_clumps(ya_ctx *c, ya_clump_batch *out) { return ya_form_clumps_impl(c, out, false); }
+extern "C" int ya_prepare_clumps(ya_ctx *c, ya_prep_batch *out) { return ya_prepare_clumps_impl(c, out, false, nullptr); }

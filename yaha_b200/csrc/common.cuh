@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include "../../include/yaha_b200.h"
+#include "finish_reads.h"
 
 #define YA_WORST (-(0x7fffff00))      // "minus infinity" of the reference DP (SW.cpp:356)
 
@@ -133,6 +134,13 @@ struct ya_ctx {
               d_keep, d_keepidx, d_frags_out, d_region_out, d_strand_out, d_misc;
     DevBuf    d_fc_count, d_fc_work, d_fc_tmp, d_fc_path, d_fc_nodes, d_fc_used, d_fc_clumps;   // ya_form_clumps
     DevBuf    d_pc_path, d_pc_gaps, d_pc_prep, d_pc_jobs;                                       // ya_prepare_clumps
+    // ya_align_batch: the reads as text, per-clump assembly records, per-read output plan, SAM text
+    DevBuf    d_chars, d_quals, d_ids, d_fin, d_asm_recs, d_asm_ops, d_fr_outs, d_text, d_out_tab;
+    ya_out_params out{}; fr_params fr{}; bool out_set = false;
+    size_t    text_pending = 0;         // text left on the device by a ya_align_batch that returned YA_E_CAPACITY
+    bool      dpr_ran = false;          // the last device DP round launched kernels (its events are valid)
+    DevBuf    d_dpr;                                                                           // plan of a device-born DP round
+    bool      dpr_bulk_packed = false; int dpr_packed_launches = 0;
     bool      big_sort_attr = false;    // seg_sort_kernel<8192,256> has its 64 KB shared-memory opt-in on this context's device
     bool      fc_valid = false;         // the clumps of the last ya_form_clumps call are on the device
     int       seed_chunks = 0;          // chunks of the last ya_seed_frags call (its survivors stay on the device when 1)

@@ -407,9 +407,11 @@ int ya_radix_sort_u64(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_
     return YA_OK;
 }
 
-extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
+// device_only (ya_align_batch): the survivors stay on the device, nothing but the counts comes back; `out` only receives
+// n_frags.  Needs the whole batch in one chunk (YA_E_STATE otherwise: the caller takes the call-by-call path).
+int ya_seed_frags_impl(ya_ctx *c, ya_frag_batch *out, bool device_only)
 {
-    if (!c || !out || !out->strands || (out->frags_cap && (!out->frags || !out->region))) return YA_E_ARG;
+    if (!c || !out || (!device_only && (!out->strands || (out->frags_cap && (!out->frags || !out->region))))) return YA_E_ARG;
     YA_CUDA(c, cudaSetDevice(c->device));
     const int n_reads = c->n_reads;
     const int n_seg = 2 * n_reads;
@@ -477,6 +479,7 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             hits += add; s1 += 2;
         }
         if (hits >= 0xFFFFFFF0ull) return ya_fail(c, YA_E_ARG, "a single read produces more than 2^32 seed hits");
+        if (device_only && (s0 != 0 || s1 != n_seg)) return ya_fail(c, YA_E_STATE, "batch needs several seed chunks");
         const uint32_t n_keys = (uint32_t)hits;
         const int cseg = s1 - s0;
         c->ctr.hits += n_keys;
@@ -577,9 +580,10 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             // results: the counts, the strand records and -- speculatively -- the first survivors (32 per read)
             uint32_t *h_cnt = c->h_stage.as<uint32_t>() + (size_t)n_seg * 2;          // 3 words after the per-segment totals
             YA_CUDA(c, cudaMemcpyAsync(h_cnt, d_tot, 12, cudaMemcpyDeviceToHost, st));
-            YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
-                                       cudaMemcpyDeviceToHost, st));
-            const size_t room = (!overflow && out->frags_cap > out_base) ? out->frags_cap - out_base : 0;
+            if (!device_only)
+                YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
+                                           cudaMemcpyDeviceToHost, st));
+            const size_t room = (!device_only && !overflow && out->frags_cap > out_base) ? out->frags_cap - out_base : 0;
             const size_t guess = std::min<size_t>(std::min<size_t>(room, NU), (size_t)16 * (size_t)cseg + 64);
             if (guess) {
                 YA_CUDA(c, cudaMemcpyAsync(out->frags + out_base, c->d_frags_out.p, guess * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
@@ -589,7 +593,8 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
             const uint32_t nf = h_cnt[0], nkeep = h_cnt[2];
             c->ctr.frags_all += nf;
             c->ctr.frags_out += nkeep;
-            if (!overflow && out_base + nkeep <= out->frags_cap) {
+            if (device_only) {
+            } else if (!overflow && out_base + nkeep <= out->frags_cap) {
                 if ((size_t)nkeep > guess) {                              // the speculative copy was too short: fetch the rest
                     YA_CUDA(c, cudaMemcpyAsync(out->frags + out_base + guess, c->d_frags_out.as<ya_frag>() + guess,
                                                ((size_t)nkeep - guess) * sizeof(ya_frag), cudaMemcpyDeviceToHost, st));
@@ -599,12 +604,12 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
                 }
             } else overflow = true;
             // strands of this chunk come back with chunk-relative `first`; fix up on the host
-            for (int s = s0; s < s1; s++) {
+            for (int s = s0; !device_only && s < s1; s++) {
                 ya_strand_frags &v = out->strands[s];
                 v.first = v.n_frags ? (uint32_t)(v.first + out_base) : (uint32_t)out_base;
             }
             out_base += nkeep;
-        } else {
+        } else if (!device_only) {
             YA_CUDA(c, cudaMemcpyAsync(out->strands + s0, d_strands + s0, (size_t)cseg * sizeof(ya_strand_frags),
                                        cudaMemcpyDeviceToHost, st));
             YA_CUDA(c, ya_stream_wait(st));
@@ -625,3 +630,5 @@ extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out)
     out->n_frags = out_base;
     return YA_OK;
 }
+
+extern "C" int ya_seed_frags(ya_ctx *c, ya_frag_batch *out) { return ya_seed_frags_impl(c, out, false); }

@@ -607,8 +607,14 @@ __global__ void __launch_bounds__(128)
 traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ ids, int n_jobs,
                       DevJobOut *__restrict__ outs, const uint16_t *__restrict__ tb, ya_op *__restrict__ ops_raw,
                       const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev,
-                      int BW, ya_dp_result *__restrict__ res, uint32_t *__restrict__ ops_cnt)
+                      int BW, ya_dp_result *__restrict__ res, uint32_t *__restrict__ ops_cnt,
+                      unsigned long long *__restrict__ acct)
 {
+    // acct != nullptr (device rounds, ya_align_batch): every job's runs are left IN PLACE in genome order -- walking order is
+    // end -> start, so forward and global jobs fill their slot from its end -- res[t].ops_off addresses ops_raw directly (no
+    // scan / compaction pass), and the counters the host would add up are accumulated here:
+    // acct[0] cells, acct[1] cells of packed-layout jobs, acct[2] error flags (1 corrupt back-pointers, 2 slot overflow)
+    const bool inPlace = acct != nullptr;
     const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = (int)(threadIdx.x & 31);
     if (warp >= n_jobs) return;
@@ -633,12 +639,16 @@ traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restric
         int y = o.maxi, x = o.maxj;
         int prev = -1; uint32_t run = 0;
         int guard = (int)J.qLen + (int)J.rLen + 8;
+        const bool fromEnd = inPlace && J.kind != YA_DP_EXT_BWD;            // (backward extensions walk in genome order, SW.cpp:1184-1185)
+        auto put = [&](uint32_t k, int op, uint32_t len) {
+            if (lane == 0 && k < J.ops_cap) {
+                ya_op *o = fromEnd ? &out[J.ops_cap - 1 - k] : &out[k];
+                o->length = (uint16_t)len; o->opcode = "MRDI"[op]; o->pad = 0;
+            }
+        };
         auto emit = [&](int op, uint32_t len) {
             if (op != prev) {
-                if (prev >= 0) {
-                    if (lane == 0 && n < J.ops_cap) { out[n].length = (uint16_t)run; out[n].opcode = "MRDI"[prev]; out[n].pad = 0; }
-                    n++;
-                }
+                if (prev >= 0) { put(n, prev, run); n++; }
                 prev = op; run = len;
             } else run += len;
         };
@@ -696,10 +706,7 @@ traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restric
             y -= p;
             guard -= p - 1;
         }
-        if (prev >= 0) {
-            if (lane == 0 && n < J.ops_cap) { out[n].length = (uint16_t)run; out[n].opcode = "MRDI"[prev]; out[n].pad = 0; }
-            n++;
-        }
+        if (prev >= 0) { put(n, prev, run); n++; }
     }
     if (lane == 0) { o.n_ops = n; outs[t] = o; }
     // result record, fused (finalize_kernel of the thread-per-job path); the run count goes to the scan that
@@ -707,13 +714,21 @@ traceback_warp_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restric
     if (lane == 0) {
         ya_dp_result r;
         uint32_t keep = (n >= 0xFFFFFFF0u) ? 0u : n;                     // traceback error marker: reported by the host
+        if (inPlace) {
+            const unsigned long long cells = ((unsigned long long)o.cells_hi << 32) | o.cells_lo;
+            atomicAdd(&acct[0], cells);
+            if (J.layout == 2) atomicAdd(&acct[1], cells);
+            if (n >= 0xFFFFFFF0u) atomicOr(&acct[2], 1ull);
+            else if (n > J.ops_cap) { atomicOr(&acct[2], 2ull); keep = 0; }
+        }
         if (ext) {
             if (o.score <= 0) { r.score = 0; r.addedQLen = 0; r.addedRLen = 0; keep = 0; }                  // SW.cpp:525,1102
             else { r.score = o.score; r.addedQLen = (uint16_t)o.maxi; r.addedRLen = (uint16_t)(o.maxi + (o.maxj - 2 * BW)); }   // SW.cpp:1109-1110
         } else { r.score = o.score; r.addedQLen = 0; r.addedRLen = 0; }
         r.ops_n = keep; r.ops_off = 0;
+        if (inPlace) r.ops_off = J.ops_off + ((J.kind != YA_DP_EXT_BWD) ? J.ops_cap - keep : 0u);
         res[t] = r;
-        ops_cnt[t] = keep;
+        if (ops_cnt) ops_cnt[t] = keep;
     }
 }
 
@@ -1077,7 +1092,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         traceback_warp_kernel<<<(n_live + 3) / 4, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, n_live, c->d_jobout.as<DevJobOut>(),
                                                                  c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases,
                                                                  c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
-                                                                 P.bandWidth, c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>());
+                                                                 P.bandWidth, c->d_res.as<ya_dp_result>(), c->d_ops_cnt.as<uint32_t>(), nullptr);
         c->ctr.launches++;
         {
             int rc = ya_exclusive_scan_u32(c, c->d_ops_cnt.as<uint32_t>(), c->d_ops_off.as<uint32_t>(), (size_t)n_live, d_tot);
@@ -1156,6 +1171,259 @@ extern "C" int ya_sw_fetch_ops(ya_ctx *c, ya_op *ops, size_t ops_cap)
     YA_CUDA(c, cudaSetDevice(c->device));
     YA_CUDA(c, cudaMemcpyAsync(ops, c->d_ops_out.p, c->ops_pending * sizeof(ya_op), cudaMemcpyDeviceToHost, c->stream));
     YA_CUDA(c, ya_stream_wait(c->stream));
+    return YA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// A DP round whose jobs were born on the device (ya_prepare_clumps) and whose answers stay there (ya_align_batch): what
+// the host loop of ya_sw_batch does per job -- clamping of findAGSExtension (SW.cpp:492-516), band geometry
+// (SW.cpp:856-866), kernel class, back-pointer / run-slot layout, longest-first order inside a class -- as kernels.
+// ------------------------------------------------------------------------------------------
+#define DPR_NCLASS   (2 * 8 + 1 + 2)          // == 2 * kNumWaveCfgs + 1 + kNumPackedCfgs
+#define DPR_DEAD     DPR_NCLASS               // jobs settled without a launch (nothing left after clamping)
+#define DPR_BUCKETS  1024                     // rows / 8, capped: the order inside a class is by length, longest first
+#define DPR_BINS     ((DPR_NCLASS + 1) * DPR_BUCKETS)
+
+struct DprFlags { int narrowExt, allowPacked, forceThread, fullThreadMaxW; long long packedStepCost; };
+__constant__ int c_waveG[8] = {8, 8, 8, 8, 16, 16, 32, 32};
+__constant__ int c_waveC[8] = {3, 4, 6, 8, 6, 8, 8, 11};
+
+__global__ void dpr_classify_kernel(const ya_dp_job *__restrict__ jobs, uint32_t n, const uint64_t *__restrict__ read_off, int n_reads,
+                                    ya_params P, uint32_t maxROff, uint64_t n_bases, DprFlags F,
+                                    DevJob *__restrict__ dj, uint32_t *__restrict__ key, uint32_t *__restrict__ tb_units,
+                                    uint32_t *__restrict__ ops_slots, uint32_t *__restrict__ rows_ints,
+                                    ya_dp_result *__restrict__ res, unsigned long long *__restrict__ acct)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ya_dp_job j = jobs[i];
+    DevJob d; memset(&d, 0, sizeof d);
+    ya_dp_result zero; zero.score = 0; zero.addedQLen = 0; zero.addedRLen = 0; zero.ops_off = 0; zero.ops_n = 0;
+    res[i] = zero;
+    uint32_t cls = DPR_DEAD, tbu = 0, slots = 0, rints = 0;
+    const int bw2 = 2 * P.bandWidth;
+    bool bad = j.read >= (uint32_t)n_reads || j.kind > YA_DP_EXT_BWD || j.strand > 1;
+    if (!bad) {
+        const uint64_t rbase = read_off[j.read];
+        const int L = (int)(read_off[j.read + 1] - rbase);
+        int qLen = j.qLen, rLen = j.rLen;
+        const uint32_t rOff = j.rOff;
+        bool live = true;
+        d.kind = j.kind; d.strand = j.strand;
+        if (j.kind >= YA_DP_EXT_FWD) {                                  // SW.cpp:492-516
+            const bool reverse = j.kind == YA_DP_EXT_BWD;
+            if (qLen <= 0) live = false;
+            else {
+                uint32_t rl = (uint32_t)(qLen + bw2);
+                if (reverse && rl > rOff) { rl = rOff + 1; qLen = (int)(rl - (uint32_t)bw2); if (qLen <= 0) live = false; }
+                if (live && !reverse && rOff + rl > maxROff) { rl = maxROff - rOff; qLen = (int)(rl - (uint32_t)bw2); if (qLen <= 0) live = false; }
+                rLen = (int)rl;
+                if (live && (reverse ? ((int)j.qOff - (qLen - 1) < 0 || (int)j.qOff >= L) : ((int)j.qOff + qLen > L))) bad = true;
+                d.lb = (uint16_t)bw2; d.rb = (uint16_t)bw2;
+            }
+        } else {
+            if (qLen <= 0 || rLen <= 0 || (int)j.qOff + qLen > L || (uint64_t)rOff + (uint64_t)rLen > n_bases) bad = true;
+            else if (j.kind == YA_DP_BANDED) {
+                d.lb = (uint16_t)(P.bandWidth + (qLen > rLen ? qLen - rLen : 0));     // SW.cpp:856-866
+                d.rb = (uint16_t)(P.bandWidth + (rLen > qLen ? rLen - qLen : 0));
+            } else { d.lb = (uint16_t)qLen; d.rb = (uint16_t)rLen; }
+        }
+        if (live && !bad) {
+            d.rOff = rOff; d.rLen = (uint16_t)rLen; d.qLen = (uint16_t)qLen;
+            d.qIdx = (uint32_t)(rbase + j.qOff);
+            const int W = d.lb + d.rb + 1;
+            int wcls = -1, pcls = -1;
+            if (F.allowPacked && j.kind >= YA_DP_EXT_FWD && W <= P.maxGap && W <= P.maxIntron &&
+                (long long)(qLen + W + 2) * F.packedStepCost < (1ll << 20)) {
+                if (W == 21) pcls = 0; else if (W == 41) pcls = 1;
+            }
+            uint64_t cells;
+            if (pcls >= 0) {
+                const int G = F.narrowExt ? (pcls == 0 ? 4 : 7) : (pcls == 0 ? 2 : 4);
+                const int C = F.narrowExt ? 6 : 11, CP = (C + 3) & ~3;
+                d.layout = 2; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * CP);
+                cells = 2ull * (uint64_t)((qLen + G + 3) / 4 + 1) * d.stride;
+                cls = 17 + pcls;
+            } else {
+                if (!F.forceThread && (j.kind != YA_DP_FULL || W > F.fullThreadMaxW))
+                    for (int k = 0; k < 8; k++) if (c_waveG[k] * c_waveC[k] >= W) { wcls = k; break; }
+                if (wcls >= 0) {
+                    const int G = c_waveG[wcls], C = c_waveC[wcls];
+                    d.layout = 1; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * C);
+                    cells = (uint64_t)(qLen + G + 1) * d.stride;
+                    cls = (j.kind >= YA_DP_EXT_FWD ? 0 : 8) + wcls;
+                } else {
+                    d.layout = 0; d.colsPerLane = 1; d.stride = (uint32_t)W;
+                    cells = (uint64_t)(qLen + 1) * d.stride;
+                    rints = 3u * (uint32_t)(W + 1);
+                    cls = 16;
+                }
+            }
+            tbu = (uint32_t)((cells + 7) >> 3);                        // 16-byte units (128-bit stores of the packed kernel)
+            slots = (uint32_t)(qLen + rLen + 2);
+            d.ops_cap = slots;
+        }
+    }
+    if (bad) atomicOr(&acct[2], 4ull);
+    dj[i] = d;
+    const uint32_t bucket = min((uint32_t)d.qLen >> 3, (uint32_t)(DPR_BUCKETS - 1));
+    key[i] = cls * DPR_BUCKETS + (DPR_BUCKETS - 1 - bucket);
+    tb_units[i] = tbu; ops_slots[i] = slots; rows_ints[i] = rints;
+}
+
+// In-place exclusive scans of up to four arrays of n words by ONE block (n is a few tens of thousands: a device-wide scan
+// would be three launches per array); totals[k] receives array k's sum (64-bit).
+__global__ void __launch_bounds__(1024)
+dpr_scan_kernel(uint32_t *a0, uint32_t *a1, uint32_t *a2, uint32_t *a3, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3,
+                unsigned long long *__restrict__ totals)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    uint32_t *arr[4] = {a0, a1, a2, a3};
+    const uint32_t cnt[4] = {n0, n1, n2, n3};
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int a = 0; a < 4; a++) {
+        uint32_t *p = arr[a];
+        if (!p) continue;
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < cnt[a]; base += 1024 * 4) {
+            const uint32_t i0 = base + threadIdx.x * 4;
+            uint32_t v[4]; unsigned long long s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { v[k] = (i0 + k < cnt[a]) ? p[i0 + k] : 0u; s += v[k]; }
+            unsigned long long inc = s;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
+            if (lane == 31) wsum[w] = inc;
+            __syncthreads();
+            if (w == 0) {
+                unsigned long long x = wsum[lane], xi = x;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, xi, dlt); if (lane >= dlt) xi += t; }
+                wsum[lane] = xi - x;
+            }
+            __syncthreads();
+            unsigned long long ex = carry + wsum[w] + inc - s;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { if (i0 + k < cnt[a]) p[i0 + k] = (uint32_t)ex; ex += v[k]; }
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = ex;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) totals[a] = carry;
+        __syncthreads();
+    }
+}
+
+__global__ void dpr_hist_kernel(const uint32_t *__restrict__ key, uint32_t n, uint32_t *__restrict__ bins)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&bins[key[i]], 1u);
+}
+
+// job offsets from the scans (the scanned arrays hold exclusive prefix sums now) and the class-ordered id list
+__global__ void dpr_place_kernel(DevJob *__restrict__ dj, uint32_t n, const uint32_t *__restrict__ key, const uint32_t *__restrict__ tb_off,
+                                 const uint32_t *__restrict__ ops_off, const uint32_t *__restrict__ rows_off,
+                                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ ids)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevJob d = dj[i];
+    d.tb_off = (d.layout == 2) ? (uint64_t)tb_off[i] * 4 : (uint64_t)tb_off[i] * 8;    // packed: 32-bit words; else 16-bit cells
+    d.ops_off = ops_off[i];
+    d.rows_off = rows_off[i];
+    dj[i] = d;
+    ids[atomicAdd(&cursor[key[i]], 1u)] = i;
+}
+
+__global__ void dpr_class_starts_kernel(const uint32_t *__restrict__ bins_scanned, uint32_t *__restrict__ starts)
+{
+    const int k = threadIdx.x;
+    if (k <= DPR_NCLASS + 1) starts[k] = (k <= DPR_NCLASS) ? bins_scanned[k * DPR_BUCKETS] : 0u;
+}
+
+// Runs the round for c->d_pc_jobs[0..n_jobs).  Afterwards c->d_res[i] answers job i with ops_off addressing c->d_ops_raw
+// directly (runs in genome order); nothing is copied to the host.  acct (device, 4 x u64) accumulates cells / packed cells /
+// error flags.  One synchronisation (the totals that size the scratch).
+int ya_sw_device_round(ya_ctx *c, uint32_t n_jobs, uint32_t n_ext, unsigned long long *d_acct, size_t *raw_slots)
+{
+    if (raw_slots) *raw_slots = 0;
+    c->dpr_ran = false;
+    if (n_jobs == 0) return YA_OK;
+    cudaStream_t st = c->stream;
+    const ya_params &P = c->P;
+    static const int fullThreadMaxW = [] { const char *e = getenv("YA_FULL_THREAD_MAXW"); return e ? atoi(e) : 0; }();
+    DprFlags F;
+    F.narrowExt = n_ext < kPackedNarrowBelow; F.allowPacked = !forbid_packed_kernel(); F.forceThread = force_thread_kernel();
+    F.fullThreadMaxW = fullThreadMaxW;
+    F.packedStepCost = std::max<long long>(std::max<long long>(std::abs(P.MScore), std::abs(P.RCost)), (long long)std::abs(P.GOCost) + std::abs(P.GECost));
+    YA_CUDA(c, c->d_jobs.reserve((size_t)n_jobs * sizeof(DevJob)));
+    YA_CUDA(c, c->d_jobout.reserve((size_t)n_jobs * sizeof(DevJobOut)));
+    YA_CUDA(c, c->d_res.reserve((size_t)n_jobs * sizeof(ya_dp_result)));
+    YA_CUDA(c, c->d_misc.reserve((size_t)n_jobs * 4 + 64));
+    YA_CUDA(c, c->d_dpr.reserve(8 * 8 + ((size_t)4 * n_jobs + DPR_BINS + 64) * 4));
+    YA_CUDA(c, c->h_stage3.reserve(1024));
+    unsigned long long *totals = c->d_dpr.as<unsigned long long>();                      // 4 totals (8 words reserved)
+    uint32_t *key = (uint32_t *)(totals + 8), *tbu = key + n_jobs, *slots = tbu + n_jobs, *rints = slots + n_jobs;
+    uint32_t *bins = rints + n_jobs, *starts = bins + DPR_BINS;                          // (starts: DPR_NCLASS + 2 words)
+    uint32_t *d_ids = c->d_misc.as<uint32_t>();
+    const unsigned nb = (n_jobs + 255) / 256;
+    YA_CUDA(c, cudaMemsetAsync(bins, 0, (size_t)DPR_BINS * 4, st));
+    dpr_classify_kernel<<<nb, 256, 0, st>>>(c->d_pc_jobs.as<ya_dp_job>(), n_jobs, c->d_read_off.as<uint64_t>(), c->n_reads, P, c->maxROff,
+                                            (uint64_t)c->n_base_bytes * 2, F, c->d_jobs.as<DevJob>(), key, tbu, slots, rints,
+                                            c->d_res.as<ya_dp_result>(), d_acct);
+    dpr_hist_kernel<<<nb, 256, 0, st>>>(key, n_jobs, bins);
+    dpr_scan_kernel<<<1, 1024, 0, st>>>(tbu, slots, rints, bins, n_jobs, n_jobs, n_jobs, DPR_BINS, totals);
+    dpr_class_starts_kernel<<<1, 64, 0, st>>>(bins, starts);
+    dpr_place_kernel<<<nb, 256, 0, st>>>(c->d_jobs.as<DevJob>(), n_jobs, key, tbu, slots, rints, bins, d_ids);
+    c->ctr.launches += 5;
+    struct HostPlan { unsigned long long totals[4]; uint32_t starts[DPR_NCLASS + 2]; } *hp = c->h_stage3.as<HostPlan>();
+    YA_CUDA(c, cudaMemcpyAsync(hp->totals, totals, 4 * 8, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, cudaMemcpyAsync(hp->starts, starts, (DPR_NCLASS + 2) * 4, cudaMemcpyDeviceToHost, st));
+    YA_CUDA(c, ya_stream_wait(st));
+    const unsigned long long tbUnits = hp->totals[0], opsSlots = hp->totals[1], rowsInts = hp->totals[2];
+    if (tbUnits >= 0xFFFF0000ull || opsSlots >= 0xFFFF0000ull || rowsInts >= 0xFFFF0000ull)
+        return ya_fail(c, YA_E_STATE, "device DP round too large for 32-bit offsets");
+    uint32_t start[DPR_NCLASS + 2];
+    for (int k = 0; k <= DPR_NCLASS; k++) start[k] = hp->starts[k];
+    start[DPR_NCLASS + 1] = n_jobs;
+    auto count = [&](int k) { return (int)(start[k + 1] - start[k]); };
+    const uint32_t n_live = start[DPR_NCLASS];                          // dead jobs sit behind every class
+    c->ctr.dp_jobs += n_jobs;
+    if (raw_slots) *raw_slots = (size_t)opsSlots;
+    if (n_live == 0) return YA_OK;
+    YA_CUDA(c, c->d_tb.reserve((size_t)tbUnits * 16 + 64));
+    YA_CUDA(c, c->d_rows.reserve((size_t)rowsInts * 4 + 64));
+    YA_CUDA(c, c->d_ops_raw.reserve((size_t)opsSlots * sizeof(ya_op) + 64));
+    DpConst K{P.GOCost, P.GECost, P.RCost, P.MScore, P.XCutoff, P.maxIntron, P.maxGap, P.bandWidth};
+    YA_CUDA(c, cudaEventRecord(c->ev[0], st));
+    for (int k = 0; k < kNumWaveCfgs; k++) {
+        if (count(k)) launch_wave_cfg(c, k, true, d_ids + start[k], count(k), K);
+        if (count(kNumWaveCfgs + k)) launch_wave_cfg(c, k, false, d_ids + start[kNumWaveCfgs + k], count(kNumWaveCfgs + k), K);
+    }
+    const int packedBase = 2 * kNumWaveCfgs + 1;
+    const int nP0 = count(packedBase), nP1 = count(packedBase + 1);
+    if (nP0 || nP1) YA_CUDA(c, cudaEventRecord(c->ev[3], st));
+    if (nP0) { if (F.narrowExt) launch_packed<4, 6, 21>(c, d_ids + start[packedBase], nP0, K); else launch_packed<2, 11, 21>(c, d_ids + start[packedBase], nP0, K); }
+    if (nP1) { if (F.narrowExt) launch_packed<7, 6, 41>(c, d_ids + start[packedBase + 1], nP1, K); else launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], nP1, K); }
+    if (nP0 || nP1) YA_CUDA(c, cudaEventRecord(c->ev[4], st));
+    if (count(2 * kNumWaveCfgs)) {
+        const int nt = count(2 * kNumWaveCfgs);
+        dp_thread_kernel<<<(nt + 63) / 64, 64, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids + start[2 * kNumWaveCfgs], nt, c->d_jobout.as<DevJobOut>(),
+            c->d_tb.as<uint16_t>(), c->d_rows.as<int>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+        c->ctr.launches++;
+    }
+    YA_CUDA(c, cudaEventRecord(c->ev[1], st));
+    traceback_warp_kernel<<<(n_live + 3) / 4, 128, 0, st>>>(c->d_jobs.as<DevJob>(), d_ids, (int)n_live, c->d_jobout.as<DevJobOut>(),
+        c->d_tb.as<uint16_t>(), c->d_ops_raw.as<ya_op>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(),
+        P.bandWidth, c->d_res.as<ya_dp_result>(), nullptr, d_acct);
+    c->ctr.launches++;
+    YA_CUDA(c, cudaEventRecord(c->ev[2], st));
+    YA_CUDA(c, cudaGetLastError());
+    c->dpr_ran = true;
+    c->dpr_bulk_packed = (size_t)(nP0 + nP1) >= 4096;
+    c->dpr_packed_launches = (nP0 ? 1 : 0) + (nP1 ? 1 : 0);
     return YA_OK;
 }
 

@@ -77,15 +77,7 @@ struct Slot {
     bool set = false;                     // fibers created
 };
 
-struct Batch {
-    uint64_t seq = 0;
-    std::vector<Read> reads;
-    std::vector<std::pair<const char *, size_t>> slices;   // FASTA records still to be parsed (by the pipeline that takes the batch)
-    std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous (kept when the batch object is recycled)
-    int nFibers = 0, fiberCap = 0;
-    struct alignas(64) OutBuf { OutText s; };   // (own cache line: every append updates the size)
-    std::vector<OutBuf> outBufs;          // formatted records, one buffer per worker thread
-};
+struct Batch;
 
 DpFuture dpSubmit(ReadCtx &rc, int kind, bool rev, uint32_t rOff, int rLen, int qOff, int qLen)
 {
@@ -153,19 +145,30 @@ static void fiberEntry()
     __builtin_trap();                     // a finished fiber is never resumed
 }
 
+static const uint64_t kStackCanary = 0x59414841464942ull;
+static inline void checkStack(const void *stack)
+{
+    if (stack && *(const uint64_t *)stack != kStackCanary) { fprintf(stderr, "yaha_b200: a read's fiber overran its %zu KB stack\n", kStackBytes >> 10); abort(); }
+}
 struct StackPool {
     std::vector<void *> free_;
     std::mutex mu;
+    std::atomic<size_t> made{0};
     void *get()
     {
         { std::lock_guard<std::mutex> g(mu); if (!free_.empty()) { void *p = free_.back(); free_.pop_back(); return p; } }
         // one guard page below the stack: recursion that outgrows it (splitHelper, the OQC quickSort on repeat-rich
         // 32 kb reads) faults instead of silently writing into the neighbouring mapping
+        // (a guard page makes every stack two mappings of the process: the first 12 K stacks get one -- far below
+        // vm.max_map_count -- the rest, which only a run with tens of thousands of parked reads ever reaches, rely on the canary
+        // word at the stack's low end that is checked whenever a fiber leaves the processor)
         const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-        char *m = (char *)mmap(nullptr, kStackBytes + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        const bool guard = made.fetch_add(1) < 12288;
+        char *m = (char *)mmap(nullptr, kStackBytes + (guard ? page : 0), PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (m == MAP_FAILED) { fprintf(stderr, "cannot allocate fiber stack\n"); exit(1); }
-        mprotect(m, page, PROT_NONE);
-        return m + page;
+        if (guard) { mprotect(m, page, PROT_NONE); m += page; }
+        *(uint64_t *)m = kStackCanary;
+        return m;
     }
     void put(void *p) { std::lock_guard<std::mutex> g(mu); free_.push_back(p); }
 };
@@ -202,6 +205,7 @@ static int slotPass(Slot &w)
             tBoot = f;
         }
         yh_switch(&w.mainSp, f->sp);
+        checkStack(f->stack);
         if (!f->done) live++;
         else { tStacks.put(f->stack); f->stack = nullptr; }
     }
@@ -233,6 +237,24 @@ template <class T> struct PinnedVec {
     }
 };
 
+struct Batch {
+    uint64_t seq = 0;
+    std::vector<Read> reads;
+    std::vector<std::pair<const char *, size_t>> slices;   // FASTA records still to be parsed (by the pipeline that takes the batch)
+    std::unique_ptr<Fiber[]> fibers;      // one per read, contiguous (kept when the batch object is recycled)
+    int nFibers = 0, fiberCap = 0;
+    struct alignas(64) OutBuf { OutText s; };   // (own cache line: every append updates the size)
+    std::vector<OutBuf> outBufs;          // formatted records, one buffer per worker thread
+    // ya_align_batch: the SAM text of the reads finished on the device (page-locked, lands here straight from the device),
+    // where each read's records start, which reads were handed back -- those are run as `residual` through the fibers
+    PinnedVec<char> devText;
+    PinnedVec<uint64_t> devTextOff;
+    PinnedVec<uint8_t> devStatus;
+    std::unique_ptr<Batch> residual;
+    std::vector<int> residualOf;          // residual read k is read residualOf[k] of this batch
+    std::vector<std::pair<const char *, size_t>> outRuns;   // what the writer emits for this batch, in input order
+};
+
 struct ResultBlock {
     PinnedVec<ya_dp_result> res;
     PinnedVec<ya_op> ops;
@@ -247,6 +269,8 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     PinnedVec<uint32_t> region;
     PinnedVec<uint8_t> codes;
     PinnedVec<uint64_t> offs;
+    PinnedVec<char> chars, quals, ids;            // ya_align_batch inputs: the reads as they stand in the file
+    PinnedVec<uint32_t> idOffs;
     PinnedVec<uint32_t> clumpFirst, clumpCount;     // ya_form_clumps outputs (clumps of seed fragments made on the device)
     PinnedVec<ya_clump_rec> clumpRecs;
     PinnedVec<ya_frag> clumpPath;
@@ -427,19 +451,10 @@ static int coalesceMicros()
 
 // Align one batch on one pipeline.  This thread drives the device (stages 1+2, then one ya_sw_batch per
 // group of published slots); the shared workers run the fibers.  Results land in each read's rc.out.
-static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
+// The call-by-call path: stages 1+2 and the DP rounds on the device, everything between them in the reads' fibers.
+static void classicPass(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
 {
     double t0 = nowSec();
-    if (!B.slices.empty()) {                                            // FASTA records cut by the reader, parsed here
-        size_t k = 0;
-        for (const auto &sl : B.slices) {
-            if (k == B.reads.size()) B.reads.emplace_back();            // (Read objects of a recycled batch are refilled in place)
-            k += (size_t)parseFastaRecord(sl.first, sl.second, B.reads[k], E.A->maxQueryLength, E.A->wordLen);
-        }
-        B.reads.resize(k);
-        B.slices.clear();
-        traceEv('p', D.device, (int)B.seq, t0, nowSec());
-    }
     const int n = (int)B.reads.size();
     B.nFibers = 0;
     if (n == 0) return;
@@ -518,15 +533,34 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         blk->users.store(users);
         if (blk->res.size() < D.capJobs) blk->res.resize(D.capJobs, false);
         if (blk->ops.size() < D.capOps) blk->ops.resize(D.capOps, false);
-        size_t need = 0;
-        int rcode = ya_sw_batch(D.ctx, jobs, nj, blk->res.data(), blk->ops.data(), blk->ops.size(), &need);
-        if (rcode == YA_E_CAPACITY) {                       // results are in; only the ops need a bigger buffer
-            D.capOps = std::max(D.capOps, 2 * need + 1024);
-            blk->ops.resize(D.capOps, false);
-            rcode = ya_sw_fetch_ops(D.ctx, blk->ops.data(), blk->ops.size());
+        // One device call holds at most 2^31 raw run slots (a job's slots: rows + window + 2, sw.cu): a round of long reads
+        // with many clumps each (10 kbp reads over repeats) is served in several calls, answers appended to one block.
+        size_t opsUsed = 0;
+        for (int lo = 0; lo < nj;) {
+            uint64_t slots = 0, rows = 0;                     // (rows bound the back-pointer scratch: <= 768 B per row, 24 GB per call)
+            int hi = lo;
+            while (hi < nj) {
+                const ya_dp_job &j = jobs[hi];
+                const uint64_t s = (uint64_t)j.qLen + (j.kind >= YA_DP_EXT_FWD ? (uint64_t)j.qLen + 2u * (uint64_t)E.A->bandWidth : (uint64_t)j.rLen) + 2u;
+                if (hi > lo && (slots + s > (1ull << 31) || rows + j.qLen > (1ull << 25))) break;
+                slots += s; rows += j.qLen; hi++;
+            }
+            size_t need = 0;
+            int rcode = ya_sw_batch(D.ctx, jobs + lo, hi - lo, blk->res.data() + lo, blk->ops.data() + opsUsed, blk->ops.size() - opsUsed, &need);
+            if (rcode == YA_E_CAPACITY) {                   // results are in; only the ops need a bigger buffer
+                D.capOps = std::max(D.capOps, 2 * (opsUsed + need) + 1024);
+                blk->ops.n = opsUsed;                       // (keep what earlier calls of this round wrote)
+                blk->ops.resize(D.capOps, true);
+                rcode = ya_sw_fetch_ops(D.ctx, blk->ops.data() + opsUsed, blk->ops.size() - opsUsed);
+            }
+            if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
+            if (opsUsed) for (int k = lo; k < hi; k++) blk->res[(size_t)k].ops_off += (uint32_t)opsUsed;
+            opsUsed += need;
+            if (opsUsed >= 0xFFFF0000ull) { fprintf(stderr, "yaha_b200: a DP round returned more than 2^32 edit operations; use a smaller -batch\n"); exit(1); }
+            lo = hi;
+            D.nRounds++;
         }
-        if (rcode != YA_OK) die(D.ctx, "ya_sw_batch");
-        D.nJobs += (uint64_t)nj; D.nRounds++;
+        D.nJobs += (uint64_t)nj;
         return blk;
     };
 
@@ -602,6 +636,114 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     for (int i = 0; i < n; i++) if (B.fibers[(size_t)i].stack) { gStacks.put(B.fibers[(size_t)i].stack); B.fibers[(size_t)i].stack = nullptr; }
 }
 
+// The whole per-read path in one device call (ya_align_batch); returns the number of reads handed back.
+static int fusedPass(const Env &E, Pipe &D, Batch &B)
+{
+    const double t0 = nowSec();
+    const int n = (int)B.reads.size();
+    const bool fastq = E.A->fastq;
+    D.offs.resize((size_t)n + 1, false);
+    D.idOffs.resize((size_t)n + 1, false);
+    size_t total = 0, idTotal = 0;
+    for (int i = 0; i < n; i++) { D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fwd.size(); D.idOffs[(size_t)i] = (uint32_t)idTotal; idTotal += B.reads[(size_t)i].id.size(); }
+    D.offs[(size_t)n] = total; D.idOffs[(size_t)n] = (uint32_t)idTotal;
+    D.chars.resize(total + 1, false); D.ids.resize(idTotal + 1, false);
+    if (fastq) D.quals.resize(total + 1, false);
+    for (int i = 0; i < n; i++) {
+        const Read &r = B.reads[(size_t)i];
+        memcpy(D.chars.data() + D.offs[(size_t)i], r.fwd.data(), r.fwd.size());
+        memcpy(D.ids.data() + D.idOffs[(size_t)i], r.id.data(), r.id.size());
+        if (fastq) memcpy(D.quals.data() + D.offs[(size_t)i], r.qual.data(), r.qual.size());
+    }
+    B.devTextOff.resize((size_t)n + 1, false);
+    B.devStatus.resize((size_t)n, false);
+    if (B.devText.size() < 2 * total + 512 * (size_t)n + 4096) B.devText.resize(2 * total + 512 * (size_t)n + 4096, false);
+    ya_text_batch tb;
+    memset(&tb, 0, sizeof tb);
+    tb.n_reads = n; tb.chars = D.chars.data(); tb.offsets = D.offs.data(); tb.quals = fastq ? D.quals.data() : nullptr;
+    tb.ids = D.ids.data(); tb.id_off = D.idOffs.data();
+    tb.text = B.devText.data(); tb.text_cap = B.devText.size(); tb.text_off = B.devTextOff.data(); tb.status = B.devStatus.data();
+    D.tUpload += nowSec() - t0;
+    const double t1 = nowSec();
+    int rcode = ya_align_batch(D.ctx, &tb);
+    if (rcode == YA_E_CAPACITY) {
+        B.devText.resize(tb.text_needed + tb.text_needed / 4 + 4096, false);
+        rcode = ya_align_fetch_text(D.ctx, B.devText.data(), B.devText.size());
+    }
+    if (rcode != YA_OK) die(D.ctx, "ya_align_batch");
+    D.tDp += nowSec() - t1;
+    D.nRounds++;
+    traceEv('F', D.device, (int)B.seq, t0, nowSec(), tb.n_handed_back);
+    return tb.n_handed_back;
+}
+
+static bool fusedWanted(const Env &E)
+{
+    static const bool off = [] { const char *e = getenv("YA_FUSED"); return e && atoi(e) == 0; }();
+    static const bool hostSteps = getenv("YA_HOST_CLUMPS") != nullptr || getenv("YA_HOST_PREP") != nullptr;
+    return !off && !hostSteps && E.A->outputSAM && !E.A->outputBlast8;
+}
+
+// what the writer emits for a batch: every read's records in input order, neighbouring pieces merged into one run
+static void addRun(Batch &B, const char *p, size_t len)
+{
+    if (!len) return;
+    if (!B.outRuns.empty() && B.outRuns.back().first + B.outRuns.back().second == p) B.outRuns.back().second += len;
+    else B.outRuns.emplace_back(p, len);
+}
+
+// Align one batch on one pipeline.  Results land in B.outRuns.
+static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
+{
+    double t0 = nowSec();
+    if (!B.slices.empty()) {                                            // FASTA records cut by the reader, parsed here
+        size_t k = 0;
+        for (const auto &sl : B.slices) {
+            if (k == B.reads.size()) B.reads.emplace_back();            // (Read objects of a recycled batch are refilled in place)
+            k += (size_t)parseFastaRecord(sl.first, sl.second, B.reads[k], E.A->maxQueryLength, E.A->wordLen);
+        }
+        B.reads.resize(k);
+        B.slices.clear();
+        traceEv('p', D.device, (int)B.seq, t0, nowSec());
+    }
+    B.outRuns.clear();
+    B.nFibers = 0;
+    const int n = (int)B.reads.size();
+    if (n == 0) return;
+    auto fiberRuns = [](Batch &X, Batch &into) {
+        for (int i = 0; i < X.nFibers; i++) { const ReadCtx &rc = X.fibers[(size_t)i].rc; if (rc.outLen) addRun(into, rc.out->data() + rc.outOff, rc.outLen); }
+    };
+    if (!fusedWanted(E) || n > 65536) { classicPass(E, D, B, pool); fiberRuns(B, B); return; }
+    const int handed = fusedPass(E, D, B);
+    if (handed == 0) {
+        addRun(B, B.devText.data(), (size_t)B.devTextOff[(size_t)n]);
+        return;
+    }
+    // the reads the device handed back (a clump to split, a crowded strand, ...) go through the fibers as a batch of their own
+    if (!B.residual) B.residual.reset(new Batch());
+    Batch &R = *B.residual;
+    B.residualOf.clear();
+    size_t k = 0;
+    for (int i = 0; i < n; i++) {
+        if (!B.devStatus[(size_t)i]) continue;
+        if (k == R.reads.size()) R.reads.emplace_back();
+        Read &dst = R.reads[k];
+        const Read &src = B.reads[(size_t)i];
+        dst.id = src.id; dst.fwd = src.fwd; dst.qual = src.qual; dst.fcode.clear(); dst.rcode.clear(); dst.rev.clear();
+        B.residualOf.push_back(i);
+        k++;
+    }
+    R.reads.resize(k);
+    R.seq = B.seq;
+    classicPass(E, D, R, pool);
+    size_t next = 0;                                                      // merge: device text for the finished reads, fiber text for the rest
+    for (int i = 0; i < n; i++) {
+        if (!B.devStatus[(size_t)i]) { addRun(B, B.devText.data() + B.devTextOff[(size_t)i], (size_t)(B.devTextOff[(size_t)i + 1] - B.devTextOff[(size_t)i])); continue; }
+        const ReadCtx &rc = R.fibers[next++].rc;
+        if (rc.outLen) addRun(B, rc.out->data() + rc.outOff, rc.outLen);
+    }
+}
+
 // ----------------------------------------------------------------------------- child fibers of a read
 struct ChildFiber { void *sp = nullptr; void *stack = nullptr; bool done = false, started = false; };
 struct ChildBoot { ReadCtx *rc; void (*fn)(void *, int); void *arg; int k; ChildFiber *cf; };
@@ -640,6 +782,7 @@ void runAsChildren(ReadCtx &rc, int n, void (*fn)(void *, int), void *arg, std::
             rc.clumps.swap(outs[k]);
             rc.childSp = &c.sp;
             yh_switch(&parentSp, c.sp);
+            checkStack(c.stack);
             rc.childSp = nullptr;
             rc.clumps.swap(outs[k]);
             if (!c.done) live++;
@@ -721,6 +864,17 @@ int runQueries(const Args &A0)
             p.ctx = ya_open_shared(first.ctx);
             if (!p.ctx) { fprintf(stderr, "yaha_b200: cannot open shared context: %s\n", ya_last_error(nullptr)); return 1; }
         }
+    }
+    {
+        // what the tail of the per-read path needs on the device (ya_align_batch): output flags and the sequence table
+        ya_out_params O;
+        O.maxDesert = A.maxDesert; O.minNonOverlap = A.minNonOverlap; O.minRawScore = A.minRawScore; O.minIdentity = A.minIdentity;
+        O.OQC = A.OQC; O.FBS = A.FBS; O.OQCMinNonOverlap = A.OQCMinNonOverlap; O.BPCost = A.BPCost; O.maxBPLog = A.maxBPLog;
+        O.FBS_PSLength = A.FBS_PSLength; O.FBS_PSScore = A.FBS_PSScore; O.hardClip = A.hardClip; O.fastq = A.fastq;
+        std::vector<const char *> names; std::vector<uint32_t> starts, lens;
+        for (const BaseSeq &bs : G.seqs) { names.push_back(bs.name.c_str()); starts.push_back(bs.start); lens.push_back(bs.length); }
+        for (Pipe &p : pipes)
+            if (ya_set_output(p.ctx, &O, (int)names.size(), names.data(), starts.data(), lens.data()) != YA_OK) die(p.ctx, "ya_set_output");
     }
     tOpen = nowSec() - tOpen;
 
@@ -846,18 +1000,7 @@ int runQueries(const Args &A0)
             }
             double w0 = nowSec();
             if (!replaying) {
-                // records of consecutive reads mostly lie back to back in their worker's buffer (a slot is a run of
-                // reads formatted in order, unless a read parked): such a stretch is one fwrite
-                const char *runP = nullptr; size_t runN = 0;
-                for (int i = 0; i < b->nFibers; i++) {
-                    const ReadCtx &rc = b->fibers[(size_t)i].rc;
-                    if (!rc.outLen) continue;
-                    const char *p = rc.out->data() + rc.outOff;
-                    if (runN && p == runP + runN) { runN += rc.outLen; continue; }
-                    if (runN) fwrite(runP, 1, runN, out);
-                    runP = p; runN = rc.outLen;
-                }
-                if (runN) fwrite(runP, 1, runN, out);
+                for (const auto &run : b->outRuns) fwrite(run.first, 1, run.second, out);
             }
             nReads += b->reads.size();
             tWrite += nowSec() - w0;
