@@ -151,6 +151,9 @@ ya_ctx *ya_open(int device, const ya_params *params,
 /* Same, but clone the device-resident index of `src` (another GPU) by peer copy over
  * NVLink instead of re-uploading from the host. */
 ya_ctx *ya_open_peer(int device, const ya_ctx *src);
+/* 1 if the replica of this context was copied with peer access enabled in both directions (a direct HBM-to-HBM copy over
+ * NVLink / NVSwitch), 0 if the driver had to stage it through the host or the context was not made by ya_open_peer. */
+int ya_peer_direct(const ya_ctx *);
 
 /* Same as ya_open, but BUILD the index on the device from the .nib2 base area instead of loading
  * an index file (replaces indexFile, Index.c:49-331, for every -L / -S / -H).  seq_start/seq_len are the

@@ -46,12 +46,31 @@ def test_sam_same_with_clumps_on_host_or_device(small, tmp_path):
     """Row N1 switches: fragments -> clumps and the first phase of their alignment on the device (default), the
     alignment phase by the workers (YA_HOST_PREP=1), or both by the workers (YA_HOST_CLUMPS=1)."""
     want = H.expected(small, "out_bw10.sam.gz")
-    for k, env in enumerate(({}, {"YA_HOST_PREP": "1"}, {"YA_HOST_CLUMPS": "1"})):
+    for k, env in enumerate(({}, {"YA_FUSED": "0"}, {"YA_HOST_PREP": "1"}, {"YA_HOST_CLUMPS": "1"})):
         out = str(tmp_path / f"c{k}.sam")
         cmd = H.command(HOST, small, "reads.fa", "-osh", out, ["-BW", "10", "-G", "100"], threads=3)
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
         assert p.returncode == 0, p.stderr[-2000:]
         assert H.sam_lines(open(out).read()) == want, env
+
+
+def test_most_reads_are_finished_on_the_device(small, tmp_path):
+    """Rows N2 / N4: with ya_align_batch (default) the reads of the golden set whose clumps need no split are aligned, scored,
+    run through OQC and formatted on the device -- the host program's counters say how many; YA_FUSED=0 takes every read
+    through the fibers.  Same SAM either way (and the reference's)."""
+    import json
+    want = H.expected(small, "out_multi_fbs.sam.gz")
+    seen = {}
+    for tag, env in (("fused", {}), ("fibers", {"YA_FUSED": "0"})):
+        out = str(tmp_path / f"{tag}.sam")
+        cmd = H.command(HOST, small, "multi.fa", "-osh", out, ["-FBS", "Y", "-PRL", "0.5", "-PSS", "0.5"], threads=2)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, YAHA_B200_STATS="1", **env))
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert H.sam_lines(open(out).read()) == want, tag
+        seen[tag] = [json.loads(l) for l in p.stderr.splitlines() if l.startswith('{"pass"')][-1]
+    assert seen["fused"]["reads_finished_on_device"] >= 200 and seen["fused"]["reads_handed_back"] <= 20
+    assert seen["fused"]["device_text_bytes"] > 100_000
+    assert seen["fibers"]["reads_finished_on_device"] == 0
 
 
 def test_sam_identical_on_10k_long_reads(tmp_path):

@@ -122,6 +122,7 @@ struct ya_ctx {
     uint8_t  *d_bases = nullptr; size_t n_base_bytes = 0;
     uint32_t  maxROff = 0;
     bool      owns_index = true;
+    bool      peer_direct = false;     // ya_open_peer: the replica was copied with peer access enabled (NVLink, no host staging)
     uint32_t *d_lowmask = nullptr;   // 2^20-bit filter: k-mers (hash & 0xFFFFF) occurring in the first 32 K reference bases
     // uploaded read batch
     int       n_reads = 0;

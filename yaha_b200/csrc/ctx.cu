@@ -163,8 +163,22 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
         (e = cudaMalloc(&c->d_bases, src->n_base_bytes + 64)) != cudaSuccess) {
         g_open_err = std::string("cudaMalloc(index): ") + cudaGetErrorString(e); ya_close(c); return nullptr;
     }
-    // Device-to-device over NVLink when peer access is possible (cudaMemcpyPeer falls back to
-    // a staged copy otherwise).
+    // Device-to-device over NVLink: with peer access enabled in both directions cudaMemcpyPeer is a direct copy between the
+    // two HBMs through NVSwitch; without it (not supported, or refused) the driver stages the copy through host memory.
+    {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+            cudaSetDevice(device);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+            cudaGetLastError();
+            cudaSetDevice(src->device);
+            pe = cudaDeviceEnablePeerAccess(device, 0);
+            cudaGetLastError();
+            cudaSetDevice(device);
+        }
+        c->peer_direct = can != 0;
+    }
     if ((e = cudaMemcpyPeer(c->d_so, device, src->d_so, src->device, src->n_so * 4)) != cudaSuccess ||
         (e = cudaMemcpyPeer(c->d_roa, device, src->d_roa, src->device, (src->n_roa + 8) * 4)) != cudaSuccess ||
         (e = cudaMemcpyPeer(c->d_bases, device, src->d_bases, src->device, src->n_base_bytes + 64)) != cudaSuccess) {
@@ -177,6 +191,8 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
     }
     return c;
 }
+
+extern "C" int ya_peer_direct(const ya_ctx *c) { return c && c->peer_direct ? 1 : 0; }
 
 extern "C" void *ya_host_alloc(size_t bytes)
 {

@@ -90,7 +90,8 @@ struct ReadText { const char *chars, *quals, *ids; const uint32_t *id_off; };
 
 // one thread per read: which records to print (fr_finish_read) and the length of their text
 __global__ void __launch_bounds__(64)
-finish_kernel(int n_reads, const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ count, const uint32_t *__restrict__ first,
+finish_kernel(int n_reads, const uint64_t *__restrict__ read_off, const ya_strand_frags *__restrict__ strands,
+              const uint32_t *__restrict__ count, const uint32_t *__restrict__ first,
               const ya_asm_rec *__restrict__ recs, const ya_op *__restrict__ asm_ops, const uint8_t *__restrict__ bases,
               const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev, ReadText T, fr_params P,
               fr_out *__restrict__ outs, uint32_t *__restrict__ n_outs, uint32_t *__restrict__ primary_count,
@@ -126,7 +127,9 @@ finish_kernel(int n_reads, const uint64_t *__restrict__ read_off, const uint32_t
         const int k = fr_finish_read(&P, fwd + base, readLen, cl, n, g, o, &primaries);
         if (k < 0) handBack = true;
         else {
-            fr_out *dst = outs + first[2 * r];                             // the read owns the slots of its two strands' fragments
+            // the read owns the slots of its two strands' surviving fragments (at least as many as its clumps); an empty
+            // strand has no place of its own, so the run starts at the first strand that has fragments
+            fr_out *dst = outs + (strands[2 * r].n_frags ? strands[2 * r].first : strands[2 * r + 1].first);
             const uint32_t idLen = T.id_off[r + 1] - T.id_off[r];
             for (int q = 0; q < k; q++) {
                 len += (uint32_t)fr_format_record(&P, bases, T.ids + T.id_off[r], (int)idLen, T.chars + base, T.quals ? T.quals + base : nullptr,
@@ -145,7 +148,7 @@ finish_kernel(int n_reads, const uint64_t *__restrict__ read_off, const uint32_t
 
 // one thread per read writes its records at the read's place in the batch's text
 __global__ void __launch_bounds__(64)
-format_kernel(int n_reads, const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ first,
+format_kernel(int n_reads, const uint64_t *__restrict__ read_off, const ya_strand_frags *__restrict__ strands,
               const ya_asm_rec *__restrict__ recs, const ya_op *__restrict__ asm_ops, const uint8_t *__restrict__ bases,
               const uint8_t *__restrict__ rev, ReadText T, fr_params P, const fr_out *__restrict__ outs,
               const uint32_t *__restrict__ n_outs, const uint32_t *__restrict__ primary_count, const uint32_t *__restrict__ text_off,
@@ -157,7 +160,7 @@ format_kernel(int n_reads, const uint64_t *__restrict__ read_off, const uint32_t
     if (k == 0) return;
     const uint64_t base = read_off[r];
     const int readLen = (int)(read_off[r + 1] - base);
-    const fr_out *o = outs + first[2 * r];
+    const fr_out *o = outs + (strands[2 * r].n_frags ? strands[2 * r].first : strands[2 * r + 1].first);
     const uint32_t idLen = T.id_off[r + 1] - T.id_off[r];
     char *w = text + text_off[r];
     for (uint32_t q = 0; q < k; q++) {
@@ -373,7 +376,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
     }
     ReadText T;
     T.chars = c->d_chars.as<char>(); T.quals = b->quals ? c->d_quals.as<char>() : nullptr; T.ids = d_ids; T.id_off = d_id_off;
-    finish_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, c->d_read_off.as<uint64_t>(), d_count, d_first, c->d_asm_recs.as<ya_asm_rec>(),
+    finish_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, c->d_read_off.as<uint64_t>(), c->d_strand_out.as<ya_strand_frags>(), d_count, d_first, c->d_asm_recs.as<ya_asm_rec>(),
         c->d_asm_ops.as<ya_op>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), T, c->fr,
         c->d_fr_outs.as<fr_out>(), d_nouts, d_prim, d_tlen, d_status);
     text_scan_kernel<<<1, 1024, 0, st>>>(d_tlen, d_status, n, d_toff, d_text_off64, d_text_tot);
@@ -392,7 +395,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
     // ---- the text
     YA_CUDA(c, c->d_text.reserve(textBytes + 64));
     if (textBytes) {
-        format_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, c->d_read_off.as<uint64_t>(), d_first, c->d_asm_recs.as<ya_asm_rec>(),
+        format_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, c->d_read_off.as<uint64_t>(), c->d_strand_out.as<ya_strand_frags>(), c->d_asm_recs.as<ya_asm_rec>(),
             c->d_asm_ops.as<ya_op>(), c->d_bases, c->d_codes_rev.as<uint8_t>(), T, c->fr, c->d_fr_outs.as<fr_out>(), d_nouts, d_prim,
             d_toff, c->d_text.as<char>());
         c->ctr.launches++;

@@ -56,6 +56,21 @@ __global__ void index_hash_kernel(const uint8_t *__restrict__ bases, uint32_t se
     }
 }
 
+// The sort orders keys by their hash bits only, and a skipped position's key (all ones) carries the largest hash there is:
+// behind the sort the keys of the all-G k-mer and the skipped ones are interleaved (in position order).  These two kernels
+// move the real ones in front, keeping their order.
+__global__ void index_tail_flag_kernel(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ flag)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = keys[i] != ~0ull;
+}
+__global__ void index_tail_scatter_kernel(const uint64_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ flag,
+                                          const uint32_t *__restrict__ idx, uint64_t *__restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[idx[i]] = keys[i];
+}
+
 __global__ void index_take_pos_kernel(const uint64_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ roa)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -213,6 +228,24 @@ extern "C" ya_ctx *ya_open_build(int device, const ya_params *params, const uint
     if (nOver) cudaMemcpy(over.data(), d_over.p, (size_t)nOver * sizeof(OverFull), cudaMemcpyDeviceToHost);
     d_over.release(); d_nover.release();
     if (ya_radix_sort_u64(c, ka, kb, n_keys, 32, 32 + 2 * K) != YA_OK) return fail("index sort failed: " + c->err);
+    {
+        // the list of the last k-mer (all G) shares its sort digits with the skipped positions' keys: bring its entries in front
+        uint32_t tailStart = 0;
+        cudaMemcpyAsync(&tailStart, c->d_so + (n_so - 2), 4, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("index build: kernel failure");
+        const uint32_t nTail = n_keys - tailStart, nValidTail = total - tailStart;
+        if (nValidTail > 0 && nTail > nValidTail) {
+            DevBuf d_flag, d_idx;
+            if (d_flag.reserve((size_t)nTail * 4 + 16) != cudaSuccess || d_idx.reserve((size_t)nTail * 4 + 16) != cudaSuccess) return fail("cudaMalloc failed");
+            index_tail_flag_kernel<<<(nTail + 255) / 256, 256, 0, c->stream>>>(ka + tailStart, nTail, d_flag.as<uint32_t>());
+            if (ya_exclusive_scan_u32(c, d_flag.as<uint32_t>(), d_idx.as<uint32_t>(), nTail, nullptr) != YA_OK) return fail("index scan failed: " + c->err);
+            index_tail_scatter_kernel<<<(nTail + 255) / 256, 256, 0, c->stream>>>(ka + tailStart, nTail, d_flag.as<uint32_t>(), d_idx.as<uint32_t>(), kb + tailStart);
+            cudaMemcpyAsync(ka + tailStart, kb + tailStart, (size_t)nValidTail * 8, cudaMemcpyDeviceToDevice, c->stream);
+            c->ctr.launches += 2;
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail("index build: kernel failure");
+            d_flag.release(); d_idx.release();
+        }
+    }
     if (nOver == 0) {
         if ((e = cudaMalloc(&c->d_roa, ((size_t)total + 8) * 4)) != cudaSuccess)
             return fail(std::string("cudaMalloc(roa): ") + cudaGetErrorString(e));

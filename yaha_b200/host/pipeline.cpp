@@ -852,11 +852,14 @@ int runQueries(const Args &A0)
     pool.start(A.threadsPerPipe > 0 ? std::min(A.threadsPerPipe, 4 * nproc) : nThreads);   // (-tpp N: explicit pool size, may oversubscribe)
     std::vector<Pipe> pipes((size_t)nPipes);
     double tOpen = nowSec();
+    double tOpenUpload = 0, tOpenPeer = 0; int peerDirect = 0;
     for (int d = 0; d < nDev; d++) {
         Pipe &first = pipes[(size_t)d * pipesPerDev];
         first.device = A.firstDev + d;
+        const double o0 = nowSec();
         first.ctx = (d == 0) ? ya_open(A.firstDev, &P, X.so, X.nSo, X.roa, X.nRoa, G.bases, G.nBaseBytes, G.maxROff)
                              : ya_open_peer(A.firstDev + d, pipes[0].ctx);                 // index replica over NVLink
+        if (d == 0) tOpenUpload = nowSec() - o0; else { tOpenPeer += nowSec() - o0; peerDirect += first.ctx ? ya_peer_direct(first.ctx) : 0; }
         if (!first.ctx) { fprintf(stderr, "yaha_b200: cannot open device %d: %s\n", A.firstDev + d, ya_last_error(nullptr)); return 1; }
         for (int k = 1; k < pipesPerDev; k++) {
             Pipe &p = pipes[(size_t)d * pipesPerDev + k];
@@ -1017,22 +1020,26 @@ int runQueries(const Args &A0)
         if (A.verbose || A.passes > 1 || getenv("YAHA_B200_STATS")) {
             ya_counters c{};
             double seed = 0, dp = 0, host = 0, upl = 0, setup = 0; uint64_t jobs = 0, rounds = 0, cells = 0, launches = 0, probes = 0, hits = 0, fragsAll = 0;
-            double msdp = 0, msseed = 0, mstb = 0, msext = 0, mslk = 0; uint64_t extCells = 0, extLaunches = 0;
+            double msdp = 0, msseed = 0, mstb = 0, msext = 0, mslk = 0, msfin = 0; uint64_t extCells = 0, extLaunches = 0, devReads = 0, handed = 0, textBytes = 0;
             for (Pipe &d : pipes) {
                 ya_get_counters(d.ctx, &c);
                 seed += d.tSeed; dp += d.tDp; host += d.tHost / std::max(1, pool.size()); upl += d.tUpload; setup += d.tSetup; jobs += d.nJobs; rounds += d.nRounds; cells += c.dp_cells;
                 msdp += c.ms_dp; msseed += c.ms_seed; mstb += c.ms_traceback; launches += c.launches; probes += c.probes; hits += c.hits;
                 fragsAll += c.frags_all; msext += c.ms_ext; mslk += c.ms_lookup; extCells += c.ext_cells; extLaunches += c.ext_launches;
+                msfin += c.ms_finish; devReads += c.reads_finished; handed += c.reads_handed_back; textBytes += c.text_bytes;
             }
             fprintf(stderr, "{\"pass\": %d, \"reads\": %llu, \"align_s\": %.5f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"read_parse_s\": %.5f, "
                     "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
                     "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
                     "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d, \"pipes\": %d, "
-                    "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu, \"dev_ms_lookup\": %.4f, \"fiber_setup_s\": %.5f}\n",
+                    "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu, \"dev_ms_lookup\": %.4f, \"fiber_setup_s\": %.5f, "
+                    "\"dev_ms_finish\": %.4f, \"reads_finished_on_device\": %llu, \"reads_handed_back\": %llu, \"device_text_bytes\": %llu, "
+                    "\"index_upload_s\": %.3f, \"index_peer_copies_s\": %.3f, \"peer_copies_direct\": %d}\n",
                     pass, (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), tRead, upl, tWrite, seed, dp, host,
                     (unsigned long long)jobs, (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb,
                     (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads,
-                    nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches, mslk, setup);
+                    nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches, mslk, setup,
+                    msfin, (unsigned long long)devReads, (unsigned long long)handed, (unsigned long long)textBytes, tOpenUpload, tOpenPeer, peerDirect);
         }
     }
     extern uint64_t gAlignProf[4];
