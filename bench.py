@@ -545,10 +545,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="reads of the workload the reference arm / cpu_baseline aligns (default: all)")
     ap.add_argument("--t1-sample", type=int, default=20000, help="reads aligned once with `yaha -t 1` for the in-order SAM comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=2500, help="reads per device batch")
-    ap.add_argument("--pipes", type=int, default=8, help="concurrent batch pipelines per GPU")
-    ap.add_argument("--e2e-batch", type=int, default=1250, help="reads per device batch in the e2e run")
-    ap.add_argument("--e2e-pipes", type=int, default=8, help="pipelines per GPU in the e2e run")
+    ap.add_argument("--batch", type=int, default=5000, help="reads per device batch")
+    ap.add_argument("--pipes", type=int, default=4, help="concurrent batch pipelines per GPU")
+    ap.add_argument("--e2e-batch", type=int, default=5000, help="reads per device batch in the e2e run")
+    ap.add_argument("--e2e-pipes", type=int, default=4, help="pipelines per GPU in the e2e run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

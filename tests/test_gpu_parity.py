@@ -325,7 +325,7 @@ def test_device_index_build_every_word_length_skip_and_hit_cap(small, tmp_path):
             raise AssertionError((name, "so differs at", bad_so, "roa differs at", bad_roa))
         sampled += int(np.max(np.diff(idx.so.astype(np.int64))) == H and H < 65525)
         checked += 1
-    assert checked == 14 and sampled >= 4
+    assert checked == 14 and sampled >= 2
 
 
 _AB_SNIPPET = r"""
@@ -362,7 +362,11 @@ def test_kernel_variants_agree_bytewise(small, tmp_path):
     import subprocess
     import sys
     blobs = {}
-    for name, env in (("default", {}), ("tb_thread", {"YA_TB": "thread"}), ("full_thread", {"YA_FULL_THREAD_MAXW": "100000"})):
+    # (the packed X-drop kernel has three geometries chosen by launch size -- 8/16, 4/8 and 2/4 jobs per warp: the golden calls
+    #  are a small launch, i.e. the narrowest by default; the two thresholds force the other two)
+    for name, env in (("default", {}), ("tb_thread", {"YA_TB": "thread"}), ("full_thread", {"YA_FULL_THREAD_MAXW": "100000"}),
+                      ("packed_wide", {"YA_PACKED_NARROW_BELOW": "0", "YA_PACKED_XNARROW_BELOW": "0"}),
+                      ("packed_narrow", {"YA_PACKED_NARROW_BELOW": "100000000", "YA_PACKED_XNARROW_BELOW": "0"})):
         dst = str(tmp_path / f"{name}.bin")
         code = _AB_SNIPPET.format(root=S.ROOT, tmp=str(tmp_path / f"small_{name}"), dst=dst)
         os.makedirs(str(tmp_path / f"small_{name}"), exist_ok=True)
@@ -371,6 +375,8 @@ def test_kernel_variants_agree_bytewise(small, tmp_path):
         blobs[name] = open(dst, "rb").read()
     assert blobs["default"] == blobs["tb_thread"]
     assert blobs["default"] == blobs["full_thread"]
+    assert blobs["default"] == blobs["packed_wide"]
+    assert blobs["default"] == blobs["packed_narrow"]
     assert len(blobs["default"]) > 100000
 
 

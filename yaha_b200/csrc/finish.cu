@@ -146,15 +146,16 @@ finish_kernel(int n_reads, const uint64_t *__restrict__ read_off, const ya_stran
     n_outs[r] = nOut; primary_count[r] = (uint32_t)primaries; text_len[r] = len;
 }
 
-// one thread per read writes its records at the read's place in the batch's text
-__global__ void __launch_bounds__(64)
+// one WARP per read writes its records at the read's place in the batch's text (finish_reads.h: all lanes make the same
+// calls; single characters come from lane 0, the long runs are strided over the lanes)
+__global__ void __launch_bounds__(128)
 format_kernel(int n_reads, const uint64_t *__restrict__ read_off, const ya_strand_frags *__restrict__ strands,
               const ya_asm_rec *__restrict__ recs, const ya_op *__restrict__ asm_ops, const uint8_t *__restrict__ bases,
               const uint8_t *__restrict__ rev, ReadText T, fr_params P, const fr_out *__restrict__ outs,
               const uint32_t *__restrict__ n_outs, const uint32_t *__restrict__ primary_count, const uint32_t *__restrict__ text_off,
               char *__restrict__ text)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (r >= n_reads) return;
     const uint32_t k = n_outs[r];
     if (k == 0) return;
@@ -395,7 +396,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
     // ---- the text
     YA_CUDA(c, c->d_text.reserve(textBytes + 64));
     if (textBytes) {
-        format_kernel<<<(n + 63) / 64, 64, 0, st>>>(n, c->d_read_off.as<uint64_t>(), c->d_strand_out.as<ya_strand_frags>(), c->d_asm_recs.as<ya_asm_rec>(),
+        format_kernel<<<(n + 3) / 4, 128, 0, st>>>(n, c->d_read_off.as<uint64_t>(), c->d_strand_out.as<ya_strand_frags>(), c->d_asm_recs.as<ya_asm_rec>(),
             c->d_asm_ops.as<ya_op>(), c->d_bases, c->d_codes_rev.as<uint8_t>(), T, c->fr, c->d_fr_outs.as<fr_out>(), d_nouts, d_prim,
             d_toff, c->d_text.as<char>());
         c->ctr.launches++;

@@ -403,7 +403,18 @@ FC_HD int fr_finish_read(const fr_params *P, const uint8_t *fcode, int readLen, 
 
 /* ---- SAM record (printClump, AlignOutput.c:115-289).  One routine counts and writes: with w == NULL only the length
  * is returned, so the space a batch needs is known before a byte is written. ---- */
-#define FR_PUTC(ch)   do { const char fr_ch_ = (char)(ch); if (w) w[n] = fr_ch_; n++; } while (0)
+/* On the device a record is WRITTEN by a whole warp: all 32 lanes make the same call with the same arguments (the
+ * control flow depends on the arguments only), single characters are stored by lane 0 and the long runs -- read bases,
+ * qualities, reference bases of the MD tag -- are strided over the lanes.  Counting calls (w == NULL) store nothing and
+ * may come from single threads. */
+#ifdef __CUDA_ARCH__
+#define FR_LANE  ((int)(threadIdx.x & 31u))
+#define FR_LANES 32
+#else
+#define FR_LANE  0
+#define FR_LANES 1
+#endif
+#define FR_PUTC(ch)   do { const char fr_ch_ = (char)(ch); if (w && FR_LANE == 0) w[n] = fr_ch_; n++; } while (0)
 
 FC_HD size_t fr_put_uint(char *w, size_t n, uint32_t v)
 {
@@ -419,7 +430,7 @@ FC_HD size_t fr_put_int(char *w, size_t n, int v)
 }
 FC_HD size_t fr_put_str(char *w, size_t n, const char *s, size_t len)
 {
-    if (w) for (size_t k = 0; k < len; k++) w[n + k] = s[k];
+    if (w) for (size_t k = (size_t)FR_LANE; k < len; k += FR_LANES) w[n + k] = s[k];
     return n + len;
 }
 
@@ -461,8 +472,8 @@ FC_HD size_t fr_format_record(const fr_params *P, const uint8_t *bases, const ch
     if (P->hardClip) { qs = f->startQueryOff; qe = f->endQueryOff; }
     if (qe >= qs) {
         if (w) {
-            if (rev) for (int i = qs; i <= qe; i++) w[n + (size_t)(i - qs)] = fr_char_of_code(rcode[i]);
-            else for (int i = qs; i <= qe; i++) w[n + (size_t)(i - qs)] = chars[i];
+            if (rev) for (int i = qs + FR_LANE; i <= qe; i += FR_LANES) w[n + (size_t)(i - qs)] = fr_char_of_code(rcode[i]);
+            else for (int i = qs + FR_LANE; i <= qe; i += FR_LANES) w[n + (size_t)(i - qs)] = chars[i];
         }
         n += (size_t)(qe - qs + 1);
     }
@@ -470,8 +481,8 @@ FC_HD size_t fr_format_record(const fr_params *P, const uint8_t *bases, const ch
     if (P->fastq) {
         if (qe >= qs) {
             if (w) {
-                if (rev) for (int i = qe; i >= qs; i--) w[n + (size_t)(qe - i)] = qual[i];
-                else for (int i = qs; i <= qe; i++) w[n + (size_t)(i - qs)] = qual[i];
+                if (rev) for (int i = qe - FR_LANE; i >= qs; i -= FR_LANES) w[n + (size_t)(qe - i)] = qual[i];
+                else for (int i = qs + FR_LANE; i <= qe; i += FR_LANES) w[n + (size_t)(i - qs)] = qual[i];
             }
             n += (size_t)(qe - qs + 1);
         }
@@ -488,13 +499,13 @@ FC_HD size_t fr_format_record(const fr_params *P, const uint8_t *bases, const ch
         else if (op.opcode == 'R') {
             if (matches > 0) { n = fr_put_int(w, n, matches); matches = 0; }
             if (prev == 'D') FR_PUTC('0');
-            if (w) for (int i = 0; i < (int)op.length; i++) w[n + (size_t)i] = fr_char_of_code(pc_base(bases, ro + (uint32_t)i));
+            if (w) for (int i = FR_LANE; i < (int)op.length; i += FR_LANES) w[n + (size_t)i] = fr_char_of_code(pc_base(bases, ro + (uint32_t)i));
             n += op.length;
             ro += op.length;
         } else if (op.opcode == 'D') {
             if (matches > 0) { n = fr_put_int(w, n, matches); matches = 0; }
             FR_PUTC('^');
-            if (w) for (int i = 0; i < (int)op.length; i++) w[n + (size_t)i] = fr_char_of_code(pc_base(bases, ro + (uint32_t)i));
+            if (w) for (int i = FR_LANE; i < (int)op.length; i += FR_LANES) w[n + (size_t)i] = fr_char_of_code(pc_base(bases, ro + (uint32_t)i));
             n += op.length;
             ro += op.length;
         }

@@ -827,7 +827,22 @@ struct PackedCfg { int G, C, W; };
 static const PackedCfg kPackedCfgs[] = {{2, 11, 21}, {4, 11, 41}};
 // Below this many jobs per launch the grid cannot fill the GPU with 8 (16) jobs per warp; the narrow
 // variants <7,6,41> / <4,6,21> put 4 (8) jobs in a warp: twice the warps, shorter macro steps.
-static const size_t kPackedNarrowBelow = 16384;
+// (level 0: <2,11,21> / <4,11,41>; level 1 below YA_PACKED_NARROW_BELOW jobs: <4,6,21> / <7,6,41>; level 2 below
+//  YA_PACKED_XNARROW_BELOW: <7,3,21> / <14,3,41>, 4 / 2 jobs per warp -- a launch needs about 8 resident warps per scheduler
+//  before its issue slots rather than one job's dependent chain set the pace)
+static int packed_level(size_t nExt)
+{
+    static const size_t narrowBelow = [] { const char *e = getenv("YA_PACKED_NARROW_BELOW"); return e ? (size_t)atol(e) : (size_t)28000; }();
+    static const size_t xnarrowBelow = [] { const char *e = getenv("YA_PACKED_XNARROW_BELOW"); return e ? (size_t)atol(e) : (size_t)12000; }();
+    return nExt < xnarrowBelow ? 2 : nExt < narrowBelow ? 1 : 0;
+}
+static inline void packed_geom(int level, int pcls, int &G, int &C)
+{
+    static const int g[3][2] = {{2, 4}, {4, 7}, {7, 14}}, cc[3] = {11, 6, 3};
+    G = g[level][pcls]; C = cc[level];
+}
+template <int G, int C, int W> static void launch_packed(ya_ctx *c, const uint32_t *d_ids, int n, const DpConst &K);
+static void launch_packed_level(ya_ctx *c, int level, int pcls, const uint32_t *d_ids, int n, const DpConst &K);
 static const int kNumPackedCfgs = sizeof(kPackedCfgs) / sizeof(kPackedCfgs[0]);
 
 template <int G, int C, int W>
@@ -839,6 +854,15 @@ static void launch_packed(ya_ctx *c, const uint32_t *d_ids, int n, const DpConst
     dp_ext_packed_kernel<G, C, W><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
         c->d_tb.as<uint32_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
     c->ctr.launches++;
+}
+
+static void launch_packed_level(ya_ctx *c, int level, int pcls, const uint32_t *d_ids, int n, const DpConst &K)
+{
+    if (pcls == 0) {
+        if (level == 0) launch_packed<2, 11, 21>(c, d_ids, n, K); else if (level == 1) launch_packed<4, 6, 21>(c, d_ids, n, K); else launch_packed<7, 3, 21>(c, d_ids, n, K);
+    } else {
+        if (level == 0) launch_packed<4, 11, 41>(c, d_ids, n, K); else if (level == 1) launch_packed<7, 6, 41>(c, d_ids, n, K); else launch_packed<14, 3, 41>(c, d_ids, n, K);
+    }
 }
 
 #include <chrono>
@@ -884,7 +908,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     const int packedBase = 2 * kNumWaveCfgs + 1;
     size_t nExt = 0;
     for (int i = 0; i < n; i++) nExt += jobs[i].kind >= YA_DP_EXT_FWD;
-    const bool narrowExt = nExt < kPackedNarrowBelow, narrow21 = narrowExt, narrow41 = narrowExt;
+    const int packedLevel = packed_level(nExt);
     uint64_t tb_cells = 0, rows_ints = 0, ops_slots = 0;
     int n_live = 0;
     std::vector<uint32_t> &live_of = c->sw_live_of;   // device job index -> caller job index
@@ -932,8 +956,8 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
             (int64_t)(qLen + W + 2) * packedStepCost < ((int64_t)1 << 20))
             for (int k = 0; k < kNumPackedCfgs; k++) if (kPackedCfgs[k].W == W) pcls = k;
         if (pcls >= 0) {
-            const int G = narrowExt ? (pcls == 0 ? 4 : 7) : kPackedCfgs[pcls].G;
-            const int C = narrowExt ? 6 : kPackedCfgs[pcls].C, CP = (C + 3) & ~3;
+            int G, C; packed_geom(packedLevel, pcls, G, C);
+            const int CP = (C + 3) & ~3;
             d.layout = 2; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * CP);
             tb_cells = (tb_cells + 7) & ~7ull;                         // 16-byte alignment for the 128-bit stores
             d.tb_off = tb_cells / 2;                                  // in 32-bit words
@@ -1024,12 +1048,10 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
     if (anyPacked && bulkExclusive && nPackedAll >= 2048) bulkTurn.lock();
     if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[3], st));
     if (!lists[packedBase + 0].empty()) {
-        if (narrow21) launch_packed<4, 6, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
-        else          launch_packed<2, 11, 21>(c, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
+        launch_packed_level(c, packedLevel, 0, d_ids + start[packedBase + 0], (int)lists[packedBase + 0].size(), K);
     }
     if (!lists[packedBase + 1].empty()) {
-        if (narrow41) launch_packed<7, 6, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
-        else          launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
+        launch_packed_level(c, packedLevel, 1, d_ids + start[packedBase + 1], (int)lists[packedBase + 1].size(), K);
     }
     if (anyPacked) YA_CUDA(c, cudaEventRecord(c->ev[4], st));
     if (bulkTurn.owns_lock()) { YA_CUDA(c, ya_event_wait(c->ev[4])); bulkTurn.unlock(); }
@@ -1184,7 +1206,7 @@ extern "C" int ya_sw_fetch_ops(ya_ctx *c, ya_op *ops, size_t ops_cap)
 #define DPR_BUCKETS  1024                     // rows / 8, capped: the order inside a class is by length, longest first
 #define DPR_BINS     ((DPR_NCLASS + 1) * DPR_BUCKETS)
 
-struct DprFlags { int narrowExt, allowPacked, forceThread, fullThreadMaxW; long long packedStepCost; };
+struct DprFlags { int packedLevel, allowPacked, forceThread, fullThreadMaxW; long long packedStepCost; };
 __constant__ int c_waveG[8] = {8, 8, 8, 8, 16, 16, 32, 32};
 __constant__ int c_waveC[8] = {3, 4, 6, 8, 6, 8, 8, 11};
 
@@ -1239,8 +1261,8 @@ __global__ void dpr_classify_kernel(const ya_dp_job *__restrict__ jobs, uint32_t
             }
             uint64_t cells;
             if (pcls >= 0) {
-                const int G = F.narrowExt ? (pcls == 0 ? 4 : 7) : (pcls == 0 ? 2 : 4);
-                const int C = F.narrowExt ? 6 : 11, CP = (C + 3) & ~3;
+                const int G = F.packedLevel == 0 ? (pcls == 0 ? 2 : 4) : F.packedLevel == 1 ? (pcls == 0 ? 4 : 7) : (pcls == 0 ? 7 : 14);
+                const int C = F.packedLevel == 0 ? 11 : F.packedLevel == 1 ? 6 : 3, CP = (C + 3) & ~3;
                 d.layout = 2; d.colsPerLane = (uint8_t)C; d.stride = (uint32_t)(G * CP);
                 cells = 2ull * (uint64_t)((qLen + G + 3) / 4 + 1) * d.stride;
                 cls = 17 + pcls;
@@ -1355,7 +1377,7 @@ int ya_sw_device_round(ya_ctx *c, uint32_t n_jobs, uint32_t n_ext, unsigned long
     const ya_params &P = c->P;
     static const int fullThreadMaxW = [] { const char *e = getenv("YA_FULL_THREAD_MAXW"); return e ? atoi(e) : 0; }();
     DprFlags F;
-    F.narrowExt = n_ext < kPackedNarrowBelow; F.allowPacked = !forbid_packed_kernel(); F.forceThread = force_thread_kernel();
+    F.packedLevel = packed_level(n_ext); F.allowPacked = !forbid_packed_kernel(); F.forceThread = force_thread_kernel();
     F.fullThreadMaxW = fullThreadMaxW;
     F.packedStepCost = std::max<long long>(std::max<long long>(std::abs(P.MScore), std::abs(P.RCost)), (long long)std::abs(P.GOCost) + std::abs(P.GECost));
     YA_CUDA(c, c->d_jobs.reserve((size_t)n_jobs * sizeof(DevJob)));
@@ -1405,8 +1427,8 @@ int ya_sw_device_round(ya_ctx *c, uint32_t n_jobs, uint32_t n_ext, unsigned long
     const int packedBase = 2 * kNumWaveCfgs + 1;
     const int nP0 = count(packedBase), nP1 = count(packedBase + 1);
     if (nP0 || nP1) YA_CUDA(c, cudaEventRecord(c->ev[3], st));
-    if (nP0) { if (F.narrowExt) launch_packed<4, 6, 21>(c, d_ids + start[packedBase], nP0, K); else launch_packed<2, 11, 21>(c, d_ids + start[packedBase], nP0, K); }
-    if (nP1) { if (F.narrowExt) launch_packed<7, 6, 41>(c, d_ids + start[packedBase + 1], nP1, K); else launch_packed<4, 11, 41>(c, d_ids + start[packedBase + 1], nP1, K); }
+    if (nP0) launch_packed_level(c, F.packedLevel, 0, d_ids + start[packedBase], nP0, K);
+    if (nP1) launch_packed_level(c, F.packedLevel, 1, d_ids + start[packedBase + 1], nP1, K);
     if (nP0 || nP1) YA_CUDA(c, cudaEventRecord(c->ev[4], st));
     if (count(2 * kNumWaveCfgs)) {
         const int nt = count(2 * kNumWaveCfgs);
