@@ -425,12 +425,49 @@ def run_ours(args):
                                                                         "8 B/probe + 20 B/hit + 12 B/fragment"},
         "clocks": sampler.summary(),
     }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()                  # (the other ranks are done: their GPUs are free for the in-process run below)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl, d, idx_path, reads, min(n_reads, args.cpu_sample), out_path, min(n_reads, args.t1_sample))
+        if world > 1 and not args.no_inprocess:
+            line["inprocess"] = inprocess_multi_gpu(args, wl, d, idx_path, world, ncores)
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def inprocess_multi_gpu(args, wl, d, idx_path, world, ncores):
+    """The product's own multi-GPU path: ONE `yaha_b200_host -gpus N` process on one file holding the reads of all
+    N ranks -- index uploaded once and replicated GPU-to-GPU (ya_open_peer), batches of the one query stream dealt to the
+    devices, SAM written in input order.  Its SAM must equal the N per-rank outputs one after the other."""
+    from yaha_b200 import synth
+    time.sleep(1.0)                                   # let the other ranks' processes leave their GPUs
+    q = os.path.join(d, f"reads_all{world}.fa")
+    with open(q, "wb") as f:
+        for r in range(world):
+            f.write(open(os.path.join(d, f"reads_rank{r}.fa"), "rb").read())
+    out = os.path.join(d, f"out_all{world}.sam")
+    host = os.path.join(ROOT, "yaha_b200", "yaha_b200_host")
+    n_pass = 3 + args.warmup + args.steps
+    cmd = [host, "-x", idx_path, "-q", q, "-osh", out, "-t", str(ncores), "-gpus", str(world), "-passes", str(n_pass),
+           "-batch", str(args.e2e_batch), "-pipes", str(args.e2e_pipes)] + REF_FLAGS[wl]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        return {"error": p.stderr[-1500:]}
+    st = [json.loads(l) for l in p.stderr.splitlines() if l.startswith('{"pass"')]
+    timed = st[-args.steps:]
+    el = sum(s["align_s"] for s in timed)
+    body = [l for l in open(out, "rb") if not l.startswith(b"@")]
+    want = []
+    for r in range(world):
+        want += [l for l in open(os.path.join(d, f"out_rank{r}.sam"), "rb") if not l.startswith(b"@")]
+    return {"what": f"one process, -gpus {world}, one query file with the {world} x {WORKLOADS[wl]['n_reads']} reads of all ranks, SAM written in input order",
+            "value": sum(s["reads"] for s in timed) / el, "unit": "reads/s", "ms_per_step": el / len(timed) * 1e3,
+            "ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed],
+            "sam_equals_the_per_rank_outputs_in_order": body == want, "sam_records": len(body),
+            "index_upload_s": st[-1].get("index_upload_s"), "index_peer_copies_s": st[-1].get("index_peer_copies_s"),
+            "peer_copies_direct": st[-1].get("peer_copies_direct"), "open_s": st[-1].get("open_s"),
+            "reads_finished_on_device": timed[-1].get("reads_finished_on_device"), "reads_handed_back": timed[-1].get("reads_handed_back")}
 
 
 def ensure_index_file(wl: str, d: str) -> str:
@@ -545,6 +582,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1 << 30, help="reads of the workload the reference arm / cpu_baseline aligns (default: all)")
     ap.add_argument("--t1-sample", type=int, default=20000, help="reads aligned once with `yaha -t 1` for the in-order SAM comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inprocess", action="store_true", help="N > 1: skip the one-process -gpus N measurement on rank 0")
     ap.add_argument("--batch", type=int, default=5000, help="reads per device batch")
     ap.add_argument("--pipes", type=int, default=4, help="concurrent batch pipelines per GPU")
     ap.add_argument("--e2e-batch", type=int, default=5000, help="reads per device batch in the e2e run")

@@ -20,8 +20,10 @@ form_clumps_kernel(const ya_strand_frags *__restrict__ strands, int n_seg, const
                    const ya_frag *__restrict__ frags, const uint32_t *__restrict__ region, fc_params P,
                    ya_frag *__restrict__ work, fc_node *__restrict__ nodes, uint8_t *__restrict__ used, ya_frag *__restrict__ tmp,
                    ya_frag *__restrict__ path, ya_clump_rec *__restrict__ clumps, uint32_t *__restrict__ count,
-                   uint32_t *__restrict__ first_out)
+                   uint32_t *__restrict__ first_out, uint32_t *__restrict__ slot_strand)
 {
+    // slot_strand[i] (zeroed by the caller): strand + 1 if slot i of the clump array holds a clump -- lets the kernels behind
+    // this one run one thread per CLUMP instead of one per strand (a crowded strand no longer sets their duration)
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const ya_strand_frags sf = strands[s];
@@ -35,7 +37,7 @@ form_clumps_kernel(const ya_strand_frags *__restrict__ strands, int n_seg, const
     for (uint32_t k = 0; k < n; k++) w[k] = frags[first + k];          // the graph edits fragments in place: work on a copy
     const int nc = fc_form_clumps(&P, w, region + first, (int)n, readLen, nodes + first, used + 2 * (size_t)first, tmp + first,
                                   path + first, clumps + first);
-    for (int k = 0; k < nc; k++) clumps[first + k].first += first;      // path indices absolute
+    for (int k = 0; k < nc; k++) { clumps[first + k].first += first; slot_strand[first + k] = (uint32_t)s + 1u; }   // path indices absolute
     count[s] = (uint32_t)nc;
 }
 
@@ -61,13 +63,16 @@ int ya_form_clumps_impl(ya_ctx *c, ya_clump_batch *out, bool device_only)
     YA_CUDA(c, c->d_fc_nodes.reserve(nk * sizeof(fc_node) + 64));
     YA_CUDA(c, c->d_fc_used.reserve(nk * 2 + 64));
     YA_CUDA(c, c->d_fc_clumps.reserve(nk * sizeof(ya_clump_rec) + 64));
+    YA_CUDA(c, c->d_fc_slot.reserve(nk * 4 + 64));
+    YA_CUDA(c, cudaMemsetAsync(c->d_fc_slot.p, 0, nk * 4 + 4, st));
     fc_params P;
     P.wordLen = c->P.wordLen; P.maxGap = c->P.maxGap; P.maxDesert = out->maxDesert; P.minMatch = c->P.minMatch;
     P.minNonOverlap = out->minNonOverlap; P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.MScore = c->P.MScore;
     YA_CUDA(c, cudaEventRecord(c->ev[0], st));
     form_clumps_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(c->d_strand_out.as<ya_strand_frags>(), n_seg, c->d_read_off.as<uint64_t>(),
         c->d_frags_out.as<ya_frag>(), c->d_region_out.as<uint32_t>(), P, c->d_fc_work.as<ya_frag>(), c->d_fc_nodes.as<fc_node>(),
-        c->d_fc_used.as<uint8_t>(), c->d_fc_tmp.as<ya_frag>(), c->d_fc_path.as<ya_frag>(), c->d_fc_clumps.as<ya_clump_rec>(), d_count, d_first);
+        c->d_fc_used.as<uint8_t>(), c->d_fc_tmp.as<ya_frag>(), c->d_fc_path.as<ya_frag>(), c->d_fc_clumps.as<ya_clump_rec>(), d_count, d_first,
+        c->d_fc_slot.as<uint32_t>());
     c->ctr.launches++;
     YA_CUDA(c, cudaEventRecord(c->ev[1], st));
     if (device_only) { YA_CUDA(c, cudaGetLastError()); c->fc_valid = true; return YA_OK; }
@@ -96,33 +101,31 @@ int ya_form_clumps_impl(ya_ctx *c, ya_clump_batch *out, bool device_only)
 // ------------------------------------------------------------------------------------------------------------
 // First phase of alignClump for those clumps (prepare_clumps.h), one thread per strand.
 __global__ void __launch_bounds__(128)
-prepare_clumps_kernel(int n_seg, const uint64_t *__restrict__ read_off, const uint32_t *__restrict__ count,
-                      const uint32_t *__restrict__ first, const ya_clump_rec *__restrict__ clumps, const ya_frag *__restrict__ path_in,
+prepare_clumps_kernel(uint32_t n_slots, const uint32_t *__restrict__ slot_strand, const uint64_t *__restrict__ read_off,
+                      const ya_clump_rec *__restrict__ clumps, const ya_frag *__restrict__ path_in,
                       const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev, pc_params P,
                       ya_frag *__restrict__ path, ya_gap_rec *__restrict__ gaps, ya_prep_rec *__restrict__ prep,
                       ya_dp_job *__restrict__ jobs, uint32_t *__restrict__ n_jobs, uint32_t jobs_cap)
 {
+    // one thread per clump (slot_strand: form_clumps_kernel)
     // n_jobs[0]: job index allocator; n_jobs[1]: extension jobs among them (sizes the extension launch of the round)
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    const uint32_t nc = count[s];
-    if (nc == 0 || nc == 0xFFFFFFFFu) return;
-    const uint32_t r = (uint32_t)(s >> 1);
-    const int strand = s & 1;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const uint32_t sp1 = slot_strand[i];
+    if (sp1 == 0) return;
+    const uint32_t s = sp1 - 1, r = s >> 1;
+    const int strand = (int)(s & 1u);
     const uint64_t base = read_off[r];
     const int readLen = (int)(read_off[r + 1] - base);
     const uint8_t *q = (strand ? rev : fwd) + base;
-    const uint32_t c0 = first[s];
-    for (uint32_t k = 0; k < nc; k++) {
-        const ya_clump_rec rec = clumps[c0 + k];
-        for (uint32_t f = 0; f < rec.n; f++) path[rec.first + f] = path_in[rec.first + f];
-        ya_prep_rec pr;
-        pr.gap_first = rec.first;
-        pc_prepare_clump(&P, bases, q, readLen, r, strand, path + rec.first, (int)rec.n, gaps + rec.first, jobs, n_jobs, jobs_cap, &pr);
-        prep[c0 + k] = pr;
-        const uint32_t ne = (pr.jobB != 0xFFFFFFFFu) + (pr.jobF != 0xFFFFFFFFu);
-        if (ne) atomicAdd(n_jobs + 1, ne);
-    }
+    const ya_clump_rec rec = clumps[i];
+    for (uint32_t f = 0; f < rec.n; f++) path[rec.first + f] = path_in[rec.first + f];
+    ya_prep_rec pr;
+    pr.gap_first = rec.first;
+    pc_prepare_clump(&P, bases, q, readLen, r, strand, path + rec.first, (int)rec.n, gaps + rec.first, jobs, n_jobs, jobs_cap, &pr);
+    prep[i] = pr;
+    const uint32_t ne = (pr.jobB != 0xFFFFFFFFu) + (pr.jobF != 0xFFFFFFFFu);
+    if (ne) atomicAdd(n_jobs + 1, ne);
 }
 
 // device_only (ya_align_batch): only the two job counts come back (out->n_jobs, *n_ext); records and jobs stay on the device.
@@ -153,7 +156,7 @@ int ya_prepare_clumps_impl(ya_ctx *c, ya_prep_batch *out, bool device_only, size
     P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.RCost = c->P.RCost; P.MScore = c->P.MScore;
     P.minExtLength = c->P.minExtLength; P.maxROff = c->maxROff;
     YA_CUDA(c, cudaEventRecord(c->ev[0], st));
-    prepare_clumps_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(n_seg, c->d_read_off.as<uint64_t>(), d_count, d_first,
+    prepare_clumps_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, st>>>((uint32_t)nk, c->d_fc_slot.as<uint32_t>(), c->d_read_off.as<uint64_t>(),
         c->d_fc_clumps.as<ya_clump_rec>(), c->d_fc_path.as<ya_frag>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), P,
         c->d_pc_path.as<ya_frag>(), c->d_pc_gaps.as<ya_gap_rec>(), c->d_pc_prep.as<ya_prep_rec>(), c->d_pc_jobs.as<ya_dp_job>(), d_njobs,
         (uint32_t)jobsCap);

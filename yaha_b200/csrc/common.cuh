@@ -133,7 +133,7 @@ struct ya_ctx {
     DevBuf    d_seg_probe_off, d_cnt, d_soff, d_hit_off, d_keys0, d_keys1, d_scan_tmp, d_hist;
     DevBuf    d_fragflag, d_fragidx, d_frags_all, d_frag_seg, d_regflag, d_regidx, d_regstart,
               d_keep, d_keepidx, d_frags_out, d_region_out, d_strand_out, d_misc;
-    DevBuf    d_fc_count, d_fc_work, d_fc_tmp, d_fc_path, d_fc_nodes, d_fc_used, d_fc_clumps;   // ya_form_clumps
+    DevBuf    d_fc_count, d_fc_work, d_fc_tmp, d_fc_path, d_fc_nodes, d_fc_used, d_fc_clumps, d_fc_slot;   // ya_form_clumps
     DevBuf    d_pc_path, d_pc_gaps, d_pc_prep, d_pc_jobs;                                       // ya_prepare_clumps
     // ya_align_batch: the reads as text, per-clump assembly records, per-read output plan, SAM text
     DevBuf    d_chars, d_quals, d_ids, d_fin, d_asm_recs, d_asm_ops, d_fr_outs, d_text, d_out_tab;

@@ -292,7 +292,7 @@ extern "C" void ya_close(ya_ctx *c)
                       &c->d_frags_all, &c->d_frag_seg, &c->d_regflag, &c->d_regidx, &c->d_regstart, &c->d_keep,
                       &c->d_keepidx, &c->d_frags_out, &c->d_region_out, &c->d_strand_out, &c->d_misc, &c->d_jobs,
                       &c->d_jobout, &c->d_tb, &c->d_rows, &c->d_ops_raw, &c->d_ops_cnt, &c->d_ops_off, &c->d_ops_out, &c->d_res,
-                      &c->d_fc_count, &c->d_fc_work, &c->d_fc_tmp, &c->d_fc_path, &c->d_fc_nodes, &c->d_fc_used, &c->d_fc_clumps,
+                      &c->d_fc_count, &c->d_fc_work, &c->d_fc_tmp, &c->d_fc_path, &c->d_fc_nodes, &c->d_fc_used, &c->d_fc_clumps, &c->d_fc_slot,
                       &c->d_pc_path, &c->d_pc_gaps, &c->d_pc_prep, &c->d_pc_jobs, &c->d_dpr, &c->d_chars, &c->d_quals, &c->d_ids, &c->d_fin,
                       &c->d_asm_recs, &c->d_asm_ops, &c->d_fr_outs, &c->d_text, &c->d_out_tab};
     for (DevBuf *b : bufs) b->release();

@@ -49,41 +49,38 @@ struct AsmDev {
     const ya_dp_result *res; const ya_op *rops;
 };
 
-// one thread per strand: every clump of the strand (a handful) is spliced, extended and scored
+// one thread per clump (slot_strand, written by form_clumps_kernel, says which slots of the clump array are clumps and whose)
 __global__ void __launch_bounds__(128)
-assemble_kernel(int n_seg, const uint64_t *__restrict__ read_off, AsmDev D, const uint8_t *__restrict__ bases,
-                const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev, ac_params P,
+assemble_kernel(uint32_t n_slots, const uint32_t *__restrict__ slot_strand, const uint64_t *__restrict__ read_off, AsmDev D,
+                const uint8_t *__restrict__ bases, const uint8_t *__restrict__ fwd, const uint8_t *__restrict__ rev, ac_params P,
                 ya_asm_rec *__restrict__ recs, ya_op *__restrict__ out_ops, uint32_t out_cap, uint32_t *__restrict__ out_used,
                 unsigned long long *__restrict__ acct)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    const uint32_t nc = D.count[s];
-    if (nc == 0 || nc == 0xFFFFFFFFu) return;
-    const uint32_t r = (uint32_t)(s >> 1);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const uint32_t sp1 = slot_strand[i];
+    if (sp1 == 0) return;
+    const uint32_t s = sp1 - 1, r = s >> 1;
     const uint64_t base = read_off[r];
     const int readLen = (int)(read_off[r + 1] - base);
     const uint8_t *q = ((s & 1) ? rev : fwd) + base;
-    const uint32_t c0 = D.first[s];
-    for (uint32_t k = 0; k < nc; k++) {
-        const ya_clump_rec cr = D.clumps[c0 + k];
-        const ya_prep_rec pr = D.prep[c0 + k];
-        const ya_gap_rec *g = D.gaps + pr.gap_first;
-        const uint32_t bound = ac_ops_bound((int)cr.n, g, pr.n_gaps, &pr, D.res, D.rops);
-        const uint32_t at = atomicAdd(out_used, bound);
-        ya_asm_rec rec;
-        if ((uint64_t)at + bound > out_cap) {                              // (cannot happen: the caller sized the array by the same bound)
-            atomicOr(&acct[2], 8ull);
-            memset(&rec, 0, sizeof rec); rec.verdict = YA_ASM_SPLIT;
-        } else {
-            if (ac_assemble_clump(&P, bases, q, readLen, D.path + cr.first, (int)cr.n, g, pr.n_gaps, &pr, D.res, D.rops, out_ops + at, &rec) != 0) {
-                atomicOr(&acct[2], 16ull);                                 // extension plan diverged (fatal on the host as well)
-                rec.verdict = YA_ASM_SPLIT;
-            }
-            rec.ops_off = at;
+    const ya_clump_rec cr = D.clumps[i];
+    const ya_prep_rec pr = D.prep[i];
+    const ya_gap_rec *g = D.gaps + pr.gap_first;
+    const uint32_t bound = ac_ops_bound((int)cr.n, g, pr.n_gaps, &pr, D.res, D.rops);
+    const uint32_t at = atomicAdd(out_used, bound);
+    ya_asm_rec rec;
+    if ((uint64_t)at + bound > out_cap) {                                  // (cannot happen: the caller sized the array by the same bound)
+        atomicOr(&acct[2], 8ull);
+        memset(&rec, 0, sizeof rec); rec.verdict = YA_ASM_SPLIT;
+    } else {
+        if (ac_assemble_clump(&P, bases, q, readLen, D.path + cr.first, (int)cr.n, g, pr.n_gaps, &pr, D.res, D.rops, out_ops + at, &rec) != 0) {
+            atomicOr(&acct[2], 16ull);                                     // extension plan diverged (fatal on the host as well)
+            rec.verdict = YA_ASM_SPLIT;
         }
-        recs[c0 + k] = rec;
+        rec.ops_off = at;
     }
+    recs[i] = rec;
 }
 
 struct ReadText { const char *chars, *quals, *ids; const uint32_t *id_off; };
@@ -371,7 +368,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
         ac_params AP;
         AP.GOCost = c->P.GOCost; AP.GECost = c->P.GECost; AP.RCost = c->P.RCost; AP.MScore = c->P.MScore;
         AP.minExtLength = c->P.minExtLength; AP.minRawScore = c->out.minRawScore; AP.maxROff = c->maxROff; AP.minIdentity = c->out.minIdentity;
-        assemble_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(n_seg, c->d_read_off.as<uint64_t>(), D, c->d_bases, c->d_codes_fwd.as<uint8_t>(),
+        assemble_kernel<<<(unsigned)((nk + 127) / 128), 128, 0, st>>>((uint32_t)nk, c->d_fc_slot.as<uint32_t>(), c->d_read_off.as<uint64_t>(), D, c->d_bases, c->d_codes_fwd.as<uint8_t>(),
             c->d_codes_rev.as<uint8_t>(), AP, c->d_asm_recs.as<ya_asm_rec>(), c->d_asm_ops.as<ya_op>(), (uint32_t)asmCap, d_asm_used, d_acct);
         c->ctr.launches++;
     }

@@ -1293,7 +1293,7 @@ __global__ void dpr_classify_kernel(const ya_dp_job *__restrict__ jobs, uint32_t
     tb_units[i] = tbu; ops_slots[i] = slots; rows_ints[i] = rints;
 }
 
-// In-place exclusive scans of up to four arrays of n words by ONE block (n is a few tens of thousands: a device-wide scan
+// In-place exclusive scans of up to four arrays of n words, ONE block per array (n is a few tens of thousands: a device-wide scan
 // would be three launches per array); totals[k] receives array k's sum (64-bit).
 __global__ void __launch_bounds__(1024)
 dpr_scan_kernel(uint32_t *a0, uint32_t *a1, uint32_t *a2, uint32_t *a3, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3,
@@ -1304,7 +1304,7 @@ dpr_scan_kernel(uint32_t *a0, uint32_t *a1, uint32_t *a2, uint32_t *a3, uint32_t
     uint32_t *arr[4] = {a0, a1, a2, a3};
     const uint32_t cnt[4] = {n0, n1, n2, n3};
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int a = 0; a < 4; a++) {
+    for (int a = (int)blockIdx.x; a < 4; a += (int)gridDim.x) {             // (launched with four blocks: one array each)
         uint32_t *p = arr[a];
         if (!p) continue;
         if (threadIdx.x == 0) carry = 0;
@@ -1396,7 +1396,7 @@ int ya_sw_device_round(ya_ctx *c, uint32_t n_jobs, uint32_t n_ext, unsigned long
                                             (uint64_t)c->n_base_bytes * 2, F, c->d_jobs.as<DevJob>(), key, tbu, slots, rints,
                                             c->d_res.as<ya_dp_result>(), d_acct);
     dpr_hist_kernel<<<nb, 256, 0, st>>>(key, n_jobs, bins);
-    dpr_scan_kernel<<<1, 1024, 0, st>>>(tbu, slots, rints, bins, n_jobs, n_jobs, n_jobs, DPR_BINS, totals);
+    dpr_scan_kernel<<<4, 1024, 0, st>>>(tbu, slots, rints, bins, n_jobs, n_jobs, n_jobs, DPR_BINS, totals);
     dpr_class_starts_kernel<<<1, 64, 0, st>>>(bins, starts);
     dpr_place_kernel<<<nb, 256, 0, st>>>(c->d_jobs.as<DevJob>(), n_jobs, key, tbu, slots, rints, bins, d_ids);
     c->ctr.launches += 5;
