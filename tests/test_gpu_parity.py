@@ -59,12 +59,16 @@ def test_dp_matches_reference_calls(small, aligner, bw, gap, mode, monkeypatch):
     assert aligner.counters().dp_cells == cells
 
 
-@pytest.mark.parametrize("sorter", ["segmented", "radix"])
+@pytest.mark.parametrize("sorter", ["fused", "segmented", "radix"])
 def test_seed_frags_match_reference_and_oracle(small, aligner, sorter, monkeypatch):
     """Stage 1+2: per strand, surviving fragments (values and order), fragCount, totalCount and
     region ids equal the oracle; the oracle equals the reference dump (test_oracle_golden)."""
+    # fused: one warp / block per strand does the whole of stage 2 in shared memory (default); segmented: the kernel chain with
+    # the shared-memory sort; radix: the kernel chain with the global LSD radix sort (strands above 8192 hits)
     if sorter == "radix":
-        monkeypatch.setenv("YA_SEED_RADIX", "1")      # force the global LSD radix sort instead of the shared-memory sort
+        monkeypatch.setenv("YA_SEED_RADIX", "1")
+    if sorter == "segmented":
+        monkeypatch.setenv("YA_SEED_CHAIN", "1")
     aligner.set_params(yaha_b200.Params.defaults(word_len=11))
     aligner.upload_read_list(small.fwd)
     strands, frags, region = aligner.seed_frags()

@@ -153,7 +153,7 @@ struct ya_ctx {
     std::vector<std::vector<uint32_t>> sw_lists;      // ya_sw_batch host scratch (reused)
     std::vector<uint32_t> sw_live_of, sw_flat, sw_cnt, sw_tmp;
     size_t ops_pending = 0;          // ops left on the device by a ya_sw_batch that returned YA_E_CAPACITY
-    std::vector<uint32_t> seed_small, seed_big;       // ya_seed_frags host scratch (segment id lists)
+    std::vector<uint32_t> seed_small, seed_big, seed_koff;   // ya_seed_frags host scratch (segment id lists, key offsets)
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ya_counters ctr{};

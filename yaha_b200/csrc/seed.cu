@@ -388,6 +388,188 @@ __global__ void init_strands_kernel(ya_strand_frags *s, const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------
+// K2, fused (the common case: every segment of the chunk has at most 8192 hits).  One warp (<= 512 hits) or one block per
+// segment does the whole of stage 2 in shared memory: expand the probes' ROA lists into (diagonal, qo) keys, sort them
+// (bitonic; keys are distinct), coalesce abutting seeds into fragments (QueryMatch.c:99-115), cut regions where neighbouring
+// diagonals differ by more than maxGap (QueryMatch.c:146-158), drop singleton regions shorter than minMatch
+// (QueryMatch.c:281-290) and write the survivors to the segment's place in a staging array.  HBM traffic: 4 B per hit read,
+// 16 B per survivor written -- against ~100 B per hit of the expand / sort / flag / scan / write chain it replaces, and two
+// launches (+ one compaction) instead of twenty.
+// ------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ uint32_t k2_block_excl_scan(uint32_t v, uint32_t *total, uint32_t *wsum)
+{
+    // exclusive scan of one value per thread over the block (THREADS = 32: a single warp)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    if (THREADS == 32) { *total = __shfl_sync(0xffffffffu, inc, 31); return inc - v; }
+    __syncthreads();                                   // (wsum may still be read from the previous scan)
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint32_t x = (lane < THREADS / 32) ? wsum[lane] : 0u;
+        uint32_t xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, xi, d); if (lane >= d) xi += t; }
+        if (lane < THREADS / 32) wsum[lane] = xi - x;
+        if (lane == 31) wsum[32] = xi;
+    }
+    __syncthreads();
+    *total = wsum[32];
+    return inc - v + wsum[w];
+}
+
+struct K2Frag { uint32_t diag; uint16_t sqo, eqo; };                 // 8 B: overlays the sorted keys
+
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k2_fused_kernel(const uint32_t *__restrict__ seg_ids, int n_list, const uint32_t *__restrict__ seg_probe_off, int seg_local0,
+                const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ soff, const uint32_t *__restrict__ roa,
+                const uint32_t *__restrict__ seg_key_off, int K, uint32_t maxGap, uint32_t minMatch,
+                ya_frag *__restrict__ stage_frags, uint32_t *__restrict__ stage_region, uint32_t *__restrict__ seg_nall,
+                uint32_t *__restrict__ seg_nkeep, uint32_t *__restrict__ totals)
+{
+    constexpr int IPT = CAP / THREADS;                               // items per thread, blocked: thread t owns [t*IPT, (t+1)*IPT)
+    static_assert(IPT <= 32, "per-thread flags are kept in 32-bit masks");
+    extern __shared__ uint64_t sh[];                                 // CAP keys, later CAP fragment records
+    __shared__ uint32_t wsum[33];
+    const int item = blockIdx.x;
+    if (item >= n_list) return;
+    const uint32_t seg = seg_ids[item];
+    const uint32_t base = seg_key_off[seg];
+    const int n = (int)(seg_key_off[seg + 1] - base);
+    const uint32_t pa = seg_probe_off[seg_local0 + seg], pb = seg_probe_off[seg_local0 + seg + 1];
+    const int t = threadIdx.x;
+    // ---- expand: probes in qo order, each probe's list in ROA order (ascending offset)
+    {
+        uint32_t run = 0;                                            // hits of the probes handled in earlier rounds
+        for (uint32_t p0 = pa; p0 < pb; p0 += THREADS) {
+            const uint32_t gp = p0 + t;
+            const uint32_t c = (gp < pb) ? cnt[gp] : 0u;
+            uint32_t tot;
+            const uint32_t at = run + k2_block_excl_scan<THREADS>(c, &tot, wsum);
+            if (c) {
+                const uint32_t qo = gp - pa;
+                const uint32_t *list = roa + soff[gp];
+                for (uint32_t k = 0; k < c; k++) {
+                    const uint32_t diag = list[k] - qo;              // wraps for roff < qo (QueryHeap.inl:70-73)
+                    sh[at + k] = ((uint64_t)diag << QO_BITS) | qo;
+                }
+            }
+            run += tot;
+        }
+    }
+    int P = 1; while (P < n) P <<= 1;
+    for (int i = n + t; i < P; i += THREADS) sh[i] = ~0ull;
+    __syncthreads();
+    // ---- sort
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < P; i += THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t x = sh[i], y = sh[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { sh[i] = y; sh[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- fragments: a key opens one unless it continues the previous key's (QueryMatch.c:99: nextDiag != curDiag || nextQO > curEQO)
+    uint64_t key[IPT];
+    uint32_t headMask = 0, tailMask = 0;                             // bit k: item t*IPT + k opens / closes a fragment
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const int i = t * IPT + k;
+        key[k] = 0;
+        if (i < n) {
+            const uint64_t b = sh[i];
+            key[k] = b;
+            bool head = true, tail = true;
+            if (i > 0) {
+                const uint64_t a = sh[i - 1];
+                if ((a >> QO_BITS) == (b >> QO_BITS) && (uint32_t)(b & QO_MASK) <= (uint32_t)(a & QO_MASK) + (uint32_t)K) head = false;
+            }
+            if (i + 1 < n) {
+                const uint64_t c2 = sh[i + 1];
+                if ((c2 >> QO_BITS) == (b >> QO_BITS) && (uint32_t)(c2 & QO_MASK) <= (uint32_t)(b & QO_MASK) + (uint32_t)K) tail = false;
+            }
+            headMask |= (head ? 1u : 0u) << k; tailMask |= (tail ? 1u : 0u) << k;
+        }
+    }
+    uint32_t nf;
+    uint32_t fid = k2_block_excl_scan<THREADS>((uint32_t)__popc(headMask), &nf, wsum);   // id of this thread's first head
+    __syncthreads();                                                 // every key is in registers: the array becomes fragment records
+    K2Frag *fr = reinterpret_cast<K2Frag *>(sh);
+    // (a fragment's last key may belong to another thread than its first: `fid - 1` there is that thread's running id, which
+    //  counts the heads at or before the key in key order -- the fragment this key closes)
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        if ((headMask >> k) & 1u) { fr[fid].diag = (uint32_t)(key[k] >> QO_BITS); fr[fid].sqo = (uint16_t)(key[k] & QO_MASK); fid++; }
+        if ((tailMask >> k) & 1u) fr[fid - 1].eqo = (uint16_t)((key[k] & QO_MASK) + K - 1);
+    }
+    __syncthreads();
+    // ---- regions and survivors: fragments blocked over the threads the same way.  A region is cut where neighbouring
+    // diagonals differ by more than maxGap (QueryMatch.c:146-158); a fragment whose region has no second member survives only
+    // with refLen >= minMatch (QueryMatch.c:281-290).
+    uint32_t rheadMask = 0, keepMask = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const uint32_t f = (uint32_t)(t * IPT + k);
+        if (f < nf) {
+            const uint32_t d = fr[f].diag;
+            bool rhead = true, rlast = true;
+            if (f > 0) { const uint32_t a = fr[f - 1].diag; if ((a > d ? a - d : d - a) <= maxGap) rhead = false; }       // FragsClumps.inl:133-137
+            if (f + 1 < nf) { const uint32_t b = fr[f + 1].diag; if ((b > d ? b - d : d - b) <= maxGap) rlast = false; }
+            const uint32_t refLen = (uint32_t)fr[f].eqo - fr[f].sqo + 1;
+            rheadMask |= (rhead ? 1u : 0u) << k;
+            keepMask |= ((!(rhead && rlast) || refLen >= minMatch) ? 1u : 0u) << k;
+        }
+    }
+    uint32_t nreg, nk;
+    const uint32_t rid0 = k2_block_excl_scan<THREADS>((uint32_t)__popc(rheadMask), &nreg, wsum);
+    uint32_t kid = k2_block_excl_scan<THREADS>((uint32_t)__popc(keepMask), &nk, wsum);
+    (void)nreg;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        if ((keepMask >> k) & 1u) {
+            const uint32_t f = (uint32_t)(t * IPT + k);
+            ya_frag g;
+            g.startRefOff = fr[f].diag + fr[f].sqo;
+            g.startQueryOff = fr[f].sqo;
+            g.endQueryOff = fr[f].eqo;
+            g.hitCount = 0;
+            g.refLen = (uint16_t)(g.endQueryOff - g.startQueryOff + 1);   // FragsClumps.inl:44-46
+            stage_frags[base + kid] = g;
+            stage_region[base + kid] = rid0 + (uint32_t)__popc(rheadMask & (0xFFFFFFFFu >> (31 - k))) - 1u;   // region ordinal within the strand
+            kid++;
+        }
+    }
+    if (t == 0) { seg_nall[seg] = nf; seg_nkeep[seg] = nk; atomicAdd(&totals[0], nf); atomicAdd(&totals[2], nk); }
+}
+
+// survivors of every segment from the staging array (at the segment's key offset) to their final, dense place; strand records
+__global__ void __launch_bounds__(128)
+k2_compact_kernel(int n_seg, const uint32_t *__restrict__ seg_key_off, const uint32_t *__restrict__ seg_nall,
+                  const uint32_t *__restrict__ seg_nkeep, const uint32_t *__restrict__ keep_off, const uint32_t *__restrict__ seg_total,
+                  const ya_frag *__restrict__ stage_frags, const uint32_t *__restrict__ stage_region,
+                  ya_frag *__restrict__ out, uint32_t *__restrict__ region_out, ya_strand_frags *__restrict__ strands)
+{
+    const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= n_seg) return;
+    const uint32_t nk = seg_nkeep[warp], from = seg_key_off[warp], to = keep_off[warp];
+    for (uint32_t k = lane; k < nk; k += 32) { out[to + k] = stage_frags[from + k]; region_out[to + k] = stage_region[from + k]; }
+    if (lane == 0) {
+        ya_strand_frags v;
+        v.first = nk ? to : 0xFFFFFFFFu; v.n_frags = nk; v.n_frags_all = seg_nall[warp]; v.total_hits = seg_total[warp];
+        strands[warp] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 int ya_radix_sort_u64(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_bit, int hi_bit)
@@ -484,6 +666,61 @@ int ya_seed_frags_impl(ya_ctx *c, ya_frag_batch *out, bool device_only)
         const int cseg = s1 - s0;
         c->ctr.hits += n_keys;
         if (n_keys > 0) {
+            uint32_t maxSeg = 0;
+            for (int sgi = s0; sgi < s1; sgi++) maxSeg = std::max(maxSeg, h_seg_eff[sgi]);
+            const bool noFused = getenv("YA_SEED_CHAIN") != nullptr || getenv("YA_SEED_RADIX") != nullptr;   // (tests: the kernel chain)
+            const size_t NU = n_keys;
+            uint32_t *d_tot = c->d_misc.as<uint32_t>() + 2 * (size_t)n_seg;    // 4 spare words: fragments, regions, survivors
+            if (maxSeg <= 8192 && !noFused) {
+                // ---- fused stage 2: one warp / block per segment in shared memory (k2_fused_kernel), then one compaction
+                YA_CUDA(c, c->d_frags_out.reserve(NU * sizeof(ya_frag) + 16));
+                YA_CUDA(c, c->d_region_out.reserve(NU * 4 + 16));
+                YA_CUDA(c, c->d_frags_all.reserve(NU * sizeof(ya_frag) + 16));          // staging: survivors at their segment's key offset
+                YA_CUDA(c, c->d_regidx.reserve(NU * 4 + 16));
+                YA_CUDA(c, c->d_regstart.reserve(((size_t)6 * cseg + 8) * 4 + 64));
+                std::vector<uint32_t> &small = c->seed_small, &big = c->seed_big, &koff = c->seed_koff;
+                small.clear(); big.clear(); koff.resize((size_t)cseg + 1);
+                uint32_t run = 0;
+                for (int sgi = s0; sgi < s1; sgi++) {
+                    const uint32_t e = h_seg_eff[sgi];
+                    koff[(size_t)(sgi - s0)] = run; run += e;
+                    if (e >= 1 && e <= 512) small.push_back((uint32_t)(sgi - s0));
+                    else if (e > 512) big.push_back((uint32_t)(sgi - s0));
+                }
+                koff[(size_t)cseg] = run;
+                uint32_t *d_sko = c->d_regstart.as<uint32_t>();
+                uint32_t *d_nall = d_sko + cseg + 1, *d_nkeep = d_nall + cseg, *d_koff = d_nkeep + cseg;
+                uint32_t *d_small = d_koff + cseg + 1, *d_big = d_small + small.size();
+                YA_CUDA(c, cudaMemcpyAsync(d_sko, koff.data(), ((size_t)cseg + 1) * 4, cudaMemcpyHostToDevice, st));
+                YA_CUDA(c, cudaMemsetAsync(d_nall, 0, (size_t)2 * cseg * 4, st));
+                YA_CUDA(c, cudaMemsetAsync(d_tot, 0, 16, st));
+                ya_frag *stage = c->d_frags_all.as<ya_frag>();
+                uint32_t *stage_reg = c->d_regidx.as<uint32_t>();
+                if (!small.empty()) {
+                    YA_CUDA(c, cudaMemcpyAsync(d_small, small.data(), small.size() * 4, cudaMemcpyHostToDevice, st));
+                    k2_fused_kernel<512, 32><<<(unsigned)small.size(), 32, 512 * 8, st>>>(d_small, (int)small.size(), d_po, s0, d_cnt, d_soff, c->d_roa,
+                        d_sko, K, (uint32_t)c->P.maxGap, (uint32_t)c->P.minMatch, stage, stage_reg, d_nall, d_nkeep, d_tot);
+                    c->ctr.launches++;
+                }
+                if (!big.empty()) {
+                    // (the opt-in to 64 KB of dynamic shared memory is per device: made once per context, which is bound to one)
+                    if (!c->big_sort_attr) {
+                        YA_CUDA(c, cudaFuncSetAttribute(k2_fused_kernel<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+                        YA_CUDA(c, cudaFuncSetAttribute(seg_sort_kernel<8192, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+                        c->big_sort_attr = true;
+                    }
+                    YA_CUDA(c, cudaMemcpyAsync(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice, st));
+                    k2_fused_kernel<8192, 256><<<(unsigned)big.size(), 256, 8192 * 8, st>>>(d_big, (int)big.size(), d_po, s0, d_cnt, d_soff, c->d_roa,
+                        d_sko, K, (uint32_t)c->P.maxGap, (uint32_t)c->P.minMatch, stage, stage_reg, d_nall, d_nkeep, d_tot);
+                    c->ctr.launches++;
+                }
+                int rc = ya_exclusive_scan_u32(c, d_nkeep, d_koff, (size_t)cseg, nullptr);
+                if (rc != YA_OK) return rc;
+                k2_compact_kernel<<<(cseg + 3) / 4, 128, 0, st>>>(cseg, d_sko, d_nall, d_nkeep, d_koff, d_seg_total + s0, stage, stage_reg,
+                    c->d_frags_out.as<ya_frag>(), c->d_region_out.as<uint32_t>(), d_strands + s0);
+                c->ctr.launches++;
+                YA_CUDA(c, cudaGetLastError());
+            } else {
             const uint32_t probe0 = h_po[s0], cprobes = h_po[s1] - h_po[s0];
             YA_CUDA(c, c->d_hit_off.reserve((size_t)cprobes * 4 + 16));
             YA_CUDA(c, c->d_keys0.reserve((size_t)n_keys * 8));
@@ -496,8 +733,6 @@ int ya_seed_frags_impl(ya_ctx *c, ya_frag_batch *out, bool device_only)
             expand_hits_kernel<<<(cseg + 3) / 4, 128, 0, st>>>(d_po, cseg, s0, d_cnt, d_soff, d_hit_off, probe0, c->d_roa, ka);
             c->ctr.launches++;
             // sort: segmented shared-memory sort when every segment fits a block, else the global radix sort
-            uint32_t maxSeg = 0;
-            for (int sgi = s0; sgi < s1; sgi++) maxSeg = std::max(maxSeg, h_seg_eff[sgi]);
             if (maxSeg <= 8192 && !getenv("YA_SEED_RADIX")) {
                 std::vector<uint32_t> &small = c->seed_small, &big = c->seed_big;
                 small.clear(); big.clear();
@@ -535,7 +770,6 @@ int ya_seed_frags_impl(ya_ctx *c, ya_frag_batch *out, bool device_only)
 
             // fragments, regions, survivors: every array is sized by the number of hits (>= fragments >= regions,
             // survivors), the counts stay on the device (d_tot[0..2]) and come back with the results
-            const size_t NU = n_keys;
             YA_CUDA(c, c->d_fragflag.reserve(NU * 4));
             YA_CUDA(c, c->d_fragidx.reserve(std::max<size_t>(NU, (size_t)cseg) * 4));
             YA_CUDA(c, c->d_frags_all.reserve(NU * sizeof(FragRaw)));
@@ -550,7 +784,6 @@ int ya_seed_frags_impl(ya_ctx *c, ya_frag_batch *out, bool device_only)
             uint32_t nb = (n_keys + 255) / 256;
             frag_flag_kernel<<<nb, 256, 0, st>>>(ka, n_keys, K, fflag);
             c->ctr.launches++;
-            uint32_t *d_tot = c->d_misc.as<uint32_t>() + 2 * (size_t)n_seg;    // 4 spare words: fragments, regions, survivors
             rc = ya_exclusive_scan_u32(c, fflag, fidx, n_keys, d_tot);
             if (rc != YA_OK) return rc;
             FragRaw *raw = c->d_frags_all.as<FragRaw>();
@@ -577,6 +810,7 @@ int ya_seed_frags_impl(ya_ctx *c, ya_frag_batch *out, bool device_only)
                                                d_strands + s0);
             c->ctr.launches++;
             YA_CUDA(c, cudaGetLastError());
+            }
             // results: the counts, the strand records and -- speculatively -- the first survivors (32 per read)
             uint32_t *h_cnt = c->h_stage.as<uint32_t>() + (size_t)n_seg * 2;          // 3 words after the per-segment totals
             YA_CUDA(c, cudaMemcpyAsync(h_cnt, d_tot, 12, cudaMemcpyDeviceToHost, st));

@@ -237,6 +237,17 @@ template <class T> struct PinnedVec {
     }
 };
 
+// Page-locked landing place of one batch's device text.  A pipeline owns a small ring of them: pinning memory in the middle
+// of a run stalls every stream of the process (YA_ALLOC_LOG), so the ring is filled during the first batches and a
+// pipeline whose buffers are all still with the writer waits for one instead of making another.
+struct TextBuf {
+    PinnedVec<char> text;
+    PinnedVec<uint64_t> off;
+    PinnedVec<uint8_t> status;
+    std::mutex *mu = nullptr; std::condition_variable *cv = nullptr; std::vector<TextBuf *> *home = nullptr;
+    void release() { { std::lock_guard<std::mutex> g(*mu); home->push_back(this); } cv->notify_one(); }
+};
+
 struct Batch {
     uint64_t seq = 0;
     std::vector<Read> reads;
@@ -245,11 +256,10 @@ struct Batch {
     int nFibers = 0, fiberCap = 0;
     struct alignas(64) OutBuf { OutText s; };   // (own cache line: every append updates the size)
     std::vector<OutBuf> outBufs;          // formatted records, one buffer per worker thread
-    // ya_align_batch: the SAM text of the reads finished on the device (page-locked, lands here straight from the device),
-    // where each read's records start, which reads were handed back -- those are run as `residual` through the fibers
-    PinnedVec<char> devText;
-    PinnedVec<uint64_t> devTextOff;
-    PinnedVec<uint8_t> devStatus;
+    // ya_align_batch: the SAM text of the reads finished on the device (page-locked, lands there straight from the device),
+    // where each read's records start, which reads were handed back -- those are run as `residual` through the fibers.
+    // The buffers belong to the pipeline that ran the batch (TextBuf ring) and go back to it once the batch is written.
+    struct TextBuf *text = nullptr;
     std::unique_ptr<Batch> residual;
     std::vector<int> residualOf;          // residual read k is read residualOf[k] of this batch
     std::vector<std::pair<const char *, size_t>> outRuns;   // what the writer emits for this batch, in input order
@@ -269,6 +279,22 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     PinnedVec<uint32_t> region;
     PinnedVec<uint8_t> codes;
     PinnedVec<uint64_t> offs;
+    std::vector<std::unique_ptr<TextBuf>> textBufs;       // ring of device-text landing buffers (at most kTextBufs)
+    std::vector<TextBuf *> freeText; std::mutex textMu; std::condition_variable textCv;
+    TextBuf *acquireText()
+    {
+        static const size_t kTextBufs = 3;
+        std::unique_lock<std::mutex> lk(textMu);
+        if (freeText.empty() && textBufs.size() < kTextBufs) {
+            textBufs.emplace_back(new TextBuf());
+            TextBuf *t = textBufs.back().get();
+            t->mu = &textMu; t->cv = &textCv; t->home = &freeText;
+            return t;
+        }
+        textCv.wait(lk, [&] { return !freeText.empty(); });
+        TextBuf *t = freeText.back(); freeText.pop_back();
+        return t;
+    }
     PinnedVec<char> chars, quals, ids;            // ya_align_batch inputs: the reads as they stand in the file
     PinnedVec<uint32_t> idOffs;
     PinnedVec<uint32_t> clumpFirst, clumpCount;     // ya_form_clumps outputs (clumps of seed fragments made on the device)
@@ -655,20 +681,22 @@ static int fusedPass(const Env &E, Pipe &D, Batch &B)
         memcpy(D.ids.data() + D.idOffs[(size_t)i], r.id.data(), r.id.size());
         if (fastq) memcpy(D.quals.data() + D.offs[(size_t)i], r.qual.data(), r.qual.size());
     }
-    B.devTextOff.resize((size_t)n + 1, false);
-    B.devStatus.resize((size_t)n, false);
-    if (B.devText.size() < 2 * total + 512 * (size_t)n + 4096) B.devText.resize(2 * total + 512 * (size_t)n + 4096, false);
+    B.text = D.acquireText();
+    TextBuf &TB = *B.text;
+    if (TB.off.size() < (size_t)n + 1) TB.off.resize((size_t)n + 1 + (size_t)n / 4, false);
+    if (TB.status.size() < (size_t)n) TB.status.resize((size_t)n + (size_t)n / 4, false);
+    if (TB.text.size() < 2 * total + 512 * (size_t)n + 4096) TB.text.resize(3 * total + 768 * (size_t)n + 4096, false);
     ya_text_batch tb;
     memset(&tb, 0, sizeof tb);
     tb.n_reads = n; tb.chars = D.chars.data(); tb.offsets = D.offs.data(); tb.quals = fastq ? D.quals.data() : nullptr;
     tb.ids = D.ids.data(); tb.id_off = D.idOffs.data();
-    tb.text = B.devText.data(); tb.text_cap = B.devText.size(); tb.text_off = B.devTextOff.data(); tb.status = B.devStatus.data();
+    tb.text = TB.text.data(); tb.text_cap = TB.text.size(); tb.text_off = TB.off.data(); tb.status = TB.status.data();
     D.tUpload += nowSec() - t0;
     const double t1 = nowSec();
     int rcode = ya_align_batch(D.ctx, &tb);
     if (rcode == YA_E_CAPACITY) {
-        B.devText.resize(tb.text_needed + tb.text_needed / 4 + 4096, false);
-        rcode = ya_align_fetch_text(D.ctx, B.devText.data(), B.devText.size());
+        TB.text.resize(tb.text_needed + tb.text_needed / 4 + 4096, false);
+        rcode = ya_align_fetch_text(D.ctx, TB.text.data(), TB.text.size());
     }
     if (rcode != YA_OK) die(D.ctx, "ya_align_batch");
     D.tDp += nowSec() - t1;
@@ -716,7 +744,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     if (!fusedWanted(E) || n > 65536) { classicPass(E, D, B, pool); fiberRuns(B, B); return; }
     const int handed = fusedPass(E, D, B);
     if (handed == 0) {
-        addRun(B, B.devText.data(), (size_t)B.devTextOff[(size_t)n]);
+        addRun(B, B.text->text.data(), (size_t)B.text->off[(size_t)n]);
         return;
     }
     // the reads the device handed back (a clump to split, a crowded strand, ...) go through the fibers as a batch of their own
@@ -725,7 +753,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     B.residualOf.clear();
     size_t k = 0;
     for (int i = 0; i < n; i++) {
-        if (!B.devStatus[(size_t)i]) continue;
+        if (!B.text->status[(size_t)i]) continue;
         if (k == R.reads.size()) R.reads.emplace_back();
         Read &dst = R.reads[k];
         const Read &src = B.reads[(size_t)i];
@@ -738,7 +766,7 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     classicPass(E, D, R, pool);
     size_t next = 0;                                                      // merge: device text for the finished reads, fiber text for the rest
     for (int i = 0; i < n; i++) {
-        if (!B.devStatus[(size_t)i]) { addRun(B, B.devText.data() + B.devTextOff[(size_t)i], (size_t)(B.devTextOff[(size_t)i + 1] - B.devTextOff[(size_t)i])); continue; }
+        if (!B.text->status[(size_t)i]) { addRun(B, B.text->text.data() + B.text->off[(size_t)i], (size_t)(B.text->off[(size_t)i + 1] - B.text->off[(size_t)i])); continue; }
         const ReadCtx &rc = R.fibers[next++].rc;
         if (rc.outLen) addRun(B, rc.out->data() + rc.outOff, rc.outLen);
     }
@@ -991,47 +1019,7 @@ int runQueries(const Args &A0)
                 }
             });
 
-        // Output: batches leave in input order.  For a regular file the order is a matter of OFFSETS, not of time: this thread
-        // assigns every finished batch its place in the file and a few writer threads put the text there with pwrite, side by
-        // side -- the batches of a step tend to finish together, and one thread copying them into the page cache one after the
-        // other was a quarter of the step.  A pipe (stdout) keeps the single ordered stream.
-        fflush(out);
-        const off_t fileStart = replaying ? (off_t)-1 : lseek(fileno(out), 0, SEEK_CUR);
-        const bool parallelWrite = !A.replay && fileStart >= 0 && A.ofile != "stdout" && getenv("YA_SERIAL_WRITE") == nullptr;
-        struct WriteJob { std::unique_ptr<Batch> b; off_t off; };
-        std::mutex wMu; std::condition_variable wCv; std::deque<WriteJob> wQ; bool wStop = false;
-        std::vector<std::thread> wth;
-        off_t filePos = fileStart;
-        if (parallelWrite) {
-            const int fd = fileno(out);
-            for (int k = 0; k < std::min(4, std::max(1, nproc / 2)); k++)
-                wth.emplace_back([&, fd]() {
-                    for (;;) {
-                        WriteJob j;
-                        {
-                            std::unique_lock<std::mutex> lk(wMu);
-                            wCv.wait(lk, [&] { return !wQ.empty() || wStop; });
-                            if (wQ.empty()) return;
-                            j = std::move(wQ.front()); wQ.pop_front();
-                        }
-                        const double w0 = nowSec();
-                        off_t at = j.off;
-                        for (const auto &run : j.b->outRuns) {
-                            size_t done = 0;
-                            while (done < run.second) {
-                                const ssize_t k2 = pwrite(fd, run.first + done, run.second - done, at + (off_t)done);
-                                if (k2 <= 0) { fprintf(stderr, "yaha_b200: write to the output file failed: %s\n", strerror(errno)); exit(1); }
-                                done += (size_t)k2;
-                            }
-                            at += (off_t)run.second;
-                        }
-                        traceEv('W', 1, (int)j.b->seq, w0, nowSec());
-                        std::lock_guard<std::mutex> lk(F.mu);
-                        tWrite += nowSec() - w0;
-                        spare.push_back(std::move(j.b));
-                    }
-                });
-        }
+        // writer: input order
         for (uint64_t next = 0;; next++) {
             std::unique_ptr<Batch> b;
             {
@@ -1043,27 +1031,16 @@ int runQueries(const Args &A0)
             }
             double w0 = nowSec();
             nReads += b->reads.size();
-            if (parallelWrite) {
-                size_t bytes = 0;
-                for (const auto &run : b->outRuns) bytes += run.second;
-                { std::lock_guard<std::mutex> lk(wMu); wQ.push_back(WriteJob{std::move(b), filePos}); }
-                wCv.notify_one();
-                filePos += (off_t)bytes;
-                continue;
-            }
             if (!replaying) {
+                // (one ordered stream: writing the batches of a step side by side with pwrite was measured SLOWER -- buffered
+                //  writes to one file serialise on its inode lock -- 1.6 ms per 2.3 MB batch with four writers against 0.5 ms)
                 for (const auto &run : b->outRuns) fwrite(run.first, 1, run.second, out);
             }
-            { std::lock_guard<std::mutex> lk(F.mu); tWrite += nowSec() - w0; }
+            tWrite += nowSec() - w0;
             traceEv('W', 0, (int)b->seq, w0, nowSec());
+            if (b->text) { b->text->release(); b->text = nullptr; }
             if (A.replay) cache.push_back(std::move(b));
             else { std::lock_guard<std::mutex> lk(F.mu); spare.push_back(std::move(b)); }
-        }
-        if (parallelWrite) {
-            { std::lock_guard<std::mutex> lk(wMu); wStop = true; }
-            wCv.notify_all();
-            for (auto &t : wth) t.join();
-            if (lseek(fileno(out), filePos, SEEK_SET) < 0) { fprintf(stderr, "yaha_b200: cannot position the output file\n"); exit(1); }
         }
         reader.join();
         for (auto &t : pth) t.join();
