@@ -183,7 +183,7 @@ int ya_form_clumps(ya_ctx *c, ya_clump_batch *out)
         const uint32_t n = sf->n_frags, first = n ? sf->first : 0;
         out->clump_first[s] = first; out->clump_count[s] = 0;
         if (!n) continue;
-        if (n > 192) { out->clump_count[s] = 0xFFFFFFFFu; continue; }   /* as the device kernel: left to the host (clumps.cu) */
+        if (n > 1024) { out->clump_count[s] = 0xFFFFFFFFu; continue; }   /* as the device kernel: left to the host (clumps.cu) */
         ya_frag *work = malloc(n * sizeof(ya_frag)), *tmp = malloc(n * sizeof(ya_frag));
         fc_node *nodes = malloc(n * sizeof(fc_node));
         uint8_t *used = malloc(2 * (size_t)n);

@@ -9,11 +9,12 @@
 // of a millisecond, which is what takes this step off the host's worker threads.  Strands with more than
 // kMaxStrandFrags fragments (repeat-rich loci, where the quadratic chain would make one thread the whole
 // kernel) are left to the host: their clump count comes back as 0xFFFFFFFF.
+#define FC_WARP_COOP 1          // form_clumps.h: one warp per strand (must precede every inclusion of the header)
 #include "common.cuh"
 #include "form_clumps.h"
 #include "prepare_clumps.h"
 
-static const uint32_t kMaxStrandFrags = 192;
+static const uint32_t kMaxStrandFrags = 1024;
 
 __global__ void __launch_bounds__(128)
 form_clumps_kernel(const ya_strand_frags *__restrict__ strands, int n_seg, const uint64_t *__restrict__ read_off,
@@ -22,23 +23,29 @@ form_clumps_kernel(const ya_strand_frags *__restrict__ strands, int n_seg, const
                    ya_frag *__restrict__ path, ya_clump_rec *__restrict__ clumps, uint32_t *__restrict__ count,
                    uint32_t *__restrict__ first_out, uint32_t *__restrict__ slot_strand)
 {
+    // one WARP per strand (form_clumps.h with FC_WARP_COOP: lane 0 runs the serial parts, the chain DP's inner loop is strided
+    // over the lanes).
     // slot_strand[i] (zeroed by the caller): strand + 1 if slot i of the clump array holds a clump -- lets the kernels behind
-    // this one run one thread per CLUMP instead of one per strand (a crowded strand no longer sets their duration)
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    // this one run one thread per CLUMP instead of one per strand
+    const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = (int)(threadIdx.x & 31u);
     if (s >= n_seg) return;
     const ya_strand_frags sf = strands[s];
     const uint32_t n = sf.n_frags;
     const uint32_t first = n ? sf.first : 0;
-    first_out[s] = first;
-    if (n == 0) { count[s] = 0; return; }
-    if (n > kMaxStrandFrags) { count[s] = 0xFFFFFFFFu; return; }
+    if (lane == 0) first_out[s] = first;
+    if (n == 0) { if (lane == 0) count[s] = 0; return; }
+    if (n > kMaxStrandFrags) { if (lane == 0) count[s] = 0xFFFFFFFFu; return; }
     const int readLen = (int)(read_off[(s >> 1) + 1] - read_off[s >> 1]);
     ya_frag *w = work + first;
-    for (uint32_t k = 0; k < n; k++) w[k] = frags[first + k];          // the graph edits fragments in place: work on a copy
+    for (uint32_t k = lane; k < n; k += 32) w[k] = frags[first + k];     // the graph edits fragments in place: work on a copy
+    __syncwarp();
     const int nc = fc_form_clumps(&P, w, region + first, (int)n, readLen, nodes + first, used + 2 * (size_t)first, tmp + first,
                                   path + first, clumps + first);
-    for (int k = 0; k < nc; k++) { clumps[first + k].first += first; slot_strand[first + k] = (uint32_t)s + 1u; }   // path indices absolute
-    count[s] = (uint32_t)nc;
+    if (lane == 0) {
+        for (int k = 0; k < nc; k++) { clumps[first + k].first += first; slot_strand[first + k] = (uint32_t)s + 1u; }   // path indices absolute
+        count[s] = (uint32_t)nc;
+    }
 }
 
 // device_only (ya_align_batch): records stay on the device, nothing is copied back and the call does not wait.
@@ -69,7 +76,7 @@ int ya_form_clumps_impl(ya_ctx *c, ya_clump_batch *out, bool device_only)
     P.wordLen = c->P.wordLen; P.maxGap = c->P.maxGap; P.maxDesert = out->maxDesert; P.minMatch = c->P.minMatch;
     P.minNonOverlap = out->minNonOverlap; P.bandWidth = c->P.bandWidth; P.GOCost = c->P.GOCost; P.GECost = c->P.GECost; P.MScore = c->P.MScore;
     YA_CUDA(c, cudaEventRecord(c->ev[0], st));
-    form_clumps_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(c->d_strand_out.as<ya_strand_frags>(), n_seg, c->d_read_off.as<uint64_t>(),
+    form_clumps_kernel<<<(n_seg + 3) / 4, 128, 0, st>>>(c->d_strand_out.as<ya_strand_frags>(), n_seg, c->d_read_off.as<uint64_t>(),
         c->d_frags_out.as<ya_frag>(), c->d_region_out.as<uint32_t>(), P, c->d_fc_work.as<ya_frag>(), c->d_fc_nodes.as<fc_node>(),
         c->d_fc_used.as<uint8_t>(), c->d_fc_tmp.as<ya_frag>(), c->d_fc_path.as<ya_frag>(), c->d_fc_clumps.as<ya_clump_rec>(), d_count, d_first,
         c->d_fc_slot.as<uint32_t>());

@@ -273,8 +273,16 @@ extern "C" int ya_align_fetch_text(ya_ctx *c, char *text, size_t text_cap)
     return YA_OK;
 }
 
+// YA_PROF=1: wall time of the phases of ya_align_batch, summed over the process, printed at exit
+static double g_prof_ab[8]; static long g_prof_ab_n;
+struct AbProfPrinter { ~AbProfPrinter() { if (getenv("YA_PROF") && g_prof_ab_n) fprintf(stderr, "ya_align_batch wall ms per call (%ld calls): upload+encode enqueue %.3f | seed stage %.3f | "
+    "clumps+prepare %.3f | dp plan+launch %.3f | assemble+finish (sync) %.3f | format+d2h (sync) %.3f\n", g_prof_ab_n, 1e3 * g_prof_ab[0] / g_prof_ab_n,
+    1e3 * g_prof_ab[1] / g_prof_ab_n, 1e3 * g_prof_ab[2] / g_prof_ab_n, 1e3 * g_prof_ab[3] / g_prof_ab_n, 1e3 * g_prof_ab[4] / g_prof_ab_n, 1e3 * g_prof_ab[5] / g_prof_ab_n); } } g_ab_prof_printer;
+
 extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
 {
+    double tq = ya_now();
+    auto lap = [&](int k) { const double t = ya_now(); g_prof_ab[k] += t - tq; tq = t; };
     if (!c || !b || b->n_reads < 0 || !b->text_off || !b->status || (b->n_reads && (!b->chars || !b->offsets || !b->ids || !b->id_off)))
         return YA_E_ARG;
     if (!c->out_set) return ya_fail(c, YA_E_STATE, "ya_align_batch: call ya_set_output first");
@@ -321,9 +329,11 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
         c->ctr.launches++;
     }
     // ---- stages 1 + 2, fragment graph, phase 1 of the alignment: all left on the device
+    lap(0);
     ya_frag_batch fb; memset(&fb, 0, sizeof fb);
     int rc = ya_seed_frags_impl(c, &fb, true);
     if (rc != YA_OK) return rc;
+    lap(1);
     const size_t nk = c->seed_nkeep;
     const int n_seg = 2 * n;
     YA_CUDA(c, c->d_fin.reserve(4 * 8 + (size_t)n * (4 * 4 + 8 + 1) + 64 + 8));
@@ -343,6 +353,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
         if (rc != YA_OK) return rc;
         rc = ya_prepare_clumps_impl(c, &pb, true, &nExt);
         if (rc != YA_OK) return rc;
+        lap(2);
         // ---- the first DP round, answers on the device
         rc = ya_sw_device_round(c, (uint32_t)pb.n_jobs, (uint32_t)nExt, d_acct, &rawSlots);
         if (rc != YA_OK) return rc;
@@ -353,6 +364,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
         d_count = c->d_fc_count.as<uint32_t>(); d_first = d_count + n_seg;
         YA_CUDA(c, cudaMemsetAsync(d_count, 0, (size_t)n_seg * 8, st));
     }
+    lap(3);
     // ---- splice + score every clump, then finish every read
     const size_t asmCap = rawSlots + 2 * nk + 64;                                // runs: DP answers + one per seed piece + one per closed-form gap
     if (asmCap >= 0xFFFF0000ull) return ya_fail(c, YA_E_STATE, "ya_align_batch: batch too large for 32-bit run offsets");
@@ -388,6 +400,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
         char msg[96]; snprintf(msg, sizeof msg, "ya_align_batch: internal error on the device (flags %llx)", h_tot[2] & 0xFFFFFFFFull);
         return ya_fail(c, YA_E_STATE, msg);
     }
+    lap(4);
     const size_t textBytes = (size_t)h_tot[4];
     if (textBytes >= 0xFFFF0000ull) return ya_fail(c, YA_E_STATE, "ya_align_batch: more than 4 GB of text, use smaller batches");
     // ---- the text
@@ -405,6 +418,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
     if (fits && textBytes) YA_CUDA(c, cudaMemcpyAsync(b->text, c->d_text.p, textBytes, cudaMemcpyDeviceToHost, st));
     YA_CUDA(c, ya_stream_wait(st));
     YA_CUDA(c, cudaGetLastError());
+    lap(5); g_prof_ab_n++;
     // counters (the DP kernels' events were recorded by ya_sw_device_round on this stream)
     c->ctr.dp_cells += h_tot[0];
     if (c->dpr_ran) {

@@ -27,6 +27,22 @@
 #define FC_HD static inline
 #endif
 
+/* On the device (clumps.cu defines FC_WARP_COOP) one WARP runs a strand: all 32 lanes execute fc_form_clumps with the same
+ * arguments; the serial parts are done by lane 0 and their results broadcast, and the quadratic part -- the inner loop of
+ * the chain DP, whose iterations update different nodes -- is strided over the lanes.  Everywhere else the macros below
+ * make the same source plain serial C. */
+#if defined(__CUDA_ARCH__) && defined(FC_WARP_COOP)
+#define FC_LANE      ((int)(threadIdx.x & 31u))
+#define FC_NLANES    32
+#define FC_SYNC()    __syncwarp()
+#define FC_BCAST(x)  ((x) = __shfl_sync(0xffffffffu, (x), 0))
+#else
+#define FC_LANE      0
+#define FC_NLANES    1
+#define FC_SYNC()    ((void)0)
+#define FC_BCAST(x)  ((void)0)
+#endif
+
 typedef struct fc_params {
     int32_t wordLen, maxGap, maxDesert, minMatch, minNonOverlap, bandWidth, GOCost, GECost, MScore;
 } fc_params;
@@ -152,25 +168,31 @@ FC_HD int fc_build_best(const fc_params *P, ya_frag *frags, int lo, int hi, cons
                         fc_node *nodes, ya_frag *tmp, uint8_t *gone, ya_frag *dst, uint16_t *matched)
 {
     int nc = 0;
-    for (int i = lo; i <= hi; i++) {
-        if (used[i - lo]) continue;
-        const ya_frag *f = &frags[i];
-        fc_node n;
-        n.prev = -1; n.pathLength = 1; n.frag = i; n.diag = fc_diag(f);
-        n.nodeLength = (int16_t)f->refLen; n.bestScore = (int16_t)(n.nodeLength * P->MScore);
-        n.SQO = f->startQueryOff; n.EQO = f->endQueryOff; n.pathSQO = n.SQO;
-        nodes[nc++] = n;
+    if (FC_LANE == 0) {
+        for (int i = lo; i <= hi; i++) {
+            if (used[i - lo]) continue;
+            const ya_frag *f = &frags[i];
+            fc_node n;
+            n.prev = -1; n.pathLength = 1; n.frag = i; n.diag = fc_diag(f);
+            n.nodeLength = (int16_t)f->refLen; n.bestScore = (int16_t)(n.nodeLength * P->MScore);
+            n.SQO = f->startQueryOff; n.EQO = f->endQueryOff; n.pathSQO = n.SQO;
+            nodes[nc++] = n;
+        }
+        if (nc) fc_sort_nodes(nodes, nc);
     }
+    FC_BCAST(nc);
+    FC_SYNC();
     *matched = 0;
     if (nc == 0) return 0;
-    fc_sort_nodes(nodes, nc);
     int bestScore = -(0x7fffff00), best = -1;
     const uint32_t maxGap = (uint32_t)P->maxGap;
     for (int i = 0; i < nc; i++) {
-        fc_node *L = &nodes[i];
+        const fc_node *L = &nodes[i];
         const int lSQO = L->SQO, lEQO = L->EQO;
         const uint32_t lSRO = L->diag + (uint32_t)lSQO, lERO = L->diag + (uint32_t)L->EQO;
-        for (int j = nc - 1; j > i; j--) {
+        /* every j updates its own node only: the iterations are strided over the lanes (nodes behind i with the same start as
+         * i sit right behind it in the sorted order, so "stop at the first such node coming from the end" is per lane) */
+        for (int j = nc - 1 - FC_LANE; j > i; j -= FC_NLANES) {
             fc_node *R = &nodes[j];
             const int rSQO = R->SQO;
             if (rSQO == lSQO) break;
@@ -199,6 +221,7 @@ FC_HD int fc_build_best(const fc_params *P, ya_frag *frags, int lo, int hi, cons
             }
             R->bestScore = (int16_t)newScore; R->prev = i; R->pathLength = (int16_t)(L->pathLength + 1); R->pathSQO = L->pathSQO;
         }
+        FC_SYNC();
         if (L->bestScore < bestScore) continue;
         int take = L->bestScore > bestScore;
         if (!take) {                                                  /* GraphPath.cpp:88-94 */
@@ -208,30 +231,38 @@ FC_HD int fc_build_best(const fc_params *P, ya_frag *frags, int lo, int hi, cons
         if (take) { best = i; bestScore = L->bestScore; }
     }
     /* the path from its end to its start (GraphPath.cpp:134-146); tmp[] holds it in insertion order, i.e. reversed */
-    int cnt = 0;
-    uint16_t mb = 0;
-    for (int k = best; k >= 0; k = nodes[k].prev) {
-        ya_frag *f1 = &frags[nodes[k].frag];
-        if (cnt > 0) {                                                /* insertFragment, AlignHelpers.c:60-90 */
-            ya_frag *f2 = &tmp[cnt - 1];                              /* the clump's current first fragment */
-            const int maxOverlap = (int)fc_max_u(fc_overlap(f1->endQueryOff, f2->startQueryOff), fc_overlap_u(fc_ero(f1), f2->startRefOff));
-            if (maxOverlap > 0) {
-                const int l1 = fc_qlen(f1), l2 = fc_qlen(f2);
-                const int chop1 = (l1 != l2) ? (l1 < l2) : (cnt == 1);
-                if (chop1) { f1->endQueryOff = (uint16_t)(f1->endQueryOff - maxOverlap); f1->refLen = (uint16_t)(f1->refLen - maxOverlap); }
-                else { f2->startQueryOff = (uint16_t)(f2->startQueryOff + maxOverlap); f2->startRefOff += (uint32_t)maxOverlap;
-                       f2->refLen = (uint16_t)(f2->refLen - maxOverlap); }
+    int result = 0, mbOut = 0;
+    if (FC_LANE == 0) {
+        int cnt = 0;
+        uint16_t mb = 0;
+        for (int k = best; k >= 0; k = nodes[k].prev) {
+            ya_frag *f1 = &frags[nodes[k].frag];
+            if (cnt > 0) {                                            /* insertFragment, AlignHelpers.c:60-90 */
+                ya_frag *f2 = &tmp[cnt - 1];                          /* the clump's current first fragment */
+                const int maxOverlap = (int)fc_max_u(fc_overlap(f1->endQueryOff, f2->startQueryOff), fc_overlap_u(fc_ero(f1), f2->startRefOff));
+                if (maxOverlap > 0) {
+                    const int l1 = fc_qlen(f1), l2 = fc_qlen(f2);
+                    const int chop1 = (l1 != l2) ? (l1 < l2) : (cnt == 1);
+                    if (chop1) { f1->endQueryOff = (uint16_t)(f1->endQueryOff - maxOverlap); f1->refLen = (uint16_t)(f1->refLen - maxOverlap); }
+                    else { f2->startQueryOff = (uint16_t)(f2->startQueryOff + maxOverlap); f2->startRefOff += (uint32_t)maxOverlap;
+                           f2->refLen = (uint16_t)(f2->refLen - maxOverlap); }
+                }
             }
+            mb = (uint16_t)(mb + f1->refLen);                         /* addFragment, AlignHelpers.c:48-56 */
+            tmp[cnt] = *f1;
+            tmp[cnt].hitCount = 0;
+            cnt++;
         }
-        mb = (uint16_t)(mb + f1->refLen);                             /* addFragment, AlignHelpers.c:48-56 */
-        tmp[cnt] = *f1;
-        tmp[cnt].hitCount = 0;
-        cnt++;
+        if ((int)mb >= P->minMatch) {
+            for (int k = 0; k < cnt; k++) dst[k] = tmp[cnt - 1 - k];
+            mbOut = mb;
+            result = fc_clean_up(P, dst, cnt, gone);
+        }
     }
-    if ((int)mb < P->minMatch) return 0;
-    for (int k = 0; k < cnt; k++) dst[k] = tmp[cnt - 1 - k];
-    *matched = mb;
-    return fc_clean_up(P, dst, cnt, gone);
+    FC_BCAST(result); FC_BCAST(mbOut);
+    FC_SYNC();
+    *matched = (uint16_t)mbOut;
+    return result;
 }
 
 /* One strand.  frags[] is edited in place (overlap chops).  Returns the number of clumps written to out_clumps
@@ -249,44 +280,54 @@ FC_HD int fc_form_clumps(const fc_params *P, ya_frag *frags, const uint32_t *reg
         while (j + 1 < n && region[j + 1] == region[i]) j++;
         if (j == i) {                                                 /* QueryMatch.c:281-290 */
             if ((int)frags[i].refLen >= P->minMatch) {
-                out_path[nPath] = frags[i];
-                out_path[nPath].hitCount = 0;
-                out_clumps[nClumps].first = nPath; out_clumps[nClumps].n = 1; out_clumps[nClumps].matchedBases = frags[i].refLen;
+                if (FC_LANE == 0) {
+                    out_path[nPath] = frags[i];
+                    out_path[nPath].hitCount = 0;
+                    out_clumps[nClumps].first = nPath; out_clumps[nClumps].n = 1; out_clumps[nClumps].matchedBases = frags[i].refLen;
+                }
                 nClumps++; nPath++;
             }
         } else {                                                      /* GraphPath.cpp:272-292 */
             const int m = j - i + 1;
-            for (int k = 0; k < m; k++) used[k] = 0;
+            for (int k = FC_LANE; k < m; k += FC_NLANES) used[k] = 0;
+            FC_SYNC();
             int unused = m;
             const int firstClumpOfRegion = nClumps;
             while (unused > 0) {
                 uint16_t matched = 0;
                 const int len = fc_build_best(P, frags, i, j, used, nodes, tmp, gone, out_path + nPath, &matched);
                 if (len == 0) break;
-                out_clumps[nClumps].first = nPath; out_clumps[nClumps].n = (uint16_t)len; out_clumps[nClumps].matchedBases = matched;
+                if (FC_LANE == 0) { out_clumps[nClumps].first = nPath; out_clumps[nClumps].n = (uint16_t)len; out_clumps[nClumps].matchedBases = matched; }
                 nClumps++; nPath += (uint32_t)len;
+                FC_SYNC();
                 /* eliminateFragments, QueryMatch.c:201-215 (+ :177-197): a fragment stays only if one of its ends
                  * (minNonOverlap bases) is untouched by every clump cut from this region so far */
                 const int minLeft = P->minNonOverlap - 1;
-                for (int k = i; k <= j; k++) {
-                    if (used[k - i]) continue;
-                    const int SQO = frags[k].startQueryOff, EQO = frags[k].endQueryOff;
-                    int keep = 0;
-                    if (EQO - SQO >= minLeft) {
-                        int freeLo = 1, freeHi = 1;
-                        for (int c = firstClumpOfRegion; c < nClumps; c++) {
-                            const ya_frag *cf = &out_path[out_clumps[c].first], *cl = &out_path[out_clumps[c].first + out_clumps[c].n - 1];
-                            const int sqo = cf->startQueryOff;
-                            int hi = sqo + (int)(uint16_t)(1 + cl->endQueryOff - cf->startQueryOff) - 1;
-                            if (hi > qSlots - 1) hi = qSlots - 1;
-                            if (hi < sqo) continue;
-                            if (sqo <= SQO + minLeft && SQO <= hi) freeLo = 0;
-                            if (sqo <= EQO && EQO - minLeft <= hi) freeHi = 0;
+                int removed = 0;
+                if (FC_LANE == 0) {
+                    for (int k = i; k <= j; k++) {
+                        if (used[k - i]) continue;
+                        const int SQO = frags[k].startQueryOff, EQO = frags[k].endQueryOff;
+                        int keep = 0;
+                        if (EQO - SQO >= minLeft) {
+                            int freeLo = 1, freeHi = 1;
+                            for (int c = firstClumpOfRegion; c < nClumps; c++) {
+                                const ya_frag *cf = &out_path[out_clumps[c].first], *cl = &out_path[out_clumps[c].first + out_clumps[c].n - 1];
+                                const int sqo = cf->startQueryOff;
+                                int hi = sqo + (int)(uint16_t)(1 + cl->endQueryOff - cf->startQueryOff) - 1;
+                                if (hi > qSlots - 1) hi = qSlots - 1;
+                                if (hi < sqo) continue;
+                                if (sqo <= SQO + minLeft && SQO <= hi) freeLo = 0;
+                                if (sqo <= EQO && EQO - minLeft <= hi) freeHi = 0;
+                            }
+                            keep = freeLo || freeHi;
                         }
-                        keep = freeLo || freeHi;
+                        if (!keep) { used[k - i] = 1; removed++; }
                     }
-                    if (!keep) { used[k - i] = 1; unused--; }
                 }
+                FC_BCAST(removed);
+                FC_SYNC();
+                unused -= removed;
             }
         }
         i = j + 1;

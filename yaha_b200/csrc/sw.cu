@@ -833,7 +833,7 @@ static const PackedCfg kPackedCfgs[] = {{2, 11, 21}, {4, 11, 41}};
 static int packed_level(size_t nExt)
 {
     static const size_t narrowBelow = [] { const char *e = getenv("YA_PACKED_NARROW_BELOW"); return e ? (size_t)atol(e) : (size_t)28000; }();
-    static const size_t xnarrowBelow = [] { const char *e = getenv("YA_PACKED_XNARROW_BELOW"); return e ? (size_t)atol(e) : (size_t)16000; }();
+    static const size_t xnarrowBelow = [] { const char *e = getenv("YA_PACKED_XNARROW_BELOW"); return e ? (size_t)atol(e) : (size_t)5000; }();
     return nExt < xnarrowBelow ? 2 : nExt < narrowBelow ? 1 : 0;
 }
 static inline void packed_geom(int level, int pcls, int &G, int &C)
