@@ -370,7 +370,10 @@ def test_kernel_variants_agree_bytewise(small, tmp_path):
     #  are a small launch, i.e. the narrowest by default; the two thresholds force the other two)
     for name, env in (("default", {}), ("tb_thread", {"YA_TB": "thread"}), ("full_thread", {"YA_FULL_THREAD_MAXW": "100000"}),
                       ("packed_wide", {"YA_PACKED_NARROW_BELOW": "0", "YA_PACKED_XNARROW_BELOW": "0"}),
-                      ("packed_narrow", {"YA_PACKED_NARROW_BELOW": "100000000", "YA_PACKED_XNARROW_BELOW": "0"})):
+                      ("packed_narrow", {"YA_PACKED_NARROW_BELOW": "100000000", "YA_PACKED_XNARROW_BELOW": "0"}),
+                      # reference windows staged into shared memory by cp.async.bulk (TMA) instead of read through L1/L2
+                      ("staged", {"YA_EXT_STAGE": "1"}),
+                      ("staged_wide", {"YA_EXT_STAGE": "1", "YA_PACKED_NARROW_BELOW": "0", "YA_PACKED_XNARROW_BELOW": "0"})):
         dst = str(tmp_path / f"{name}.bin")
         code = _AB_SNIPPET.format(root=S.ROOT, tmp=str(tmp_path / f"small_{name}"), dst=dst)
         os.makedirs(str(tmp_path / f"small_{name}"), exist_ok=True)
@@ -381,6 +384,8 @@ def test_kernel_variants_agree_bytewise(small, tmp_path):
     assert blobs["default"] == blobs["full_thread"]
     assert blobs["default"] == blobs["packed_wide"]
     assert blobs["default"] == blobs["packed_narrow"]
+    assert blobs["default"] == blobs["staged"]
+    assert blobs["default"] == blobs["staged_wide"]
     assert len(blobs["default"]) > 100000
 
 

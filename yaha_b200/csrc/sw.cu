@@ -228,11 +228,40 @@ dp_wave_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ job
 // (W <= 64, W <= maxGap, W <= maxIntron); other parameter sets use dp_wave_kernel.
 // Back-pointer bytes are accumulated 4 macro steps per 32-bit word and stored 16 B at a time.
 // ------------------------------------------------------------------------------------------
+// ---- reference-window staging (north_star: "reference windows staged into shared memory via TMA"; replaces decompressRef,
+// SW.cpp:444-456).  A job's window is rLen = rows + 2*BW bases = a few hundred bytes of the packed genome.  With STAGE the
+// first lane of every warp issues one 1-D bulk copy (cp.async.bulk, the TMA engine without a tensor map) per job of the warp
+// into the warp's shared-memory slots and all lanes wait on the warp's mbarrier; the DP loop then reads its one reference
+// nibble per macro step from shared memory instead of the L1/L2 path.  Windows above kStageBytes stay on the global path.
+#define kStageBytes 512
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
 #define PK_WORST (-(1 << 29))
 #define PK_TAGE  0x40
 #define PK_TAGF  0x80
 
-template <int G, int C, int W>
+template <int G, int C, int W, bool STAGE = false>
 __global__ void __launch_bounds__(128)
 dp_ext_packed_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict__ job_ids, int n_jobs,
                      DevJobOut *__restrict__ outs, uint32_t *__restrict__ tbw,
@@ -265,6 +294,44 @@ dp_ext_packed_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict
     const uint32_t rOff = have ? J.rOff : 0;
     uint32_t *mytb = tbw + (have ? J.tb_off : 0);
 
+    // ---- STAGE: the warp's reference windows into shared memory by bulk copies
+    __shared__ __align__(16) uint8_t s_win[STAGE ? 4 : 1][STAGE ? GPW : 1][STAGE ? kStageBytes : 16];
+    __shared__ __align__(8) uint64_t s_bar[4];
+    const uint8_t *win = nullptr;                // this job's staged window (byte `winBase` of the genome at win[0]), or null
+    uint32_t winBase = 0;
+    if (STAGE) {
+        const int wib = threadIdx.x >> 5;
+        // byte range of the window, widened to 16-byte granules (the genome array is padded: ctx.cu)
+        const uint32_t loB = have ? (bwd ? rOff - (uint32_t)(rLen - 1) : rOff) : 0u;
+        const uint32_t a0 = (loB >> 1) & ~15u;
+        const uint32_t nby = have ? ((((loB + (uint32_t)rLen - 1u) >> 1) - a0 + 1u + 15u) & ~15u) : 0u;
+        const bool fits = have && rLen > 0 && nby <= (uint32_t)kStageBytes;
+        if (lane == 0) mbar_init(&s_bar[wib], 1);
+        __syncwarp();
+        uint32_t total = 0;
+#pragma unroll
+        for (int q = 0; q < GPW; q++) {
+            const uint32_t nb = __shfl_sync(full, fits ? nby : 0u, q * G);
+            total += nb;
+        }
+        if (lane == 0 && total) mbar_expect_tx(&s_bar[wib], total);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < GPW; q++) {
+            const uint32_t nb = __shfl_sync(full, fits ? nby : 0u, q * G);
+            const uint32_t aq = __shfl_sync(full, a0, q * G);
+            if (lane == 0 && nb) bulk_g2s(&s_win[wib][q][0], bases + aq, nb, &s_bar[wib]);
+        }
+        bool arrived = total == 0;
+        for (int spin = 0; !arrived && spin < (1 << 20); spin++) arrived = mbar_try_wait(&s_bar[wib], 0);
+        arrived = __all_sync(full, arrived);     // (a copy that never lands would only cost the staging: fall back to global loads)
+        if (fits && arrived && laneUsed) { win = &s_win[wib][g][0]; winBase = a0; }
+    }
+    auto refc = [&](uint32_t off) -> int {
+        if (STAGE && win) { const uint32_t b = win[(off >> 1) - winBase]; return (off & 1) ? (int)(b & 15u) : (int)(b >> 4); }
+        return nib(bases, off);
+    };
+
     const int MS8 = K.MS << 8, RC8 = K.RC << 8;
     const int CONT = 1 - (K.GEC << 8);
     const int NEWE = PK_TAGE - ((K.GOC + K.GEC) << 8), NEWF = PK_TAGF - ((K.GOC + K.GEC) << 8);
@@ -286,7 +353,7 @@ dp_ext_packed_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict
 #pragma unroll
     for (int k = 0; k < C; k++) {
         const int ri = ridx0 + k;
-        rc[k] = (ri >= 0 && ri < rLen) ? nib(bases, bwd ? rOff - (uint32_t)ri : rOff + (uint32_t)ri) : 0xFF;
+        rc[k] = (ri >= 0 && ri < rLen) ? refc(bwd ? rOff - (uint32_t)ri : rOff + (uint32_t)ri) : 0xFF;
     }
     int qi = 1 - l;
     int qc = (qi >= 1 && qi <= rows) ? codes[bwd ? qIdx - (uint32_t)(qi - 1) : qIdx + (uint32_t)(qi - 1)] : 0xFE;
@@ -311,7 +378,7 @@ dp_ext_packed_kernel(const DevJob *__restrict__ jobs, const uint32_t *__restrict
         const int qn = i + 1;
         const int qc_next = (qn >= 1 && qn <= rows) ? codes[bwd ? qIdx - (uint32_t)(qn - 1) : qIdx + (uint32_t)(qn - 1)] : 0xFE;
         const int rn = ridx0 + C;
-        const int rc_next = (rn >= 0 && rn < rLen) ? nib(bases, bwd ? rOff - (uint32_t)rn : rOff + (uint32_t)rn) : 0xFF;
+        const int rc_next = (rn >= 0 && rn < rLen) ? refc(bwd ? rOff - (uint32_t)rn : rOff + (uint32_t)rn) : 0xFF;
 
         const bool general = m < LB + G;          // some lane of the group may still be inside the leading triangle
         int V0r = PK_WORST, F0r = F_NONE;
@@ -845,14 +912,24 @@ template <int G, int C, int W> static void launch_packed(ya_ctx *c, const uint32
 static void launch_packed_level(ya_ctx *c, int level, int pcls, const uint32_t *d_ids, int n, const DpConst &K);
 static const int kNumPackedCfgs = sizeof(kPackedCfgs) / sizeof(kPackedCfgs[0]);
 
+// YA_EXT_STAGE=1: the reference windows of the extension kernel staged into shared memory by bulk copies (see above).
+static bool ext_stage_on()
+{
+    static const bool on = [] { const char *e = getenv("YA_EXT_STAGE"); return e && atoi(e) != 0; }();
+    return on;
+}
 template <int G, int C, int W>
 static void launch_packed(ya_ctx *c, const uint32_t *d_ids, int n, const DpConst &K)
 {
     const int threads = 128;
     const int groups_per_block = (threads / 32) * (32 / G);
     int blocks = (n + groups_per_block - 1) / groups_per_block;
-    dp_ext_packed_kernel<G, C, W><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
-        c->d_tb.as<uint32_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+    if (ext_stage_on())
+        dp_ext_packed_kernel<G, C, W, true><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
+            c->d_tb.as<uint32_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
+    else
+        dp_ext_packed_kernel<G, C, W><<<blocks, threads, 0, c->stream>>>(c->d_jobs.as<DevJob>(), d_ids, n, c->d_jobout.as<DevJobOut>(),
+            c->d_tb.as<uint32_t>(), c->d_bases, c->d_codes_fwd.as<uint8_t>(), c->d_codes_rev.as<uint8_t>(), K);
     c->ctr.launches++;
 }
 
