@@ -1,26 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- reads/s and banded-SW GCUPS of the yaha alignment job on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg3|cfg2|cfg1s]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg3|cfg1|cfg2|cfg4|cfg5]
 
-One "step" = one complete alignment of the workload's synthetic read set by the product's host
-program `yaha_b200/yaha_b200_host` (FASTA cut into records and parsed -> reads uploaded -> seed lookup ->
-hits->fragments->regions -> fragment graph and first alignment phase (ya_form_clumps, ya_prepare_clumps) ->
-banded affine-gap DP rounds with X-drop + traceback on the device -> host assembly/split/score/OQC -> SAM written).  The SAM is byte-identical to the reference's (`cpu_baseline.
-sam_identical_to_reference`).  `e2e` times all of that; `value` excludes FASTA parsing, the H2D copy
-of the reads and the SAM fwrite (inputs resident).  Device stage times come from CUDA events inside the
-library (`ya_get_counters`), on the stream the kernels are launched on.
+One "step" = one complete alignment of the workload's synthetic read set by the product's host program
+`yaha_b200/yaha_b200_host` (the call a user makes): the FASTA file is cut into records and parsed on the host, every batch of
+reads goes to the device as characters, and ONE call of the C ABI (`ya_align_batch`) encodes them, runs the seed lookup,
+hits -> fragments -> regions, the fragment graph, the first DP round with X-drop extensions and traceback (jobs born, laid out and
+answered on the device), splices and scores every clump, runs OQC / filter by similarity and writes the SAM records; the host
+writes the text.  The few reads whose clumps have to be split (0.16 % on cfg3) go through the call-by-call ABI in fibers.  The
+SAM is byte-identical to the reference's (`cpu_baseline.sam_identical_to_reference`, `..._in_order_to_t1`).
+`e2e` times all of that from the FASTA file to the SAM file; `value` replays the parsed reads from host memory and skips the
+SAM fwrite (inputs resident; the H2D copy of the read characters is still inside).  Device stage times come from CUDA events
+inside the library (`ya_get_counters`), on the stream the kernels are launched on.
 
-Workloads follow BASELINE.json `configs`:
-  cfg3 (default): 100 Mbp i.i.d. reference, 20 000 x 500 bp reads at 10 % error, -BW 10 -G 100
-                  (SW-extension-bound; the config the metric quotes at 1/2/4/8 B200)
-  cfg2          : 100 Mbp reference, 100 000 x 100 bp reads at 5 % error (seed-lookup-bound)
-  cfg1s         : 10 Mbp reference, 10 000 x 1000 bp reads at 2 % (the CPU-runnable case)
-Multi-GPU: one process per GPU (torchrun), replicated index, every rank aligns its own read set of the
-same shape (weak scaling), no collective on the data path; time = max over ranks.
+Workloads follow BASELINE.json `configs`; cfg3 is the default (the config the metric quotes at
+1/2/4/8 B200).  Multi-GPU: one process per GPU (torchrun), replicated index, every rank aligns its own read set of the same
+shape (weak scaling), no collective on the data path; time = max over ranks.  Rank 0 additionally times the product's own
+in-process path (`-gpus N`, one query file, `inprocess` in the JSON line).
 
-`--impl reference` times the UNMODIFIED reference (oracle/_ref/yaha, built by oracle/Makefile) on the
-host cores with `-t <all cores>` on the same workload.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/yaha, built by oracle/Makefile) on the host cores with
+`-t <all cores>` on the same workload.
 """
 from __future__ import annotations
 
@@ -334,9 +334,11 @@ def run_ours(args):
     k2_gbs = k2_bytes / ((ms_seed - ms_lookup) * 1e-3) / 1e9 if ms_seed > ms_lookup else 0.0
     iso_k2_ms = sum(s["dev_ms_seed"] - s["dev_ms_lookup"] for s in stats_c)
     iso_k2_gbs = sum(20.0 * s["hits"] + 12.0 * s["frags_all"] for s in stats_c) / (iso_k2_ms * 1e-3) / 1e9 if iso_k2_ms > 0 else 0.0
-    codes_bytes = sum(len(s) for _, s in reads) + 8 * (len(reads) + 1)
-    h2d = int(codes_bytes + 16 * tot("dp_jobs") / args.steps + 40 * tot("dp_jobs") / args.steps)
-    d2h = int(16 * tot("dp_jobs") / args.steps + 16 * 2 * n_reads)
+    # bytes that cross PCIe per step in the e2e run: the reads as characters + ids + offsets up, SAM text + offsets + status down
+    # (plus the call-by-call traffic of the few reads handed back: their codes up, fragments / DP answers down -- counted at 2 KB each)
+    handed = timed_a[-1].get("reads_handed_back", 0)
+    h2d = int(sum(len(s) for _, s in reads) + sum(len(n) for n, _ in reads) + 12 * (len(reads) + 1) + 1024 * handed)
+    d2h = int(timed_a[-1].get("device_text_bytes", 0) + 9 * (len(reads) + 1) + 2048 * handed)
 
     # DRAM bytes of the two dominant kernels from the committed `ncu --set full` captures, scaled from the
     # captured launch to this run's average launch (per cell / per probe)
@@ -368,7 +370,7 @@ def run_ours(args):
         "stage_ms_per_step": {"note": f"value run; device_* are CUDA-event spans on each pipeline's stream ({pipes} pipelines overlap on the device, so "
                                       "the spans overlap and include queueing); wall_host_logic is worker-pool busy time per thread",
                               "device_seed": ms_seed / args.steps, "device_dp_fill": ms_dp / args.steps,
-                              "device_traceback": ms_tb / args.steps,
+                              "device_traceback": ms_tb / args.steps, "device_assemble_finish_format": tot("dev_ms_finish") / args.steps,
                               "wall_seed_call": tot("seed_wall_s") / args.steps * 1e3, "wall_dp_calls": tot("dp_wall_s") / args.steps * 1e3,
                               "wall_host_logic": tot("host_wall_s") / args.steps * 1e3, "wall_parse": tot("read_parse_s") / args.steps * 1e3,
                               "wall_upload": tot("upload_s") / args.steps * 1e3, "wall_write": tot("write_s") / args.steps * 1e3},
@@ -376,7 +378,8 @@ def run_ours(args):
                 "ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed_a],
                 "ms_per_untimed_step": [round(s["align_s"] * 1e3, 2) for s in stats_a[:extra_warm + args.warmup]]},
         "value_ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed],
-        "gpu_launches": int(tot("launches")),
+        "gpu_launches": int(tot("launches")), "gpu_launches_per_step": int(tot("launches")) // args.steps,
+        "reads_finished_on_device_per_step": timed[-1].get("reads_finished_on_device"), "reads_handed_back_per_step": timed[-1].get("reads_handed_back"),
         # frac is the figure of the run that produces `value` (the product's own launches); the same kernel timed alone on
         # whole-shard launches (run C) is reported beside it as `isolated`
         "roofline": {"bound": "int32-issue", "kernel": "dp_ext_packed_kernel",
