@@ -281,15 +281,21 @@ struct Pipe {                              // one batch pipeline: a ya_ctx plus 
     PinnedVec<uint64_t> offs;
     std::vector<std::unique_ptr<TextBuf>> textBufs;       // ring of device-text landing buffers (at most kTextBufs)
     std::vector<TextBuf *> freeText; std::mutex textMu; std::condition_variable textCv;
-    TextBuf *acquireText()
+    // (the whole ring is pinned when the pipeline sees its first batch, sized for that batch with room to spare: every later
+    //  acquisition is a pointer hand-over unless a much larger batch turns up)
+    TextBuf *acquireText(size_t nReads, size_t totalBases)
     {
         static const size_t kTextBufs = 3;
         std::unique_lock<std::mutex> lk(textMu);
-        if (freeText.empty() && textBufs.size() < kTextBufs) {
-            textBufs.emplace_back(new TextBuf());
-            TextBuf *t = textBufs.back().get();
-            t->mu = &textMu; t->cv = &textCv; t->home = &freeText;
-            return t;
+        if (textBufs.empty()) {
+            for (size_t k = 0; k < kTextBufs; k++) {
+                textBufs.emplace_back(new TextBuf());
+                TextBuf *t = textBufs.back().get();
+                t->mu = &textMu; t->cv = &textCv; t->home = &freeText;
+                t->off.resize(nReads + 1 + nReads / 2, false); t->status.resize(nReads + nReads / 2 + 1, false);
+                t->text.resize(3 * totalBases + 768 * nReads + 4096, false);
+                freeText.push_back(t);
+            }
         }
         textCv.wait(lk, [&] { return !freeText.empty(); });
         TextBuf *t = freeText.back(); freeText.pop_back();
@@ -681,7 +687,7 @@ static int fusedPass(const Env &E, Pipe &D, Batch &B)
         memcpy(D.ids.data() + D.idOffs[(size_t)i], r.id.data(), r.id.size());
         if (fastq) memcpy(D.quals.data() + D.offs[(size_t)i], r.qual.data(), r.qual.size());
     }
-    B.text = D.acquireText();
+    B.text = D.acquireText((size_t)n, total);
     TextBuf &TB = *B.text;
     if (TB.off.size() < (size_t)n + 1) TB.off.resize((size_t)n + 1 + (size_t)n / 4, false);
     if (TB.status.size() < (size_t)n) TB.status.resize((size_t)n + (size_t)n / 4, false);
