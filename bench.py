@@ -395,6 +395,13 @@ def run_ours(args):
                                     "which holds HBM and bf16 figures only)",
                      "peak_dp_mix": int_mix, "ops_per_cell": INT_OPS_PER_CELL_EXT, "gcups": ext_gcups,
                      "gcups_roof": int_add / INT_OPS_PER_CELL_EXT,
+                     "device_level": {"what": "the same cells over the UNION of the launches' spans on the device's time axis: the pipelines "
+                                              "overlap their launches, which stretches every one of them (per-launch frac above) while the "
+                                              "device as a whole does more",
+                                      "union_ms_per_step": tot("dev_ms_ext_union") / args.steps,
+                                      "gcups": ext_cells / (tot("dev_ms_ext_union") * 1e-3) / 1e9 if tot("dev_ms_ext_union") > 0 else None,
+                                      "frac": ext_cells / (tot("dev_ms_ext_union") * 1e-3) / 1e9 * INT_OPS_PER_CELL_EXT / int_add
+                                              if tot("dev_ms_ext_union") > 0 and int_add else None},
                      "hardware_utilisation_ncu": {"alu_pipe_pct": (t_ext or {}).get("alu_pipe_pct"), "issue_active_pct": (t_ext or {}).get("issue_active_pct"),
                                                   "thread_instructions_per_cell": (t_ext or {}).get("thread_inst_per_cell"),
                                                   "note": "frac divides ALGORITHMIC ops (33/cell, SURVEY 8d) by an instruction rate; DPX fuses 2-3 of them "

@@ -327,6 +327,11 @@ int ya_perfect_ext(ya_ctx *, const ya_dp_job *jobs, int n, uint16_t *count);
 /* Read-and-reset the counters. */
 int ya_get_counters(ya_ctx *, ya_counters *);
 
+/* The [start, end) spans, in ms on a time axis common to all contexts of the device, of the bulk (>= 4096 jobs)
+ * dp_ext_packed_kernel launches since the last call (pairs of floats).  The pipelines of a device overlap their launches; the
+ * union of the spans is the time the kernel class occupied the device.  YA_E_CAPACITY: *n_pairs says how many there are. */
+int ya_get_ext_intervals(ya_ctx *, float *start_end_ms, int cap_pairs, int *n_pairs);
+
 /* Device-side self measurements used by bench.py for roofline denominators. */
 /* Sustained INT32 issue rate of this GPU in 1e9 lane-operations per second, all SMs busy:
  * *giops_add from a pure dependent-free IADD3 stream, *giops_mix from the add / compare /

@@ -421,3 +421,31 @@ def test_device_clumps_match_cpu_build_of_the_same_source(small, aligner):
                 n_checked += 1
         assert n_checked > 300
     aligner.set_params(yaha_b200.Params.defaults(word_len=11))
+
+
+def test_align_batch_through_the_abi_gives_the_reference_sam(small):
+    """Rows N2 / N4 through the C ABI (ctypes, no host program): ya_align_batch takes the golden reads as text and must return,
+    for every read it does not hand back, exactly the lines the UNMODIFIED reference wrote for that read (golden SAMs, default
+    flags and -FBS Y), in the reference's order; the reads it hands back are few."""
+    import gzip
+    for golden, reads_file, fbs in (("out_bw5.sam.gz", "reads.fa", False), ("out_multi.sam.gz", "multi.fa", False), ("out_fbs.sam.gz", "reads.fa", True)):
+        want = {}
+        for line in gzip.open(os.path.join(small.golden, golden), "rt"):
+            if not line.startswith("@"):
+                want.setdefault(line.split("\t", 1)[0], []).append(line)
+        reads = [(n, bytes(s)) for n, s in refio.read_queries(os.path.join(small.dir, reads_file), word_len=11)]
+        al = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11), device=0)
+        al.set_output(yaha_b200.OutParams.defaults(fbs=fbs))
+        text, toff, status = al.align_batch(reads)
+        c = al.counters()
+        al.close()
+        assert int(status.sum()) <= len(reads) // 20 and c.reads_finished == len(reads) - int(status.sum())
+        n_lines = 0
+        for r, (name, _) in enumerate(reads):
+            mine = text[int(toff[r]):int(toff[r + 1])].decode()
+            if status[r]:
+                assert mine == ""
+                continue
+            assert mine == "".join(want.get(name, [])), name
+            n_lines += len(want.get(name, []))
+        assert n_lines > 400

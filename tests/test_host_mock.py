@@ -96,3 +96,27 @@ def test_other_word_lengths_and_skip_distances(small, mock_host, tmp_path, word_
     subprocess.run([S.REF_BIN, "-x", idx, "-q", reads, "-osh", str(tmp_path / "want.sam"), "-t", "1"], check=True, capture_output=True, timeout=600)
     subprocess.run([mock_host, "-x", idx, "-q", reads, "-osh", str(tmp_path / "got.sam"), "-t", "2"], check=True, capture_output=True, timeout=600)
     assert H.sam_lines(open(tmp_path / "got.sam").read()) == H.sam_lines(open(tmp_path / "want.sam").read())
+
+
+def test_queries_from_standard_input(small, mock_host, tmp_path):
+    """Without -q the queries come from standard input, as in the reference (Main.c:173-178, Query.c:63-74): FASTA and FASTQ,
+    same SAM as from the file.  (`-q stdin` fails in the reference -- it maps the name to "stdout" -- and here.)"""
+    for golden, reads, outflag, extra in (("out_bw5.sam.gz", "reads.fa", "-osh", ["-BW", "5", "-G", "50"]), ("out_fastq_oss.sam.gz", "reads.fq", "-oss", [])):
+        out = str(tmp_path / f"{reads}.sam")
+        cmd = [mock_host, "-x", small.idx_path, outflag, out, "-t", "2"] + extra
+        with open(os.path.join(small.dir, reads), "rb") as f:
+            p = subprocess.run(cmd, stdin=f, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        assert H.sam_lines(open(out).read()) == H.expected(small, golden)
+
+
+def test_index_mode_compresses_the_genome_like_the_reference(small, mock_host, tmp_path):
+    """`-g genome.fa`: the .nib2 the C++ host writes (host/indexer.cpp; compressFile, Compress.c:140-331) has the digest of the
+    file the unmodified reference wrote (golden/small/files.sha256).  The index itself is built on the device (ya_open_build):
+    the mock has none and says so -- tests/test_host_sam.py checks both files on the GPU."""
+    import hashlib
+    import shutil
+    shutil.copy(os.path.join(small.dir, "ref.fa"), tmp_path / "ref.fa")
+    p = subprocess.run([mock_host, "-g", str(tmp_path / "ref.fa"), "-L", "11"], capture_output=True, text=True, timeout=600)
+    assert p.returncode != 0 and "cannot build the index" in p.stderr
+    assert hashlib.sha256(open(tmp_path / "ref.nib2", "rb").read()).hexdigest() == small.sha["ref.nib2"]

@@ -73,6 +73,24 @@ def test_most_reads_are_finished_on_the_device(small, tmp_path):
     assert seen["fibers"]["reads_finished_on_device"] == 0
 
 
+def test_index_mode_writes_the_reference_files(small, tmp_path):
+    """`yaha_b200_host -g ref.fa -L 11 -S 1`: .nib2 and index file (built on the device) under the reference's names with the
+    digests of the files `yaha -g` wrote (golden/small/files.sha256); and one -S / -H variant against index_variants.json."""
+    import hashlib
+    import json
+    import shutil
+    shutil.copy(os.path.join(small.dir, "ref.fa"), tmp_path / "ref.fa")
+    p = subprocess.run([HOST, "-g", str(tmp_path / "ref.fa"), "-L", "11"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    for name in ("ref.nib2", "ref.X11_01_65525S"):
+        assert hashlib.sha256(open(tmp_path / name, "rb").read()).hexdigest() == small.sha[name], name
+    want = json.load(open(os.path.join(small.golden, "index_variants.json")))
+    shutil.copy(tmp_path / "ref.nib2", tmp_path / "small.nib2")
+    p = subprocess.run([HOST, "-g", str(tmp_path / "small.nib2"), "-L", "9", "-S", "1", "-H", "20"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert hashlib.sha256(open(tmp_path / "small.X09_01_00020S", "rb").read()).hexdigest() == want["small.X09_01_00020S"]
+
+
 def test_sam_identical_on_10k_long_reads(tmp_path):
     """BASELINE configs[0] shape at reduced reference size, against the reference binary when it is
     on this box (oracle/_ref travels with the snapshot): 1 Mbp, 2 000 x 1000 bp reads at 2 %."""

@@ -77,9 +77,26 @@ class Counters(C.Structure):
                 ("reads_handed_back", C.c_uint64), ("text_bytes", C.c_uint64)]
 
 
+class OutParams(C.Structure):
+    """ya_out_params: the AlignmentArgs_t fields the tail of the per-read path reads (defaults: AlignArgs.c:48-169)."""
+    _fields_ = [("maxDesert", C.c_int32), ("minNonOverlap", C.c_int32), ("minRawScore", C.c_int32), ("minIdentity", C.c_float),
+                ("OQC", C.c_int32), ("FBS", C.c_int32), ("OQCMinNonOverlap", C.c_int32), ("BPCost", C.c_int32), ("maxBPLog", C.c_int32),
+                ("FBS_PSLength", C.c_float), ("FBS_PSScore", C.c_float), ("hardClip", C.c_int32), ("fastq", C.c_int32)]
+
+    @classmethod
+    def defaults(cls, min_match=25, max_desert=50, fbs=False, oqc=True, hard_clip=True, fastq=False):
+        return cls(max_desert, min_match, min_match, 0.9, int(oqc), int(fbs), min_match, 5, 5, 0.9, 0.9, int(hard_clip), int(fastq))
+
+
+class _TextBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("chars", C.c_void_p), ("offsets", C.c_void_p), ("quals", C.c_void_p), ("ids", C.c_void_p),
+                ("id_off", C.c_void_p), ("text", C.c_void_p), ("text_cap", C.c_size_t), ("text_off", C.c_void_p), ("status", C.c_void_p),
+                ("text_len", C.c_size_t), ("text_needed", C.c_size_t), ("n_handed_back", C.c_int32)]
+
+
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
            "ya_reads_upload", "ya_seed_frags", "ya_form_clumps", "ya_prepare_clumps", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_host_alloc", "ya_host_free", "ya_get_counters",
-           "ya_measure_int32_peak", "ya_measure_gather_peak", "ya_set_output", "ya_align_batch", "ya_align_fetch_text", "ya_peer_direct")
+           "ya_measure_int32_peak", "ya_measure_gather_peak", "ya_set_output", "ya_align_batch", "ya_align_fetch_text", "ya_peer_direct", "ya_get_ext_intervals")
 
 _lib = None
 
@@ -123,6 +140,10 @@ def load_library() -> C.CDLL:
     lib.ya_get_counters.argtypes = [vp, C.POINTER(Counters)]
     lib.ya_measure_int32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.ya_measure_gather_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.ya_set_output.argtypes = [vp, C.POINTER(OutParams), C.c_int, C.POINTER(C.c_char_p), vp, vp]
+    lib.ya_align_batch.argtypes = [vp, C.POINTER(_TextBatch)]
+    lib.ya_align_fetch_text.argtypes = [vp, vp, C.c_size_t]
+    lib.ya_peer_direct.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -256,6 +277,40 @@ class Aligner:
                 rc = self.lib.ya_sw_fetch_ops(self.ctx, ops.ctypes.data, len(ops))
             self._check(rc)
             return res, ops[:need.value]
+
+    def set_output(self, out: "OutParams | None" = None):
+        """ya_set_output: output flags + the sequence table of the loaded .nib2 (names, starts, lengths)."""
+        out = out or OutParams.defaults(min_match=self.params.minMatch)
+        names = (C.c_char_p * len(self.nib2.names))(*[n.encode() if isinstance(n, str) else bytes(n) for n in self.nib2.names])
+        st = np.ascontiguousarray(self.nib2.starts, dtype=np.uint32)
+        ln = np.ascontiguousarray(self.nib2.lengths, dtype=np.uint32)
+        self._check(self.lib.ya_set_output(self.ctx, C.byref(out), len(st), names, st.ctypes.data, ln.ctypes.data))
+
+    def align_batch(self, reads: "list[tuple[str, bytes]]", quals: "list[bytes] | None" = None):
+        """ya_align_batch: reads as (id, characters) -> (SAM text of the reads finished on the device as bytes, per-read text
+        offsets uint64[n+1], status uint8[n]: 1 = handed back)."""
+        n = len(reads)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        idoff = np.zeros(n + 1, dtype=np.uint32)
+        if n:
+            offs[1:] = np.cumsum([len(s) for _, s in reads])
+            idoff[1:] = np.cumsum([len(i) for i, _ in reads])
+        chars = np.frombuffer(b"".join(bytes(s) for _, s in reads) + b"\0", dtype=np.uint8).copy()
+        ids = np.frombuffer("".join(i for i, _ in reads).encode() + b"\0", dtype=np.uint8).copy()
+        q = np.frombuffer(b"".join(quals) + b"\0", dtype=np.uint8).copy() if quals is not None else None
+        cap = 4 * int(offs[-1]) + 1024 * n + 4096
+        text = np.zeros(cap, dtype=np.uint8)
+        toff = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        tb = _TextBatch(n, chars.ctypes.data, offs.ctypes.data, q.ctypes.data if q is not None else None, ids.ctypes.data,
+                        idoff.ctypes.data, text.ctypes.data, cap, toff.ctypes.data, status.ctypes.data, 0, 0, 0)
+        rc = self.lib.ya_align_batch(self.ctx, C.byref(tb))
+        if rc == YA_E_CAPACITY:
+            text = np.zeros(int(tb.text_needed) + 16, dtype=np.uint8)
+            rc = self.lib.ya_align_fetch_text(self.ctx, text.ctypes.data, len(text))
+        self._check(rc)
+        self.n_reads = n
+        return text[:tb.text_len].tobytes(), toff, status[:n]
 
     def perfect_ext(self, jobs: np.ndarray) -> np.ndarray:
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DT)

@@ -139,6 +139,7 @@ struct ya_ctx {
     DevBuf    d_chars, d_quals, d_ids, d_fin, d_asm_recs, d_asm_ops, d_fr_outs, d_text, d_out_tab;
     ya_out_params out{}; fr_params fr{}; bool out_set = false;
     size_t    text_pending = 0;         // text left on the device by a ya_align_batch that returned YA_E_CAPACITY
+    std::vector<float> ext_iv;          // [start, end) of every bulk extension launch, ms since the device's base event
     bool      dpr_ran = false;          // the last device DP round launched kernels (its events are valid)
     DevBuf    d_dpr;                                                                           // plan of a device-born DP round
     bool      dpr_bulk_packed = false; int dpr_packed_launches = 0;
@@ -181,6 +182,8 @@ int ya_radix_sort_u64(ya_ctx *c, uint64_t *&a, uint64_t *&b, uint32_t n, int lo_
 // seed.cu / sw.cu / peak.cu / index.cu hold the C-ABI entry points declared in yaha_b200.h
 
 // ctx.cu
+cudaEvent_t ya_device_base_event(int device, cudaStream_t st);   // recorded once per device and process: a common time origin
+void ya_note_ext_interval(ya_ctx *c, cudaEvent_t a, cudaEvent_t b);
 int ya_build_lowmask(ya_ctx *c, const uint8_t *host_bases, size_t n_base_bytes);
 ya_ctx *ya_open_common_for_index(int device, const ya_params *params);
 void ya_set_open_error(const std::string &m);

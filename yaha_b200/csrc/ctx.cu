@@ -192,6 +192,38 @@ extern "C" ya_ctx *ya_open_peer(int device, const ya_ctx *src)
     return c;
 }
 
+cudaEvent_t ya_device_base_event(int device, cudaStream_t st)
+{
+    static cudaEvent_t base[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    cudaEvent_t &e = base[(unsigned)device & 63u];
+    if (!e) { cudaEventCreate(&e); cudaEventRecord(e, st); cudaEventSynchronize(e); }
+    return e;
+}
+
+// the span of a bulk extension launch on the device's common time axis (the pipelines of a device overlap their launches: the
+// UNION of the spans is the time the kernel class occupies the device, which per-launch durations cannot tell)
+void ya_note_ext_interval(ya_ctx *c, cudaEvent_t a, cudaEvent_t b)
+{
+    cudaEvent_t base = ya_device_base_event(c->device, c->stream);
+    float t0 = 0, t1 = 0;
+    if (cudaEventElapsedTime(&t0, base, a) == cudaSuccess && cudaEventElapsedTime(&t1, base, b) == cudaSuccess && c->ext_iv.size() < (1u << 20)) {
+        c->ext_iv.push_back(t0); c->ext_iv.push_back(t1);
+    } else cudaGetLastError();
+}
+
+extern "C" int ya_get_ext_intervals(ya_ctx *c, float *start_end_ms, int cap_pairs, int *n_pairs)
+{
+    if (!c || !n_pairs) return YA_E_ARG;
+    const int n = (int)(c->ext_iv.size() / 2);
+    *n_pairs = n;
+    if (n > cap_pairs || (n && !start_end_ms)) return YA_E_CAPACITY;
+    if (n) memcpy(start_end_ms, c->ext_iv.data(), (size_t)n * 2 * sizeof(float));
+    c->ext_iv.clear();
+    return YA_OK;
+}
+
 extern "C" int ya_peer_direct(const ya_ctx *c) { return c && c->peer_direct ? 1 : 0; }
 
 extern "C" void *ya_host_alloc(size_t bytes)

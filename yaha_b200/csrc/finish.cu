@@ -427,6 +427,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
         if (cudaEventElapsedTime(&ms1, c->ev[1], c->ev[2]) == cudaSuccess) c->ctr.ms_traceback += ms1;
         if (c->dpr_bulk_packed && cudaEventElapsedTime(&ms2, c->ev[3], c->ev[4]) == cudaSuccess) {
             c->ctr.ms_ext += ms2; c->ctr.ext_cells += h_tot[1]; c->ctr.ext_launches += (uint64_t)c->dpr_packed_launches;
+            ya_note_ext_interval(c, c->ev[3], c->ev[4]);
         }
         float ms3 = 0;
         if (cudaEventElapsedTime(&ms3, c->ev[2], c->ev[5]) == cudaSuccess) c->ctr.ms_finish += ms3;

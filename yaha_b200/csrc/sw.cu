@@ -1247,6 +1247,7 @@ extern "C" int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result
         cudaEventElapsedTime(&ms2, c->ev[3], c->ev[4]);
         c->ctr.ms_ext += ms2;
         c->ctr.ext_launches += (lists[packedBase + 0].empty() ? 0 : 1) + (lists[packedBase + 1].empty() ? 0 : 1);
+        ya_note_ext_interval(c, c->ev[3], c->ev[4]);
     }
     for (int k = 0; k < n_live; k++) {
         if (hout[k].n_ops >= 0xFFFFFFF0u) return ya_fail(c, YA_E_STATE, "internal: traceback walked off the band (corrupt back-pointers)");

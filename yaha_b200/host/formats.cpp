@@ -122,7 +122,8 @@ struct QueryReader::Buf {
 
 bool QueryReader::open(const std::string &path, std::string &err)
 {
-    f = fopen(path.c_str(), "r");
+    // "stdin" / "-": the query stream is standard input (Main.c:173-178, Query.c:63-74)
+    f = (path == "stdin" || path == "-") ? stdin : fopen(path.c_str(), "r");
     if (!f) { err = "Failure to open input file: " + path + ".  Error number:" + std::to_string(errno); return false; }
     setvbuf(f, nullptr, _IONBF, 0);
     buf = new Buf();
@@ -132,7 +133,7 @@ bool QueryReader::open(const std::string &path, std::string &err)
 
 void QueryReader::close()
 {
-    if (f) fclose(f);
+    if (f && f != stdin) fclose(f);
     f = nullptr;
     delete buf;
     buf = nullptr;

@@ -855,12 +855,16 @@ int runQueries(const Args &A0)
                 "Mimimum of two (%d) will be used.\n", X.maxHits, A.maxHits, X.maxHits);
         A.maxHits = X.maxHits;
     }
-    {
+    // Queries from standard input (`-q stdin`, the reference's default: Main.c:173-178): the stream cannot be mapped or read
+    // twice, so the reader opened here to tell FASTA from FASTQ is the one the reader thread goes on with (sequential reader).
+    const bool fromStdin = (A.qfile == "stdin" || A.qfile == "-");
+    QueryReader stdinReader;
+    if (fromStdin) {
+        if (A.passes > 1) { fprintf(stderr, "yaha_b200: -passes needs a query file, not standard input\n"); return 1; }
+        if (!stdinReader.open(A.qfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+        A.fastq = stdinReader.fastq;
+    } else {
         QueryReader probe;                                              // sniff FASTA vs FASTQ before the header is written
-        if (A.qfile == "stdout" || A.qfile == "stdin" || A.qfile == "-") {
-            fprintf(stderr, "yaha_b200: reading queries from stdin is not supported; give -q a file\n");
-            return 1;
-        }
         if (!probe.open(A.qfile, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
         A.fastq = probe.fastq;
         probe.close();
@@ -945,8 +949,9 @@ int runQueries(const Args &A0)
                 QueryReader qr;
                 RecordSlicer sl;
                 std::string e2;
-                const bool sliced = !A.fastq && getenv("YA_SEQ_READER") == nullptr;
-                if (!(sliced ? sl.open(A.qfile, e2) : qr.open(A.qfile, e2))) { fprintf(stderr, "%s\n", e2.c_str()); exit(1); }
+                const bool sliced = !A.fastq && !fromStdin && getenv("YA_SEQ_READER") == nullptr;
+                if (fromStdin) { qr = stdinReader; stdinReader.f = nullptr; stdinReader.buf = nullptr; }
+                else if (!(sliced ? sl.open(A.qfile, e2) : qr.open(A.qfile, e2))) { fprintf(stderr, "%s\n", e2.c_str()); exit(1); }
                 qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
                 bool eof = false;
                 while (sliced && !eof) {                                  // FASTA: cut records here, parse them in the pipelines
@@ -1065,18 +1070,37 @@ int runQueries(const Args &A0)
                 fragsAll += c.frags_all; msext += c.ms_ext; mslk += c.ms_lookup; extCells += c.ext_cells; extLaunches += c.ext_launches;
                 msfin += c.ms_finish; devReads += c.reads_finished; handed += c.reads_handed_back; textBytes += c.text_bytes;
             }
+            // time the bulk extension launches occupied the devices: union of their spans per device (pipelines overlap them)
+            double extUnion = 0;
+            {
+                std::map<int, std::vector<std::pair<float, float>>> byDev;
+                std::vector<float> buf;
+                for (Pipe &d : pipes) {
+                    int np = 0;
+                    ya_get_ext_intervals(d.ctx, nullptr, 0, &np);
+                    buf.resize((size_t)2 * np + 2);
+                    if (np && ya_get_ext_intervals(d.ctx, buf.data(), np, &np) == YA_OK)
+                        for (int k = 0; k < np; k++) byDev[d.device].emplace_back(buf[(size_t)2 * k], buf[(size_t)2 * k + 1]);
+                }
+                for (auto &kv : byDev) {
+                    auto &v = kv.second;
+                    std::sort(v.begin(), v.end());
+                    float hi = -1e30f;
+                    for (const auto &iv : v) { if (iv.second <= hi) continue; extUnion += iv.second - std::max(iv.first, hi); hi = iv.second; }
+                }
+            }
             fprintf(stderr, "{\"pass\": %d, \"reads\": %llu, \"align_s\": %.5f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"read_parse_s\": %.5f, "
                     "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
                     "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
                     "\"launches\": %llu, \"probes\": %llu, \"hits\": %llu, \"frags_all\": %llu, \"gpus\": %d, \"threads\": %d, \"pipes\": %d, "
                     "\"replay\": %d, \"dev_ms_ext\": %.4f, \"ext_cells\": %llu, \"ext_launches\": %llu, \"dev_ms_lookup\": %.4f, \"fiber_setup_s\": %.5f, "
                     "\"dev_ms_finish\": %.4f, \"reads_finished_on_device\": %llu, \"reads_handed_back\": %llu, \"device_text_bytes\": %llu, "
-                    "\"index_upload_s\": %.3f, \"index_peer_copies_s\": %.3f, \"peer_copies_direct\": %d}\n",
+                    "\"index_upload_s\": %.3f, \"index_peer_copies_s\": %.3f, \"peer_copies_direct\": %d, \"dev_ms_ext_union\": %.4f}\n",
                     pass, (unsigned long long)nReads, tAlign, tOpen, nReads / std::max(tAlign, 1e-9), tRead, upl, tWrite, seed, dp, host,
                     (unsigned long long)jobs, (unsigned long long)rounds, (unsigned long long)cells, msseed, msdp, mstb,
                     (unsigned long long)launches, (unsigned long long)probes, (unsigned long long)hits, (unsigned long long)fragsAll, nDev, nThreads,
                     nPipes, replaying ? 1 : 0, msext, (unsigned long long)extCells, (unsigned long long)extLaunches, mslk, setup,
-                    msfin, (unsigned long long)devReads, (unsigned long long)handed, (unsigned long long)textBytes, tOpenUpload, tOpenPeer, peerDirect);
+                    msfin, (unsigned long long)devReads, (unsigned long long)handed, (unsigned long long)textBytes, tOpenUpload, tOpenPeer, peerDirect, extUnion);
         }
     }
     extern uint64_t gAlignProf[4];
@@ -1094,15 +1118,6 @@ int runQueries(const Args &A0)
     traceDump();
     for (int p = nPipes - 1; p >= 0; p--) ya_close(pipes[(size_t)p].ctx);      // shared contexts before their owners
     return 0;
-}
-
-int runIndex(const Args &A)
-{
-    (void)A;
-    fprintf(stderr, "yaha_b200: index creation is provided by the Python front end, with the reference's flags and file names:\n"
-                    "    python -m yaha_b200.refio -g genome.(fa|nib2) [-L wordLen] [-S skipDist] [-H maxHits]\n"
-                    "(byte-identical .nib2 and index files; `yaha -g` works as well -- the alignment hot path reads either unchanged).\n");
-    return 2;
 }
 
 }  // namespace yh
