@@ -55,6 +55,7 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = 2 * bytes + 256;                // generous: a re-allocation (cudaFree) synchronises the whole device
+        if (want < ((size_t)256 << 10)) want = (size_t)256 << 10;     // (and never small: tiny batches of varying size must not re-pin)
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         ya_note_alloc("pinned", old, want, t0);

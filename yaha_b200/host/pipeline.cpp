@@ -226,7 +226,9 @@ template <class T> struct PinnedVec {
     void resize(size_t want, bool keep = true)   // new elements are not initialised
     {
         if (want > cap) {
-            size_t nc = std::max(want, cap + cap / 2);
+            // (never a small block: the batches of handed-back reads are a handful of reads of varying size, and every growth is a
+            //  cudaHostAlloc + cudaFreeHost -- milliseconds during which no stream of the process makes progress)
+            size_t nc = std::max(std::max(want, cap + cap / 2), ((size_t)256 << 10) / sizeof(T));
             T *q = (T *)ya_host_alloc(nc * sizeof(T));
             if (!q) { fprintf(stderr, "yaha_b200: cannot allocate %zu bytes of page-locked memory\n", nc * sizeof(T)); exit(1); }
             if (n && keep) memcpy(q, p, n * sizeof(T));
@@ -549,7 +551,10 @@ static void classicPass(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     auto callDp = [&](const ya_dp_job *jobs, int nj, int users) -> ResultBlock * {
         // Every block of a pipeline has the pipeline-wide capacity (monotonic): re-pinning host memory in the
         // middle of a run stalls the whole process (cudaFreeHost / cudaHostAlloc synchronise the device).
-        if (D.capJobs == 0) D.capJobs = (size_t)16 * (size_t)n;        // ~8 jobs per read is typical; doubled when exceeded
+        // (~8 jobs per read is typical; doubled when exceeded.  Never below 4096: the batches that come here after
+        //  ya_align_batch are the handful of reads it handed back, and a capacity tailored to the first of them would be outgrown --
+        //  i.e. re-pinned, a stall of milliseconds for every stream of the process -- by the next slightly larger one)
+        if (D.capJobs == 0) D.capJobs = std::max<size_t>((size_t)16 * (size_t)n, 4096);
         if ((size_t)nj > D.capJobs) D.capJobs = 2 * (size_t)nj;
         D.capOps = std::max(D.capOps, 32 * D.capJobs);
         if (D.blocks.empty()) {                                        // first call of this pipeline: pin a few blocks up front
