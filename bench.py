@@ -209,6 +209,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+_BARRIER_SEQ = [0]
+
+
+def start_barrier_env(d: str, rank: int, world: int) -> dict:
+    """N > 1: the ranks' host processes wait for each other once their index is resident (YA_START_BARRIER), so that every
+    rank's timed passes run while all the others run theirs -- not while the others still upload 5 GB of index."""
+    if world <= 1:
+        return {}
+    _BARRIER_SEQ[0] += 1
+    bdir = os.path.join(d, f"barrier_{_BARRIER_SEQ[0]}")
+    os.makedirs(bdir, exist_ok=True)
+    try:
+        os.remove(os.path.join(bdir, f"ready.{rank}"))
+    except OSError:
+        pass
+    return {"YA_START_BARRIER": f"{bdir}:{rank}:{world}"}
+
+
 def run_host(idx_path, reads_path, out_path, flags, threads, device, passes, batch, pipes, replay=False, tpp=0, env=None):
     """Run the product's host program (the call a user makes) and return its per-pass stats."""
     host = os.path.join(ROOT, "yaha_b200", "yaha_b200_host")
@@ -279,8 +297,14 @@ def run_ours(args):
     # of a 20 K-read job: small batches on 8 overlapping pipelines served by one pool of worker threads.
     e2e_tpp = 0                      # shared worker pool of `threads` workers serves every pipeline
     extra_warm = 5                   # (page-locked / device scratch of 8 pipelines reaches its final size in the first passes)
+    def benv(extra=None):
+        # (every rank clears its own ready file, then all meet, then the host processes meet again with their index resident)
+        e = dict(few_cores_env, **(extra or {}), **start_barrier_env(d, rank, world))
+        if world > 1:
+            dist.barrier()
+        return e
     stats_a = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, extra_warm + args.warmup + args.steps,
-                       args.e2e_batch, e2e_pipes, tpp=e2e_tpp, env=few_cores_env)
+                       args.e2e_batch, e2e_pipes, tpp=e2e_tpp, env=benv())
     timed_a = stats_a[extra_warm + args.warmup:]
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
@@ -288,7 +312,7 @@ def run_ours(args):
     # the kernel rooflines (kernels of up to 8 pipelines share the SMs here, which stretches their event timings;
     # run C below times the same kernels alone).
     stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + extra_warm + args.warmup + args.steps,
-                       args.batch, pipes, replay=True, env=few_cores_env)
+                       args.batch, pipes, replay=True, env=benv())
     timed = stats_b[1 + extra_warm + args.warmup:]
     assert len(timed) == args.steps
     el_res = sum(s["align_s"] for s in timed)
@@ -296,17 +320,21 @@ def run_ours(args):
     # lock step -> every extension launch carries the workload's ~40 K jobs and no other pipeline shares the SMs.
     # This is the timed region the kernel rooflines are quoted on; run B's small launches are reported beside it.
     stats_c = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + args.warmup + args.steps,
-                       n_reads, 1, replay=True, env={"YA_COALESCE_US": "20000"})[1 + args.warmup:]
+                       n_reads, 1, replay=True, env=benv({"YA_COALESCE_US": "20000"}))[1 + args.warmup:]
     iso_cells, iso_ms, iso_n = (sum(s[k] for s in stats_c) for k in ("ext_cells", "dev_ms_ext", "ext_launches"))
     iso_gcups = iso_cells / (iso_ms * 1e-3) / 1e9 if iso_ms > 0 else 0.0
     iso_lookup_ms, iso_probes = sum(s["dev_ms_lookup"] for s in stats_c), sum(s["probes"] for s in stats_c)
     iso_pps = iso_probes / (iso_lookup_ms * 1e-3) if iso_lookup_ms > 0 else 0.0
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    per_rank = None
     if world > 1:
-        tt = torch.tensor([el_e2e, el_res], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        el_e2e, el_res = float(tt[0].item()), float(tt[1].item())
+        mine_t = torch.tensor([el_e2e, el_res], device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        per_rank = {"e2e_ms_per_step": [round(float(t[0]) / args.steps * 1e3, 3) for t in allt],
+                    "value_ms_per_step": [round(float(t[1]) / args.steps * 1e3, 3) for t in allt]}
+        el_e2e, el_res = max(float(t[0]) for t in allt), max(float(t[1]) for t in allt)
 
     def tot(k):
         return sum(s[k] for s in timed)
@@ -435,6 +463,8 @@ def run_ours(args):
                                                                         "8 B/probe + 20 B/hit + 12 B/fragment"},
         "clocks": sampler.summary(),
     }
+    if per_rank:
+        line["per_rank"] = per_rank
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()                  # (the other ranks are done: their GPUs are free for the in-process run below)

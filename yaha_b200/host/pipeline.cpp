@@ -923,6 +923,25 @@ int runQueries(const Args &A0)
             if (ya_set_output(p.ctx, &O, (int)names.size(), names.data(), starts.data(), lens.data()) != YA_OK) die(p.ctx, "ya_set_output");
     }
     tOpen = nowSec() - tOpen;
+    // YA_START_BARRIER=<dir>:<rank>:<world> (bench.py, one process per GPU): wait here, index resident, until every rank's
+    // process is -- otherwise a rank that finishes its 5 GB index upload a moment earlier runs all of its (millisecond) passes
+    // while the others still saturate host memory and PCIe with theirs, and the max-over-ranks time measures start-up skew.
+    if (const char *sb = getenv("YA_START_BARRIER")) {
+        std::string spec(sb);
+        const size_t c2 = spec.rfind(':'), c1 = (c2 == std::string::npos) ? c2 : spec.rfind(':', c2 - 1);
+        if (c1 != std::string::npos && c2 != std::string::npos) {
+            const std::string dir = spec.substr(0, c1);
+            const int rank = atoi(spec.substr(c1 + 1, c2 - c1 - 1).c_str()), world = atoi(spec.substr(c2 + 1).c_str());
+            FILE *f = fopen((dir + "/ready." + std::to_string(rank)).c_str(), "w");
+            if (f) fclose(f);
+            for (int waited = 0; waited < 600000; waited++) {            // (ten minutes at most)
+                int have = 0;
+                for (int r = 0; r < world; r++) have += access((dir + "/ready." + std::to_string(r)).c_str(), F_OK) == 0;
+                if (have == world) break;
+                usleep(1000);
+            }
+        }
+    }
 
     std::vector<std::unique_ptr<Batch>> cache;                          // -replay: parsed batches of pass 0
     std::vector<std::unique_ptr<Batch>> spare;                          // written batches, refilled by the reader (strings keep their capacity)
