@@ -306,6 +306,9 @@ def run_ours(args):
     stats_a = run_host(idx_path, reads_path, out_path, REF_FLAGS[wl], threads, local, extra_warm + args.warmup + args.steps,
                        args.e2e_batch, e2e_pipes, tpp=e2e_tpp, env=benv())
     timed_a = stats_a[extra_warm + args.warmup:]
+    if os.environ.get("YAHA_BENCH_DUMP_STATS"):              # per-rank, per-pass stats of the e2e run (debugging stragglers)
+        with open(os.path.join(os.environ["YAHA_BENCH_DUMP_STATS"], f"stats_a_rank{rank}.json"), "w") as f:
+            json.dump(stats_a, f)
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
     # run B: parsed reads replayed from host memory, SAM formatted but not written -> value, stage times and
