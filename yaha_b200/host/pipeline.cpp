@@ -1113,6 +1113,7 @@ int runQueries(const Args &A0)
                     for (const auto &iv : v) { if (iv.second <= hi) continue; extUnion += iv.second - std::max(iv.first, hi); hi = iv.second; }
                 }
             }
+            if (getenv("YA_PASS_CLOCK")) fprintf(stderr, "pass %d started at %.6f (wall clock)\n", pass, std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count() - tAlign);
             fprintf(stderr, "{\"pass\": %d, \"reads\": %llu, \"align_s\": %.5f, \"open_s\": %.3f, \"reads_per_s\": %.1f, \"read_parse_s\": %.5f, "
                     "\"upload_s\": %.5f, \"write_s\": %.5f, \"seed_wall_s\": %.5f, \"dp_wall_s\": %.5f, \"host_wall_s\": %.5f, \"dp_jobs\": %llu, "
                     "\"dp_rounds\": %llu, \"dp_cells\": %llu, \"dev_ms_seed\": %.3f, \"dev_ms_dp\": %.3f, \"dev_ms_traceback\": %.3f, "
