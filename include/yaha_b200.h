@@ -183,6 +183,11 @@ int ya_set_params(ya_ctx *, const ya_params *);
  * that the caller's CUDA events bracket the kernels.  NULL restores the library's stream. */
 int ya_set_stream(ya_ctx *, void *cuda_stream);
 
+/* Make the context's device the calling thread's current CUDA device.  A host thread that allocates page-locked memory
+ * (ya_host_alloc) before it has made any call with a context would otherwise do so against device 0 and create a CUDA
+ * context there -- in every process of a multi-GPU job. */
+int ya_bind_thread(const ya_ctx *);
+
 /* Page-locked host memory for the buffers handed to the calls below (optional: any host pointer
  * works, page-locked ones are copied by DMA without an intermediate staging copy).  NULL on failure. */
 void *ya_host_alloc(size_t bytes);

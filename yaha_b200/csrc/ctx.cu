@@ -226,6 +226,12 @@ extern "C" int ya_get_ext_intervals(ya_ctx *c, float *start_end_ms, int cap_pair
 
 extern "C" int ya_peer_direct(const ya_ctx *c) { return c && c->peer_direct ? 1 : 0; }
 
+extern "C" int ya_bind_thread(const ya_ctx *c)
+{
+    if (!c) return YA_E_ARG;
+    return cudaSetDevice(c->device) == cudaSuccess ? YA_OK : YA_E_CUDA;
+}
+
 extern "C" void *ya_host_alloc(size_t bytes)
 {
     void *p = nullptr;

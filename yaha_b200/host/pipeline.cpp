@@ -1036,6 +1036,7 @@ int runQueries(const Args &A0)
         std::vector<std::thread> pth;
         for (int p = 0; p < nPipes; p++)
             pth.emplace_back([&, p]() {
+                ya_bind_thread(pipes[(size_t)p].ctx);                   // (page-locked buffers of this thread belong to its device)
                 for (;;) {
                     std::unique_ptr<Batch> b;
                     {
