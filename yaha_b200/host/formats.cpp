@@ -307,6 +307,44 @@ int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen)
     return (fail || m == 0) ? 0 : 1;
 }
 
+// The same record straight into flat buffers (the page-locked inputs of ya_align_batch): id (cut to 200 characters, blanks
+// replaced) appended at ids + *idLen, sequence characters at chars + *seqLen.  Returns 1 and advances both lengths, or 0 (record
+// skipped with the reference's warning: too long / shorter than wordLen / empty) and leaves them alone.  chars must have room
+// for the record's n bytes, ids for 200.
+int parseFastaRecordInto(const char *s, size_t n, char *chars, size_t *seqLen, char *ids, size_t *idLen, int maxLen, int wordLen)
+{
+    const char *nl = (const char *)memchr(s, '\n', n);
+    const size_t idl = nl ? (size_t)(nl - s) : n;
+    const size_t keep = idl < 200 ? idl : 200;
+    char *idDst = ids + *idLen;
+    for (size_t k = 0; k < keep; k++) idDst[k] = s[k] == ' ' ? '_' : s[k];
+    if (idl > 200)
+        fprintf(stderr, "Warning, Query Id length of %d exceeds maximum length %d.  Id will be truncated.\n", (int)idl, 200);
+    char *dst = chars + *seqLen;
+    size_t m = 0, p = nl ? idl + 1 : n;
+    bool fail = false;
+    while (p < n) {
+        const char *nl2 = (const char *)memchr(s + p, '\n', n - p);
+        const size_t l = nl2 ? (size_t)(nl2 - (s + p)) : n - p;
+        if ((int)(m + l) > maxLen) {
+            fprintf(stderr, "Warning.  Query sequence exceeds maximum length of %d.  Query will be skipped.\n", maxLen);
+            fail = true;
+            break;
+        }
+        memcpy(dst + m, s + p, l);
+        m += l;
+        p += l;
+        if (nl2) p++;
+    }
+    if (!fail && m > 0 && (int)m < wordLen) {
+        fprintf(stderr, "Query length must be at least wordlen bases long. Query will be skipped.\n");
+        fail = true;
+    }
+    if (fail || m == 0) return 0;
+    *seqLen += m; *idLen += keep;
+    return 1;
+}
+
 // codeOfChar for 16 characters per step.  A letter's code depends on its low five bits only (upper and lower case agree), so
 // the 256-entry table folds into two 16-entry byte shuffles; everything that is not an ASCII letter is X (14) like the table
 // says.  The routine is compared with the table on all 256 byte values before it is first used, and left unused otherwise.

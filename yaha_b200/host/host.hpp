@@ -103,6 +103,8 @@ struct RecordSlicer {
 };
 // 1: r filled; 0: record skipped with the reference's warning (too long / shorter than wordLen / empty)
 int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen);
+// the same record appended to flat buffers (ids cut to 200 characters): 1 and both lengths advanced, or 0 (skipped, same warnings)
+int parseFastaRecordInto(const char *s, size_t n, char *chars, size_t *seqLen, char *ids, size_t *idLen, int maxLen, int wordLen);
 
 // ----------------------------------------------------------------------------- small-block pool
 // Per-thread free lists of power-of-two blocks (32 B .. 64 KB), carved from slabs that are never handed back.

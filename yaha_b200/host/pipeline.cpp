@@ -265,6 +265,7 @@ struct Batch {
     std::unique_ptr<Batch> residual;
     std::vector<int> residualOf;          // residual read k is read residualOf[k] of this batch
     std::vector<std::pair<const char *, size_t>> outRuns;   // what the writer emits for this batch, in input order
+    size_t nReads = 0;                    // reads of the batch (they live in `reads`, or only in the pipeline's flat buffers)
 };
 
 struct ResultBlock {
@@ -674,23 +675,46 @@ static void classicPass(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
 }
 
 // The whole per-read path in one device call (ya_align_batch); returns the number of reads handed back.
-static int fusedPass(const Env &E, Pipe &D, Batch &B)
+// FASTA records of a batch parsed straight into the pipeline's page-locked input buffers (no Read objects, no second copy)
+static int parseFlat(const Env &E, Pipe &D, Batch &B)
+{
+    size_t bytes = 0;
+    for (const auto &sl : B.slices) bytes += sl.second;
+    const size_t cap = B.slices.size();
+    D.offs.resize(cap + 1, false); D.idOffs.resize(cap + 1, false);
+    D.chars.resize(bytes + 1, false); D.ids.resize(200 * cap + 1, false);
+    size_t total = 0, idTotal = 0;
+    int n = 0;
+    for (const auto &sl : B.slices) {
+        D.offs[(size_t)n] = total; D.idOffs[(size_t)n] = (uint32_t)idTotal;
+        n += parseFastaRecordInto(sl.first, sl.second, D.chars.data(), &total, D.ids.data(), &idTotal, E.A->maxQueryLength, E.A->wordLen);
+    }
+    D.offs[(size_t)n] = total; D.idOffs[(size_t)n] = (uint32_t)idTotal;
+    B.slices.clear();
+    return n;
+}
+
+static int fusedPass(const Env &E, Pipe &D, Batch &B, int nFlat)
 {
     const double t0 = nowSec();
-    const int n = (int)B.reads.size();
+    const int n = nFlat >= 0 ? nFlat : (int)B.reads.size();
     const bool fastq = E.A->fastq;
-    D.offs.resize((size_t)n + 1, false);
-    D.idOffs.resize((size_t)n + 1, false);
-    size_t total = 0, idTotal = 0;
-    for (int i = 0; i < n; i++) { D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fwd.size(); D.idOffs[(size_t)i] = (uint32_t)idTotal; idTotal += B.reads[(size_t)i].id.size(); }
-    D.offs[(size_t)n] = total; D.idOffs[(size_t)n] = (uint32_t)idTotal;
-    D.chars.resize(total + 1, false); D.ids.resize(idTotal + 1, false);
-    if (fastq) D.quals.resize(total + 1, false);
-    for (int i = 0; i < n; i++) {
-        const Read &r = B.reads[(size_t)i];
-        memcpy(D.chars.data() + D.offs[(size_t)i], r.fwd.data(), r.fwd.size());
-        memcpy(D.ids.data() + D.idOffs[(size_t)i], r.id.data(), r.id.size());
-        if (fastq) memcpy(D.quals.data() + D.offs[(size_t)i], r.qual.data(), r.qual.size());
+    size_t total = 0;
+    if (nFlat >= 0) total = (size_t)D.offs[(size_t)n];                 // (parseFlat has filled the buffers)
+    else {
+        D.offs.resize((size_t)n + 1, false);
+        D.idOffs.resize((size_t)n + 1, false);
+        size_t idTotal = 0;
+        for (int i = 0; i < n; i++) { D.offs[(size_t)i] = total; total += B.reads[(size_t)i].fwd.size(); D.idOffs[(size_t)i] = (uint32_t)idTotal; idTotal += B.reads[(size_t)i].id.size(); }
+        D.offs[(size_t)n] = total; D.idOffs[(size_t)n] = (uint32_t)idTotal;
+        D.chars.resize(total + 1, false); D.ids.resize(idTotal + 1, false);
+        if (fastq) D.quals.resize(total + 1, false);
+        for (int i = 0; i < n; i++) {
+            const Read &r = B.reads[(size_t)i];
+            memcpy(D.chars.data() + D.offs[(size_t)i], r.fwd.data(), r.fwd.size());
+            memcpy(D.ids.data() + D.idOffs[(size_t)i], r.id.data(), r.id.size());
+            if (fastq) memcpy(D.quals.data() + D.offs[(size_t)i], r.qual.data(), r.qual.size());
+        }
     }
     B.text = D.acquireText((size_t)n, total);
     TextBuf &TB = *B.text;
@@ -735,6 +759,13 @@ static void addRun(Batch &B, const char *p, size_t len)
 static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
 {
     double t0 = nowSec();
+    int nFlat = -1;
+    // (-replay keeps the parsed reads of pass 0 as objects; everything else on the ya_align_batch path parses flat)
+    if (!B.slices.empty() && fusedWanted(E) && !E.A->replay && B.slices.size() <= 65536) {
+        nFlat = parseFlat(E, D, B);
+        B.reads.clear();
+        traceEv('p', D.device, (int)B.seq, t0, nowSec());
+    }
     if (!B.slices.empty()) {                                            // FASTA records cut by the reader, parsed here
         size_t k = 0;
         for (const auto &sl : B.slices) {
@@ -747,13 +778,14 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     }
     B.outRuns.clear();
     B.nFibers = 0;
-    const int n = (int)B.reads.size();
+    const int n = nFlat >= 0 ? nFlat : (int)B.reads.size();
+    B.nReads = (size_t)n;
     if (n == 0) return;
     auto fiberRuns = [](Batch &X, Batch &into) {
         for (int i = 0; i < X.nFibers; i++) { const ReadCtx &rc = X.fibers[(size_t)i].rc; if (rc.outLen) addRun(into, rc.out->data() + rc.outOff, rc.outLen); }
     };
-    if (!fusedWanted(E) || n > 65536) { classicPass(E, D, B, pool); fiberRuns(B, B); return; }
-    const int handed = fusedPass(E, D, B);
+    if (nFlat < 0 && (!fusedWanted(E) || n > 65536)) { classicPass(E, D, B, pool); fiberRuns(B, B); return; }
+    const int handed = fusedPass(E, D, B, nFlat);
     if (handed == 0) {
         addRun(B, B.text->text.data(), (size_t)B.text->off[(size_t)n]);
         return;
@@ -767,8 +799,15 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
         if (!B.text->status[(size_t)i]) continue;
         if (k == R.reads.size()) R.reads.emplace_back();
         Read &dst = R.reads[k];
-        const Read &src = B.reads[(size_t)i];
-        dst.id = src.id; dst.fwd = src.fwd; dst.qual = src.qual; dst.fcode.clear(); dst.rcode.clear(); dst.rev.clear();
+        if (nFlat >= 0) {                                              // (the batch was parsed flat: the read is in the input buffers)
+            dst.id.assign(D.ids.data() + D.idOffs[(size_t)i], D.idOffs[(size_t)i + 1] - D.idOffs[(size_t)i]);
+            dst.fwd.assign(D.chars.data() + D.offs[(size_t)i], (size_t)(D.offs[(size_t)i + 1] - D.offs[(size_t)i]));
+            dst.qual.clear();
+        } else {
+            const Read &src = B.reads[(size_t)i];
+            dst.id = src.id; dst.fwd = src.fwd; dst.qual = src.qual;
+        }
+        dst.fcode.clear(); dst.rcode.clear(); dst.rev.clear();
         B.residualOf.push_back(i);
         k++;
     }
@@ -1066,7 +1105,7 @@ int runQueries(const Args &A0)
                 F.done.erase(next);
             }
             double w0 = nowSec();
-            nReads += b->reads.size();
+            nReads += b->nReads;
             if (!replaying) {
                 // (one ordered stream: writing the batches of a step side by side with pwrite was measured SLOWER -- buffered
                 //  writes to one file serialise on its inode lock -- 1.6 ms per 2.3 MB batch with four writers against 0.5 ms)
