@@ -7,6 +7,6 @@ timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c
     yaha_b200/yaha_b200_host -x $X -q $Q -osh /tmp/c5.sam -t 8 -batch 5000 -pipes 1 -H 650 -MD 50 > gpurun_out/ncu_cfg5.log 2>&1
 python tools/launch_summary.py gpurun_out/launches_cfg5.csv > gpurun_out/launches_cfg5.md
 head -30 gpurun_out/launches_cfg5.md
-YAHAB=1 YAHA_B200_STATS=1 yaha_b200/yaha_b200_host -x $X -q $Q -osh /tmp/c5.sam -t 8 -batch 5000 -pipes 1 -passes 3 -H 650 -MD 50 2>&1 | grep '"pass"' | tail -1 | python3 -c "
+YAHA_B200_STATS=1 yaha_b200/yaha_b200_host -x $X -q $Q -osh /tmp/c5.sam -t 8 -batch 5000 -pipes 1 -passes 3 -H 650 -MD 50 2>&1 | grep '"pass"' | tail -1 | python3 -c "
 import sys, json
 d=json.loads(sys.stdin.read()); print({k: d[k] for k in ('align_s','dev_ms_seed','dev_ms_lookup','dev_ms_dp','dev_ms_traceback','dev_ms_finish','hits','probes','frags_all','reads_handed_back','dp_jobs','launches')})"
