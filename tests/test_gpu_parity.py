@@ -449,3 +449,39 @@ def test_align_batch_through_the_abi_gives_the_reference_sam(small):
             assert mine == "".join(want.get(name, [])), name
             n_lines += len(want.get(name, []))
         assert n_lines > 400
+
+
+def test_align_batch_capacity_protocol_and_degenerate_batches(small):
+    """ya_align_batch: a text buffer that is too small returns YA_E_CAPACITY with text_needed, offsets and status valid and the
+    text fetched afterwards (ya_align_fetch_text) identical to a call with room; an empty batch and a batch of reads without a
+    single hit are fine; calling before ya_set_output is a state error."""
+    import ctypes as C
+    reads = [(n, bytes(s)) for n, s in refio.read_queries(os.path.join(small.dir, "reads.fa"), word_len=11)][:100]
+    al = yaha_b200.Aligner(small.nib, small.idx, yaha_b200.Params.defaults(word_len=11), device=0)
+    with pytest.raises(yaha_b200.YahaError):
+        al.align_batch(reads)
+    al.set_output(yaha_b200.OutParams.defaults())
+    text, toff, status = al.align_batch(reads)
+    assert len(text) > 10000 and int(toff[-1]) == len(text)
+    # too small a buffer: go through the ABI by hand
+    n = len(reads)
+    offs = np.zeros(n + 1, dtype=np.uint64); offs[1:] = np.cumsum([len(s) for _, s in reads])
+    idoff = np.zeros(n + 1, dtype=np.uint32); idoff[1:] = np.cumsum([len(i) for i, _ in reads])
+    chars = np.frombuffer(b"".join(s for _, s in reads), dtype=np.uint8).copy()
+    ids = np.frombuffer("".join(i for i, _ in reads).encode(), dtype=np.uint8).copy()
+    small_text = np.zeros(64, dtype=np.uint8); toff2 = np.zeros(n + 1, dtype=np.uint64); st2 = np.zeros(n, dtype=np.uint8)
+    tb = yaha_b200._TextBatch(n, chars.ctypes.data, offs.ctypes.data, None, ids.ctypes.data, idoff.ctypes.data, small_text.ctypes.data, 64,
+                              toff2.ctypes.data, st2.ctypes.data, 0, 0, 0)
+    rc = al.lib.ya_align_batch(al.ctx, C.byref(tb))
+    assert rc == yaha_b200.YA_E_CAPACITY and tb.text_needed == len(text)
+    assert np.array_equal(toff2, toff) and np.array_equal(st2, status)
+    full = np.zeros(int(tb.text_needed), dtype=np.uint8)
+    assert al.lib.ya_align_fetch_text(al.ctx, full.ctypes.data, len(full)) == 0
+    assert full.tobytes() == text
+    # degenerate batches
+    t0, o0, s0 = al.align_batch([])
+    assert t0 == b"" and len(s0) == 0
+    junk = [("junk%d" % k, b"ACGT" * 40) for k in range(3)] + [("nnn", b"N" * 100)]
+    t1, o1, s1 = al.align_batch(junk)
+    assert int(s1.sum()) == 0 and int(o1[-1]) == len(t1)
+    al.close()
