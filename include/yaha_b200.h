@@ -24,7 +24,9 @@ extern "C" {
 #define YA_E_ARG       1   /* bad argument / unsupported parameter combination            */
 #define YA_E_CUDA      2   /* CUDA runtime error, text in ya_last_error()                 */
 #define YA_E_CAPACITY  3   /* a caller-provided output buffer is too small; *_needed set  */
-#define YA_E_STATE     4   /* call order violated (e.g. no reads uploaded)                */
+#define YA_E_STATE     4   /* call order violated (e.g. no reads uploaded), or -- ya_align_batch -- the batch does not
+                              fit one device pass (caller: smaller batches, or the call-by-call path)              */
+#define YA_E_INTERNAL  5   /* a consistency check on the device failed (a bug: never retried on another path)      */
 
 /* ---- scoring / seeding parameters: POD copy of the AlignmentArgs_t fields the hot path
  *      reads (ref: Math.h:281-304, defaults AlignArgs.c:48-87, derived :108-169) ---- */

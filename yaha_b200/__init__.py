@@ -22,7 +22,7 @@ from . import refio
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libyaha_b200.so")
 
-YA_OK, YA_E_ARG, YA_E_CUDA, YA_E_CAPACITY, YA_E_STATE = 0, 1, 2, 3, 4
+YA_OK, YA_E_ARG, YA_E_CUDA, YA_E_CAPACITY, YA_E_STATE, YA_E_INTERNAL = 0, 1, 2, 3, 4, 5
 DP_FULL, DP_BANDED, DP_EXT_FWD, DP_EXT_BWD = 0, 1, 2, 3
 
 

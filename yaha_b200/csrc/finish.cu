@@ -398,7 +398,7 @@ extern "C" int ya_align_batch(ya_ctx *c, ya_text_batch *b)
     YA_CUDA(c, cudaGetLastError());
     if (h_tot[2] & 0xFFFFFFFFull) {
         char msg[96]; snprintf(msg, sizeof msg, "ya_align_batch: internal error on the device (flags %llx)", h_tot[2] & 0xFFFFFFFFull);
-        return ya_fail(c, YA_E_STATE, msg);
+        return ya_fail(c, YA_E_INTERNAL, msg);
     }
     lap(4);
     const size_t textBytes = (size_t)h_tot[4];

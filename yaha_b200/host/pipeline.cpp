@@ -733,6 +733,10 @@ static int fusedPass(const Env &E, Pipe &D, Batch &B, int nFlat)
         TB.text.resize(tb.text_needed + tb.text_needed / 4 + 4096, false);
         rcode = ya_align_fetch_text(D.ctx, TB.text.data(), TB.text.size());
     }
+    if (rcode == YA_E_STATE) {                        // the batch does not fit one device pass (e.g. > 2^28 seed hits): call-by-call path
+        B.text->release(); B.text = nullptr;
+        return -1;
+    }
     if (rcode != YA_OK) die(D.ctx, "ya_align_batch");
     D.tDp += nowSec() - t1;
     D.nRounds++;
@@ -786,6 +790,20 @@ static void processBatch(const Env &E, Pipe &D, Batch &B, WorkerPool &pool)
     };
     if (nFlat < 0 && (!fusedWanted(E) || n > 65536)) { classicPass(E, D, B, pool); fiberRuns(B, B); return; }
     const int handed = fusedPass(E, D, B, nFlat);
+    if (handed < 0) {                                                   // not as one device pass: every read through the fibers
+        if (nFlat >= 0) {
+            B.reads.resize((size_t)n);
+            for (int i = 0; i < n; i++) {
+                Read &r = B.reads[(size_t)i];
+                r.id.assign(D.ids.data() + D.idOffs[(size_t)i], D.idOffs[(size_t)i + 1] - D.idOffs[(size_t)i]);
+                r.fwd.assign(D.chars.data() + D.offs[(size_t)i], (size_t)(D.offs[(size_t)i + 1] - D.offs[(size_t)i]));
+                r.qual.clear(); r.fcode.clear(); r.rcode.clear(); r.rev.clear();
+            }
+        }
+        classicPass(E, D, B, pool);
+        fiberRuns(B, B);
+        return;
+    }
     if (handed == 0) {
         addRun(B, B.text->text.data(), (size_t)B.text->off[(size_t)n]);
         return;
