@@ -345,6 +345,7 @@ int ya_align_batch(ya_ctx *c, ya_text_batch *b)
     c->text_pending = 0;
     if (!c->out_set) return YA_E_STATE;
     if (n == 0) return 0;
+    if (getenv("YA_MOCK_ALIGN_TOO_BIG")) return YA_E_STATE;       /* "does not fit one device pass": the host takes the call-by-call path */
     const uint64_t total = b->offsets[n];
     uint8_t *codes = malloc(total + 1);
     for (uint64_t i = 0; i < total; i++) codes[i] = (uint8_t)code_of_char((unsigned char)b->chars[i]);

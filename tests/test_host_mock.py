@@ -120,3 +120,13 @@ def test_index_mode_compresses_the_genome_like_the_reference(small, mock_host, t
     p = subprocess.run([mock_host, "-g", str(tmp_path / "ref.fa"), "-L", "11"], capture_output=True, text=True, timeout=600)
     assert p.returncode != 0 and "cannot build the index" in p.stderr
     assert hashlib.sha256(open(tmp_path / "ref.nib2", "rb").read()).hexdigest() == small.sha["ref.nib2"]
+
+
+def test_batch_that_does_not_fit_one_device_pass_takes_the_call_by_call_path(small, mock_host, tmp_path):
+    """ya_align_batch answering YA_E_STATE (a batch with more seed hits than one pass holds) is not fatal: the host builds the
+    reads from its flat input buffers and runs the whole batch through the fibers.  Same SAM."""
+    out = str(tmp_path / "o.sam")
+    p = subprocess.run(H.command(mock_host, small, "reads.fa", "-osh", out, ["-BW", "5", "-G", "50"], threads=2), capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, YA_MOCK_ALIGN_TOO_BIG="1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert H.sam_lines(open(out).read()) == H.expected(small, "out_bw5.sam.gz")
