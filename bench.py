@@ -311,14 +311,19 @@ def run_ours(args):
             json.dump(stats_a, f)
     assert len(timed_a) == args.steps, (len(stats_a), args.warmup, args.steps)
     el_e2e = sum(s["align_s"] for s in timed_a)
-    # run B: parsed reads replayed from host memory, SAM formatted but not written -> value, stage times and
-    # the kernel rooflines (kernels of up to 8 pipelines share the SMs here, which stretches their event timings;
-    # run C below times the same kernels alone).
+    # run B: parsed reads replayed from host memory, SAM formatted but not written -> value, stage times and the kernel
+    # rooflines.  Two pipelines x 10 000-read batches: every extension launch carries ~20 K jobs (0.7 of the INT32 roofline per
+    # launch).  The latency-tuned configuration of the e2e run (four pipelines x 5000 reads) is replayed as run D and reported
+    # beside it (`value_at_e2e_config`: more reads/s, launches half the size); run C times the kernels alone on whole-shard batches.
     stats_b = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + extra_warm + args.warmup + args.steps,
                        args.batch, pipes, replay=True, env=benv())
     timed = stats_b[1 + extra_warm + args.warmup:]
     assert len(timed) == args.steps
     el_res = sum(s["align_s"] for s in timed)
+    stats_d = run_host(idx_path, reads_path, out_path + ".replay", REF_FLAGS[wl], threads, local, 1 + extra_warm + args.warmup + args.steps,
+                       args.e2e_batch, e2e_pipes, replay=True, env=benv())[1 + extra_warm + args.warmup:]
+    d_el = sum(s["align_s"] for s in stats_d)
+    d_cells, d_ms, d_union = (sum(s[k] for s in stats_d) for k in ("ext_cells", "dev_ms_ext", "dev_ms_ext_union"))
     # run C (not part of value/e2e): the same job with the whole shard as ONE batch on one pipeline, DP rounds in
     # lock step -> every extension launch carries the workload's ~40 K jobs and no other pipeline shares the SMs.
     # This is the timed region the kernel rooflines are quoted on; run B's small launches are reported beside it.
@@ -409,6 +414,11 @@ def run_ours(args):
                 "ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed_a],
                 "ms_per_untimed_step": [round(s["align_s"] * 1e3, 2) for s in stats_a[:extra_warm + args.warmup]]},
         "value_ms_per_timed_step": [round(s["align_s"] * 1e3, 2) for s in timed],
+        "value_at_e2e_config": {"what": f"the same replay with the e2e run's configuration ({args.e2e_batch}-read batches on {e2e_pipes} pipelines): "
+                                        "higher throughput, extension launches half the size",
+                                "value_this_rank": n_reads * args.steps / d_el, "unit": "reads/s", "ms_per_step": d_el / args.steps * 1e3,
+                                "roofline_frac_per_launch": d_cells / (d_ms * 1e-3) / 1e9 * INT_OPS_PER_CELL_EXT / int_add if d_ms > 0 and int_add else None,
+                                "roofline_frac_device_level": d_cells / (d_union * 1e-3) / 1e9 * INT_OPS_PER_CELL_EXT / int_add if d_union > 0 and int_add else None},
         "gpu_launches": int(tot("launches")), "gpu_launches_per_step": int(tot("launches")) // args.steps,
         "reads_finished_on_device_per_step": timed[-1].get("reads_finished_on_device"), "reads_handed_back_per_step": timed[-1].get("reads_handed_back"),
         # frac is the figure of the run that produces `value` (the product's own launches); the same kernel timed alone on
@@ -626,8 +636,8 @@ def main():
     ap.add_argument("--t1-sample", type=int, default=20000, help="reads aligned once with `yaha -t 1` for the in-order SAM comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inprocess", action="store_true", help="N > 1: skip the one-process -gpus N measurement on rank 0")
-    ap.add_argument("--batch", type=int, default=5000, help="reads per device batch")
-    ap.add_argument("--pipes", type=int, default=4, help="concurrent batch pipelines per GPU")
+    ap.add_argument("--batch", type=int, default=10000, help="reads per device batch in the value run")
+    ap.add_argument("--pipes", type=int, default=2, help="concurrent batch pipelines per GPU in the value run")
     ap.add_argument("--e2e-batch", type=int, default=5000, help="reads per device batch in the e2e run")
     ap.add_argument("--e2e-pipes", type=int, default=4, help="pipelines per GPU in the e2e run")
     args = ap.parse_args()
