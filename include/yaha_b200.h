@@ -190,6 +190,11 @@ int ya_set_stream(ya_ctx *, void *cuda_stream);
  * context there -- in every process of a multi-GPU job. */
 int ya_bind_thread(const ya_ctx *);
 
+/* Urgency of this context's work among the contexts that share its device (pipelines of one host program): level 0 (default)
+ * = most urgent, up to 3.  Maps to CUDA stream priorities; call between batches.  The host gives the batches in flight
+ * descending urgency in input order so that they finish one after the other and the ordered writer overlaps with compute. */
+int ya_set_priority(ya_ctx *, int level);
+
 /* Page-locked host memory for the buffers handed to the calls below (optional: any host pointer
  * works, page-locked ones are copied by DMA without an intermediate staging copy).  NULL on failure. */
 void *ya_host_alloc(size_t bytes);

@@ -74,6 +74,7 @@ ya_ctx *ya_open_peer(int device, const ya_ctx *src)
 ya_ctx *ya_open_shared(const ya_ctx *src) { return ya_open_peer(0, src); }
 int ya_peer_direct(const ya_ctx *c) { (void)c; return 0; }
 int ya_bind_thread(const ya_ctx *c) { (void)c; return 0; }
+int ya_set_priority(ya_ctx *c, int level) { (void)c; return level < 0 ? YA_E_ARG : 0; }
 int ya_get_ext_intervals(ya_ctx *c, float *b, int cap, int *n) { (void)c; (void)b; (void)cap; *n = 0; return 0; }
 ya_ctx *ya_open_build(int d, const ya_params *p, const uint8_t *b, size_t n, const uint32_t *s, const uint32_t *l, int ns, uint32_t mh, uint32_t sk)
 { (void)d; (void)p; (void)b; (void)n; (void)s; (void)l; (void)ns; (void)mh; (void)sk; return NULL; }

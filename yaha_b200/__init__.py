@@ -96,7 +96,7 @@ class _TextBatch(C.Structure):
 
 EXPORTS = ("ya_open", "ya_open_build", "ya_index_sizes", "ya_index_download", "ya_open_peer", "ya_open_shared", "ya_close", "ya_last_error", "ya_set_params", "ya_set_stream",
            "ya_reads_upload", "ya_seed_frags", "ya_form_clumps", "ya_prepare_clumps", "ya_sw_batch", "ya_sw_fetch_ops", "ya_perfect_ext", "ya_host_alloc", "ya_host_free", "ya_get_counters",
-           "ya_measure_int32_peak", "ya_measure_gather_peak", "ya_set_output", "ya_align_batch", "ya_align_fetch_text", "ya_peer_direct", "ya_get_ext_intervals", "ya_bind_thread")
+           "ya_measure_int32_peak", "ya_measure_gather_peak", "ya_set_output", "ya_align_batch", "ya_align_fetch_text", "ya_peer_direct", "ya_get_ext_intervals", "ya_bind_thread", "ya_set_priority")
 
 _lib = None
 

@@ -113,7 +113,9 @@ struct DeviceTurn {
 struct ya_ctx {
     int          device = -1;
     ya_params    P{};
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr;    // = prio_streams[prio_level]
+    cudaStream_t prio_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // ya_set_priority: level 0 = the device's greatest priority
+    int          prio_level = 0;
     cudaStream_t bulk_stream = nullptr;   // lowest priority: DP calls with many jobs
     cudaStream_t stream = nullptr;
     std::string  err;

@@ -92,6 +92,7 @@ static ya_ctx *open_common(int device, const ya_params *params)
         g_open_err = "cudaStreamCreate failed"; delete c; return nullptr;
     }
     c->stream = c->own_stream;
+    c->prio_streams[0] = c->own_stream;
     for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     return c;
 }
@@ -337,7 +338,7 @@ extern "C" void ya_close(ya_ctx *c)
     PinBuf *pins[] = {&c->h_stage, &c->h_stage2, &c->h_stage3, &c->h_jobs, &c->h_res, &c->h_ops};
     for (PinBuf *b : pins) b->release();
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (cudaStream_t ps : c->prio_streams) if (ps) cudaStreamDestroy(ps);
     if (c->bulk_stream) cudaStreamDestroy(c->bulk_stream);
     delete c;
 }
@@ -361,6 +362,32 @@ extern "C" int ya_set_stream(ya_ctx *c, void *s)
 {
     if (!c) return YA_E_ARG;
     c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return YA_OK;
+}
+
+// Urgency of the context's own work among the contexts sharing its device: level 0 (default) is the device's greatest stream
+// priority, every further level one step lower (clamped one above the bulk stream's).  The host program gives the batches in
+// flight on one device descending urgency in input order, so that they FINISH one after the other -- the ordered writer then
+// works on batch k while batch k+1 still computes -- instead of all at once.  To be called between batches (context idle).
+extern "C" int ya_set_priority(ya_ctx *c, int level)
+{
+    if (!c || level < 0) return YA_E_ARG;
+    if (level > 3) level = 3;
+    if (level == c->prio_level) return YA_OK;
+    YA_CUDA(c, cudaSetDevice(c->device));
+    if (!c->prio_streams[level]) {
+        int prLeast = 0, prGreatest = 0;
+        YA_CUDA(c, cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));
+        int pr = prGreatest + level;                                  // (numerically greater = less urgent)
+        if (pr > prLeast - 1) pr = prLeast - 1;
+        if (pr < prGreatest) pr = prGreatest;
+        YA_CUDA(c, cudaStreamCreateWithPriority(&c->prio_streams[level], cudaStreamNonBlocking, pr));
+    }
+    YA_CUDA(c, cudaStreamSynchronize(c->own_stream));                 // (idle by contract; scratch freed there is reusable after this)
+    const bool installed = (c->stream == c->own_stream);
+    c->own_stream = c->prio_streams[level];
+    c->prio_level = level;
+    if (installed) c->stream = c->own_stream;
     return YA_OK;
 }
 

@@ -949,6 +949,7 @@ int runQueries(const Args &A0)
     const int pipesPerDev = std::max(1, A.pipes);
     const int nPipes = nDev * pipesPerDev;
     WorkerPool pool;                                                    // -t worker threads, shared by all pipelines
+    const int prioLevels = [&] { const char *e = getenv("YA_PRIO"); return std::max(1, std::min(std::min(e ? atoi(e) : 4, 4), pipesPerDev)); }();   // (default: 4 levels; YA_PRIO=0: off)
     pool.start(A.threadsPerPipe > 0 ? std::min(A.threadsPerPipe, 4 * nproc) : nThreads);   // (-tpp N: explicit pool size, may oversubscribe)
     std::vector<Pipe> pipes((size_t)nPipes);
     double tOpen = nowSec();
@@ -1104,6 +1105,10 @@ int runQueries(const Args &A0)
                         F.in.pop_front();
                         F.cvSpace.notify_one();
                     }
+                    // Batches in flight on one device get descending urgency in input order (ya_set_priority): they then finish one
+                    // after the other and the ordered writer works on batch k while batch k+1 still computes, instead of four
+                    // batches finishing together and their writes queueing behind each other.  YA_PRIO=0: all alike.
+                    if (prioLevels > 1) ya_set_priority(pipes[(size_t)p].ctx, (int)((b->seq / (uint64_t)nDev) % (uint64_t)prioLevels));
                     processBatch(E, pipes[(size_t)p], *b, pool);
                     std::lock_guard<std::mutex> lk(F.mu);
                     uint64_t s = b->seq;
