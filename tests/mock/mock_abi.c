@@ -253,9 +253,9 @@ int ya_sw_batch(ya_ctx *c, const ya_dp_job *jobs, int n, ya_dp_result *res, ya_o
         int aq = 0, ar = 0, no = 0; int64_t cells = 0;
         int score = orc_dp(&c->P, c->bases, c->maxROff, codes, j->kind, j->rOff, j->rLen, j->qOff, j->qLen, &aq, &ar, tmp, 70000, &no, &cells);
         res[i].score = score; res[i].addedQLen = (uint16_t)aq; res[i].addedRLen = (uint16_t)ar; res[i].ops_off = (uint32_t)used; res[i].ops_n = (uint32_t)no;
-        if (used + no <= ops_cap) memcpy(ops + used, tmp, no * sizeof(ya_op)); else overflow = 1;
+        if (used + no > ops_cap) overflow = 1; else if (no) memcpy(ops + used, tmp, no * sizeof(ya_op));
         if (used + no > c->pendingCap) { c->pendingCap = 2 * (used + no) + 1024; c->pending = realloc(c->pending, c->pendingCap * sizeof(ya_op)); }
-        memcpy(c->pending + used, tmp, no * sizeof(ya_op));
+        if (no) memcpy(c->pending + used, tmp, no * sizeof(ya_op));
         used += no;
         c->ctr.dp_cells += cells; c->ctr.dp_jobs++;
     }

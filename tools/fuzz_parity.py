@@ -67,7 +67,7 @@ def draw_reference(rng, heavy=False):
     return ref, bounds
 
 
-def draw_reads(rng, ref, bounds, heavy=False):
+def draw_reads(rng, ref, bounds, heavy=False, chars=False):
     import make_golden as MG
     L = len(ref)
     reads = []
@@ -89,6 +89,21 @@ def draw_reads(rng, ref, bounds, heavy=False):
         reads += MG.chimera_reads(ref, int(rng.integers(1, 1 << 30)), n_reads=int(rng.integers(5, 40)))
     if kind in (2, 3, 4, 5):
         reads += MG.multi_reads(ref, int(rng.integers(1, 1 << 30)), n=int(rng.integers(10, 80)))
+    # character-level noise: lower case, IUPAC codes, stray symbols (Math.c:141-157: the code table of the reader)
+    if chars:
+        noisy = []
+        for name, r in reads:
+            r = np.array(r, dtype=np.uint8, copy=True)
+            u = rng.random()
+            if u < 0.10 and len(r):
+                a = int(rng.integers(0, len(r))); b = int(rng.integers(a, len(r) + 1))
+                seg = r[a:b]; up = (seg >= 65) & (seg <= 90); seg[up] += 32
+            elif u < 0.16 and len(r):
+                k = int(rng.integers(1, 6))
+                pos = rng.integers(0, len(r), size=k)
+                r[pos] = np.frombuffer(b"RYKMSWBDHVNXryn.-*", dtype=np.uint8)[rng.integers(0, 18, size=k)]
+            noisy.append((name, r))
+        reads = noisy
     # order shuffled so that batches mix kinds
     order = rng.permutation(len(reads))
     return [reads[int(k)] for k in order]
@@ -99,7 +114,7 @@ FLAG_POOL = H.FLAG_SWEEP + [[], [], [], ["-OQC", "N"], ["-FBS", "Y"], ["-FBS", "
 
 
 def one_case(args):
-    seed, keep, heavy, binary, wordlens = args
+    seed, keep, heavy, binary, wordlens, chars = args
     rng = np.random.default_rng(seed)
     tmp = tempfile.mkdtemp(prefix=f"fuzz{seed}_")
     try:
@@ -114,7 +129,7 @@ def one_case(args):
         idx = [f for f in os.listdir(tmp) if f.startswith("ref.X")]
         assert len(idx) == 1, idx
         fastq = bool(rng.integers(0, 5) == 0)
-        reads = draw_reads(rng, ref, bounds, heavy)
+        reads = draw_reads(rng, ref, bounds, heavy, chars)
         qf = "reads.fq" if fastq else "reads.fa"
         synth.write_reads(tmp + "/" + qf, reads, fastq=fastq)
         flags = list(FLAG_POOL[int(rng.integers(0, len(FLAG_POOL)))])
@@ -166,6 +181,7 @@ def main():
     ap.add_argument("--keep", default="/tmp/fuzz_fail")
     ap.add_argument("--heavy", action="store_true", help="repeat families with 40-300 copies, reads of 1-30 kbp")
     ap.add_argument("--binary", default=MOCK, help="host program under test (default: the CPU mock build; on a GPU box: yaha_b200/yaha_b200_host)")
+    ap.add_argument("--chars", action="store_true", help="lower case, IUPAC codes and stray symbols in a quarter of the reads")
     ap.add_argument("--wordlens", default="11,11,12,13,15", help="-L values drawn from (an -L 15 index is a 4.3 GB file)")
     a = ap.parse_args()
     a.binary = os.path.abspath(a.binary)
@@ -177,7 +193,7 @@ def main():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "mock"), "SAN="])
     nbad = nskip = 0
     with ProcessPoolExecutor(a.jobs) as ex:
-        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl) for s in range(lo, hi)]):
+        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars) for s in range(lo, hi)]):
             print(("FAIL" if bad else "ok  "), seed, desc, flush=True)
             nskip += desc.startswith(("skip", "timeout"))
             if bad:
