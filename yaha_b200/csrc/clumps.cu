@@ -2,13 +2,11 @@
 //
 // ya_form_clumps runs yaha_b200/csrc/form_clumps.h (the region loop of processFragmentsGapped, the fragment
 // graph of buildBestClumpFromFragmentRange, insertFragment's overlap chops, cleanUpClump, eliminateFragments:
-// QueryMatch.c:170-303, GraphPath.cpp:161-292, AlignHelpers.c:48-193) with one thread per strand on the
-// survivors ya_seed_frags left on the device.  The work per strand is a few thousand scalar, branchy
-// instructions (a dozen fragments, an O(n^2) chain DP with the reference's tie rules): it is bound by the
-// divergence of 32 unrelated strands per warp, not by memory -- 40 K strands keep every SM busy for a fraction
-// of a millisecond, which is what takes this step off the host's worker threads.  Strands with more than
-// kMaxStrandFrags fragments (repeat-rich loci, where the quadratic chain would make one thread the whole
-// kernel) are left to the host: their clump count comes back as 0xFFFFFFFF.
+// QueryMatch.c:170-303, GraphPath.cpp:161-292, AlignHelpers.c:48-193) with one WARP per strand on the
+// survivors ya_seed_frags left on the device: lane 0 runs the serial parts (a dozen fragments per strand as a
+// rule), the inner loop of the O(n^2) chain DP is strided over the lanes.  Strands with more than
+// kMaxStrandFrags fragments (repeat-rich loci) are left to the host: their clump count comes back as
+// 0xFFFFFFFF.  ya_prepare_clumps (prepare_clumps.h) then runs one thread per CLUMP.
 #define FC_WARP_COOP 1          // form_clumps.h: one warp per strand (must precede every inclusion of the header)
 #include "common.cuh"
 #include "form_clumps.h"
@@ -106,7 +104,7 @@ int ya_form_clumps_impl(ya_ctx *c, ya_clump_batch *out, bool device_only)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// First phase of alignClump for those clumps (prepare_clumps.h), one thread per strand.
+// First phase of alignClump for those clumps (prepare_clumps.h), one thread per clump.
 __global__ void __launch_bounds__(128)
 prepare_clumps_kernel(uint32_t n_slots, const uint32_t *__restrict__ slot_strand, const uint64_t *__restrict__ read_off,
                       const ya_clump_rec *__restrict__ clumps, const ya_frag *__restrict__ path_in,

@@ -1,6 +1,6 @@
 /* form_clumps.h -- fragments of one strand -> clumps of seed fragments.
  *
- * ONE statement of the algorithm, plain C99, compiled three ways: as device code by clumps.cu (one thread per
+ * ONE statement of the algorithm, plain C99, compiled three ways: as device code by clumps.cu (one warp per
  * strand, ya_form_clumps), as host code by the host program (yaha_b200/host/graph.cpp) and by the oracle-backed
  * mock of the ABI (tests/mock/mock_abi.c).  The host program's golden tests therefore pin the very code the
  * kernel runs.
