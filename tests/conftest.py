@@ -25,7 +25,7 @@ class Small:
     def __init__(self, tmpdir):
         g = os.path.join(ROOT, "tests", "golden", "small")
         self.dir = str(tmpdir)
-        for name in ("ref.fa", "reads.fa", "reads.fq", "weird.fa", "chimera.fa", "weird.fq", "weird2.fa", "multi.fa"):
+        for name in ("ref.fa", "reads.fa", "reads.fq", "weird.fa", "chimera.fa", "weird.fq", "weird2.fa", "multi.fa", "weird3.fa", "weird3.fq"):
             with gzip.open(os.path.join(g, name + ".gz"), "rb") as f, open(os.path.join(self.dir, name), "wb") as o:
                 o.write(f.read())
         self.golden = g

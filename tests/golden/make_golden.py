@@ -235,7 +235,47 @@ def only_weird_headers():
     shutil.rmtree(tmp)
 
 
+def only_empty_first():
+    """Adds weird3.fa.gz / weird3.fq.gz and their outputs: an EMPTY record in front.  A record without bases ends the run like
+    EOF (the loop of processQueries runs while queryLen > 0, Query.c:306) -- but the first record readNextQuery returns gets a
+    second chance (Query.c:304 after main's own first read, Query.c:637), also behind records that were skipped as too short.
+    The empty record further down ends the run: the reads behind it are never aligned.  Found by tools/fuzz_parity.py --weird."""
+    tmp = tempfile.mkdtemp()
+    for name in ("ref.fa", "reads.fa"):
+        with gzip.open(f"{OUT}/{name}.gz", "rb") as f, open(f"{tmp}/{name}", "wb") as o:
+            o.write(f.read())
+    subprocess.check_call([REF + "/yaha", "-g", "ref.fa", "-L", "11", "-S", "1"], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lines = open(tmp + "/reads.fa").read().split(">")[20:32]
+    rs = [(l.split("\n", 1)[0], l.split("\n", 1)[1].replace("\n", "")) for l in lines]
+    with open(tmp + "/weird3.fa", "w") as f:
+        f.write(f">tooshort\nACGTAC\n")                       # skipped with a warning: not a returned record
+        f.write(f">empty_first\n")                            # the first record returned, empty: read once more
+        for k in range(0, 6):
+            f.write(f">{rs[k][0]}\n{rs[k][1]}\n")
+        f.write(f">empty_again\n\n")                          # ends the run
+        for k in range(6, 12):
+            f.write(f">{rs[k][0]}\n{rs[k][1]}\n")
+    with open(tmp + "/weird3.fq", "w") as f:
+        f.write("@empty_first\n\n+\n\n")
+        for k in range(0, 6):
+            f.write(f"@{rs[k][0]}\n{rs[k][1]}\n+\n{'H' * len(rs[k][1])}\n")
+        f.write("@empty_again\n\n+\n\n")
+        for k in range(6, 12):
+            f.write(f"@{rs[k][0]}\n{rs[k][1]}\n+\n{'H' * len(rs[k][1])}\n")
+    for q, flag, out in (("weird3.fa", "-osh", "out_weird3.sam"), ("weird3.fq", "-oss", "out_weird3_fastq.sam")):
+        subprocess.check_call([REF + "/yaha", "-x", "ref.X11_01_65525S", "-q", q, flag, out, "-t", "1"], cwd=tmp,
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        n = sum(1 for l in open(f"{tmp}/{out}") if not l.startswith("@"))
+        assert n >= 6, (q, n)
+        gz(f"{tmp}/{out}", f"{OUT}/{out}.gz")
+        gz(f"{tmp}/{q}", f"{OUT}/{q}.gz")
+    shutil.rmtree(tmp)
+
+
 def main():
+    if "--only-empty-first" in sys.argv:
+        only_empty_first()
+        return
     if "--only-multi" in sys.argv:
         only_multi()
         return

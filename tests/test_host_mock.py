@@ -51,7 +51,7 @@ def test_sliced_and_sequential_fasta_readers_agree(small, mock_host, tmp_path):
     # FASTA is cut into records by the reader and parsed by the pipelines (RecordSlicer / parseFastaRecord);
     # YA_SEQ_READER=1 keeps the sequential reader of the FASTQ path.  Both must give the reference's records,
     # including the odd inputs (CRLF, over-long, too-short, empty and multi-line records, '>' inside a line).
-    for reads, golden in (("weird.fa", "out_weird.sam.gz"), ("reads.fa", "out_bw5.sam.gz")):
+    for reads, golden in (("weird.fa", "out_weird.sam.gz"), ("reads.fa", "out_bw5.sam.gz"), ("weird3.fa", "out_weird3.sam.gz")):
         want = H.expected(small, golden)
         extra = ["-BW", "5", "-G", "50"] if reads == "reads.fa" else []
         for k, env in enumerate(({}, {"YA_SEQ_READER": "1"})):

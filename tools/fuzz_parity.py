@@ -109,12 +109,51 @@ def draw_reads(rng, ref, bounds, heavy=False, chars=False):
     return [reads[int(k)] for k in order]
 
 
+def write_queries(path, reads, fastq, rng, weird):
+    """The query file.  weird: the reader's corner cases (Query.c:102-228) -- descriptions and record markers inside id lines,
+    multi-line sequences, blank lines, CRLF, empty records, missing final newline, random qualities, '+' lines with names."""
+    if not weird:
+        return synth.write_reads(path, reads, fastq=fastq)
+    eol = b"\r\n" if rng.integers(0, 6) == 0 else b"\n"
+    out = bytearray()
+    last_len = 1
+    for name, seq in reads:
+        seq = np.asarray(seq, dtype=np.uint8)
+        nm = name.encode()
+        u = int(rng.integers(0, 10))
+        if u == 0: nm += b" some description"
+        elif u == 1: nm += b"\tx=1"
+        elif u == 2: nm += b" >inner @at +plus"
+        elif u == 3: nm += b">" 
+        if rng.integers(0, 60) == 0:
+            seq = seq[:0]                                             # empty record
+        last_len = len(seq)
+        if fastq:
+            q = rng.integers(35, 127, size=len(seq)).astype(np.uint8)  # (no '!' / '"' / '#': nothing special, just printable)
+            if len(q) and rng.integers(0, 4) == 0: q[0] = ord("@")
+            if len(q) > 1 and rng.integers(0, 4) == 0: q[int(rng.integers(0, len(q)))] = ord("+")
+            plus = b"+" + (nm if rng.integers(0, 4) == 0 else b"")
+            out += b"@" + nm + eol + seq.tobytes() + eol + plus + eol + q.tobytes() + eol
+        else:
+            out += b">" + nm + eol
+            w = int(rng.choice([0, 0, 60, 70, 13])) or max(1, len(seq))
+            if rng.integers(0, 8) == 0: w = int(rng.integers(1, 200))
+            for a in range(0, len(seq), w):
+                out += seq[a:a + w].tobytes() + eol
+                if rng.integers(0, 300) == 0: out += eol               # blank line inside a record
+            if rng.integers(0, 30) == 0: out += eol
+    if rng.integers(0, 5) == 0 and out.endswith(eol) and last_len > 0:
+        del out[-len(eol):]
+    open(path, "wb").write(bytes(out))
+    return len(reads)
+
+
 FLAG_POOL = H.FLAG_SWEEP + [[], [], [], ["-OQC", "N"], ["-FBS", "Y"], ["-FBS", "Y", "-PRL", "0.3", "-PSS", "0.3"], ["-BW", "10", "-G", "100"],
                             ["-MGDP", "3", "-BP", "3"], ["-M", "18", "-P", "0.6"], ["-X", "15", "-BW", "15", "-G", "150"]]
 
 
 def one_case(args):
-    seed, keep, heavy, binary, wordlens, chars = args
+    seed, keep, heavy, binary, wordlens, chars, weird = args
     rng = np.random.default_rng(seed)
     tmp = tempfile.mkdtemp(prefix=f"fuzz{seed}_")
     try:
@@ -131,7 +170,7 @@ def one_case(args):
         fastq = bool(rng.integers(0, 5) == 0)
         reads = draw_reads(rng, ref, bounds, heavy, chars)
         qf = "reads.fq" if fastq else "reads.fa"
-        synth.write_reads(tmp + "/" + qf, reads, fastq=fastq)
+        write_queries(tmp + "/" + qf, reads, fastq, rng, weird)
         flags = list(FLAG_POOL[int(rng.integers(0, len(FLAG_POOL)))])
         if rng.integers(0, 3) == 0:
             more = FLAG_POOL[int(rng.integers(0, len(FLAG_POOL)))]
@@ -182,6 +221,7 @@ def main():
     ap.add_argument("--heavy", action="store_true", help="repeat families with 40-300 copies, reads of 1-30 kbp")
     ap.add_argument("--binary", default=MOCK, help="host program under test (default: the CPU mock build; on a GPU box: yaha_b200/yaha_b200_host)")
     ap.add_argument("--chars", action="store_true", help="lower case, IUPAC codes and stray symbols in a quarter of the reads")
+    ap.add_argument("--weird", action="store_true", help="query files with the reader's corner cases (multi-line, CRLF, markers in id lines, random qualities ...)")
     ap.add_argument("--wordlens", default="11,11,12,13,15", help="-L values drawn from (an -L 15 index is a 4.3 GB file)")
     a = ap.parse_args()
     a.binary = os.path.abspath(a.binary)
@@ -193,7 +233,7 @@ def main():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "mock"), "SAN="])
     nbad = nskip = 0
     with ProcessPoolExecutor(a.jobs) as ex:
-        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars) for s in range(lo, hi)]):
+        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars, a.weird) for s in range(lo, hi)]):
             print(("FAIL" if bad else "ok  "), seed, desc, flush=True)
             nskip += desc.startswith(("skip", "timeout"))
             if bad:

@@ -220,7 +220,12 @@ bool QueryReader::next(Read &r)
             fail = true;
         }
         if (fail) continue;
-        if (n == 0) return false;                    // end of input (or an empty record, as in the reference)
+        // A record without bases ends the input like EOF does (the caller's loop runs while queryLen > 0, Query.c:306) -- except
+        // when it is the first record readNextQuery returns: the reference then reads once more ("make sure we have read a
+        // first query", Query.c:304, after main's own first read at :637).
+        const bool firstReturn = !returnedOnce;
+        returnedOnce = true;
+        if (n == 0) { if (firstReturn) continue; return false; }
         // codes are derived later, off the reader thread: forward by the pipeline that uploads the batch
         // (Read::encode), reverse-complement by the worker that owns the read (Read::finish)
         r.fcode.clear();
@@ -257,6 +262,7 @@ void RecordSlicer::close()
 
 bool RecordSlicer::next(const char *&s, size_t &n)
 {
+  for (;;) {
     if (done) return false;
     if (pos > len) { done = true; return false; }
     s = base + pos;
@@ -270,8 +276,19 @@ bool RecordSlicer::next(const char *&s, size_t &n)
     // a record without sequence characters ends the input (Query.c:222): id line, then nothing but newlines
     size_t q = idEnd;
     while (q < n && s[q] == '\n') q++;
-    if (q >= n) { done = true; return false; }
+    if (q >= n) {
+        // ... except when no record before it was a good one (the parser skips records that are too long or shorter than
+        // wordLen): it is then the first record readNextQuery RETURNS, and the reference reads once more (Query.c:304,637).
+        if (!anyGood && !skippedEmpty) { skippedEmpty = true; continue; }
+        done = true; return false;
+    }
+    if (!anyGood && !skippedEmpty) {
+        size_t m = 0;
+        for (size_t k = idEnd; k < n; k++) m += s[k] != '\n';
+        if ((int64_t)m >= wordLen && (int64_t)m <= maxLen) anyGood = true;
+    }
     return true;
+  }
 }
 
 int parseFastaRecord(const char *s, size_t n, Read &r, int maxLen, int wordLen)

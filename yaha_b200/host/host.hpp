@@ -87,6 +87,7 @@ struct Read {
 struct QueryReader {                 // readNextQuery, Query.c:102-228
     struct Buf;
     FILE *f = nullptr; Buf *buf = nullptr; bool fastq = false; int maxLen = 32000, wordLen = 15;
+    bool returnedOnce = false;                                 // (an empty record is skipped if it is the first one returned, Query.c:304)
     bool open(const std::string &path, std::string &err);     // Query.c:63-74
     bool next(Read &r);                                        // false at EOF
     void close();
@@ -97,6 +98,7 @@ struct QueryReader {                 // readNextQuery, Query.c:102-228
 // records (parseFastaRecord) -- so parsing runs on as many threads as there are pipelines.
 struct RecordSlicer {
     const char *base = nullptr; size_t len = 0, pos = 0; bool done = true;
+    int maxLen = 32000, wordLen = 15; bool anyGood = false, skippedEmpty = false;   // for the same rule (set after open)
     bool open(const std::string &path, std::string &err);      // maps the file; the first character is the first marker
     bool next(const char *&s, size_t &n);                      // false at end of input or at an empty record (Query.c:222)
     void close();

@@ -1035,6 +1035,7 @@ int runQueries(const Args &A0)
                 if (fromStdin) { qr = stdinReader; stdinReader.f = nullptr; stdinReader.buf = nullptr; }
                 else if (!(sliced ? sl.open(A.qfile, e2) : qr.open(A.qfile, e2))) { fprintf(stderr, "%s\n", e2.c_str()); exit(1); }
                 qr.wordLen = A.wordLen; qr.maxLen = A.maxQueryLength;
+                sl.wordLen = A.wordLen; sl.maxLen = A.maxQueryLength;
                 bool eof = false;
                 while (sliced && !eof) {                                  // FASTA: cut records here, parse them in the pipelines
                     double r0 = nowSec();
