@@ -127,19 +127,31 @@ def write_queries(path, reads, fastq, rng, weird):
         elif u == 3: nm += b">" 
         if rng.integers(0, 60) == 0:
             seq = seq[:0]                                             # empty record
+        if rng.integers(0, 150) == 0 and len(seq):
+            seq = np.tile(seq, 32100 // len(seq) + 1)[:int(rng.integers(32001, 32100))]   # longer than the reader's 32 000 bases
+        if rng.integers(0, 100) == 0:
+            nm = nm + b"_" + b"x" * int(rng.integers(190, 230))        # id around the 200-character cut
         last_len = len(seq)
         if fastq:
             q = rng.integers(35, 127, size=len(seq)).astype(np.uint8)  # (no '!' / '"' / '#': nothing special, just printable)
             if len(q) and rng.integers(0, 4) == 0: q[0] = ord("@")
             if len(q) > 1 and rng.integers(0, 4) == 0: q[int(rng.integers(0, len(q)))] = ord("+")
             plus = b"+" + (nm if rng.integers(0, 4) == 0 else b"")
-            out += b"@" + nm + eol + seq.tobytes() + eol + plus + eol + q.tobytes() + eol
+            if rng.integers(0, 40) == 0 and len(q) > 2: q = q[:-1]      # quality shorter than the sequence: record skipped
+            sb, qb = seq.tobytes(), q.tobytes()
+            if rng.integers(0, 25) == 0 and len(sb) > 20:                # multi-line FASTQ
+                h = len(sb) // 2
+                sb = sb[:h] + eol + sb[h:]
+                qb = qb[:h] + eol + qb[h:]
+            out += b"@" + nm + eol + sb + eol + plus + eol + qb + eol
         else:
             out += b">" + nm + eol
             w = int(rng.choice([0, 0, 60, 70, 13])) or max(1, len(seq))
             if rng.integers(0, 8) == 0: w = int(rng.integers(1, 200))
             for a in range(0, len(seq), w):
-                out += seq[a:a + w].tobytes() + eol
+                line = seq[a:a + w].tobytes()
+                if rng.integers(0, 400) == 0 and len(line) > 4: line = line[:2] + b">" + line[2:]   # a marker inside a sequence line
+                out += line + eol
                 if rng.integers(0, 300) == 0: out += eol               # blank line inside a record
             if rng.integers(0, 30) == 0: out += eol
     if rng.integers(0, 5) == 0 and out.endswith(eol) and last_len > 0:
