@@ -32,7 +32,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "yaha")
 MOCK = os.path.join(ROOT, "tests", "_build", "yaha_host_mock")
 
 
-def draw_reference(rng, heavy=False):
+def draw_reference(rng, heavy=False, manyseq=False):
     n = int(rng.integers(40_000, 160_000))
     ref = synth.random_reference(n, int(rng.integers(1, 1 << 30))).copy()
     # repeat families: an element pasted many times with divergence
@@ -63,7 +63,9 @@ def draw_reference(rng, heavy=False):
         p = int(rng.integers(0, n - 300))
         ref[p:p + int(rng.integers(1, 200))] = ord("N")
     k = int(rng.integers(1, 5))
-    bounds = sorted(set([0, n] + [int(x) for x in rng.integers(1000, n - 1000, size=k - 1)]))
+    if manyseq:
+        k = int(rng.integers(40, 400))                                # hundreds of short sequences: boundaries everywhere
+    bounds = sorted(set([0, n] + [int(x) for x in rng.integers(100 if manyseq else 1000, n - (100 if manyseq else 1000), size=k - 1)]))
     return ref, bounds
 
 
@@ -165,11 +167,11 @@ FLAG_POOL = H.FLAG_SWEEP + [[], [], [], ["-OQC", "N"], ["-FBS", "Y"], ["-FBS", "
 
 
 def one_case(args):
-    seed, keep, heavy, binary, wordlens, chars, weird = args
+    seed, keep, heavy, binary, wordlens, chars, weird, manyseq = args
     rng = np.random.default_rng(seed)
     tmp = tempfile.mkdtemp(prefix=f"fuzz{seed}_")
     try:
-        ref, bounds = draw_reference(rng, heavy)
+        ref, bounds = draw_reference(rng, heavy, manyseq)
         synth.write_fasta(tmp + "/ref.fa", [(f"chr{k + 1} desc", ref[bounds[k]:bounds[k + 1]]) for k in range(len(bounds) - 1)],
                           width=int(rng.choice([50, 60, 70])))
         Lw = int(rng.choice(wordlens))
@@ -234,6 +236,7 @@ def main():
     ap.add_argument("--binary", default=MOCK, help="host program under test (default: the CPU mock build; on a GPU box: yaha_b200/yaha_b200_host)")
     ap.add_argument("--chars", action="store_true", help="lower case, IUPAC codes and stray symbols in a quarter of the reads")
     ap.add_argument("--weird", action="store_true", help="query files with the reader's corner cases (multi-line, CRLF, markers in id lines, random qualities ...)")
+    ap.add_argument("--manyseq", action="store_true", help="references of 40-400 short sequences")
     ap.add_argument("--wordlens", default="11,11,12,13,15", help="-L values drawn from (an -L 15 index is a 4.3 GB file)")
     a = ap.parse_args()
     a.binary = os.path.abspath(a.binary)
@@ -245,7 +248,7 @@ def main():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "mock"), "SAN="])
     nbad = nskip = 0
     with ProcessPoolExecutor(a.jobs) as ex:
-        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars, a.weird) for s in range(lo, hi)]):
+        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars, a.weird, a.manyseq) for s in range(lo, hi)]):
             print(("FAIL" if bad else "ok  "), seed, desc, flush=True)
             nskip += desc.startswith(("skip", "timeout"))
             if bad:
