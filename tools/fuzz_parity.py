@@ -167,7 +167,7 @@ FLAG_POOL = H.FLAG_SWEEP + [[], [], [], ["-OQC", "N"], ["-FBS", "Y"], ["-FBS", "
 
 
 def one_case(args):
-    seed, keep, heavy, binary, wordlens, chars, weird, manyseq = args
+    seed, keep, heavy, binary, wordlens, chars, weird, manyseq, from_stdin = args
     rng = np.random.default_rng(seed)
     tmp = tempfile.mkdtemp(prefix=f"fuzz{seed}_")
     try:
@@ -193,8 +193,9 @@ def one_case(args):
                 if a not in have:
                     flags += [a, b]
         outflag = str(rng.choice(["-osh", "-osh", "-osh", "-oss", "-o8"]))
-        base = ["-x", idx[0], "-q", qf]
-        r = subprocess.run([REF] + base + [outflag, "want.out", "-t", "1"] + flags, cwd=tmp, capture_output=True, text=True, timeout=900)
+        base = ["-x", idx[0]] + ([] if from_stdin else ["-q", qf])            # (no -q: queries from standard input, Main.c:173-178)
+        r = subprocess.run([REF] + base + [outflag, "want.out", "-t", "1"] + flags, cwd=tmp, capture_output=True, text=True, timeout=900,
+                           stdin=open(tmp + "/" + qf, "rb") if from_stdin else subprocess.DEVNULL)
         if r.returncode != 0:
             return seed, f"skip (reference failed rc={r.returncode}: {r.stderr.strip()[-160:]!r}): " + " ".join(flags), None
         host = ["-t", str(int(rng.integers(1, 4))), "-batch", str(int(rng.choice([7, 33, 100, 5000]))), "-pipes", str(int(rng.integers(1, 3)))]
@@ -203,7 +204,8 @@ def one_case(args):
         env = dict(os.environ)
         if rng.integers(0, 4) == 0:
             env["YA_FUSED"] = "0"
-        m = subprocess.run([binary] + base + [outflag, "got.out"] + host + flags, cwd=tmp, capture_output=True, text=True, timeout=1800, env=env)
+        m = subprocess.run([binary] + base + [outflag, "got.out"] + host + flags, cwd=tmp, capture_output=True, text=True, timeout=1800, env=env,
+                           stdin=open(tmp + "/" + qf, "rb") if from_stdin else subprocess.DEVNULL)
         desc = f"L{Lw} S{Sk} H{Hh} {qf} {outflag} {' '.join(flags)} | host {' '.join(host)} fused={env.get('YA_FUSED', '1')} reads={len(reads)} ref={len(ref)}"
         if m.returncode != 0:
             bad = "mock failed rc=%d: %s" % (m.returncode, m.stderr[-600:])
@@ -237,6 +239,7 @@ def main():
     ap.add_argument("--chars", action="store_true", help="lower case, IUPAC codes and stray symbols in a quarter of the reads")
     ap.add_argument("--weird", action="store_true", help="query files with the reader's corner cases (multi-line, CRLF, markers in id lines, random qualities ...)")
     ap.add_argument("--manyseq", action="store_true", help="references of 40-400 short sequences")
+    ap.add_argument("--stdin", action="store_true", help="queries through standard input (no -q)")
     ap.add_argument("--wordlens", default="11,11,12,13,15", help="-L values drawn from (an -L 15 index is a 4.3 GB file)")
     a = ap.parse_args()
     a.binary = os.path.abspath(a.binary)
@@ -248,7 +251,7 @@ def main():
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "mock"), "SAN="])
     nbad = nskip = 0
     with ProcessPoolExecutor(a.jobs) as ex:
-        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars, a.weird, a.manyseq) for s in range(lo, hi)]):
+        for seed, desc, bad in ex.map(one_case, [(s, a.keep, a.heavy, a.binary, wl, a.chars, a.weird, a.manyseq, a.stdin) for s in range(lo, hi)]):
             print(("FAIL" if bad else "ok  "), seed, desc, flush=True)
             nskip += desc.startswith(("skip", "timeout"))
             if bad:
